@@ -1,0 +1,262 @@
+/*
+ * psulvsb.h -- C ABI of the B200-native PSULVSB registration hot path (libpsulvsb_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes, no C++/torch types.
+ * It replaces, for the PSULVSB path only, what a binding to the reference would call:
+ *
+ *   teaser::RobustRegistrationSolver::Params                     (registration.h:378-473)
+ *   teaser::RobustRegistrationSolver::RobustRegistrationSolver   (registration.cc:465-468)
+ *   teaser::RobustRegistrationSolver::solve(src, dst)            (registration.cc:622-1535)
+ *   teaser::RobustRegistrationSolver::getSolution()              (registration.h:553)
+ *   teaser::RegistrationSolution                                 (registration.h:34-41)
+ *
+ * plus stage-level entry points for the four CUDA stages (device pointers + stream), which the
+ * parity tests and the benchmark drive directly.  Matrices follow Eigen's default layout:
+ * a 3xN point set is a column-major double[3*N] (== Eigen::Matrix<double,3,Dynamic>::data()).
+ *
+ * All functions return PSULVSB_OK (0) or an error code; psulvsb_last_error() gives the message
+ * of the last failure on the calling thread.  Nothing throws across this boundary.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * PSULVSB_ERR_NO_DEVICE.
+ */
+#ifndef PSULVSB_H_
+#define PSULVSB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSULVSB_VERSION 100 /* 0.1.0 */
+
+enum {
+  PSULVSB_OK = 0,
+  PSULVSB_ERR_INVALID = 1,     /* bad argument                                                  */
+  PSULVSB_ERR_CUDA = 2,        /* CUDA runtime failure (see psulvsb_last_error)                 */
+  PSULVSB_ERR_NO_DEVICE = 3,   /* no usable sm_100 device                                       */
+  PSULVSB_ERR_CAPACITY = 4,    /* a caller-provided buffer is too small                         */
+  PSULVSB_ERR_UNSUPPORTED = 5, /* configuration outside the implemented hot path                */
+  PSULVSB_ERR_INTERNAL = 6
+};
+
+/* Philox sample-stream domains (DESIGN.md "Sample stream").  A draw is addressed by
+ * (seed, domain, event, k); nothing depends on how many draws other events consumed. */
+enum {
+  PSULVSB_DOMAIN_L_SAMPLED = 1, /* registration.cc:852-861, event = host round                  */
+  PSULVSB_DOMAIN_BASIC = 2,     /* registration.cc:916-932, event = global local-iteration index */
+  PSULVSB_DOMAIN_UNIFORM = 3,   /* registration.cc:604-609 draws at :1428/:1438, k = point index */
+  PSULVSB_DOMAIN_SCALE = 4      /* registration.cc:90                                           */
+};
+
+/* ---- Params: RobustRegistrationSolver::Params (registration.h:378-473) plus the reference's
+ * compile-time constants and in-loop overrides lifted into fields (defaults = reference values,
+ * see psulvsb_default_params). ori_src / ori_dst / keep_mask / reduce_map travel in
+ * psulvsb_problem_t because they are per-problem data. */
+typedef struct psulvsb_params {
+  double noise_bound;             /* registration.h:383                                         */
+  double cbar2;                   /* registration.h:388                                         */
+  int estimate_scaling;           /* registration.h:396; 1 is PSULVSB_ERR_UNSUPPORTED this round */
+  int rotation_max_iterations;    /* registration.h:416                                         */
+  double rotation_gnc_factor;     /* registration.h:411                                         */
+  double rotation_cost_threshold; /* registration.h:426                                         */
+  int inlier_selection_mode;      /* registration.h:365-370 (0 PMC_EXACT .. 3 NONE)             */
+  double kcore_heuristic_threshold;
+  double score_noise_bound;       /* registration.cc:33  NOISE_BOUND; PrNoise = 2x (:36)        */
+  double inloop_noise_bound;      /* registration.cc:938                                        */
+  double inloop_cbar2;            /* registration.cc:939                                        */
+  int inloop_max_iterations;      /* registration.cc:941                                        */
+  double inloop_gnc_factor;       /* registration.cc:942                                        */
+  double inloop_cost_threshold;   /* registration.cc:945                                        */
+  double rotation_similar;        /* registration.cc:48                                         */
+  int local_max_iter;             /* registration.cc:49                                         */
+  double tpro_host;               /* registration.cc:772                                        */
+  double tpro_local;              /* registration.cc:898                                        */
+  int host_round_limit;           /* registration.cc:781                                        */
+  double wallclock_cap_s;         /* registration.cc:1475; <= 0 disables (replay mode)          */
+  int self_update;                /* registration.cc:786-832 on/off                             */
+  uint64_t seed;                  /* Philox key of the sample stream                            */
+} psulvsb_params_t;
+
+/* One registration problem, host pointers (reference: the arguments of solve() plus the four
+ * PSULVSB Params fields, registration.h:469-472). */
+typedef struct psulvsb_problem {
+  const double* src;     /* 3xC column-major: reduced source correspondences                    */
+  const double* dst;     /* 3xC                                                                 */
+  int C;
+  const double* ori_src; /* 3xM: Params::ori_src                                                */
+  const double* ori_dst; /* 3xM: Params::ori_dst                                                */
+  int M;
+  const int* keep_mask;  /* [M] in {-1,0,1}: Params::keep_mask                                  */
+  const int* reduce_map; /* [M] reduced column of original j, -1 if absent (dense form of the   */
+                         /*     reference's std::map<int,int> Params::reduce_map)               */
+} psulvsb_problem_t;
+
+/* RegistrationSolution (registration.h:34-41) + diagnostics. */
+typedef struct psulvsb_solution {
+  int valid;
+  double scale;
+  int final_inlier_count;
+  double translation[3];
+  double rotation[9]; /* column-major, == Eigen::Matrix3d::data()                               */
+  int host_rounds;
+  int local_iters;
+  long long n_line_vectors; /* C(C-1)/2                                                         */
+  long long n_reduced;      /* |L_reduced| after the one-time consistency pass                  */
+  int final_C;              /* working-set size after self-update appends                       */
+  int refined;              /* weighted-SVD refinement accepted (registration.cc:1516)          */
+  int escalations;          /* rate escalations taken (registration.cc:1377-1388)               */
+  long long borderline_pairs; /* K1 pairs re-evaluated in FP64 (inside the FP32 error band)     */
+  int status;               /* PSULVSB_OK or the per-problem error                              */
+} psulvsb_solution_t;
+
+/* Per local-iteration / per host-scoring trace records (same content as the oracle's, so parity
+ * tests can compare the two solvers step by step). */
+typedef struct psulvsb_local_trace {
+  int host_round, local_iter, n_sampled_lines, n_sampled_points, basic_choose, gnc_iterations;
+  int rot_inliers, n_rot_points, similar, curr_count, best_count, local_r;
+  double p_local, l_rate, b_rate, scale;
+  double R[9];
+  double t[3];
+} psulvsb_local_trace_t;
+
+typedef struct psulvsb_host_trace {
+  int host_round, curr_count, best_host, new_corr_count, inlier_map_size, host_r;
+  double p_host;
+} psulvsb_host_trace_t;
+
+typedef struct psulvsb_trace {
+  psulvsb_local_trace_t* local;
+  int local_cap, local_n;
+  psulvsb_host_trace_t* host;
+  int host_cap, host_n;
+  int* final_inliers;  /* optional [M]                                                          */
+  int* inlier_counter; /* optional [M]                                                          */
+} psulvsb_trace_t;
+
+typedef struct psulvsb_handle_s* psulvsb_handle_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* lifecycle                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+int psulvsb_version(void);
+const char* psulvsb_last_error(void);
+void psulvsb_default_params(psulvsb_params_t* p);
+/* Number of CUDA devices the library can use (0 when none; never fails). */
+int psulvsb_device_count(void);
+/* One handle = one device, one stream, private device arenas; handles are independent and may
+ * be used from different threads (the reference's solver is neither re-entrant nor thread safe,
+ * registration.cc:40-50). */
+int psulvsb_create(psulvsb_handle_t* out, int device);
+int psulvsb_destroy(psulvsb_handle_t h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* end-to-end: RobustRegistrationSolver(params).solve(src, dst); getSolution()                 */
+/* ------------------------------------------------------------------------------------------ */
+/* Host buffers in, host solution out (H2D, all stages, D2H inside the call). */
+int psulvsb_solve(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                  psulvsb_solution_t* solution, psulvsb_trace_t* trace /* may be NULL */);
+/* B independent problems advanced in lock step on the device (batched registration mode).
+ * seeds: optional per-problem Philox keys (default params->seed + index). */
+int psulvsb_solve_batch(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problems,
+                        int B, const uint64_t* seeds, psulvsb_solution_t* solutions);
+/* Resident variant: upload once, then solve the resident batch any number of times (inputs stay
+ * in HBM; only the solutions come back).  Used for the device-resident throughput figure. */
+int psulvsb_batch_upload(psulvsb_handle_t h, const psulvsb_problem_t* problems, int B);
+int psulvsb_batch_solve_resident(psulvsb_handle_t h, const psulvsb_params_t* params, const uint64_t* seeds,
+                                 psulvsb_solution_t* solutions);
+/* Kernel launches issued by the handle since creation / device time (ms) of the last solve call,
+ * measured with CUDA events on the handle's stream. */
+long long psulvsb_launch_count(psulvsb_handle_t h);
+double psulvsb_last_device_ms(psulvsb_handle_t h);
+/* Device time (ms) spent in stage `which` during the last solve call (0 K1 mask+compaction,
+ * 1 sampling, 2 GNC-TLS rotation, 3 translation+scoring+control, 4 refinement). */
+double psulvsb_last_stage_ms(psulvsb_handle_t h, int which);
+
+/* ------------------------------------------------------------------------------------------ */
+/* stage entry points: DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL) */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Points: column-major double 3xN -> float4 (x-cx, y-cy, z-cz, 0).  center may be NULL (0). */
+int psulvsb_pack_points(void* stream, const double* d_pts, int n, const double center[3], void* d_out_float4);
+
+/* Stage 1 -- line-vector length-consistency mask (registration.cc:693-732 + :418-434).
+ * bit j of row i (word j>>5 of d_mask + i*row_stride_words) is set iff j > i and
+ * | |s_j-s_i| - |t_j-t_i| | <= beta evaluated exactly as the FP64 reference does: the kernel
+ * evaluates in FP32 from the float4 tiles and re-evaluates every pair inside the rigorous FP32
+ * error band in FP64 from d_src64/d_dst64, counting them in *d_border_count.
+ * coord_bound: max |coordinate| over the float4 inputs (sets the band).
+ * d_row_counts[n] receives the popcount of each (upper-triangular) row. */
+int psulvsb_consistency_mask(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,
+                             const double* d_dst64, int n, double beta, double coord_bound, uint32_t* d_mask,
+                             int row_stride_words, uint32_t* d_row_counts, unsigned long long* d_border_count);
+/* Rows [row_begin, row_end) only (row-block sharding across GPUs; same layout, same bits). */
+int psulvsb_consistency_mask_rows(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,
+                                  const double* d_dst64, int n, int row_begin, int row_end, double beta,
+                                  double coord_bound, uint32_t* d_mask, int row_stride_words,
+                                  uint32_t* d_row_counts, unsigned long long* d_border_count);
+/* Mirror the upper triangle into the lower one (full symmetric adjacency, zero diagonal). */
+int psulvsb_mask_symmetrize(void* stream, uint32_t* d_mask, int n, int row_stride_words);
+/* Reduced set in reference order (registration.cc:756-766): edges[k] = (i, j), i < j, row-major.
+ * d_row_offsets[n+1] (u64) receives the exclusive scan of d_row_counts; *d_n_edges the total. */
+int psulvsb_compact_edges(void* stream, const uint32_t* d_mask, int n, int row_stride_words,
+                          const uint32_t* d_row_counts, unsigned long long* d_row_offsets, void* d_edges_uint2,
+                          unsigned long long edge_capacity, unsigned long long* d_n_edges);
+
+/* Stage 2 -- replayable sampling without replacement (registration.cc:852-861, :916-932):
+ * d_out[r] = r-th distinct value of rand31(seed, domain, event, k) % n, k = 0,1,2,...
+ * d_work: >= psulvsb_sample_workspace_bytes(n, count) bytes.  d_status[0] = draws consumed
+ * (0 if max_draws was too small: call again with a larger max_draws). */
+unsigned long long psulvsb_sample_workspace_bytes(unsigned long long n, unsigned long long count,
+                                                  unsigned long long max_draws);
+unsigned long long psulvsb_sample_default_max_draws(unsigned long long n, unsigned long long count);
+int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long n,
+                   unsigned long long count, unsigned long long max_draws, uint32_t* d_out, void* d_work,
+                   unsigned long long* d_status);
+/* Raw stream access for replay checks. */
+int psulvsb_philox_fill(void* stream, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long first_k,
+                        unsigned long long count, uint32_t* d_out_rand31);
+
+/* Stage 3a -- GNC-TLS rotation over K line vectors given as endpoint pairs into a point set
+ * (registration.cc:1563-1692 + utils.h:121-136).  d_edges: uint2[K] (a, b): sv = s[b]-s[a].
+ * R_init: device pointer to a column-major warm start or NULL (first_time).
+ * Outputs: d_R[9] column-major, d_inliers[K] (u8), d_info[4] = {iterations, inlier count, 0, 0},
+ * d_cost[1].  d_weights: K doubles of scratch. */
+int psulvsb_gnc_tls_rotation(void* stream, const double* d_src64, const double* d_dst64, const void* d_edges_uint2,
+                             unsigned long long K, double inv_scale, double noise_bound, int max_iterations,
+                             double gnc_factor, double cost_threshold, const double* d_R_init, double* d_weights,
+                             double* d_R, uint8_t* d_inliers, int* d_info, double* d_cost);
+/* Stage 3b -- batched closed-form Kabsch, one warp per hypothesis (utils.h:121-136): hypothesis h
+ * uses the k line vectors d_sets[h*k .. h*k+k) (indices into d_edges).  Outputs d_R[h*9..]
+ * (column-major) and, if d_t != NULL, the translation of the centroid of the sampled endpoints. */
+int psulvsb_kabsch_batch(void* stream, const double* d_src64, const double* d_dst64, const void* d_edges_uint2,
+                         const uint32_t* d_sets, int k, unsigned long long n_hyp, double* d_R, double* d_t);
+
+/* Max-stabbing translation (registration.cc:436-463 + :121-203) over the points flagged in
+ * d_point_flags[n]; d_last_best = NULL when first_time.  d_t_out[3]. */
+int psulvsb_tls_translation(void* stream, const double* d_src64, const double* d_dst64, const uint8_t* d_point_flags,
+                            int n, double scale, const double* d_R, double noise, const double* d_last_best,
+                            double* d_t_out, int* d_n_points);
+
+/* Stage 4 -- fused transform + score + argmax (registration.cc:1303-1336, :1417-1444):
+ * counts[h] = #{ j : | q_j - s (R_h p_j + t_h) | <= tau } over all n points, evaluated in FP32
+ * from float4 tiles with every point inside the FP32 error band re-evaluated in FP64, plus the
+ * argmax packed as (count << 32) | (0xFFFFFFFF - h) in *d_best (first best hypothesis wins).
+ * d_hyp: n_hyp x 12 doubles (R column-major then t).  hyp_begin offsets the ids written into
+ * d_best (hypothesis sharding across GPUs).  center_src / center_dst: the (host) centres the
+ * float4 tiles were packed with (psulvsb_pack_points), NULL = 0; coord_bound: max |coordinate|
+ * of the packed tiles. */
+int psulvsb_score_batch(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,
+                        const double* d_dst64, int n, const double* d_hyp, unsigned long long n_hyp,
+                        unsigned long long hyp_begin, double scale, double tau, double coord_bound,
+                        const double center_src[3], const double center_dst[3], uint32_t* d_counts,
+                        unsigned long long* d_best, unsigned long long* d_border_count);
+/* Single-hypothesis FP64 scoring with per-point outputs (inlier flags, residuals). */
+int psulvsb_score_one(void* stream, const double* d_src64, const double* d_dst64, int n, double scale,
+                      const double* d_R, const double* d_t, double tau, uint8_t* d_inliers, double* d_residuals,
+                      int* d_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSULVSB_H_ */

@@ -1,0 +1,129 @@
+// common.cuh -- shared device/host helpers of the PSULVSB B200 library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/psulvsb.h"
+
+namespace psulvsb {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing (thread-local message behind psulvsb_last_error)
+// ------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define PSU_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      return ::psulvsb::fail(PSULVSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    }                                                                                               \
+  } while (0)
+
+#define PSU_CHECK_LAUNCH(name)                                                                      \
+  do {                                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                                           \
+    if (e__ != cudaSuccess) {                                                                       \
+      return ::psulvsb::fail(PSULVSB_ERR_CUDA, std::string(name) + " launch: " + cudaGetErrorString(e__)); \
+    }                                                                                               \
+  } while (0)
+
+inline unsigned long long ceil_div_ull(unsigned long long a, unsigned long long b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): the replayable sample stream.
+//   counter = (block_lo, block_hi, event, domain), key = (seed_lo, seed_hi)
+//   rand31(k)    = word[k & 3] of block k>>2, shifted right by one (31 bits, like glibc rand())
+//   uniform01(k) = 53-bit fraction from words 0,1 of block k
+// ------------------------------------------------------------------------------------------
+struct Philox4 {
+  uint32_t w[4];
+};
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint32_t domain, uint32_t event,
+                                                          uint64_t block) {
+  uint32_t c0 = (uint32_t)block, c1 = (uint32_t)(block >> 32), c2 = event, c3 = domain;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  Philox4 o;
+  o.w[0] = c0;
+  o.w[1] = c1;
+  o.w[2] = c2;
+  o.w[3] = c3;
+  return o;
+}
+
+__host__ __device__ __forceinline__ uint32_t philox_rand31(uint64_t seed, uint32_t domain, uint32_t event,
+                                                           uint64_t k) {
+  Philox4 o = philox4x32_10(seed, domain, event, k >> 2);
+  return o.w[k & 3] >> 1;
+}
+
+__host__ __device__ __forceinline__ double philox_uniform01(uint64_t seed, uint32_t domain, uint32_t event,
+                                                            uint64_t k) {
+  Philox4 o = philox4x32_10(seed, domain, event, k);
+  return ((double)(o.w[0] >> 5) * 67108864.0 + (double)(o.w[1] >> 6)) / 9007199254740992.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 helpers with the reference's operation order and NO fused multiply-add, so results are
+// bit-identical to an x86-64 build without FMA contraction (the reference's default Release
+// build, CMakeLists.txt:9-13,21).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+// (x^2 + y^2) + z^2, as Eigen's 3-element reduction evaluates it
+__device__ __forceinline__ double sqnorm3(double x, double y, double z) {
+  return dadd(dadd(dmul(x, x), dmul(y, y)), dmul(z, z));
+}
+
+struct Mat3d {
+  double m[3][3];  // row-major
+};
+
+// ------------------------------------------------------------------------------------------
+// warp / block reductions
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace psulvsb

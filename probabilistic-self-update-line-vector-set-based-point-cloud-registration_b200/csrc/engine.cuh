@@ -1,0 +1,154 @@
+// engine.cuh -- internal interfaces between the stage kernels, the lock-step batch engine and the
+// C ABI (capi.cu).  Nothing here is exported.
+//
+// Every stage kernel takes an ARRAY of device-resident job descriptors and handles job
+// blockIdx.{y|z}: the stage entry points of the C ABI run them with one job, the batch engine with
+// one job per registration, rewritten on the device by its control kernels between ticks (no host
+// round trip inside the RANSAC loops).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace psulvsb {
+
+// ---- stage 1 --------------------------------------------------------------------------------
+struct K1Consts {
+  float half_bias;  // c/2, c = beta^2 (1 + 2^-6) (+ rounding head-room): A' = A - c/2, S' = S - c
+  float two_beta2;  // 2 beta^2
+  float r0;         // 2 beta^2 c - beta^4   ( r = 2 beta^2 S - beta^4 = two_beta2 * S' + r0 )
+  float kappa;      // band slope: |v - v_c| <= kappa * S
+  float w_thr;      // kappa * c (+slack): pair flagged iff |v| - kappa S' <= w_thr  or  S' <= 0
+  double beta;      // FP64 threshold of the exact test
+};
+K1Consts make_k1_consts(double beta, double coord_bound);
+
+struct K1Job {
+  const float4* src;  // packed (centred) points
+  const float4* dst;
+  const double* src64;  // column-major 3 x n, original coordinates
+  const double* dst64;
+  int n, row_begin, row_end;
+  K1Consts c;
+  uint32_t* mask;
+  int stride;                    // words per mask row
+  uint32_t* row_counts;          // [n], accumulated with atomicAdd (caller zeroes)
+  unsigned long long* border;    // accumulated
+  int active;
+};
+
+struct CompactJob {
+  const uint32_t* mask;
+  int n, stride;
+  const uint32_t* row_counts;
+  unsigned long long* offsets;  // [n+1]
+  uint2* edges;
+  unsigned long long cap;
+  unsigned long long* n_edges;
+  int active;
+};
+
+// ---- stage 2 --------------------------------------------------------------------------------
+struct SampleJob {
+  uint64_t seed;
+  uint32_t domain, event;
+  unsigned long long n, count, max_draws;
+  uint32_t* first;               // [n] first-occurrence table, all 0xFFFFFFFF on entry and on exit
+  uint32_t* out;                 // [count]
+  unsigned long long* status;    // draws consumed (0: max_draws too small)
+  int identity;                  // 1: out[r] = r (registration.cc:839-847, empty-sample fallback)
+  // optional post-processing fused into the emission kernel (batch engine):
+  int post;                      // 0 none, 1 endpoint flags of the sampled edges, 2 gather basic edges
+  const uint2* edges;            // post 1/2: the reduced set
+  const uint32_t* via;           // post 2: L_sampled (out[r] indexes it)
+  uint2* gathered;               // post 2: gathered[r] = edges[via[out[r]]]
+  uint8_t* flags;                // post 1: [n_points] endpoint flags
+  int n_points;
+  int* flag_count;               // post 1: number of flagged points
+  int active;
+};
+
+// ---- stage 3 --------------------------------------------------------------------------------
+struct GncJob {
+  const double* src;     // column-major 3 x n_points
+  const double* dst;
+  const uint2* edges;    // K endpoint pairs (a, b): sv = s[b] - s[a], tv = (t[b] - t[a]) * inv_scale
+  unsigned long long K;
+  double inv_scale;
+  double noise_bound;    // already multiplied by 2 / scale (registration.cc:1106-1108)
+  double gnc_factor;
+  double cost_threshold;
+  int max_iterations;
+  int use_init;          // 1: first iteration uses R_init (registration.cc:1617-1621)
+  double R_init[9];      // column-major
+  double* weights;       // K doubles of scratch (overflow beyond the shared-memory capacity)
+  double* R_out;         // column-major
+  uint8_t* inliers;      // [K] or NULL
+  uint8_t* point_flags;  // [n_points] or NULL: endpoints of inlier line vectors
+  int n_points;
+  int* info;             // [4]: iterations, inlier count
+  double* cost;
+  int active;
+};
+
+// ---- stage launchers (k1_consistency.cu, k2_sampler.cu, k3_rotation.cu, k4_score.cu) -----------
+int launch_pack_points(cudaStream_t st, const double* pts, int n, const double center[3], float4* out);
+// max_n / max_rows: grid extents over all jobs
+int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows);
+int launch_symmetrize(cudaStream_t st, uint32_t* mask, int n, int stride);
+int launch_compact_edges(cudaStream_t st, const CompactJob* d_jobs, int n_jobs, int max_n, bool scan, bool emit);
+
+// Draw budget for `count` distinct values out of n by rejection (mean + 8 sigma; coupon collector
+// tail for count == n).  Same formula on host and device so both agree on the stream window.
+__host__ __device__ inline unsigned long long sample_max_draws_formula(unsigned long long n,
+                                                                       unsigned long long count) {
+  if (n == 0 || count == 0) return 0;
+  if (count > n) count = n;
+  double e;
+  if (count == n) {
+    e = (double)n * (log((double)n) + 0.5772156649 + 10.0);
+  } else {
+    const double f = (double)count / (double)n;
+    const double mean = -(double)n * log1p(-f);
+    e = mean * 1.02 + 8.0 * sqrt(mean + 1.0) + 64.0;
+  }
+  unsigned long long m = (unsigned long long)e + 8;
+  m = (m + 3) & ~3ull;
+  if (m > 0xFFFFFFF0ull) m = 0xFFFFFFF0ull;
+  return m;
+}
+unsigned long long sample_default_max_draws(unsigned long long n, unsigned long long count);
+int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound);
+int launch_philox_fill(cudaStream_t st, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long first_k,
+                       unsigned long long count, uint32_t* out);
+
+int gnc_default_capacity();
+int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta);
+int launch_kabsch_batch(cudaStream_t st, const double* src, const double* dst, const uint2* edges,
+                        const uint32_t* sets, int k, unsigned long long n_hyp, double* R, double* t);
+
+int launch_tls_translation(cudaStream_t st, const double* src, const double* dst, const uint8_t* flags, int n,
+                           double scale, const double* R, double noise, const double* last_best, double* t_out,
+                           int* n_points);
+int launch_score_one(cudaStream_t st, const double* src, const double* dst, int n, double scale, const double* R,
+                     const double* t, double tau, uint8_t* inliers, double* residuals, int* count);
+int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, const double* src64, const double* dst64,
+                       int n, const double* hyp, unsigned long long n_hyp, unsigned long long hyp_begin, double scale,
+                       double tau, double coord_bound, const double* csrc, const double* cdst, uint32_t* counts,
+                       unsigned long long* best, unsigned long long* border);
+
+// ---- batch engine (engine.cu) -------------------------------------------------------------------
+class Engine;
+int engine_create(Engine** out, int device);
+void engine_destroy(Engine* e);
+int engine_upload(Engine* e, const psulvsb_problem_t* problems, int B);
+int engine_solve_resident(Engine* e, const psulvsb_params_t* params, const uint64_t* seeds,
+                          psulvsb_solution_t* solutions, psulvsb_trace_t* trace_first);
+long long engine_launch_count(const Engine* e);
+double engine_last_device_ms(const Engine* e);
+double engine_last_stage_ms(const Engine* e, int which);
+
+}  // namespace psulvsb

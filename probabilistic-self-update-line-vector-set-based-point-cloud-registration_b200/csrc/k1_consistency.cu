@@ -1,0 +1,403 @@
+// k1_consistency.cu -- stage 1: line-vector length-consistency bit mask, edge compaction.
+//
+// Replaces the reference's O(C^2) line-vector set build and the ScaleInliersSelector pass
+// (registration.cc:693-732, :418-434, :756-766).  The reference materialises every line vector
+// (~130 B per pair, twice); here a pair costs ~20 FP32-pipe instructions and one output BIT.
+//
+// Arithmetic.  The reference decides   | sqrt(A) - sqrt(B) | <= beta   in FP64 with
+// A = |s_j - s_i|^2, B = |t_j - t_i|^2.  With D = A - B, S = A + B this is, for a + b > beta,
+//        v := D^2 - 2 beta^2 S + beta^4 = (u^2 - beta^2)((a+b)^2 - beta^2) <= 0 ,   u = |a - b| ,
+// a sqrt-free polynomial whose FP32 evaluation error is bounded by  kappa * S  (derivation in
+// DESIGN.md "K1 error band").  Every pair with |v| inside that band, or with S <= ~beta^2 (where
+// the factor (a+b)^2 - beta^2 may change sign), is re-evaluated in FP64 with the reference's exact
+// operation order, so the emitted bits equal the FP64 reference's bit for bit; the number of
+// re-evaluated pairs is counted.
+//
+// Mapping.  One thread owns R rows (its points live in registers), the CTA's column tile is staged
+// in shared memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) and read as warp-wide
+// broadcasts; a thread accumulates the 32 result bits of a mask word with a funnel shift of v's
+// sign bit, so no ballot and no divergence on the fast path.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace psulvsb {
+
+namespace {
+
+constexpr int K1_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// exact FP64 test, reference operation order (registration.cc:425-433)
+__device__ __forceinline__ bool exact_consistent(const double* __restrict__ s64, const double* __restrict__ t64, int i,
+                                                 int j, double beta) {
+  const double sx = dsub(s64[3 * j + 0], s64[3 * i + 0]);
+  const double sy = dsub(s64[3 * j + 1], s64[3 * i + 1]);
+  const double sz = dsub(s64[3 * j + 2], s64[3 * i + 2]);
+  const double tx = dsub(t64[3 * j + 0], t64[3 * i + 0]);
+  const double ty = dsub(t64[3 * j + 1], t64[3 * i + 1]);
+  const double tz = dsub(t64[3 * j + 2], t64[3 * i + 2]);
+  const double a = sqrt(sqnorm3(sx, sy, sz));
+  const double b = sqrt(sqnorm3(tx, ty, tz));
+  return fabs(dsub(a, b)) <= beta;
+}
+
+// FP32 evaluation of one pair: returns v (sign bit set <=> consistent), w = |v| - kappa S', sp = S'
+__device__ __forceinline__ void pair_eval(const float4 si, const float4 ti, const float4 sj, const float4 tj,
+                                          const K1Consts& c, float& v, float& w, float& sp) {
+  const float sx = sj.x - si.x, sy = sj.y - si.y, sz = sj.z - si.z;
+  const float tx = tj.x - ti.x, ty = tj.y - ti.y, tz = tj.z - ti.z;
+  const float A = fmaf(sz, sz, fmaf(sy, sy, fmaf(sx, sx, -c.half_bias)));
+  const float B = fmaf(tz, tz, fmaf(ty, ty, fmaf(tx, tx, -c.half_bias)));
+  const float D = A - B;
+  sp = A + B;
+  const float r = fmaf(c.two_beta2, sp, c.r0);
+  v = fmaf(D, D, -r);
+  w = fmaf(-c.kappa, sp, fabsf(v));
+}
+
+template <int R, int TJ>
+__global__ void __launch_bounds__(K1_THREADS) k1_mask_kernel(const K1Job* __restrict__ jobs) {
+  const K1Job& job = jobs[blockIdx.z];
+  if (!job.active) return;
+  const float4* __restrict__ src = job.src;
+  const float4* __restrict__ dst = job.dst;
+  const double* __restrict__ src64 = job.src64;
+  const double* __restrict__ dst64 = job.dst64;
+  const int n = job.n, row_begin = job.row_begin, row_end = job.row_end;
+  const K1Consts c = job.c;
+  uint32_t* __restrict__ mask = job.mask;
+  const int stride = job.stride;
+  uint32_t* __restrict__ row_counts = job.row_counts;
+  unsigned long long* __restrict__ border_count = job.border;
+  constexpr int TI = K1_THREADS * R;
+  constexpr int WORDS = TJ / 32;
+  __shared__ __align__(128) float4 cs[TJ];
+  __shared__ __align__(128) float4 ct[TJ];
+  __shared__ __align__(8) uint64_t bar;
+
+  const int col0 = blockIdx.x * TJ;
+  const int row0 = row_begin + blockIdx.y * TI;
+  if (col0 >= n || row0 >= row_end) return;  // grid is sized for the largest job
+  const int ncols = min(TJ, n - col0);
+  const int tid = threadIdx.x;
+
+  // tile entirely on/below the diagonal: defined output (zeros), no work
+  if (col0 + ncols - 1 <= row0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = row0 + tid + r * K1_THREADS;
+      if (i < row_end) {
+        for (int wj = 0; wj < WORDS; ++wj)
+          if (col0 + wj * 32 < n) mask[(size_t)i * stride + (col0 >> 5) + wj] = 0u;
+      }
+    }
+    return;
+  }
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // slots past the end of the arrays hold a dummy point; their bits are masked off below
+  for (int k = ncols + tid; k < TJ; k += K1_THREADS) {
+    cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ct[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)ncols * (uint32_t)sizeof(float4);
+    mbar_expect_tx(&bar, 2 * bytes);
+    tma_load_1d(cs, src + col0, bytes, &bar);
+    tma_load_1d(ct, dst + col0, bytes, &bar);
+  }
+
+  // row points -> registers (overlaps the bulk copy)
+  float4 si[R], ti[R];
+  int irow[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    irow[r] = row0 + tid + r * K1_THREADS;
+    const bool ok = irow[r] < row_end;
+    si[r] = ok ? src[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ti[r] = ok ? dst[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  mbar_wait(&bar, 0);
+
+  uint32_t cnt[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) cnt[r] = 0;
+  unsigned int nborder = 0;
+
+  for (int wj = 0; wj < WORDS; ++wj) {
+    const int cb = col0 + wj * 32;  // first column of this word
+    if (cb >= n) break;
+    uint32_t acc[R];
+    float mw[R], ms[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      acc[r] = 0u;
+      mw[r] = 3.0e38f;
+      ms[r] = 3.0e38f;
+    }
+#pragma unroll 8
+    for (int jj = 31; jj >= 0; --jj) {
+      const float4 sj = cs[wj * 32 + jj];
+      const float4 tj = ct[wj * 32 + jj];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float v, w, sp;
+        pair_eval(si[r], ti[r], sj, tj, c, v, w, sp);
+        acc[r] = __funnelshift_l(__float_as_uint(v), acc[r], 1);  // bit jj <- sign(v)
+        mw[r] = fminf(mw[r], w);
+        ms[r] = fminf(ms[r], sp);
+      }
+    }
+    const uint32_t valid = (cb + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - cb)) - 1u);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = irow[r];
+      if (i >= row_end) continue;
+      const uint32_t upper = (i < cb) ? 0xFFFFFFFFu : ((i >= cb + 31) ? 0u : (0xFFFFFFFFu << (i - cb + 1)));
+      const uint32_t live = valid & upper;
+      uint32_t word = acc[r] & live;
+      // rare: some pair of this word lies inside the FP32 error band -> exact FP64 re-evaluation
+      if (live != 0u && (!(mw[r] > c.w_thr) || !(ms[r] > 0.f))) {
+        uint32_t todo = live;
+        while (todo) {
+          const int b = __ffs(todo) - 1;
+          todo &= todo - 1;
+          float v, w, sp;
+          pair_eval(si[r], ti[r], cs[wj * 32 + b], ct[wj * 32 + b], c, v, w, sp);
+          if (!(w > c.w_thr) || !(sp > 0.f)) {
+            ++nborder;
+            const bool in = exact_consistent(src64, dst64, i, cb + b, c.beta);
+            word = in ? (word | (1u << b)) : (word & ~(1u << b));
+          }
+        }
+      }
+      mask[(size_t)i * stride + (cb >> 5)] = word;
+      cnt[r] += __popc(word);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (irow[r] < row_end && cnt[r] != 0u && row_counts) atomicAdd(&row_counts[irow[r]], cnt[r]);
+  if (border_count) {
+    unsigned int tot = (unsigned int)warp_sum_int((int)nborder);
+    if ((tid & 31) == 0 && tot) atomicAdd(border_count, (unsigned long long)tot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void pack_points_kernel(const double* __restrict__ pts, int n, double cx, double cy, double cz,
+                                   float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = make_float4((float)(pts[3 * i] - cx), (float)(pts[3 * i + 1] - cy), (float)(pts[3 * i + 2] - cz), 0.f);
+}
+
+// mirror the upper triangle into the lower one: one warp per 32x32 bit block (bi >= bj)
+__global__ void symmetrize_kernel(uint32_t* __restrict__ mask, int n, int stride, int nblk) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  // warp -> (bi, bj) with bj <= bi
+  const long long total = (long long)nblk * (nblk + 1) / 2;
+  if (warp >= total) return;
+  int bi = (int)((sqrt(8.0 * (double)warp + 1.0) - 1.0) * 0.5);
+  while ((long long)bi * (bi + 1) / 2 > warp) --bi;
+  while ((long long)(bi + 1) * (bi + 2) / 2 <= warp) ++bi;
+  const int bj = warp - (int)((long long)bi * (bi + 1) / 2);
+  // source: rows of block bj, word bi
+  const int jrow = bj * 32 + lane;
+  const uint32_t s = (jrow < n) ? mask[(size_t)jrow * stride + bi] : 0u;
+  uint32_t mine = 0u;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    const uint32_t t = __ballot_sync(0xffffffffu, (s >> b) & 1u);
+    if (lane == b) mine = t;
+  }
+  const int irow = bi * 32 + lane;
+  if (irow < n) {
+    uint32_t* dstw = &mask[(size_t)irow * stride + bj];
+    if (bi == bj)
+      *dstw = *dstw | mine;
+    else
+      *dstw = mine;
+  }
+}
+
+// exclusive scan of row_counts -> u64 offsets (one CTA per job; n <= a few 10^5)
+__global__ void __launch_bounds__(1024) row_scan_kernel(const CompactJob* __restrict__ jobs) {
+  const CompactJob& job = jobs[blockIdx.x];
+  if (!job.active) return;
+  const uint32_t* __restrict__ counts = job.row_counts;
+  unsigned long long* __restrict__ offsets = job.offsets;
+  const int n = job.n;
+  __shared__ unsigned long long part[1024];
+  const int tid = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  unsigned long long s = 0;
+  for (int i = lo; i < hi; ++i) s += counts[i];
+  part[tid] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    unsigned long long v = (tid >= off) ? part[tid - off] : 0ull;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  unsigned long long run = part[tid] - s;
+  for (int i = lo; i < hi; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+  if (tid == 1023) {
+    offsets[n] = part[1023];
+    if (job.n_edges) *job.n_edges = part[1023];
+  }
+}
+
+// one warp per row: emit (i, j) for every set bit j > i, ascending j, at offsets[i]
+__global__ void compact_edges_kernel(const CompactJob* __restrict__ jobs) {
+  const CompactJob& job = jobs[blockIdx.y];
+  if (!job.active || !job.edges) return;
+  const uint32_t* __restrict__ mask = job.mask;
+  const int n = job.n, stride = job.stride;
+  const unsigned long long cap = job.cap;
+  uint2* __restrict__ edges = job.edges;
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const int W = (n + 31) >> 5;
+  unsigned long long base = job.offsets[row];
+  for (int w0 = row >> 5; w0 < W; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t word = (w < W) ? mask[(size_t)row * stride + w] : 0u;
+    const int pc = __popc(word);
+    int incl = pc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    unsigned long long pos = base + (unsigned long long)(incl - pc);
+    while (word) {
+      const int b = __ffs(word) - 1;
+      word &= word - 1;
+      if (pos < cap) edges[pos] = make_uint2((unsigned)row, (unsigned)(w * 32 + b));
+      ++pos;
+    }
+    base += (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+}  // namespace
+
+K1Consts make_k1_consts(double beta, double coord_bound) {
+  const double mu = 5.9604644775390625e-08;  // 2^-24
+  const double cmax = coord_bound > beta ? coord_bound : beta;
+  const double b2 = beta * beta;
+  double cpad = b2 / 64.0;
+  const double need = 32.0 * mu * (b2 + beta * cmax);
+  if (need > cpad) cpad = need;
+  const double cc = b2 + cpad;
+  K1Consts k;
+  k.half_bias = (float)(0.5 * cc);
+  k.two_beta2 = (float)(2.0 * b2);
+  k.r0 = (float)(2.0 * b2 * cc - b2 * b2);
+  const double kappa = 384.0 * mu * beta * cmax;  // DESIGN.md "K1 error band": 353 mu beta Cmax, rounded up
+  k.kappa = (float)(kappa * 1.0001);
+  k.w_thr = (float)(kappa * cc * 1.01 + 1e-30);
+  k.beta = beta;
+  return k;
+}
+
+int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows) {
+  if (n_jobs <= 0 || max_n < 1 || max_rows < 1) return PSULVSB_OK;
+  // tile shape: small problems want many CTAs, large ones want register/smem reuse
+  const long long pairs = (long long)max_rows * max_n;
+  if (pairs >= (1ll << 28)) {
+    constexpr int R = 4, TJ = 256;
+    dim3 grid((max_n + TJ - 1) / TJ, (max_rows + K1_THREADS * R - 1) / (K1_THREADS * R), n_jobs);
+    k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs);
+  } else if (pairs >= (1ll << 25) || n_jobs >= 8) {
+    constexpr int R = 2, TJ = 128;
+    dim3 grid((max_n + TJ - 1) / TJ, (max_rows + K1_THREADS * R - 1) / (K1_THREADS * R), n_jobs);
+    k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs);
+  } else {
+    constexpr int R = 1, TJ = 128;
+    dim3 grid((max_n + TJ - 1) / TJ, (max_rows + K1_THREADS * R - 1) / (K1_THREADS * R), n_jobs);
+    k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs);
+  }
+  PSU_CHECK_LAUNCH("k1_mask_kernel");
+  return PSULVSB_OK;
+}
+
+int launch_pack_points(cudaStream_t st, const double* pts, int n, const double center[3], float4* out) {
+  if (n <= 0) return PSULVSB_OK;
+  const double cx = center ? center[0] : 0.0, cy = center ? center[1] : 0.0, cz = center ? center[2] : 0.0;
+  pack_points_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, cx, cy, cz, out);
+  PSU_CHECK_LAUNCH("pack_points_kernel");
+  return PSULVSB_OK;
+}
+
+int launch_symmetrize(cudaStream_t st, uint32_t* mask, int n, int stride) {
+  const int nblk = (n + 31) / 32;
+  const long long warps = (long long)nblk * (nblk + 1) / 2;
+  const long long threads = warps * 32;
+  symmetrize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(mask, n, stride, nblk);
+  PSU_CHECK_LAUNCH("symmetrize_kernel");
+  return PSULVSB_OK;
+}
+
+int launch_compact_edges(cudaStream_t st, const CompactJob* d_jobs, int n_jobs, int max_n, bool scan, bool emit) {
+  if (n_jobs <= 0 || max_n < 1) return PSULVSB_OK;
+  if (scan) {
+    row_scan_kernel<<<n_jobs, 1024, 0, st>>>(d_jobs);
+    PSU_CHECK_LAUNCH("row_scan_kernel");
+  }
+  if (emit) {
+    const long long threads = (long long)max_n * 32;
+    dim3 grid((unsigned)((threads + 255) / 256), n_jobs);
+    compact_edges_kernel<<<grid, 256, 0, st>>>(d_jobs);
+    PSU_CHECK_LAUNCH("compact_edges_kernel");
+  }
+  return PSULVSB_OK;
+}
+
+}  // namespace psulvsb

@@ -1,0 +1,403 @@
+// k3_rotation.cu -- stage 3: GNC-TLS rotation (thread-block cluster per hypothesis) and batched
+// closed-form Kabsch (one warp per hypothesis).
+//
+// Reference: GNCTLSRotationSolver::solveForRotation (registration.cc:1563-1692) around
+// teaser::utils::svdRot (utils.h:121-136).  All arithmetic is FP64: the rotation feeds
+// discontinuous decisions downstream (w >= 0.5 inlier test, max-stabbing translation), so FP32
+// here would break the 1e-5 parity bar (DESIGN.md "Why FP64 in stage 3").
+//
+// One GNC iteration is ONE pass over the K line vectors: with R_i known every thread computes
+// r^2 = |tv - R_i sv|^2, adds w_{i-1} r^2 to the cost, updates the weight in closed form and
+// accumulates H_{i+1} += w_i sv tv^T; the 9+1 partial sums are reduced warp -> CTA -> cluster
+// through distributed shared memory in a fixed order (deterministic), and every CTA's thread 0
+// turns H into R_{i+1} with a 3x3 Jacobi SVD.  Line vectors (and weights) of a CTA live in its
+// shared memory for the whole solve; only the overflow beyond the smem capacity is recomputed
+// from the points each pass.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "svd3.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace psulvsb {
+
+namespace {
+
+constexpr int GNC_THREADS = 512;
+constexpr int GNC_WARPS = GNC_THREADS / 32;
+constexpr int GNC_NRED = 12;  // 9 H + cost + max/aux + count
+
+struct GncSmem {
+  double part[2][GNC_NRED];           // this CTA's partial sums, double-buffered by iteration parity
+  double warp_part[GNC_WARPS][GNC_NRED];
+  double R[9];                        // row-major current rotation
+  double total[GNC_NRED];
+  int flag;
+};
+
+__device__ __forceinline__ void load_lv(const double* __restrict__ src, const double* __restrict__ dst, uint2 e,
+                                        double inv_scale, double sv[3], double tv[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    sv[r] = src[3 * (size_t)e.y + r] - src[3 * (size_t)e.x + r];
+    // pruned_dst_tims_ *= (1 / solution_.scale)   (registration.cc:1102)
+    tv[r] = (dst[3 * (size_t)e.y + r] - dst[3 * (size_t)e.x + r]) * inv_scale;
+  }
+}
+
+// CTA-level then cluster-level sum (or max for index MAXI) of NRED values; result in sm->total.
+template <int NC>
+__device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED], int parity, int max_index) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int i = 0; i < GNC_NRED; ++i) {
+    double v = vals[i];
+    if (i == max_index)
+      v = warp_max(v);
+    else
+      v = warp_sum(v);
+    if (lane == 0) sm->warp_part[wid][i] = v;
+  }
+  __syncthreads();
+  if (tid < GNC_NRED) {
+    double acc = sm->warp_part[0][tid];
+    for (int w = 1; w < GNC_WARPS; ++w) {
+      const double x = sm->warp_part[w][tid];
+      acc = (tid == max_index) ? fmax(acc, x) : acc + x;
+    }
+    sm->part[parity][tid] = acc;
+  }
+  if (NC > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (tid < GNC_NRED) {
+      double acc = 0.0;
+      for (int r = 0; r < NC; ++r) {
+        const GncSmem* peer = cluster.map_shared_rank(sm, r);
+        const double x = peer->part[parity][tid];
+        acc = (r == 0) ? x : ((tid == max_index) ? fmax(acc, x) : acc + x);
+      }
+      sm->total[tid] = acc;
+    }
+  } else {
+    __syncthreads();
+    if (tid < GNC_NRED) sm->total[tid] = sm->part[parity][tid];
+  }
+  __syncthreads();
+}
+
+template <int NC>
+__global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GncSmem* sm = reinterpret_cast<GncSmem*>(smem_raw);
+  double* lv = reinterpret_cast<double*>(smem_raw + ((sizeof(GncSmem) + 15) & ~size_t(15)));
+  // layout: lv[0..5][cap] = sv.xyz, tv.xyz ; lv[6][cap] = weight
+  const GncJob job = jobs[blockIdx.y];
+  if (!job.active) return;  // uniform over the cluster
+  const int tid = threadIdx.x;
+  const unsigned rank = (NC > 1) ? cg::this_cluster().block_rank() : 0u;
+  const unsigned long long K = job.K;
+  // contiguous slice of the line vectors for this CTA
+  const unsigned long long per = (K + NC - 1) / NC;
+  const unsigned long long k_lo = (per * rank < K) ? per * rank : K;
+  const unsigned long long k_hi = (k_lo + per < K) ? k_lo + per : K;
+  const unsigned long long nloc = k_hi - k_lo;
+  const unsigned long long ncached = nloc < (unsigned long long)cap_per_cta ? nloc : (unsigned long long)cap_per_cta;
+  const double* __restrict__ src = job.src;
+  const double* __restrict__ dst = job.dst;
+  const uint2* __restrict__ edges = job.edges;
+  double* __restrict__ gw = job.weights;  // weights of the overflow part live in global memory
+  const size_t cap = (size_t)cap_per_cta;
+
+  double nb2 = job.noise_bound * job.noise_bound;
+  if (nb2 < 1e-16) nb2 = 1e-2;  // registration.cc:1592-1595
+
+  // ---- prologue: stage line vectors, H_0 = sum sv tv^T with unit weights
+  double acc[GNC_NRED];
+#pragma unroll
+  for (int i = 0; i < GNC_NRED; ++i) acc[i] = 0.0;
+  for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+    double sv[3], tv[3];
+    load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
+    if (l < ncached) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        lv[(size_t)r * cap + l] = sv[r];
+        lv[(size_t)(3 + r) * cap + l] = tv[r];
+      }
+      lv[6 * cap + l] = 1.0;
+    } else {
+      gw[k_lo + l] = 1.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[r * 3 + c] += sv[r] * tv[c];
+  }
+  int parity = 0;
+  if (job.use_init) {
+    if (tid < 9) sm->R[tid] = job.R_init[(tid % 3) * 3 + tid / 3];  // column-major -> row-major
+    __syncthreads();
+  } else {
+    cluster_reduce<NC>(sm, acc, parity, -1);
+    parity ^= 1;
+    if (tid == 0) {
+      double H[3][3], R[3][3];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) H[r][c] = sm->total[r * 3 + c];
+      kabsch_rotation(H, R);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = R[r][c];
+    }
+    __syncthreads();
+  }
+
+  double mu = 1.0, prev_cost = INFINITY, cost = INFINITY;
+  int it_done = 0;
+  bool weights_are_unit = true;
+  for (int it = 0; it < job.max_iterations; ++it) {
+    it_done = it + 1;
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = sm->R[i];
+    if (it == 0) {
+      // mu initialisation needs max r^2 first (registration.cc:1628-1639)
+      double mx[GNC_NRED];
+#pragma unroll
+      for (int i = 0; i < GNC_NRED; ++i) mx[i] = 0.0;
+      for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+        double sv[3], tv[3];
+        if (l < ncached) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            sv[r] = lv[(size_t)r * cap + l];
+            tv[r] = lv[(size_t)(3 + r) * cap + l];
+          }
+        } else {
+          load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
+        }
+        const double d0 = tv[0] - ((R[0] * sv[0] + R[1] * sv[1]) + R[2] * sv[2]);
+        const double d1 = tv[1] - ((R[3] * sv[0] + R[4] * sv[1]) + R[5] * sv[2]);
+        const double d2 = tv[2] - ((R[6] * sv[0] + R[7] * sv[1]) + R[8] * sv[2]);
+        mx[0] = fmax(mx[0], (d0 * d0 + d1 * d1) + d2 * d2);
+      }
+      cluster_reduce<NC>(sm, mx, parity, 0);
+      parity ^= 1;
+      const double max_residual = sm->total[0];
+      mu = 1.0 / (2.0 * max_residual / nb2 - 1.0);
+      if (mu <= 0.0) break;  // degenerate: residuals already tiny; weights stay 1, R stays
+    }
+    const double th1 = (mu + 1.0) / mu * nb2;
+    const double th2 = mu / (mu + 1.0) * nb2;
+    const double wnum = nb2 * mu * (mu + 1.0);
+#pragma unroll
+    for (int i = 0; i < GNC_NRED; ++i) acc[i] = 0.0;
+    for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+      double sv[3], tv[3], w;
+      const bool cached = l < ncached;
+      if (cached) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          sv[r] = lv[(size_t)r * cap + l];
+          tv[r] = lv[(size_t)(3 + r) * cap + l];
+        }
+        w = lv[6 * cap + l];
+      } else {
+        load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
+        w = gw[k_lo + l];
+      }
+      const double d0 = tv[0] - ((R[0] * sv[0] + R[1] * sv[1]) + R[2] * sv[2]);
+      const double d1 = tv[1] - ((R[3] * sv[0] + R[4] * sv[1]) + R[5] * sv[2]);
+      const double d2 = tv[2] - ((R[6] * sv[0] + R[7] * sv[1]) + R[8] * sv[2]);
+      const double r2 = (d0 * d0 + d1 * d1) + d2 * d2;
+      acc[9] += w * r2;  // cost uses the previous weights (registration.cc:1648)
+      double wn;
+      if (r2 >= th1)
+        wn = 0.0;
+      else if (r2 <= th2)
+        wn = 1.0;
+      else
+        wn = sqrt(wnum / r2) - mu;
+      if (cached)
+        lv[6 * cap + l] = wn;
+      else
+        gw[k_lo + l] = wn;
+      if (wn != 0.0) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double xs = sv[r] * wn;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[r * 3 + c] += xs * tv[c];
+        }
+      }
+    }
+    weights_are_unit = false;
+    cluster_reduce<NC>(sm, acc, parity, -1);
+    parity ^= 1;
+    cost = sm->total[9];
+    const double cost_diff = fabs(cost - prev_cost);
+    mu *= job.gnc_factor;
+    prev_cost = cost;
+    if (cost_diff < job.cost_threshold) break;
+    if (it + 1 < job.max_iterations) {
+      if (tid == 0) {
+        double H[3][3], Rn[3][3];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) H[r][c] = sm->total[r * 3 + c];
+        kabsch_rotation(H, Rn);
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = Rn[r][c];
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue: inlier mask w >= 0.5 (all when <= 10), endpoint flags (registration.cc:1676-1691,
+  // :1114-1155).  The stale-bit defect of the reference is resolved as "zero then set".
+  double cntv[GNC_NRED];
+#pragma unroll
+  for (int i = 0; i < GNC_NRED; ++i) cntv[i] = 0.0;
+  for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+    const double w = weights_are_unit ? 1.0 : ((l < ncached) ? lv[6 * cap + l] : gw[k_lo + l]);
+    cntv[0] += (w >= 0.5) ? 1.0 : 0.0;
+  }
+  if (job.point_flags) {
+    // zero this cluster's share of the flags before anyone sets them (cluster_reduce syncs)
+    for (int i = rank * GNC_THREADS + tid; i < job.n_points; i += NC * GNC_THREADS) job.point_flags[i] = 0;
+  }
+  cluster_reduce<NC>(sm, cntv, parity, -1);
+  parity ^= 1;
+  const long long gf = (long long)(sm->total[0] + 0.5);
+  const bool all_in = gf <= 10;
+  for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+    const double w = weights_are_unit ? 1.0 : ((l < ncached) ? lv[6 * cap + l] : gw[k_lo + l]);
+    const bool in = all_in || (w >= 0.5);
+    if (job.inliers) job.inliers[k_lo + l] = in ? 1 : 0;
+    if (in && job.point_flags) {
+      const uint2 e = edges[k_lo + l];
+      job.point_flags[e.x] = 1;
+      job.point_flags[e.y] = 1;
+    }
+  }
+  if (rank == 0 && tid == 0) {
+    if (job.R_out) {
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) job.R_out[c * 3 + r] = sm->R[r * 3 + c];  // column-major out
+    }
+    if (job.info) {
+      job.info[0] = it_done;
+      job.info[1] = (int)(all_in ? (long long)K : gf);
+      job.info[2] = 0;
+      job.info[3] = 0;
+    }
+    if (job.cost) job.cost[0] = cost;
+  }
+  if (NC > 1) cg::this_cluster().sync();  // peers may still be reading this CTA's partial sums
+}
+
+// ------------------------------------------------------------------------------------------
+// batched closed-form Kabsch: one warp per hypothesis
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    kabsch_batch_kernel(const double* __restrict__ src, const double* __restrict__ dst, const uint2* __restrict__ edges,
+                        const uint32_t* __restrict__ sets, int k, unsigned long long n_hyp, double* __restrict__ Rout,
+                        double* __restrict__ tout) {
+  const unsigned long long h = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (h >= n_hyp) return;
+  double H[9], cs[3] = {0, 0, 0}, cd[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 9; ++i) H[i] = 0.0;
+  for (int l = lane; l < k; l += 32) {
+    const uint2 e = edges[sets[h * (unsigned long long)k + l]];
+    double sv[3], tv[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double sa = src[3 * (size_t)e.x + r], sb = src[3 * (size_t)e.y + r];
+      const double da = dst[3 * (size_t)e.x + r], db = dst[3 * (size_t)e.y + r];
+      sv[r] = sb - sa;
+      tv[r] = db - da;
+      cs[r] += sa + sb;
+      cd[r] += da + db;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) H[r * 3 + c] += sv[r] * tv[c];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) H[i] = warp_sum(H[i]);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    cs[r] = warp_sum(cs[r]);
+    cd[r] = warp_sum(cd[r]);
+  }
+  if (lane == 0) {
+    double Hm[3][3], R[3][3];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Hm[r][c] = H[r * 3 + c];
+    kabsch_rotation(Hm, R);
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) Rout[h * 9 + c * 3 + r] = R[r][c];
+    if (tout) {
+      const double invn = 1.0 / (2.0 * (double)k);
+      for (int r = 0; r < 3; ++r)
+        tout[h * 3 + r] = cd[r] * invn - ((R[r][0] * cs[0] + R[r][1] * cs[1]) + R[r][2] * cs[2]) * invn;
+    }
+  }
+}
+
+constexpr int GNC_CLUSTER = 8;
+
+size_t gnc_smem_bytes(int cap) { return ((sizeof(GncSmem) + 15) & ~size_t(15)) + (size_t)7 * cap * sizeof(double); }
+
+}  // namespace
+
+int gnc_default_capacity() {
+  // 227 KB usable per CTA; keep a little head-room for static allocations
+  const size_t budget = 220 * 1024;
+  const size_t fixed = (sizeof(GncSmem) + 15) & ~size_t(15);
+  int cap = (int)((budget - fixed) / (7 * sizeof(double)));
+  cap &= ~31;
+  return cap;
+}
+
+int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta) {
+  if (n_jobs <= 0) return PSULVSB_OK;
+  static bool attr_set = false;
+  const size_t smem = gnc_smem_bytes(cap_per_cta);
+  if (!attr_set) {
+    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<GNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)gnc_smem_bytes(gnc_default_capacity())));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(GNC_CLUSTER, (unsigned)n_jobs, 1);
+  cfg.blockDim = dim3(GNC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GNC_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<GNC_CLUSTER>, d_jobs, cap_per_cta));
+  return PSULVSB_OK;
+}
+
+int launch_kabsch_batch(cudaStream_t st, const double* src, const double* dst, const uint2* edges,
+                        const uint32_t* sets, int k, unsigned long long n_hyp, double* R, double* t) {
+  if (n_hyp == 0) return PSULVSB_OK;
+  if (k < 1) return fail(PSULVSB_ERR_INVALID, "kabsch_batch: k < 1");
+  const unsigned long long threads = n_hyp * 32ull;
+  kabsch_batch_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, dst, edges, sets, k, n_hyp, R, t);
+  PSU_CHECK_LAUNCH("kabsch_batch_kernel");
+  return PSULVSB_OK;
+}
+
+}  // namespace psulvsb

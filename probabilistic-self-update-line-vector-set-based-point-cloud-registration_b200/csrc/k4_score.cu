@@ -1,0 +1,326 @@
+// k4_score.cu -- stage 4: fused transform + score + argmax, plus the single-hypothesis FP64 scorer
+// and the stand-alone max-stabbing translation kernel.
+//
+// Reference: the three scoring loops of solve(), registration.cc:1303-1311, :1329-1336 (sampled
+// points) and :1417-1444 (all M points): count_j [ | q_j - s (R p_j + t) | <= tau ].
+//
+// score_batch_kernel: a thread owns HPT hypotheses (s*R, s*t' in registers), the CTA streams ALL n
+// correspondences through shared memory in double-buffered tiles staged by 1-D TMA bulk copies, so a
+// thread finishes with the complete inlier count of its hypotheses: no cross-thread reduction of
+// counts, only a warp-shuffle / block / grid argmax of (count, hypothesis) packed in 64 bits.
+// FP32 evaluation on centred coordinates; u = |d|^2 - tau^2 is accumulated with its sign, and a
+// hypothesis with any point inside the FP32 error band of the threshold is re-scored exactly: the
+// borderline points are re-evaluated in FP64 with the reference's formula (counted).
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "solve_dev.cuh"
+
+namespace psulvsb {
+
+namespace {
+
+constexpr int SB_THREADS = 256;
+constexpr int SB_HPT = 4;    // hypotheses per thread
+constexpr int SB_TP = 1024;  // points per smem tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct ScoreArgs {
+  double scale, tau;
+  double csrc[3], cdst[3];  // centres the float4 tiles were packed with
+  float coord_bound;
+};
+
+__global__ void __launch_bounds__(SB_THREADS)
+    score_batch_kernel(const float4* __restrict__ srcf, const float4* __restrict__ dstf,
+                       const double* __restrict__ src64, const double* __restrict__ dst64, int n,
+                       const double* __restrict__ hyp, unsigned long long n_hyp, unsigned long long hyp_begin,
+                       ScoreArgs a, uint32_t* __restrict__ counts, unsigned long long* __restrict__ best,
+                       unsigned long long* __restrict__ border_count) {
+  __shared__ __align__(128) float4 ps[2][SB_TP];
+  __shared__ __align__(128) float4 qs[2][SB_TP];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ unsigned long long warp_best[SB_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned long long h0 = ((unsigned long long)blockIdx.x * SB_THREADS + tid) * SB_HPT;
+
+  // ---- hypotheses -> registers: Rf = s R, tf = s (R c_src + t) - c_dst  (centred coordinates)
+  float Rf[SB_HPT][9], tf[SB_HPT][3], eps[SB_HPT], mn[SB_HPT];
+  int cnt[SB_HPT];
+  const float tau2 = (float)(a.tau * a.tau);
+#pragma unroll
+  for (int k = 0; k < SB_HPT; ++k) {
+    const unsigned long long h = h0 + k;
+    cnt[k] = 0;
+    mn[k] = 3.0e38f;
+    if (h < n_hyp) {
+      const double* H = hyp + h * 12;
+      double tmax = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double r0 = H[0 * 3 + r], r1 = H[1 * 3 + r], r2 = H[2 * 3 + r];  // column-major R
+        Rf[k][r * 3 + 0] = (float)(a.scale * r0);
+        Rf[k][r * 3 + 1] = (float)(a.scale * r1);
+        Rf[k][r * 3 + 2] = (float)(a.scale * r2);
+        const double tp = a.scale * (r0 * a.csrc[0] + r1 * a.csrc[1] + r2 * a.csrc[2] + H[9 + r]) - a.cdst[r];
+        tf[k][r] = (float)tp;
+        tmax = fmax(tmax, fabs(tp));
+      }
+      // |u - u_c| <= 64 mu tau (G + tau),  G = |t'|_inf + (1 + sqrt3 s) Cmax   (DESIGN.md "K4 error band")
+      const double G = tmax + (1.0 + 1.7320508 * fabs(a.scale)) * (double)a.coord_bound;
+      eps[k] = (float)(64.0 * 5.9604644775390625e-08 * a.tau * (G + a.tau) * 1.0001) + 1e-37f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rf[k][i] = 0.f;
+      tf[k][0] = tf[k][1] = tf[k][2] = 0.f;
+      eps[k] = 0.f;
+    }
+  }
+
+  const int ntiles = (n + SB_TP - 1) / SB_TP;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int tile) {
+    const int st = tile & 1;
+    const int p0 = tile * SB_TP;
+    const uint32_t bytes = (uint32_t)min(SB_TP, n - p0) * (uint32_t)sizeof(float4);
+    mbar_expect_tx(&bar[st], 2 * bytes);
+    tma_load_1d(ps[st], srcf + p0, bytes, &bar[st]);
+    tma_load_1d(qs[st], dstf + p0, bytes, &bar[st]);
+  };
+  if (tid == 0) {
+    issue(0);
+    if (ntiles > 1) issue(1);
+  }
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int st = tile & 1;
+    mbar_wait(&bar[st], (tile >> 1) & 1);
+    const int np = min(SB_TP, n - tile * SB_TP);
+#pragma unroll 4
+    for (int j = 0; j < np; ++j) {
+      const float4 p = ps[st][j];
+      const float4 q = qs[st][j];
+#pragma unroll
+      for (int k = 0; k < SB_HPT; ++k) {
+        const float d0 = fmaf(Rf[k][0], p.x, fmaf(Rf[k][1], p.y, fmaf(Rf[k][2], p.z, tf[k][0] - q.x)));
+        const float d1 = fmaf(Rf[k][3], p.x, fmaf(Rf[k][4], p.y, fmaf(Rf[k][5], p.z, tf[k][1] - q.y)));
+        const float d2 = fmaf(Rf[k][6], p.x, fmaf(Rf[k][7], p.y, fmaf(Rf[k][8], p.z, tf[k][2] - q.z)));
+        const float u = fmaf(d2, d2, fmaf(d1, d1, fmaf(d0, d0, -tau2)));
+        cnt[k] += (int)(__float_as_uint(u) >> 31);
+        mn[k] = fminf(mn[k], fabsf(u));
+      }
+    }
+    __syncthreads();  // everyone is done with stage st
+    if (tid == 0 && tile + 2 < ntiles) issue(tile + 2);
+  }
+
+  // ---- exact fix-up for hypotheses with a point inside the band (rare)
+  unsigned int nborder = 0;
+#pragma unroll
+  for (int k = 0; k < SB_HPT; ++k) {
+    const unsigned long long h = h0 + k;
+    if (h < n_hyp && !(mn[k] > eps[k])) {
+      const double* H = hyp + h * 12;
+      double R[9], t[3];
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = H[c * 3 + r];
+        t[r] = H[9 + r];
+      }
+      for (int j = 0; j < n; ++j) {
+        const float4 p = srcf[j];
+        const float4 q = dstf[j];
+        const float d0 = fmaf(Rf[k][0], p.x, fmaf(Rf[k][1], p.y, fmaf(Rf[k][2], p.z, tf[k][0] - q.x)));
+        const float d1 = fmaf(Rf[k][3], p.x, fmaf(Rf[k][4], p.y, fmaf(Rf[k][5], p.z, tf[k][1] - q.y)));
+        const float d2 = fmaf(Rf[k][6], p.x, fmaf(Rf[k][7], p.y, fmaf(Rf[k][8], p.z, tf[k][2] - q.z)));
+        const float u = fmaf(d2, d2, fmaf(d1, d1, fmaf(d0, d0, -tau2)));
+        if (!(fabsf(u) > eps[k])) {
+          ++nborder;
+          const bool fast_in = (__float_as_uint(u) >> 31) != 0u;
+          const bool exact_in = residual_ref(src64 + 3 * (size_t)j, dst64 + 3 * (size_t)j, a.scale, R, t) <= a.tau;
+          cnt[k] += (exact_in ? 1 : 0) - (fast_in ? 1 : 0);
+        }
+      }
+    }
+  }
+
+  // ---- outputs: counts, then warp -> block -> grid argmax (first best hypothesis wins)
+  unsigned long long mybest = 0ull;
+#pragma unroll
+  for (int k = 0; k < SB_HPT; ++k) {
+    const unsigned long long h = h0 + k;
+    if (h < n_hyp) {
+      counts[h] = (uint32_t)cnt[k];
+      const unsigned long long key =
+          ((unsigned long long)(uint32_t)cnt[k] << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(hyp_begin + h));
+      mybest = key > mybest ? key : mybest;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long x = __shfl_xor_sync(0xffffffffu, mybest, o);
+    mybest = x > mybest ? x : mybest;
+  }
+  if (lane == 0) warp_best[wid] = mybest;
+  const unsigned int nb = (unsigned int)warp_sum_int((int)nborder);
+  if (lane == 0 && nb && border_count) atomicAdd(border_count, (unsigned long long)nb);
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long b = warp_best[0];
+    for (int w = 1; w < SB_THREADS / 32; ++w) b = warp_best[w] > b ? warp_best[w] : b;
+    if (best) atomicMax(best, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    score_one_kernel(const double* __restrict__ src, const double* __restrict__ dst, int n, double scale,
+                     const double* __restrict__ Rcm, const double* __restrict__ tt, double tau,
+                     uint8_t* __restrict__ inliers, double* __restrict__ residuals, int* __restrict__ count) {
+  double R[9], t[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = Rcm[c * 3 + r];
+    t[r] = tt[r];
+  }
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  bool in = false;
+  if (j < n) {
+    const double res = residual_ref(src + 3 * (size_t)j, dst + 3 * (size_t)j, scale, R, t);
+    in = res <= tau;
+    if (inliers) inliers[j] = in ? 1 : 0;
+    if (residuals) residuals[j] = res;
+  }
+  // warp popc reduction of the predicate
+  const unsigned int bal = __ballot_sync(0xffffffffu, in);
+  if ((threadIdx.x & 31) == 0 && bal && count) atomicAdd(count, __popc(bal));
+}
+
+// stand-alone translation stage: compact the flagged points (ascending), then block_translation
+__global__ void __launch_bounds__(BLK)
+    tls_translation_kernel(const double* __restrict__ src, const double* __restrict__ dst,
+                           const uint8_t* __restrict__ flags, int n, double scale, const double* __restrict__ Rcm,
+                           double sigma, const double* __restrict__ last_best, int* __restrict__ idx,
+                           double* __restrict__ xs, double* __restrict__ t_out, int* __restrict__ n_points) {
+  __shared__ BlockScratch scratch;
+  __shared__ int base_s;
+  const int tid = threadIdx.x;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += BLK) {
+    const int j = j0 + tid;
+    const int f = (j < n && flags[j]) ? 1 : 0;
+    int ea, eb, ta, tb;
+    block_scan2(&scratch, f, 0, ea, eb, ta, tb);
+    const int base = base_s;
+    if (f) idx[base + ea] = j;
+    __syncthreads();
+    if (tid == 0) base_s = base + ta;
+    __syncthreads();
+  }
+  const int P = base_s;
+  double R[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = Rcm[c * 3 + r];
+  double t[3] = {0.0, 0.0, 0.0};
+  double lb[3];
+  if (last_best) {
+    lb[0] = last_best[0];
+    lb[1] = last_best[1];
+    lb[2] = last_best[2];
+  }
+  block_translation(&scratch, src, dst, idx, P, scale, R, sigma, last_best ? lb : nullptr, xs, t);
+  if (tid == 0) {
+    t_out[0] = t[0];
+    t_out[1] = t[1];
+    t_out[2] = t[2];
+    if (n_points) *n_points = P;
+  }
+}
+
+}  // namespace
+
+int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, const double* src64, const double* dst64,
+                       int n, const double* hyp, unsigned long long n_hyp, unsigned long long hyp_begin, double scale,
+                       double tau, double coord_bound, const double* csrc, const double* cdst, uint32_t* counts,
+                       unsigned long long* best, unsigned long long* border) {
+  if (n_hyp == 0 || n <= 0) return PSULVSB_OK;
+  if (hyp_begin + n_hyp > 0xFFFFFFFFull) return fail(PSULVSB_ERR_UNSUPPORTED, "score_batch: hypothesis id > 32 bits");
+  ScoreArgs a;
+  a.scale = scale;
+  a.tau = tau;
+  for (int r = 0; r < 3; ++r) {
+    a.csrc[r] = csrc ? csrc[r] : 0.0;
+    a.cdst[r] = cdst ? cdst[r] : 0.0;
+  }
+  a.coord_bound = (float)(coord_bound * 1.0000002);
+  const unsigned long long per_cta = (unsigned long long)SB_THREADS * SB_HPT;
+  const unsigned long long grid = (n_hyp + per_cta - 1) / per_cta;
+  score_batch_kernel<<<(unsigned)grid, SB_THREADS, 0, st>>>(src, dst, src64, dst64, n, hyp, n_hyp, hyp_begin, a, counts,
+                                                            best, border);
+  PSU_CHECK_LAUNCH("score_batch_kernel");
+  return PSULVSB_OK;
+}
+
+int launch_score_one(cudaStream_t st, const double* src, const double* dst, int n, double scale, const double* R,
+                     const double* t, double tau, uint8_t* inliers, double* residuals, int* count) {
+  if (n <= 0) return PSULVSB_OK;
+  score_one_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n, scale, R, t, tau, inliers, residuals, count);
+  PSU_CHECK_LAUNCH("score_one_kernel");
+  return PSULVSB_OK;
+}
+
+int launch_tls_translation(cudaStream_t st, const double* src, const double* dst, const uint8_t* flags, int n,
+                           double scale, const double* R, double noise, const double* last_best, double* t_out,
+                           int* n_points) {
+  if (n <= 0) return fail(PSULVSB_ERR_INVALID, "tls_translation: n <= 0");
+  int* idx = nullptr;
+  double* xs = nullptr;
+  PSU_CUDA(cudaMallocAsync((void**)&idx, sizeof(int) * (size_t)n, st));
+  PSU_CUDA(cudaMallocAsync((void**)&xs, sizeof(double) * 3 * ((size_t)n + 1), st));
+  tls_translation_kernel<<<1, BLK, 0, st>>>(src, dst, flags, n, scale, R, noise, last_best, idx, xs, t_out, n_points);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(idx, st);
+  cudaFreeAsync(xs, st);
+  if (e != cudaSuccess) return fail(PSULVSB_ERR_CUDA, std::string("tls_translation_kernel launch: ") + cudaGetErrorString(e));
+  return PSULVSB_OK;
+}
+
+}  // namespace psulvsb

@@ -1,0 +1,197 @@
+// solve_dev.cuh -- block-wide FP64 device routines shared by the stage kernels (k4_score.cu) and the
+// lock-step batch engine (engine_kernels.cu): block scan / reductions, residual, max-stabbing
+// translation.
+#pragma once
+
+#include "common.cuh"
+
+namespace psulvsb {
+
+constexpr int BLK = 1024;  // all block-wide routines below assume blockDim.x == BLK
+
+struct BlockScratch {
+  double d[32][4];
+  int i[32][2];
+  double bd[4];
+  int bi[2];
+  unsigned long long u[32];
+  unsigned long long bu;
+};
+
+// exclusive block scan of a pair of small ints (packed 32+32); returns exclusive prefixes and totals
+__device__ __forceinline__ void block_scan2(BlockScratch* s, int a, int b, int& ea, int& eb, int& ta, int& tb) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned long long v = ((unsigned long long)(unsigned)a << 32) | (unsigned)b;
+  unsigned long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s->u[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long t = s->u[lane], ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long x = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += x;
+    }
+    s->u[lane] = ti - t;
+    if (lane == 31) s->bu = ti;
+  }
+  __syncthreads();
+  const unsigned long long ex = s->u[wid] + (incl - v);
+  const unsigned long long tot = s->bu;
+  ea = (int)(ex >> 32);
+  eb = (int)(ex & 0xffffffffull);
+  ta = (int)(tot >> 32);
+  tb = (int)(tot & 0xffffffffull);
+  __syncthreads();
+}
+
+// block sum of up to 4 doubles (fixed order: lanes by xor-shuffle, warps ascending) -> every thread
+template <int N>
+__device__ __forceinline__ void block_sum(BlockScratch* s, double v[N]) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double x = warp_sum(v[k]);
+    if (lane == 0) s->d[wid][k] = x;
+  }
+  __syncthreads();
+  if (tid < N) {
+    double acc = 0.0;
+    for (int w = 0; w < BLK / 32; ++w) acc += s->d[w][tid];
+    s->bd[tid] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = s->bd[k];
+  __syncthreads();
+}
+
+__device__ __forceinline__ int block_sum_int2(BlockScratch* s, int& a, int& b) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int xa = warp_sum_int(a), xb = warp_sum_int(b);
+  if (lane == 0) {
+    s->i[wid][0] = xa;
+    s->i[wid][1] = xb;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    int acc = 0;
+    for (int w = 0; w < BLK / 32; ++w) acc += s->i[w][tid];
+    s->bi[tid] = acc;
+  }
+  __syncthreads();
+  a = s->bi[0];
+  b = s->bi[1];
+  __syncthreads();
+  return a;
+}
+
+// | q - s (R p + t) | exactly as the reference forms it (registration.cc:1303-1308, :1417-1423):
+// the entries of (s * TRANSFORM) first, then the 4-term row products, no fused multiply-add.
+// R row-major.
+__device__ __forceinline__ double residual_ref(const double* __restrict__ p, const double* __restrict__ q, double s,
+                                               const double R[9], const double t[3]) {
+  double d[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double x = dadd(dadd(dadd(dmul(dmul(s, R[r * 3 + 0]), p[0]), dmul(dmul(s, R[r * 3 + 1]), p[1])),
+                               dmul(dmul(s, R[r * 3 + 2]), p[2])),
+                          dmul(dmul(s, t[r]), 1.0));
+    d[r] = dsub(q[r], x);
+  }
+  return sqrt(sqnorm3(d[0], d[1], d[2]));
+}
+
+// ------------------------------------------------------------------------------------------
+// Max-stabbing translation (TLSTranslationSolver, registration.cc:436-463, with the rewritten
+// ScalarTLSEstimator translation branch, :121-203), one CTA.
+//
+// The reference sorts the 2N interval endpoints x_k -+ sigma and sweeps, keeping the mean of the
+// open set at the first closing endpoint whose depth strictly exceeds every earlier one.  The
+// depth seen at the closing endpoint of k is  #{ m : lo_m <= hi_k  and  hi_m >= hi_k }, so the
+// sweep's answer is the candidate k maximising that depth (ties -> smallest hi_k) and the mean of
+// its member set -- computed here without the sort: one warp per candidate, lanes over members.
+//
+// idx[0..P): compacted indices of the participating points (ascending), xs: scratch 3*(P+1)
+// doubles (lo/hi are recomputed), last_best: NULL or the pseudo-measurement (registration.cc:136-161).
+// Returns the estimate of each axis in t_out (unchanged for P == 0 without pseudo-measurement).
+// ------------------------------------------------------------------------------------------
+struct StabBest {
+  int depth;
+  double hi;
+  int k;
+};
+
+__device__ inline void block_translation(BlockScratch* s, const double* __restrict__ src,
+                                         const double* __restrict__ dst, const int* __restrict__ idx, int P,
+                                         double scale, const double R[9], double sigma, const double* last_best,
+                                         double* __restrict__ xs, double t_out[3]) {
+  __shared__ StabBest warp_best[BLK / 32];
+  __shared__ StabBest blk_best;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int N = P + (last_best ? 1 : 0);
+  // x_m per axis: raw_translation = dst - (s*R) * src  (registration.cc:446 with :1248's argument)
+  for (int m = tid; m < P; m += BLK) {
+    const double* p = src + 3 * (size_t)idx[m];
+    const double* q = dst + 3 * (size_t)idx[m];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double v1 = dadd(dadd(dmul(dmul(scale, R[r * 3 + 0]), p[0]), dmul(dmul(scale, R[r * 3 + 1]), p[1])),
+                             dmul(dmul(scale, R[r * 3 + 2]), p[2]));
+      xs[(size_t)r * (P + 1) + m] = dsub(q[r], v1);
+    }
+  }
+  if (last_best && tid < 3) xs[(size_t)tid * (P + 1) + P] = last_best[tid];
+  __syncthreads();
+  for (int axis = 0; axis < 3; ++axis) {
+    const double* x = xs + (size_t)axis * (P + 1);
+    StabBest best;
+    best.depth = 0;
+    best.hi = 0.0;
+    best.k = -1;
+    for (int k = wid; k < N; k += BLK / 32) {
+      const double hik = dadd(x[k], sigma);
+      int cnt = 0;
+      for (int m = lane; m < N; m += 32) {
+        const double xm = x[m];
+        cnt += (dsub(xm, sigma) <= hik && dadd(xm, sigma) >= hik) ? 1 : 0;
+      }
+      cnt = warp_sum_int(cnt);
+      if (cnt > best.depth || (cnt == best.depth && best.k >= 0 && hik < best.hi)) {
+        best.depth = cnt;
+        best.hi = hik;
+        best.k = k;
+      }
+    }
+    if (lane == 0) warp_best[wid] = best;
+    __syncthreads();
+    if (tid == 0) {
+      StabBest b = warp_best[0];
+      for (int w = 1; w < BLK / 32; ++w) {
+        const StabBest c = warp_best[w];
+        if (c.k >= 0 && (b.k < 0 || c.depth > b.depth || (c.depth == b.depth && (c.hi < b.hi || (c.hi == b.hi && c.k < b.k)))))
+          b = c;
+      }
+      blk_best = b;
+    }
+    __syncthreads();
+    const StabBest b = blk_best;
+    if (b.k >= 0) {
+      double sum[1] = {0.0};
+      for (int m = tid; m < N; m += BLK) {
+        const double xm = x[m];
+        if (dsub(xm, sigma) <= b.hi && dadd(xm, sigma) >= b.hi) sum[0] += xm;
+      }
+      block_sum<1>(s, sum);
+      t_out[axis] = sum[0] / (double)b.depth;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace psulvsb
