@@ -169,9 +169,13 @@ int psulvsb_batch_solve_resident(psulvsb_handle_t h, const psulvsb_params_t* par
  * measured with CUDA events on the handle's stream. */
 long long psulvsb_launch_count(psulvsb_handle_t h);
 double psulvsb_last_device_ms(psulvsb_handle_t h);
-/* Device time (ms) spent in stage `which` during the last solve call (0 K1 mask+compaction,
- * 1 sampling, 2 GNC-TLS rotation, 3 translation+scoring+control, 4 refinement). */
+/* Device time (ms), CUDA events on the handle's stream, of part `which` of the last solve call:
+ * 0 stage 1 in full (float4 packing, mask, row scan, n_red read-back, edge compaction, state init),
+ * 1 the tick loop (sampling, GNC-TLS, translation, scoring, control), 2 the consistency-mask kernel
+ * alone (one launch over the whole batch), 3 reserved, 4 refinement + solution copy. */
 double psulvsb_last_stage_ms(psulvsb_handle_t h, int which);
+/* Engine ticks (lock-step local iterations over the whole batch) of the last solve call. */
+int psulvsb_last_ticks(psulvsb_handle_t h);
 
 /* ------------------------------------------------------------------------------------------ */
 /* stage entry points: DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL) */

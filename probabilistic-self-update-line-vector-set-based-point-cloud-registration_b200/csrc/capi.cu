@@ -1,0 +1,373 @@
+// capi.cu -- the C ABI of libpsulvsb_b200.so (include/psulvsb.h): argument checking, error plumbing,
+// single-job descriptors for the stage entry points, and the handle API over the batch engine.
+// Nothing throws across this boundary and there is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace psulvsb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+namespace {
+
+int need_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(PSULVSB_ERR_NO_DEVICE, "no CUDA device available (there is no CPU fallback)");
+  }
+  return PSULVSB_OK;
+}
+
+// single job descriptor -> device, freed in stream order after the kernels that read it
+template <typename T>
+struct DeviceJob {
+  T* d = nullptr;
+  cudaStream_t st;
+  explicit DeviceJob(cudaStream_t s) : st(s) {}
+  int put(const T& h) {
+    PSU_CUDA(cudaMallocAsync((void**)&d, sizeof(T), st));
+    PSU_CUDA(cudaMemcpyAsync(d, &h, sizeof(T), cudaMemcpyHostToDevice, st));
+    return PSULVSB_OK;
+  }
+  ~DeviceJob() {
+    if (d) cudaFreeAsync(d, st);
+  }
+};
+
+}  // namespace
+}  // namespace psulvsb
+
+using namespace psulvsb;
+
+struct psulvsb_handle_s {
+  Engine* engine;
+};
+
+extern "C" {
+
+int psulvsb_version(void) { return PSULVSB_VERSION; }
+
+const char* psulvsb_last_error(void) { return g_last_error.c_str(); }
+
+void psulvsb_default_params(psulvsb_params_t* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->noise_bound = 0.01;             // registration.h:383
+  p->cbar2 = 1;                      // registration.h:388
+  p->estimate_scaling = 1;           // registration.h:396
+  p->rotation_max_iterations = 100;  // registration.h:416
+  p->rotation_gnc_factor = 1.4;      // registration.h:411
+  p->rotation_cost_threshold = 1e-6; // registration.h:426
+  p->inlier_selection_mode = 0;      // PMC_EXACT, registration.h:443
+  p->kcore_heuristic_threshold = 0.5;
+  p->score_noise_bound = 0.01;       // registration.cc:33
+  p->inloop_noise_bound = 0.05;      // registration.cc:938
+  p->inloop_cbar2 = 1;               // registration.cc:939
+  p->inloop_max_iterations = 100;    // registration.cc:941
+  p->inloop_gnc_factor = 1.4;        // registration.cc:942
+  p->inloop_cost_threshold = 0.005;  // registration.cc:945
+  p->rotation_similar = 0.01;        // registration.cc:48
+  p->local_max_iter = 10;            // registration.cc:49
+  p->tpro_host = 0.99;               // registration.cc:772
+  p->tpro_local = 0.99;              // registration.cc:898
+  p->host_round_limit = 5;           // registration.cc:781
+  p->wallclock_cap_s = 60.0;         // registration.cc:1475
+  p->self_update = 1;                // registration.cc:786-832
+  p->seed = 0;
+}
+
+int psulvsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int psulvsb_create(psulvsb_handle_t* out, int device) {
+  if (!out) return fail(PSULVSB_ERR_INVALID, "psulvsb_create: out is NULL");
+  *out = nullptr;
+  if (int rc = need_device()) return rc;
+  psulvsb_handle_s* h = new (std::nothrow) psulvsb_handle_s();
+  if (!h) return fail(PSULVSB_ERR_INTERNAL, "out of host memory");
+  const int rc = engine_create(&h->engine, device);
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return PSULVSB_OK;
+}
+
+int psulvsb_destroy(psulvsb_handle_t h) {
+  if (!h) return PSULVSB_OK;
+  engine_destroy(h->engine);
+  delete h;
+  return PSULVSB_OK;
+}
+
+int psulvsb_solve(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                  psulvsb_solution_t* solution, psulvsb_trace_t* trace) {
+  if (!h || !params || !problem || !solution) return fail(PSULVSB_ERR_INVALID, "psulvsb_solve: NULL argument");
+  if (int rc = engine_upload(h->engine, problem, 1)) return rc;
+  return engine_solve_resident(h->engine, params, nullptr, solution, trace);
+}
+
+int psulvsb_solve_batch(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,
+                        const uint64_t* seeds, psulvsb_solution_t* solutions) {
+  if (!h || !params || !problems || !solutions || B <= 0)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_solve_batch: NULL argument or B <= 0");
+  if (int rc = engine_upload(h->engine, problems, B)) return rc;
+  return engine_solve_resident(h->engine, params, seeds, solutions, nullptr);
+}
+
+int psulvsb_batch_upload(psulvsb_handle_t h, const psulvsb_problem_t* problems, int B) {
+  if (!h || !problems || B <= 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_upload: NULL argument or B <= 0");
+  return engine_upload(h->engine, problems, B);
+}
+
+int psulvsb_batch_solve_resident(psulvsb_handle_t h, const psulvsb_params_t* params, const uint64_t* seeds,
+                                 psulvsb_solution_t* solutions) {
+  if (!h || !params || !solutions) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_solve_resident: NULL argument");
+  return engine_solve_resident(h->engine, params, seeds, solutions, nullptr);
+}
+
+long long psulvsb_launch_count(psulvsb_handle_t h) { return h ? engine_launch_count(h->engine) : 0; }
+double psulvsb_last_device_ms(psulvsb_handle_t h) { return h ? engine_last_device_ms(h->engine) : 0.0; }
+double psulvsb_last_stage_ms(psulvsb_handle_t h, int which) { return h ? engine_last_stage_ms(h->engine, which) : 0.0; }
+int psulvsb_last_ticks(psulvsb_handle_t h) { return h ? engine_last_ticks(h->engine) : 0; }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* stage entry points                                                                              */
+/* ---------------------------------------------------------------------------------------------- */
+
+int psulvsb_pack_points(void* stream, const double* d_pts, int n, const double center[3], void* d_out_float4) {
+  if (int rc = need_device()) return rc;
+  if (!d_pts || !d_out_float4 || n < 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_pack_points: bad argument");
+  return launch_pack_points((cudaStream_t)stream, d_pts, n, center, (float4*)d_out_float4);
+}
+
+int psulvsb_consistency_mask_rows(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,
+                                  const double* d_dst64, int n, int row_begin, int row_end, double beta,
+                                  double coord_bound, uint32_t* d_mask, int row_stride_words, uint32_t* d_row_counts,
+                                  unsigned long long* d_border_count) {
+  if (int rc = need_device()) return rc;
+  if (!d_src_f4 || !d_dst_f4 || !d_src64 || !d_dst64 || !d_mask)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_consistency_mask: NULL array");
+  if (n < 1 || row_begin < 0 || row_end > n || row_begin > row_end)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_consistency_mask: bad n / row range");
+  if (row_stride_words < (n + 31) / 32)
+    return fail(PSULVSB_ERR_CAPACITY, "psulvsb_consistency_mask: row_stride_words < ceil(n / 32)");
+  if (!(beta >= 0.0) || !(coord_bound >= 0.0) || !std::isfinite(beta) || !std::isfinite(coord_bound))
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_consistency_mask: beta / coord_bound must be finite and >= 0");
+  if (((uintptr_t)d_src_f4 & 15) || ((uintptr_t)d_dst_f4 & 15))
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_consistency_mask: float4 arrays must be 16-byte aligned");
+  if (row_begin == row_end) return PSULVSB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  K1Job j;
+  std::memset(&j, 0, sizeof(j));
+  j.src = (const float4*)d_src_f4;
+  j.dst = (const float4*)d_dst_f4;
+  j.src64 = d_src64;
+  j.dst64 = d_dst64;
+  j.n = n;
+  j.row_begin = row_begin;
+  j.row_end = row_end;
+  j.c = make_k1_consts(beta, coord_bound);
+  j.mask = d_mask;
+  j.stride = row_stride_words;
+  j.row_counts = d_row_counts;
+  j.border = d_border_count;
+  j.active = 1;
+  if (d_row_counts) PSU_CUDA(cudaMemsetAsync(d_row_counts + row_begin, 0, sizeof(uint32_t) * (size_t)(row_end - row_begin), st));
+  DeviceJob<K1Job> dj(st);
+  if (int rc = dj.put(j)) return rc;
+  return launch_consistency_mask(st, dj.d, 1, n, row_end - row_begin);
+}
+
+int psulvsb_consistency_mask(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,
+                             const double* d_dst64, int n, double beta, double coord_bound, uint32_t* d_mask,
+                             int row_stride_words, uint32_t* d_row_counts, unsigned long long* d_border_count) {
+  return psulvsb_consistency_mask_rows(stream, d_src_f4, d_dst_f4, d_src64, d_dst64, n, 0, n, beta, coord_bound, d_mask,
+                                       row_stride_words, d_row_counts, d_border_count);
+}
+
+int psulvsb_mask_symmetrize(void* stream, uint32_t* d_mask, int n, int row_stride_words) {
+  if (int rc = need_device()) return rc;
+  if (!d_mask || n < 1 || row_stride_words < (n + 31) / 32)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_mask_symmetrize: bad argument");
+  return launch_symmetrize((cudaStream_t)stream, d_mask, n, row_stride_words);
+}
+
+int psulvsb_compact_edges(void* stream, const uint32_t* d_mask, int n, int row_stride_words,
+                          const uint32_t* d_row_counts, unsigned long long* d_row_offsets, void* d_edges_uint2,
+                          unsigned long long edge_capacity, unsigned long long* d_n_edges) {
+  if (int rc = need_device()) return rc;
+  if (!d_mask || !d_row_counts || !d_row_offsets || n < 1 || row_stride_words < (n + 31) / 32)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_compact_edges: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CompactJob j;
+  std::memset(&j, 0, sizeof(j));
+  j.mask = d_mask;
+  j.n = n;
+  j.stride = row_stride_words;
+  j.row_counts = d_row_counts;
+  j.offsets = d_row_offsets;
+  j.edges = (uint2*)d_edges_uint2;
+  j.cap = edge_capacity;
+  j.n_edges = d_n_edges;
+  j.active = 1;
+  DeviceJob<CompactJob> dj(st);
+  if (int rc = dj.put(j)) return rc;
+  return launch_compact_edges(st, dj.d, 1, n, true, d_edges_uint2 != nullptr);
+}
+
+unsigned long long psulvsb_sample_default_max_draws(unsigned long long n, unsigned long long count) {
+  return sample_default_max_draws(n, count);
+}
+
+unsigned long long psulvsb_sample_workspace_bytes(unsigned long long n, unsigned long long count,
+                                                  unsigned long long max_draws) {
+  (void)count;
+  (void)max_draws;
+  return n * sizeof(uint32_t);
+}
+
+int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long n,
+                   unsigned long long count, unsigned long long max_draws, uint32_t* d_out, void* d_work,
+                   unsigned long long* d_status) {
+  if (int rc = need_device()) return rc;
+  if (!d_out || !d_work || !d_status) return fail(PSULVSB_ERR_INVALID, "psulvsb_sample: NULL array");
+  if (n == 0 || count > n) return fail(PSULVSB_ERR_INVALID, "psulvsb_sample: need 0 < n and count <= n");
+  if (n >= 0x7FFFFFFFull) return fail(PSULVSB_ERR_UNSUPPORTED, "psulvsb_sample: n must fit the 31-bit draws");
+  if (max_draws == 0) max_draws = sample_default_max_draws(n, count);
+  if (max_draws >= 0xFFFFFFFFull) return fail(PSULVSB_ERR_UNSUPPORTED, "psulvsb_sample: max_draws must be < 2^32 - 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  PSU_CUDA(cudaMemsetAsync(d_work, 0xFF, n * sizeof(uint32_t), st));
+  PSU_CUDA(cudaMemsetAsync(d_status, 0, sizeof(unsigned long long), st));
+  if (count == 0) return PSULVSB_OK;
+  SampleJob j;
+  std::memset(&j, 0, sizeof(j));
+  j.seed = seed;
+  j.domain = domain;
+  j.event = event;
+  j.n = n;
+  j.count = count;
+  j.max_draws = max_draws;
+  j.first = (uint32_t*)d_work;
+  j.out = d_out;
+  j.status = d_status;
+  j.active = 1;
+  DeviceJob<SampleJob> dj(st);
+  if (int rc = dj.put(j)) return rc;
+  return launch_sample(st, dj.d, 1, max_draws);
+}
+
+int psulvsb_philox_fill(void* stream, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long first_k,
+                        unsigned long long count, uint32_t* d_out_rand31) {
+  if (int rc = need_device()) return rc;
+  if (!d_out_rand31 && count) return fail(PSULVSB_ERR_INVALID, "psulvsb_philox_fill: NULL output");
+  return launch_philox_fill((cudaStream_t)stream, seed, domain, event, first_k, count, d_out_rand31);
+}
+
+int psulvsb_gnc_tls_rotation(void* stream, const double* d_src64, const double* d_dst64, const void* d_edges_uint2,
+                             unsigned long long K, double inv_scale, double noise_bound, int max_iterations,
+                             double gnc_factor, double cost_threshold, const double* d_R_init, double* d_weights,
+                             double* d_R, uint8_t* d_inliers, int* d_info, double* d_cost) {
+  if (int rc = need_device()) return rc;
+  if (!d_src64 || !d_dst64 || (!d_edges_uint2 && K) || !d_R || (!d_weights && K))
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_gnc_tls_rotation: NULL array");
+  if (max_iterations < 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_gnc_tls_rotation: max_iterations < 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  GncJob j;
+  std::memset(&j, 0, sizeof(j));
+  j.src = d_src64;
+  j.dst = d_dst64;
+  j.edges = (const uint2*)d_edges_uint2;
+  j.K = K;
+  j.inv_scale = inv_scale;
+  j.noise_bound = noise_bound;
+  j.gnc_factor = gnc_factor;
+  j.cost_threshold = cost_threshold;
+  j.max_iterations = max_iterations;
+  j.use_init = d_R_init ? 1 : 0;
+  if (d_R_init) PSU_CUDA(cudaMemcpyAsync(j.R_init, d_R_init, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
+  if (d_R_init) PSU_CUDA(cudaStreamSynchronize(st));
+  j.weights = d_weights;
+  j.R_out = d_R;
+  j.inliers = d_inliers;
+  j.point_flags = nullptr;
+  j.n_points = 0;
+  j.info = d_info;
+  j.cost = d_cost;
+  j.active = 1;
+  DeviceJob<GncJob> dj(st);
+  if (int rc = dj.put(j)) return rc;
+  int cap = (int)((K + 7) / 8) + 32;
+  cap = (cap + 31) & ~31;
+  if (cap > gnc_default_capacity()) cap = gnc_default_capacity();
+  return launch_gnc_tls(st, dj.d, 1, cap);
+}
+
+int psulvsb_kabsch_batch(void* stream, const double* d_src64, const double* d_dst64, const void* d_edges_uint2,
+                         const uint32_t* d_sets, int k, unsigned long long n_hyp, double* d_R, double* d_t) {
+  if (int rc = need_device()) return rc;
+  if (!d_src64 || !d_dst64 || !d_edges_uint2 || !d_sets || !d_R)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_kabsch_batch: NULL array");
+  return launch_kabsch_batch((cudaStream_t)stream, d_src64, d_dst64, (const uint2*)d_edges_uint2, d_sets, k, n_hyp, d_R,
+                             d_t);
+}
+
+int psulvsb_tls_translation(void* stream, const double* d_src64, const double* d_dst64, const uint8_t* d_point_flags,
+                            int n, double scale, const double* d_R, double noise, const double* d_last_best,
+                            double* d_t_out, int* d_n_points) {
+  if (int rc = need_device()) return rc;
+  if (!d_src64 || !d_dst64 || !d_point_flags || !d_R || !d_t_out)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_tls_translation: NULL array");
+  return launch_tls_translation((cudaStream_t)stream, d_src64, d_dst64, d_point_flags, n, scale, d_R, noise, d_last_best,
+                                d_t_out, d_n_points);
+}
+
+int psulvsb_score_batch(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,
+                        const double* d_dst64, int n, const double* d_hyp, unsigned long long n_hyp,
+                        unsigned long long hyp_begin, double scale, double tau, double coord_bound,
+                        const double center_src[3], const double center_dst[3], uint32_t* d_counts,
+                        unsigned long long* d_best, unsigned long long* d_border_count) {
+  if (int rc = need_device()) return rc;
+  if (!d_src_f4 || !d_dst_f4 || !d_src64 || !d_dst64 || !d_hyp || !d_counts)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_score_batch: NULL array");
+  if (((uintptr_t)d_src_f4 & 15) || ((uintptr_t)d_dst_f4 & 15))
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_score_batch: float4 arrays must be 16-byte aligned");
+  if (!(tau >= 0.0) || !std::isfinite(tau) || !std::isfinite(scale) || !(coord_bound >= 0.0))
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_score_batch: bad tau / scale / coord_bound");
+  return launch_score_batch((cudaStream_t)stream, (const float4*)d_src_f4, (const float4*)d_dst_f4, d_src64, d_dst64, n,
+                            d_hyp, n_hyp, hyp_begin, scale, tau, coord_bound, center_src, center_dst, d_counts, d_best,
+                            d_border_count);
+}
+
+int psulvsb_score_one(void* stream, const double* d_src64, const double* d_dst64, int n, double scale,
+                      const double* d_R, const double* d_t, double tau, uint8_t* d_inliers, double* d_residuals,
+                      int* d_count) {
+  if (int rc = need_device()) return rc;
+  if (!d_src64 || !d_dst64 || !d_R || !d_t) return fail(PSULVSB_ERR_INVALID, "psulvsb_score_one: NULL array");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_count) PSU_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+  return launch_score_one(st, d_src64, d_dst64, n, scale, d_R, d_t, tau, d_inliers, d_residuals, d_count);
+}
+
+}  // extern "C"

@@ -1,0 +1,608 @@
+// engine.cu -- host side of the lock-step batch engine: device arenas, problem upload, and the
+// launch sequence that replaces RobustRegistrationSolver::solve (registration.cc:622-1535) for a
+// batch of B independent registrations on one B200.
+//
+//   upload : problems -> one pinned staging buffer -> HBM (one copy per element type)
+//   solve  : pack float4 tiles -> K1 bit mask (all jobs, one launch) -> row scan -> [n_red to host:
+//            sizes the edge arena] -> edge compaction -> init -> ticks until every job is done
+//            -> refinement -> solutions to host.
+// The only host synchronisations are the n_red read-back and one 4-byte "jobs done" poll per tick.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "engine.cuh"
+#include "engine_kernels.cuh"
+#include "engine_state.cuh"
+
+namespace psulvsb {
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return PSULVSB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(PSULVSB_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+    }
+    cap = want;
+    return PSULVSB_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return PSULVSB_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(PSULVSB_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    }
+    cap = want;
+    return PSULVSB_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over one arena (sizes first with base == nullptr, then hands out pointers)
+struct Bump {
+  char* base = nullptr;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 128);
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+struct PackJob {
+  const double* pts;
+  float4* out;
+  int n;
+  double c[3];
+  uint32_t* zero;  // optional [n]: K1 row counters (accumulated with atomics) cleared on the way
+};
+
+__global__ void engine_pack_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob& j = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < j.n) {
+    j.out[i] = make_float4((float)(j.pts[3 * i] - j.c[0]), (float)(j.pts[3 * i + 1] - j.c[1]),
+                           (float)(j.pts[3 * i + 2] - j.c[2]), 0.f);
+    if (j.zero) j.zero[i] = 0u;
+  }
+}
+
+struct ProbLayout {
+  int C0, M, Ccap;
+  size_t in_dbl;   // offset (doubles) of src0 in the input arena: src0, dst0, ori_src, ori_dst
+  size_t in_int;   // offset (ints): keep_mask0, reduce_map0
+  double csrc[3], cdst[3];
+  double coord_bound;
+  int stride;  // mask row stride in words
+};
+
+}  // namespace
+
+class Engine {
+ public:
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k1 = nullptr, ev_loop = nullptr, ev_m0 = nullptr, ev_m1 = nullptr;
+  int B = 0;
+  std::vector<ProbLayout> lay;
+  std::vector<unsigned long long> reserve;  // self-update edge head-room per job
+  size_t in_dbl_total = 0, in_int_total = 0;
+  DevBuf d_in_dbl, d_in_int, d_work, d_mask, d_edge, d_jobs, d_misc;
+  PinBuf h_stage, h_small;
+  long long launches = 0;
+  double last_ms = 0.0;
+  double stage_ms[5] = {0, 0, 0, 0, 0};
+  int last_ticks = 0;
+
+  ~Engine() {
+    if (st) cudaStreamSynchronize(st);
+    d_in_dbl.release();
+    d_in_int.release();
+    d_work.release();
+    d_mask.release();
+    d_edge.release();
+    d_jobs.release();
+    d_misc.release();
+    h_stage.release();
+    h_small.release();
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    if (ev_k1) cudaEventDestroy(ev_k1);
+    if (ev_loop) cudaEventDestroy(ev_loop);
+    if (ev_m0) cudaEventDestroy(ev_m0);
+    if (ev_m1) cudaEventDestroy(ev_m1);
+    if (st) cudaStreamDestroy(st);
+  }
+
+  int init(int dev) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(PSULVSB_ERR_NO_DEVICE, "no CUDA device");
+    if (dev < 0 || dev >= n) return fail(PSULVSB_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    PSU_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+      return fail(PSULVSB_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                             ", this library is built for sm_100a only");
+    device = dev;
+    PSU_CUDA(cudaSetDevice(dev));
+    PSU_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    PSU_CUDA(cudaEventCreate(&ev_begin));
+    PSU_CUDA(cudaEventCreate(&ev_end));
+    PSU_CUDA(cudaEventCreate(&ev_k1));
+    PSU_CUDA(cudaEventCreate(&ev_loop));
+    PSU_CUDA(cudaEventCreate(&ev_m0));
+    PSU_CUDA(cudaEventCreate(&ev_m1));
+    return PSULVSB_OK;
+  }
+
+  int upload(const psulvsb_problem_t* problems, int nb);
+  int solve(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb_solution_t* solutions,
+            psulvsb_trace_t* trace_first);
+
+ private:
+  int solve_once(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb_solution_t* solutions,
+                 psulvsb_trace_t* trace_first);
+};
+
+int Engine::upload(const psulvsb_problem_t* problems, int nb) {
+  if (!problems || nb <= 0) return fail(PSULVSB_ERR_INVALID, "upload: no problems");
+  PSU_CUDA(cudaSetDevice(device));
+  lay.assign((size_t)nb, ProbLayout());
+  size_t od = 0, oi = 0;
+  for (int b = 0; b < nb; ++b) {
+    const psulvsb_problem_t& p = problems[b];
+    if (!p.src || !p.dst || !p.ori_src || !p.ori_dst || !p.keep_mask || !p.reduce_map || p.C < 2 || p.M < 1)
+      return fail(PSULVSB_ERR_INVALID, "upload: problem " + std::to_string(b) + " has a null array, C < 2 or M < 1");
+    ProbLayout& L = lay[(size_t)b];
+    L.C0 = p.C;
+    L.M = p.M;
+    int zeros = 0;
+    for (int j = 0; j < p.M; ++j) zeros += (p.keep_mask[j] == 0) ? 1 : 0;
+    L.Ccap = p.C + zeros;  // every original correspondence can be appended at most once (registration.cc:828)
+    L.stride = (int)align_up((size_t)(p.C + 31) / 32, 4);
+    od = align_up(od, 16);
+    L.in_dbl = od;
+    od += (size_t)6 * p.C + (size_t)6 * p.M;
+    oi = align_up(oi, 32);
+    L.in_int = oi;
+    oi += (size_t)2 * p.M;
+  }
+  in_dbl_total = od;
+  in_int_total = oi;
+  const size_t bytes_d = od * sizeof(double), bytes_i = oi * sizeof(int);
+  if (int rc = h_stage.ensure(align_up(bytes_d, 256) + bytes_i)) return rc;
+  if (int rc = d_in_dbl.ensure(bytes_d)) return rc;
+  if (int rc = d_in_int.ensure(bytes_i)) return rc;
+  double* hd = reinterpret_cast<double*>(h_stage.p);
+  int* hi = reinterpret_cast<int*>(reinterpret_cast<char*>(h_stage.p) + align_up(bytes_d, 256));
+  for (int b = 0; b < nb; ++b) {
+    const psulvsb_problem_t& p = problems[b];
+    ProbLayout& L = lay[(size_t)b];
+    double* d = hd + L.in_dbl;
+    std::memcpy(d, p.src, sizeof(double) * 3 * (size_t)p.C);
+    std::memcpy(d + 3 * (size_t)p.C, p.dst, sizeof(double) * 3 * (size_t)p.C);
+    std::memcpy(d + 6 * (size_t)p.C, p.ori_src, sizeof(double) * 3 * (size_t)p.M);
+    std::memcpy(d + 6 * (size_t)p.C + 3 * (size_t)p.M, p.ori_dst, sizeof(double) * 3 * (size_t)p.M);
+    std::memcpy(hi + L.in_int, p.keep_mask, sizeof(int) * (size_t)p.M);
+    std::memcpy(hi + L.in_int + p.M, p.reduce_map, sizeof(int) * (size_t)p.M);
+    // centres / coordinate bound of the FP32 tiles (differences are translation invariant)
+    for (int s = 0; s < 2; ++s) {
+      const double* pts = s ? p.dst : p.src;
+      double lo[3] = {pts[0], pts[1], pts[2]}, hi3[3] = {pts[0], pts[1], pts[2]};
+      for (int i = 1; i < p.C; ++i)
+        for (int r = 0; r < 3; ++r) {
+          const double v = pts[3 * (size_t)i + r];
+          lo[r] = v < lo[r] ? v : lo[r];
+          hi3[r] = v > hi3[r] ? v : hi3[r];
+        }
+      double* c = s ? L.cdst : L.csrc;
+      double bound = 0.0;
+      for (int r = 0; r < 3; ++r) {
+        c[r] = 0.5 * (lo[r] + hi3[r]);
+        const double h = 0.5 * (hi3[r] - lo[r]);
+        bound = h > bound ? h : bound;
+      }
+      if (s == 0)
+        L.coord_bound = bound;
+      else
+        L.coord_bound = bound > L.coord_bound ? bound : L.coord_bound;
+    }
+    L.coord_bound = L.coord_bound * (1.0 + 1e-6) + 1e-30;
+    for (int r = 0; r < 3; ++r)
+      if (!std::isfinite(L.csrc[r]) || !std::isfinite(L.cdst[r]) || !std::isfinite(L.coord_bound))
+        return fail(PSULVSB_ERR_INVALID, "upload: problem " + std::to_string(b) + " has non-finite coordinates");
+  }
+  PSU_CUDA(cudaMemcpyAsync(d_in_dbl.p, hd, bytes_d, cudaMemcpyHostToDevice, st));
+  PSU_CUDA(cudaMemcpyAsync(d_in_int.p, hi, bytes_i, cudaMemcpyHostToDevice, st));
+  PSU_CUDA(cudaStreamSynchronize(st));
+  B = nb;
+  reserve.assign((size_t)nb, 0ull);
+  for (int b = 0; b < nb; ++b) {
+    const ProbLayout& L = lay[(size_t)b];
+    if (L.Ccap > L.C0) reserve[(size_t)b] = 65536ull;
+  }
+  return PSULVSB_OK;
+}
+
+int Engine::solve(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb_solution_t* solutions,
+                  psulvsb_trace_t* trace_first) {
+  if (B <= 0) return fail(PSULVSB_ERR_INVALID, "solve: nothing uploaded");
+  if (!params || !solutions) return fail(PSULVSB_ERR_INVALID, "solve: null params / solutions");
+  if (params->estimate_scaling)
+    return fail(PSULVSB_ERR_UNSUPPORTED, "estimate_scaling = 1 (unknown-scale path, registration.cc:958-983) is not built yet");
+  if (params->host_round_limit < 0 || params->rotation_max_iterations < 0 || params->inloop_max_iterations < 0)
+    return fail(PSULVSB_ERR_INVALID, "solve: negative iteration limits");
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    if (int rc = solve_once(params, seeds, solutions, trace_first)) return rc;
+    // self-update outgrew the edge head-room of some job: enlarge and redo (results are
+    // deterministic, so the retry reproduces the same run with room to finish)
+    bool again = false;
+    for (int b = 0; b < B; ++b)
+      if (solutions[b].status == PSULVSB_ERR_CAPACITY) {
+        const ProbLayout& L = lay[(size_t)b];
+        const unsigned long long full = (unsigned long long)(L.Ccap - L.C0) * (unsigned long long)L.Ccap;
+        if (reserve[(size_t)b] < full) {
+          unsigned long long r = reserve[(size_t)b] * 8ull;
+          reserve[(size_t)b] = r > full ? full : r;
+          again = true;
+        }
+      }
+    if (!again) break;
+  }
+  return PSULVSB_OK;
+}
+
+int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb_solution_t* solutions,
+                       psulvsb_trace_t* trace_first) {
+  PSU_CUDA(cudaSetDevice(device));
+  const auto t_begin = std::chrono::steady_clock::now();
+  const int local_cap = 512;
+  const int host_cap = params->host_round_limit > 0 ? params->host_round_limit : 1;
+
+  // ---- working arena (everything whose size is known before K1)
+  std::vector<JobCtl> jobs((size_t)B);
+  std::vector<K1Job> k1((size_t)B);
+  std::vector<CompactJob> cj((size_t)B);
+  std::vector<PackJob> pj((size_t)2 * B);
+  struct Misc {
+    K1Job* k1;
+    CompactJob* cj;
+    PackJob* pj;
+    JobCtl* jobs;
+    SampleJob* sl;
+    SampleJob* sb;
+    GncJob* gj;
+    unsigned long long* n_edges;
+    unsigned long long* border;
+    int* n_done;
+    psulvsb_solution_t* sols;
+  } m;
+  {
+    Bump bm;
+    for (int pass = 0; pass < 2; ++pass) {
+      bm.off = 0;
+      m.k1 = bm.take<K1Job>((size_t)B);
+      m.cj = bm.take<CompactJob>((size_t)B);
+      m.pj = bm.take<PackJob>((size_t)2 * B);
+      m.jobs = bm.take<JobCtl>((size_t)B);
+      m.sl = bm.take<SampleJob>((size_t)B);
+      m.sb = bm.take<SampleJob>((size_t)B);
+      m.gj = bm.take<GncJob>((size_t)B);
+      m.n_edges = bm.take<unsigned long long>((size_t)B);
+      m.border = bm.take<unsigned long long>((size_t)B);
+      m.n_done = bm.take<int>(4);
+      m.sols = bm.take<psulvsb_solution_t>((size_t)B);
+      if (pass == 0) {
+        if (int rc = d_misc.ensure(bm.off)) return rc;
+        bm.base = reinterpret_cast<char*>(d_misc.p);
+      }
+    }
+  }
+  const double* in_dbl = reinterpret_cast<const double*>(d_in_dbl.p);
+  const int* in_int = reinterpret_cast<const int*>(d_in_int.p);
+  int maxC = 0, maxM = 0;
+  {
+    Bump bw, bk;
+    for (int pass = 0; pass < 2; ++pass) {
+      bw.off = 0;
+      bk.off = 0;
+      for (int b = 0; b < B; ++b) {
+        const ProbLayout& L = lay[(size_t)b];
+        JobCtl& J = jobs[(size_t)b];
+        std::memset(&J, 0, sizeof(J));
+        J.C0 = L.C0;
+        J.M = L.M;
+        J.Ccap = L.Ccap;
+        J.src0 = in_dbl + L.in_dbl;
+        J.dst0 = J.src0 + 3 * (size_t)L.C0;
+        J.ori_src = J.src0 + 6 * (size_t)L.C0;
+        J.ori_dst = J.ori_src + 3 * (size_t)L.M;
+        J.keep_mask0 = in_int + L.in_int;
+        J.reduce_map0 = J.keep_mask0 + L.M;
+        J.src = bw.take<double>((size_t)3 * L.Ccap);
+        J.dst = bw.take<double>((size_t)3 * L.Ccap);
+        J.residual_history = bw.take<double>((size_t)L.M);
+        J.xs = bw.take<double>((size_t)3 * (L.Ccap + 1));
+        J.keep_mask = bw.take<int>((size_t)L.M);
+        J.reduce_map = bw.take<int>((size_t)L.M);
+        J.inlier_counter = bw.take<int>((size_t)L.M);
+        J.new_corr = bw.take<int>((size_t)L.M);
+        J.inlier_history = bw.take<int>((size_t)L.M);
+        J.final_inliers = bw.take<int>((size_t)L.M);
+        J.inlier_map = bw.take<int>((size_t)L.Ccap);
+        J.idx = bw.take<int>((size_t)L.Ccap);
+        J.sampled_flags = bw.take<uint8_t>((size_t)L.Ccap);
+        J.rot_flags = bw.take<uint8_t>((size_t)L.Ccap);
+        J.local_trace = bw.take<psulvsb_local_trace_t>((size_t)local_cap);
+        J.host_trace = bw.take<psulvsb_host_trace_t>((size_t)host_cap);
+        J.local_trace_cap = local_cap;
+        J.host_trace_cap = host_cap;
+        J.seed = seeds ? seeds[b] : params->seed + (uint64_t)b;
+        const float a = 1 + (((float)L.C0) / (long)L.M);  // registration.cc:669 (float on purpose)
+        J.tau = 2 * params->score_noise_bound * a;
+        float4* sf = bw.take<float4>((size_t)L.C0);
+        float4* df = bw.take<float4>((size_t)L.C0);
+        K1Job& K = k1[(size_t)b];
+        std::memset(&K, 0, sizeof(K));
+        K.src = sf;
+        K.dst = df;
+        K.src64 = J.src0;
+        K.dst64 = J.dst0;
+        K.n = L.C0;
+        K.row_begin = 0;
+        K.row_end = L.C0;
+        K.c = make_k1_consts(2.0 * params->noise_bound * std::sqrt(params->cbar2), L.coord_bound);
+        K.mask = bk.take<uint32_t>((size_t)L.C0 * L.stride);
+        K.stride = L.stride;
+        K.row_counts = bk.take<uint32_t>((size_t)L.C0);
+        K.border = m.border + b;
+        K.active = 1;
+        CompactJob& Cj = cj[(size_t)b];
+        std::memset(&Cj, 0, sizeof(Cj));
+        Cj.mask = K.mask;
+        Cj.n = L.C0;
+        Cj.stride = L.stride;
+        Cj.row_counts = K.row_counts;
+        Cj.offsets = bk.take<unsigned long long>((size_t)L.C0 + 1);
+        Cj.n_edges = m.n_edges + b;
+        Cj.active = 1;
+        PackJob& p0 = pj[(size_t)2 * b];
+        PackJob& p1 = pj[(size_t)2 * b + 1];
+        p0.pts = J.src0;
+        p0.out = sf;
+        p0.n = L.C0;
+        p0.zero = K.row_counts;
+        p1.zero = nullptr;
+        p1.pts = J.dst0;
+        p1.out = df;
+        p1.n = L.C0;
+        for (int r = 0; r < 3; ++r) {
+          p0.c[r] = L.csrc[r];
+          p1.c[r] = L.cdst[r];
+        }
+        maxC = L.C0 > maxC ? L.C0 : maxC;
+        maxM = L.M > maxM ? L.M : maxM;
+      }
+      if (pass == 0) {
+        if (int rc = d_work.ensure(bw.off)) return rc;
+        if (int rc = d_mask.ensure(bk.off)) return rc;
+        bw.base = reinterpret_cast<char*>(d_work.p);
+        bk.base = reinterpret_cast<char*>(d_mask.p);
+      }
+    }
+    PSU_CUDA(cudaEventRecord(ev_begin, st));
+  }
+  PSU_CUDA(cudaMemsetAsync(m.border, 0, sizeof(unsigned long long) * (size_t)B, st));
+  PSU_CUDA(cudaMemsetAsync(m.n_done, 0, sizeof(int) * 4, st));
+  PSU_CUDA(cudaMemcpyAsync(m.k1, k1.data(), sizeof(K1Job) * (size_t)B, cudaMemcpyHostToDevice, st));
+  PSU_CUDA(cudaMemcpyAsync(m.cj, cj.data(), sizeof(CompactJob) * (size_t)B, cudaMemcpyHostToDevice, st));
+  PSU_CUDA(cudaMemcpyAsync(m.pj, pj.data(), sizeof(PackJob) * (size_t)2 * B, cudaMemcpyHostToDevice, st));
+
+  // ---- stage 1: float4 tiles, bit mask, row scan
+  {
+    dim3 grid((unsigned)((maxC + 255) / 256), (unsigned)(2 * B));
+    engine_pack_kernel<<<grid, 256, 0, st>>>(m.pj);
+    PSU_CHECK_LAUNCH("engine_pack_kernel");
+    ++launches;
+  }
+  PSU_CUDA(cudaEventRecord(ev_m0, st));
+  if (int rc = launch_consistency_mask(st, m.k1, B, maxC, maxC)) return rc;
+  PSU_CUDA(cudaEventRecord(ev_m1, st));
+  ++launches;
+  if (int rc = launch_compact_edges(st, m.cj, B, maxC, true, false)) return rc;
+  ++launches;
+  if (int rc = h_small.ensure(sizeof(unsigned long long) * (size_t)B + 64)) return rc;
+  unsigned long long* h_nedges = reinterpret_cast<unsigned long long*>(h_small.p);
+  volatile int* h_done = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(h_small.p) + sizeof(unsigned long long) * (size_t)B);
+  PSU_CUDA(cudaMemcpyAsync(h_nedges, m.n_edges, sizeof(unsigned long long) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  PSU_CUDA(cudaStreamSynchronize(st));
+
+  // ---- edge arena, sized from the measured reduced-set sizes
+  unsigned long long max_cap = 0, max_nred = 0;
+  {
+    Bump be;
+    for (int pass = 0; pass < 2; ++pass) {
+      be.off = 0;
+      for (int b = 0; b < B; ++b) {
+        JobCtl& J = jobs[(size_t)b];
+        unsigned long long cap = h_nedges[b] + reserve[(size_t)b];
+        if (cap < 64) cap = 64;
+        J.edge_cap = cap;
+        J.edges = be.take<uint2>((size_t)cap);
+        J.first = be.take<uint32_t>((size_t)cap);
+        J.L_sampled = be.take<uint32_t>((size_t)cap);
+        J.basic_idx = be.take<uint32_t>((size_t)cap);
+        J.basic_edges = be.take<uint2>((size_t)cap);
+        J.weights = be.take<double>((size_t)cap);
+        cj[(size_t)b].edges = J.edges;
+        cj[(size_t)b].cap = cap;
+        max_cap = cap > max_cap ? cap : max_cap;
+        max_nred = h_nedges[b] > max_nred ? h_nedges[b] : max_nred;
+      }
+      if (pass == 0) {
+        if (int rc = d_edge.ensure(be.off)) return rc;
+        be.base = reinterpret_cast<char*>(d_edge.p);
+      }
+    }
+  }
+  if (max_cap >= 0xFFFFFFF0ull) return fail(PSULVSB_ERR_UNSUPPORTED, "reduced set exceeds 32-bit sampling indices");
+  PSU_CUDA(cudaMemcpyAsync(m.cj, cj.data(), sizeof(CompactJob) * (size_t)B, cudaMemcpyHostToDevice, st));
+  PSU_CUDA(cudaMemcpyAsync(m.jobs, jobs.data(), sizeof(JobCtl) * (size_t)B, cudaMemcpyHostToDevice, st));
+  if (int rc = launch_compact_edges(st, m.cj, B, maxC, false, true)) return rc;
+  ++launches;
+
+  EngineParams P;
+  P.caller = SubParams{params->noise_bound, params->cbar2, params->rotation_max_iterations, params->rotation_gnc_factor,
+                       params->rotation_cost_threshold};
+  P.inloop = SubParams{params->inloop_noise_bound, params->inloop_cbar2, params->inloop_max_iterations,
+                       params->inloop_gnc_factor, params->inloop_cost_threshold};
+  P.pr_noise = 2 * params->score_noise_bound;
+  P.score_sigma = params->score_noise_bound;
+  P.rotation_similar = params->rotation_similar;
+  P.local_max_iter = params->local_max_iter;
+  P.tpro_host = params->tpro_host;
+  P.tpro_local = params->tpro_local;
+  P.host_round_limit = params->host_round_limit;
+  P.wallclock_cap_s = params->wallclock_cap_s;
+  P.self_update = params->self_update;
+  P.inlier_selection_mode = params->inlier_selection_mode;
+  P.max_local_iters = 4096;
+  engine_init_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.n_edges, P, m.n_done);
+  PSU_CHECK_LAUNCH("engine_init_kernel");
+  ++launches;
+  PSU_CUDA(cudaEventRecord(ev_k1, st));
+
+  // ---- ticks
+  int gnc_cap = (int)((0.03 * (double)max_nred) / 8.0) + 64;
+  gnc_cap = (gnc_cap + 31) & ~31;
+  if (gnc_cap > gnc_default_capacity()) gnc_cap = gnc_default_capacity();
+  const unsigned long long draws_bound = sample_default_max_draws(max_cap, max_cap / 8 + 1);
+  int ticks = 0;
+  const int max_ticks = P.max_local_iters + P.host_round_limit + 8;
+  while (true) {
+    const double elapsed =
+        std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count() / 1e6;
+    engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, P, m.n_done);
+    PSU_CHECK_LAUNCH("engine_round_start_kernel");
+    if (int rc = launch_sample(st, m.sl, B, draws_bound)) return rc;
+    if (int rc = launch_sample(st, m.sb, B, draws_bound)) return rc;
+    if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap)) return rc;
+    engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, P, elapsed, m.n_done);
+    PSU_CHECK_LAUNCH("engine_local_control_kernel");
+    launches += 7;
+    ++ticks;
+    PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSU_CUDA(cudaStreamSynchronize(st));
+    if (*h_done >= B) break;
+    if (ticks >= max_ticks) return fail(PSULVSB_ERR_INTERNAL, "engine did not converge within the tick limit");
+  }
+  last_ticks = ticks;
+  PSU_CUDA(cudaEventRecord(ev_loop, st));
+  engine_refine_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sols, m.border);
+  PSU_CHECK_LAUNCH("engine_refine_kernel");
+  ++launches;
+  PSU_CUDA(cudaMemcpyAsync(solutions, m.sols, sizeof(psulvsb_solution_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  PSU_CUDA(cudaEventRecord(ev_end, st));
+  PSU_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev_begin, ev_end);
+  last_ms = ms;
+  cudaEventElapsedTime(&ms, ev_begin, ev_k1);
+  stage_ms[0] = ms;
+  cudaEventElapsedTime(&ms, ev_k1, ev_loop);
+  stage_ms[1] = ms;
+  cudaEventElapsedTime(&ms, ev_loop, ev_end);
+  stage_ms[4] = ms;
+  cudaEventElapsedTime(&ms, ev_m0, ev_m1);
+  stage_ms[2] = ms;  // the consistency-mask kernel alone (one launch over the whole batch)
+  stage_ms[3] = 0.0;
+
+  if (trace_first) {
+    JobCtl j0;
+    PSU_CUDA(cudaMemcpy(&j0, m.jobs, sizeof(JobCtl), cudaMemcpyDeviceToHost));
+    trace_first->local_n = 0;
+    trace_first->host_n = 0;
+    if (trace_first->local && trace_first->local_cap > 0) {
+      const int n = j0.n_local_trace < trace_first->local_cap ? j0.n_local_trace : trace_first->local_cap;
+      if (n > 0)
+        PSU_CUDA(cudaMemcpy(trace_first->local, j0.local_trace, sizeof(psulvsb_local_trace_t) * (size_t)n,
+                            cudaMemcpyDeviceToHost));
+      trace_first->local_n = n;
+    }
+    if (trace_first->host && trace_first->host_cap > 0) {
+      const int n = j0.n_host_trace < trace_first->host_cap ? j0.n_host_trace : trace_first->host_cap;
+      if (n > 0)
+        PSU_CUDA(cudaMemcpy(trace_first->host, j0.host_trace, sizeof(psulvsb_host_trace_t) * (size_t)n,
+                            cudaMemcpyDeviceToHost));
+      trace_first->host_n = n;
+    }
+    if (trace_first->final_inliers)
+      PSU_CUDA(cudaMemcpy(trace_first->final_inliers, j0.final_inliers, sizeof(int) * (size_t)j0.M, cudaMemcpyDeviceToHost));
+    if (trace_first->inlier_counter)
+      PSU_CUDA(cudaMemcpy(trace_first->inlier_counter, j0.inlier_counter, sizeof(int) * (size_t)j0.M, cudaMemcpyDeviceToHost));
+  }
+  return PSULVSB_OK;
+}
+
+// ---- C-linkage-free façade used by capi.cu ---------------------------------------------------
+int engine_create(Engine** out, int device) {
+  Engine* e = new Engine();
+  const int rc = e->init(device);
+  if (rc) {
+    delete e;
+    *out = nullptr;
+    return rc;
+  }
+  *out = e;
+  return PSULVSB_OK;
+}
+void engine_destroy(Engine* e) { delete e; }
+int engine_upload(Engine* e, const psulvsb_problem_t* problems, int B) { return e->upload(problems, B); }
+int engine_solve_resident(Engine* e, const psulvsb_params_t* params, const uint64_t* seeds,
+                          psulvsb_solution_t* solutions, psulvsb_trace_t* trace_first) {
+  return e->solve(params, seeds, solutions, trace_first);
+}
+int engine_batch_size(const Engine* e) { return e->B; }
+long long engine_launch_count(const Engine* e) { return e->launches; }
+double engine_last_device_ms(const Engine* e) { return e->last_ms; }
+double engine_last_stage_ms(const Engine* e, int which) { return (which >= 0 && which < 5) ? e->stage_ms[which] : 0.0; }
+int engine_last_ticks(const Engine* e) { return e->last_ticks; }
+
+}  // namespace psulvsb

@@ -147,6 +147,8 @@ void engine_destroy(Engine* e);
 int engine_upload(Engine* e, const psulvsb_problem_t* problems, int B);
 int engine_solve_resident(Engine* e, const psulvsb_params_t* params, const uint64_t* seeds,
                           psulvsb_solution_t* solutions, psulvsb_trace_t* trace_first);
+int engine_batch_size(const Engine* e);
+int engine_last_ticks(const Engine* e);
 long long engine_launch_count(const Engine* e);
 double engine_last_device_ms(const Engine* e);
 double engine_last_stage_ms(const Engine* e, int which);

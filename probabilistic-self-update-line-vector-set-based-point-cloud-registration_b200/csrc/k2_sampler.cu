@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(1024) sample_emit_kernel(const SampleJob* __re
   __syncthreads();
   if (job.identity) {
     for (unsigned long long r = tid; r < count; r += 1024) out[r] = (uint32_t)r;
-    if (tid == 0 && job.status) job.status[0] = 0ull;
+    if (tid == 0 && job.status) job.status[0] = 1ull;  // nothing drawn; non-zero = success
   } else {
     const unsigned long long nblocks = (max_draws + 3) >> 2;
     unsigned long long consumed = 0ull;  // meaningful in the thread that emits the last sample

@@ -23,7 +23,7 @@ namespace {
 
 constexpr int SB_THREADS = 256;
 constexpr int SB_HPT = 4;    // hypotheses per thread
-constexpr int SB_TP = 1024;  // points per smem tile
+constexpr int SB_TP = 512;   // points per smem tile (2 stages x 2 arrays x 8 KB static smem)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -1,0 +1,191 @@
+"""End-to-end GPU parity: psulvsb_solve (C ABI, host buffers) vs the CPU oracle on the same inputs and
+the same replayed Philox sample stream, compared step by step through the per-iteration traces.
+
+Bars (north_star): inlier sets / counts / control flow bit-exact; R within 1e-5 rad, t within 1e-5.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+R_TOL = 1e-5   # rad  (north_star)
+T_TOL = 1e-5   # units (north_star)
+
+
+@pytest.fixture(scope="module")
+def env():
+    import psulvsb_b200  # noqa: F401
+    from oracle import oracle
+    from psulvsb_b200 import capi, synth
+
+    if capi.lib().psulvsb_device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU fallback")
+    return {"capi": capi, "synth": synth, "O": oracle, "h": capi.Handle(0)}
+
+
+PKW = dict(noise_bound=0.05, cbar2=1.0, estimate_scaling=0, rotation_cost_threshold=0.005, wallclock_cap_s=0.0)
+
+
+def both(env, pair, pre=None, seed=0, **kw):
+    capi, O = env["capi"], env["O"]
+    args = dict(PKW)
+    args.update(kw)
+    po = O.default_params(seed=seed, **args)
+    pg = capi.default_params(seed=seed, **args)
+    if pre is None:
+        so, to = O.solve(po, pair["src"], pair["dst"])
+        prob = capi.HostProblem(pair["src"], pair["dst"])
+    else:
+        so, to = O.solve(po, pre["src_reduce"], pre["dst_reduce"], pair["src"], pair["dst"], pre["keep_mask"],
+                         pre["reduce_map"])
+        prob = capi.HostProblem(pre["src_reduce"], pre["dst_reduce"], pair["src"], pair["dst"], pre["keep_mask"],
+                                pre["reduce_map"])
+    sg, tg = env["h"].solve(pg, prob, trace_cap=4096)
+    return so, to, sg, tg
+
+
+def assert_same_run(env, so, to, sg, tg):
+    synth, O = env["synth"], env["O"]
+    assert sg.status == 0
+    assert sg.n_line_vectors == so.n_line_vectors and sg.n_reduced == so.n_reduced
+    assert len(tg["local"]) == len(to["local"]) and len(tg["host"]) == len(to["host"])
+    int_fields = ["host_round", "local_iter", "n_sampled_lines", "n_sampled_points", "basic_choose", "gnc_iterations",
+                  "rot_inliers", "n_rot_points", "similar", "curr_count", "best_count", "local_r"]
+    for a, b in zip(tg["local"], to["local"]):
+        for f in int_fields:
+            assert getattr(a, f) == getattr(b, f), (f, a.local_iter, getattr(a, f), getattr(b, f))
+        assert a.l_rate == b.l_rate and a.b_rate == b.b_rate
+        assert abs(a.p_local - b.p_local) < 1e-12
+        Ra, Rb = np.array(a.R[:]).reshape(3, 3, order="F"), np.array(b.R[:]).reshape(3, 3, order="F")
+        assert synth.rotation_error(Ra, Rb) < R_TOL
+        assert np.abs(np.array(a.t[:]) - np.array(b.t[:])).max() < T_TOL
+    for a, b in zip(tg["host"], to["host"]):
+        for f in ["host_round", "curr_count", "best_host", "new_corr_count", "inlier_map_size", "host_r"]:
+            assert getattr(a, f) == getattr(b, f), (f, getattr(a, f), getattr(b, f))
+        assert abs(a.p_host - b.p_host) < 1e-12
+    assert bool(sg.valid) == bool(so.valid)
+    assert sg.final_inlier_count == so.final_inlier_count
+    assert sg.host_rounds == so.host_rounds and sg.local_iters == so.local_iters
+    assert sg.final_C == so.final_C and sg.escalations == so.escalations and sg.refined == so.refined
+    assert np.array_equal(tg["final_inliers"], to["final_inliers"])      # inlier set bit-exact
+    assert np.array_equal(tg["inlier_counter"], to["inlier_counter"])
+    assert synth.rotation_error(sg.R, O.solution_R(so)) < R_TOL
+    assert np.abs(sg.t - O.solution_t(so)).max() < T_TOL
+    assert sg.scale == so.scale
+
+
+@pytest.mark.parametrize("n,ratio,outl,seed", [(200, 0.5, "gross", 1), (500, 0.8, "fpfh", 2), (1000, 0.9, "fpfh", 3),
+                                               (1000, 0.9, "gross", 4), (2000, 0.95, "fpfh", 5)])
+def test_solve_matches_oracle_full_set(env, n, ratio, outl, seed):
+    pair = env["synth"].make_pair(n, ratio, seed, outliers=outl)
+    so, to, sg, tg = both(env, pair, seed=seed)
+    assert_same_run(env, so, to, sg, tg)
+    assert env["synth"].rotation_error(sg.R, pair["R"]) < 0.05
+
+
+@pytest.mark.parametrize("n,ratio,seed", [(600, 0.7, 11), (1500, 0.9, 12), (3000, 0.9, 13)])
+def test_solve_matches_oracle_with_self_update(env, n, ratio, seed):
+    """keep_mask pre-filter emulation: the working set grows through the probabilistic self-update."""
+    synth = env["synth"]
+    pair = synth.make_pair(n, ratio, seed)
+    pre = synth.prefilter(pair, seed)
+    so, to, sg, tg = both(env, pair, pre, seed=seed)
+    assert_same_run(env, so, to, sg, tg)
+    assert sg.final_C >= pre["src_reduce"].shape[1]
+
+
+def test_solve_cfg_a_5k_95pct(env):
+    """BASELINE config[1]: N = 5000 correspondences, 95 % outliers."""
+    pair = env["synth"].make_pair(5000, 0.95, 101)
+    so, to, sg, tg = both(env, pair, seed=101)
+    assert_same_run(env, so, to, sg, tg)
+    assert sg.final_inlier_count >= 240
+    assert env["synth"].rotation_error(sg.R, pair["R"]) < 0.01
+
+
+def test_solve_golden_registration_test(env, golden):
+    """registration-test.cc:229-308 known answer (0.2 rad / 0.1 m) on objectIn/sceneIn."""
+    capi = env["capi"]
+    reg, meta = golden["reg"], golden["meta"]
+    p = capi.default_params(noise_bound=0.0067364, cbar2=1.0, estimate_scaling=0, rotation_cost_threshold=0.005,
+                            wallclock_cap_s=0.0, score_noise_bound=0.02, seed=3)
+    sol, _ = env["h"].solve(p, capi.HostProblem(reg["objectIn"], reg["sceneIn"]))
+    Rexp = np.array(meta["registration_expected_R"]).reshape(3, 3)
+    texp = np.array(meta["registration_expected_t"])
+    assert sol.valid and sol.status == 0
+    assert env["synth"].rotation_error(sol.R, Rexp) < 0.2
+    assert np.linalg.norm(sol.t - texp) < 0.1
+
+
+def test_batch_equals_individual_solves(env):
+    capi, synth = env["capi"], env["synth"]
+    pairs = [synth.make_pair(n, 0.9, 50 + i) for i, n in enumerate([300, 800, 1200, 500, 64])]
+    probs = [capi.HostProblem(p["src"], p["dst"]) for p in pairs]
+    seeds = [7, 8, 9, 10, 11]
+    params = capi.default_params(**PKW)
+    batch = env["h"].solve_batch(params, probs, seeds)
+    for prob, seed, b in zip(probs, seeds, batch):
+        params.seed = seed
+        one, _ = env["h"].solve(params, prob)
+        assert b.status == 0 and one.status == 0
+        assert np.array_equal(np.array(b.rotation[:]), np.array(one.rotation[:]))     # deterministic: bit-equal
+        assert np.array_equal(np.array(b.translation[:]), np.array(one.translation[:]))
+        assert b.final_inlier_count == one.final_inlier_count and b.local_iters == one.local_iters
+
+
+def test_resident_solve_is_repeatable(env):
+    capi, synth = env["capi"], env["synth"]
+    probs = [capi.HostProblem(*(lambda p: (p["src"], p["dst"]))(synth.make_pair(700, 0.9, 70 + i))) for i in range(3)]
+    h = env["h"]
+    h.upload(probs)
+    params = capi.default_params(seed=5, **PKW)
+    a = h.solve_resident(params)
+    b = h.solve_resident(params)
+    for x, y in zip(a, b):
+        assert np.array_equal(np.array(x.rotation[:]), np.array(y.rotation[:]))
+        assert x.final_inlier_count == y.final_inlier_count
+    assert h.launch_count > 0 and h.last_device_ms > 0
+
+
+def test_degenerate_inputs(env):
+    capi = env["capi"]
+    h = env["h"]
+    # no consistent pair at all: invalid solution, no hang (the reference would spin forever)
+    rng = np.random.default_rng(0)
+    src = rng.uniform(-1, 1, (3, 40))
+    dst = src * 50.0
+    sol, _ = h.solve(capi.default_params(**PKW), capi.HostProblem(src, dst))
+    assert sol.status == 0 and not sol.valid and sol.n_reduced == 0
+    # identical clouds, identity transform
+    sol, _ = h.solve(capi.default_params(**PKW), capi.HostProblem(src, src.copy()))
+    assert sol.status == 0 and sol.valid
+    assert env["synth"].rotation_error(sol.R, np.eye(3)) < 1e-6 and np.abs(sol.t).max() < 1e-6
+
+
+def test_mirror_solver_api(env):
+    """RobustRegistrationSolver mirror: Params, solve(src, dst), getSolution() as the reference's drivers use them."""
+    from psulvsb_b200 import RobustRegistrationSolver
+
+    synth = env["synth"]
+    pair = synth.make_pair(800, 0.8, 5)
+    pre = synth.prefilter(pair, 5)
+    params = RobustRegistrationSolver.Params()
+    params.noise_bound = 0.05
+    params.cbar2 = 1
+    params.estimate_scaling = False
+    params.rotation_max_iterations = 100
+    params.rotation_gnc_factor = 1.4
+    params.rotation_estimation_algorithm = RobustRegistrationSolver.ROTATION_ESTIMATION_ALGORITHM.GNC_TLS
+    params.rotation_cost_threshold = 0.005
+    params.ori_src, params.ori_dst = pair["src"], pair["dst"]
+    params.keep_mask = pre["keep_mask"]
+    params.reduce_map = {int(o): int(r) for o, r in enumerate(pre["reduce_map"]) if r >= 0}
+    params.replay = True
+    solver = RobustRegistrationSolver(params)
+    solver.solve(pre["src_reduce"], pre["dst_reduce"])
+    sol = solver.getSolution()
+    assert sol.valid
+    assert synth.rotation_error(sol.rotation, pair["R"]) < 0.05
+    assert np.linalg.norm(sol.translation - pair["t"]) < 0.05
