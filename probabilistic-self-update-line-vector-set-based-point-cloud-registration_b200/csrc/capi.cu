@@ -243,9 +243,8 @@ unsigned long long psulvsb_sample_default_max_draws(unsigned long long n, unsign
 
 unsigned long long psulvsb_sample_workspace_bytes(unsigned long long n, unsigned long long count,
                                                   unsigned long long max_draws) {
-  (void)count;
-  (void)max_draws;
-  return n * sizeof(uint32_t);
+  if (max_draws == 0) max_draws = sample_default_max_draws(n, count);
+  return ((n * sizeof(uint32_t) + 15) & ~15ull) + sample_chunk_slots(max_draws) * sizeof(unsigned long long) + 16;
 }
 
 int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long n,
@@ -258,7 +257,10 @@ int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event,
   if (max_draws == 0) max_draws = sample_default_max_draws(n, count);
   if (max_draws >= 0xFFFFFFFFull) return fail(PSULVSB_ERR_UNSUPPORTED, "psulvsb_sample: max_draws must be < 2^32 - 1");
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t first_bytes = (n * sizeof(uint32_t) + 15) & ~15ull;
+  const size_t slots = sample_chunk_slots(max_draws);
   PSU_CUDA(cudaMemsetAsync(d_work, 0xFF, n * sizeof(uint32_t), st));
+  PSU_CUDA(cudaMemsetAsync((char*)d_work + first_bytes + slots * sizeof(unsigned long long), 0, 16, st));
   PSU_CUDA(cudaMemsetAsync(d_status, 0, sizeof(unsigned long long), st));
   if (count == 0) return PSULVSB_OK;
   SampleJob j;
@@ -270,6 +272,8 @@ int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event,
   j.count = count;
   j.max_draws = max_draws;
   j.first = (uint32_t*)d_work;
+  j.chunk_prefix = (unsigned long long*)((char*)d_work + first_bytes);
+  j.ticket = (unsigned int*)((char*)d_work + first_bytes + slots * sizeof(unsigned long long));
   j.out = d_out;
   j.status = d_status;
   j.active = 1;
@@ -309,6 +313,8 @@ int psulvsb_gnc_tls_rotation(void* stream, const double* d_src64, const double* 
   if (d_R_init) PSU_CUDA(cudaMemcpyAsync(j.R_init, d_R_init, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
   if (d_R_init) PSU_CUDA(cudaStreamSynchronize(st));
   j.weights = d_weights;
+  j.lv = nullptr;
+  j.lv_cap = 0;
   j.R_out = d_R;
   j.inliers = d_inliers;
   j.point_flags = nullptr;
@@ -320,8 +326,7 @@ int psulvsb_gnc_tls_rotation(void* stream, const double* d_src64, const double* 
   if (int rc = dj.put(j)) return rc;
   int cap = (int)((K + 7) / 8) + 32;
   cap = (cap + 31) & ~31;
-  if (cap > gnc_default_capacity()) cap = gnc_default_capacity();
-  return launch_gnc_tls(st, dj.d, 1, cap);
+  return launch_gnc_tls(st, dj.d, 1, cap, 8);
 }
 
 int psulvsb_kabsch_batch(void* stream, const double* d_src64, const double* d_dst64, const void* d_edges_uint2,

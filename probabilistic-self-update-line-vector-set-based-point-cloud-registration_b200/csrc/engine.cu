@@ -467,10 +467,15 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.edge_cap = cap;
         J.edges = be.take<uint2>((size_t)cap);
         J.first = be.take<uint32_t>((size_t)cap);
+        J.chunk_prefix = be.take<unsigned long long>((size_t)sample_chunk_slots(sample_default_max_draws(cap, cap)));
+        J.ticket = be.take<unsigned int>(4);
         J.L_sampled = be.take<uint32_t>((size_t)cap);
         J.basic_idx = be.take<uint32_t>((size_t)cap);
         J.basic_edges = be.take<uint2>((size_t)cap);
         J.weights = be.take<double>((size_t)cap);
+        // covers the basic subsets up to the (0.5, 0.3) rate pair; the (1, 1) escalation recomputes the rest
+        J.lv_cap = cap / 6 + 64;
+        J.lv = be.take<double>((size_t)6 * J.lv_cap);
         cj[(size_t)b].edges = J.edges;
         cj[(size_t)b].cap = cap;
         max_cap = cap > max_cap ? cap : max_cap;
@@ -510,27 +515,33 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   PSU_CUDA(cudaEventRecord(ev_k1, st));
 
   // ---- ticks
-  int gnc_cap = (int)((0.03 * (double)max_nred) / 8.0) + 64;
+  const int gnc_cluster = gnc_cluster_for(B);
+  int gnc_cap = (int)((0.03 * (double)max_nred) / (double)gnc_cluster) + 64;
   gnc_cap = (gnc_cap + 31) & ~31;
   if (gnc_cap > gnc_default_capacity()) gnc_cap = gnc_default_capacity();
   const unsigned long long draws_bound = sample_default_max_draws(max_cap, max_cap / 8 + 1);
   int ticks = 0;
   const int max_ticks = P.max_local_iters + P.host_round_limit + 8;
+  bool round_start_pending = true;  // every job begins with a round start
   while (true) {
     const double elapsed =
         std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count() / 1e6;
-    engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, P, m.n_done);
-    PSU_CHECK_LAUNCH("engine_round_start_kernel");
-    if (int rc = launch_sample(st, m.sl, B, draws_bound)) return rc;
+    if (round_start_pending) {
+      engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, P, m.n_done);
+      PSU_CHECK_LAUNCH("engine_round_start_kernel");
+      if (int rc = launch_sample(st, m.sl, B, draws_bound)) return rc;
+      launches += 4;
+    }
     if (int rc = launch_sample(st, m.sb, B, draws_bound)) return rc;
-    if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap)) return rc;
+    if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster)) return rc;
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");
-    launches += 7;
+    launches += 5;
     ++ticks;
-    PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     PSU_CUDA(cudaStreamSynchronize(st));
-    if (*h_done >= B) break;
+    if (h_done[0] >= B) break;
+    round_start_pending = h_done[1] > 0;
     if (ticks >= max_ticks) return fail(PSULVSB_ERR_INTERNAL, "engine did not converge within the tick limit");
   }
   last_ticks = ticks;

@@ -57,6 +57,8 @@ struct SampleJob {
   uint32_t domain, event;
   unsigned long long n, count, max_draws;
   uint32_t* first;               // [n] first-occurrence table, all 0xFFFFFFFF on entry and on exit
+  unsigned long long* chunk_prefix;  // [sample_chunk_slots(max_draws)] accepted draws before each chunk
+  unsigned int* ticket;          // zero on entry and on exit (last-CTA-done counter of the count pass)
   uint32_t* out;                 // [count]
   unsigned long long* status;    // draws consumed (0: max_draws too small)
   int identity;                  // 1: out[r] = r (registration.cc:839-847, empty-sample fallback)
@@ -67,7 +69,6 @@ struct SampleJob {
   uint2* gathered;               // post 2: gathered[r] = edges[via[out[r]]]
   uint8_t* flags;                // post 1: [n_points] endpoint flags
   int n_points;
-  int* flag_count;               // post 1: number of flagged points
   int active;
 };
 
@@ -85,6 +86,8 @@ struct GncJob {
   int use_init;          // 1: first iteration uses R_init (registration.cc:1617-1621)
   double R_init[9];      // column-major
   double* weights;       // K doubles of scratch (overflow beyond the shared-memory capacity)
+  double* lv;            // optional SoA scratch [6][lv_cap] for the line vectors beyond that capacity
+  unsigned long long lv_cap;
   double* R_out;         // column-major
   uint8_t* inliers;      // [K] or NULL
   uint8_t* point_flags;  // [n_points] or NULL: endpoints of inlier line vectors
@@ -121,12 +124,14 @@ __host__ __device__ inline unsigned long long sample_max_draws_formula(unsigned 
   return m;
 }
 unsigned long long sample_default_max_draws(unsigned long long n, unsigned long long count);
+unsigned long long sample_chunk_slots(unsigned long long max_draws);
 int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound);
 int launch_philox_fill(cudaStream_t st, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long first_k,
                        unsigned long long count, uint32_t* out);
 
 int gnc_default_capacity();
-int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta);
+int gnc_cluster_for(int n_jobs);
+int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster);
 int launch_kabsch_batch(cudaStream_t st, const double* src, const double* dst, const uint2* edges,
                         const uint32_t* sets, int k, unsigned long long n_hyp, double* R, double* t);
 

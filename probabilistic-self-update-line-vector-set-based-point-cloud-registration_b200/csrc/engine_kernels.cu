@@ -53,6 +53,8 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, const EngineP
   sb.count = (unsigned long long)J.basic_choose;
   sb.max_draws = sample_max_draws_formula(sb.n, sb.count);
   sb.first = J.first;
+  sb.chunk_prefix = J.chunk_prefix;
+  sb.ticket = J.ticket;
   sb.out = J.basic_idx;
   sb.status = &J.sample_status[1];
   sb.identity = 0;
@@ -62,7 +64,6 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, const EngineP
   sb.gathered = J.basic_edges;
   sb.flags = nullptr;
   sb.n_points = 0;
-  sb.flag_count = nullptr;
   sb.active = (J.basic_choose > 0) ? 1 : 0;
   J.sample_status[1] = 1ull;
   const double scale = 1.0;  // known scale (registration.cc:984-991)
@@ -81,6 +82,8 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, const EngineP
 #pragma unroll
     for (int r = 0; r < 3; ++r) g.R_init[c * 3 + r] = J.last_best.R[r * 3 + c];
   g.weights = J.weights;
+  g.lv = J.lv;
+  g.lv_cap = J.lv_cap;
   g.R_out = J.R_gnc;
   g.inliers = nullptr;
   g.point_flags = J.rot_flags;
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(BLK)
   }
   for (unsigned long long i = tid; i < J.edge_cap; i += BLK) J.first[i] = 0xFFFFFFFFu;
   if (tid == 0) {
+    *J.ticket = 0u;
     J.C = J.C0;
     J.n_red0 = n_edges[blockIdx.x];
     J.n_red = J.n_red0;
@@ -174,6 +178,8 @@ __global__ void __launch_bounds__(BLK)
       // the reference never terminates here (p_local = NaN, registration.cc:1352/:1399): report invalid
       J.phase = PHASE_DONE;
       atomicAdd(n_done, 1);
+    } else {
+      atomicAdd(n_done + 1, 1);  // n_done[1]: registrations waiting for a round start
     }
   }
 }
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(BLK)
     return;
   }
   __shared__ int ok_s;
+  if (tid == 0) atomicSub(n_done + 1, 1);
   const int nnew = (P.self_update ? J.new_corr_count : 0);
   const int m0 = J.inlier_map_size;
   const int C = J.C;
@@ -270,6 +277,8 @@ __global__ void __launch_bounds__(BLK)
     L.count = n_ls;
     L.max_draws = L.identity ? 0ull : sample_max_draws_formula(L.n, L.count);
     L.first = J.first;
+    L.chunk_prefix = J.chunk_prefix;
+    L.ticket = J.ticket;
     L.out = J.L_sampled;
     L.status = &J.sample_status[0];
     L.post = 1;
@@ -278,7 +287,6 @@ __global__ void __launch_bounds__(BLK)
     L.gathered = nullptr;
     L.flags = J.sampled_flags;
     L.n_points = J.C;
-    L.flag_count = &J.n_sampled_pts;
     L.active = 1;
     J.sample_status[0] = 1ull;
     J.phase = PHASE_LOCAL;
@@ -317,6 +325,15 @@ __global__ void __launch_bounds__(BLK)
       atomicAdd(n_done, 1);
     }
     return;
+  }
+
+  // ---- |src_sampled| (registration.cc:870-894): the sampler leaves the endpoint set as flags
+  if (J.sampled_first_time) {
+    int c = 0, dummy = 0;
+    for (int j = tid; j < C; j += BLK) c += J.sampled_flags[j] ? 1 : 0;
+    block_sum_int2(&scratch, c, dummy);
+    if (tid == 0) J.n_sampled_pts = c;
+    __syncthreads();
   }
 
   // ---- rotation result (column-major) -> row-major
@@ -533,6 +550,7 @@ __global__ void __launch_bounds__(BLK)
       gj[blockIdx.x].active = 0;
       if (J.pro_host_not_over && J.rounds_left > 0) {
         J.phase = PHASE_ROUND_START;
+        atomicAdd(n_done + 1, 1);
       } else {
         J.valid = 1;
         J.phase = PHASE_DONE;

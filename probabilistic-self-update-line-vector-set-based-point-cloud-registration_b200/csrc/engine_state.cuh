@@ -68,10 +68,14 @@ struct JobCtl {
   uint2* edges;              // reduced set (L_reduced_set) as endpoint pairs
   unsigned long long edge_cap;
   uint32_t* first;  // [edge_cap] sampler first-occurrence table
+  unsigned long long* chunk_prefix;  // sampler scratch
+  unsigned int* ticket;              // sampler scratch (zero between uses)
   uint32_t* L_sampled;
   uint32_t* basic_idx;
   uint2* basic_edges;
   double* weights;
+  double* lv;  // GNC-TLS line-vector scratch, SoA [6][lv_cap]
+  unsigned long long lv_cap;
   psulvsb_local_trace_t* local_trace;
   psulvsb_host_trace_t* host_trace;
   int local_trace_cap, host_trace_cap;

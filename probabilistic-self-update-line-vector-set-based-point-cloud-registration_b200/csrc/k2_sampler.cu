@@ -8,6 +8,12 @@
 // That is exactly the rejection rule, so the output equals the sequential algorithm's for the same
 // stream, and the stream position after the call (draws consumed) is reported for replay.
 //
+// Three fully parallel passes over the draw window, every one a grid of (chunks x jobs) CTAs:
+//   mark  : first[v_k] = min(first[v_k], k)
+//   count : accepted draws per 1024-draw chunk; the last CTA of a job to finish turns the chunk
+//           counts into exclusive prefixes (threadfence reduction, no CTA ever waits on another)
+//   emit  : rank = prefix[chunk] + position in chunk -> out[rank]; restores first[] on the way;
+//           optional fused post-processing for the batch engine (endpoint flags / edge gather)
 // Kernels take device-resident SampleJob arrays (one job per registration in the batch engine,
 // whose control kernels rewrite n / count / event between ticks).
 #include <cuda_runtime.h>
@@ -19,12 +25,17 @@ namespace psulvsb {
 
 namespace {
 
-__global__ void __launch_bounds__(256) sample_mark_kernel(const SampleJob* __restrict__ jobs) {
+constexpr int SMP_THREADS = 256;
+constexpr int SMP_CHUNK = SMP_THREADS * 4;  // draws per chunk (one Philox block per thread)
+
+__device__ __forceinline__ uint32_t draw_value(uint32_t word, uint32_t n) { return (word >> 1) % n; }
+
+__global__ void __launch_bounds__(SMP_THREADS) sample_mark_kernel(const SampleJob* __restrict__ jobs) {
   const SampleJob& job = jobs[blockIdx.y];
   if (!job.active || job.identity) return;
-  const unsigned long long n = job.n, max_draws = job.max_draws;
+  const uint32_t n = (uint32_t)job.n;
+  const unsigned long long max_draws = job.max_draws;
   uint32_t* __restrict__ first = job.first;
-  // one Philox block (4 draws) per thread iteration
   const unsigned long long nblocks = (max_draws + 3) >> 2;
   for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < nblocks;
        q += (unsigned long long)gridDim.x * blockDim.x) {
@@ -32,122 +43,169 @@ __global__ void __launch_bounds__(256) sample_mark_kernel(const SampleJob* __res
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       const unsigned long long k = (q << 2) + l;
-      if (k < max_draws) {
-        const unsigned long long v = (unsigned long long)(o.w[l] >> 1) % n;
-        atomicMin(&first[v], (uint32_t)k);
-      }
+      if (k < max_draws) atomicMin(&first[draw_value(o.w[l], n)], (uint32_t)k);
     }
   }
 }
 
-// one CTA per job: ordered emission of the accepted draws; restores first[] to 0xFFFFFFFF on the way
-__global__ void __launch_bounds__(1024) sample_emit_kernel(const SampleJob* __restrict__ jobs) {
-  const SampleJob& job = jobs[blockIdx.x];
-  if (!job.active) return;
-  __shared__ unsigned int warp_tot[32];
-  __shared__ unsigned long long base_s;
-  __shared__ int flag_total;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned long long n = job.n, count = job.count, max_draws = job.max_draws;
-  uint32_t* __restrict__ first = job.first;
-  uint32_t* __restrict__ out = job.out;
-  if (tid == 0) {
-    base_s = 0ull;
-    flag_total = 0;
-  }
-  if (job.post == 1)
-    for (int i = tid; i < job.n_points; i += 1024) job.flags[i] = 0;
+__device__ __forceinline__ unsigned int block_sum_u32(unsigned int v, unsigned int* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[wid] = v;
   __syncthreads();
-  if (job.identity) {
-    for (unsigned long long r = tid; r < count; r += 1024) out[r] = (uint32_t)r;
-    if (tid == 0 && job.status) job.status[0] = 1ull;  // nothing drawn; non-zero = success
-  } else {
-    const unsigned long long nblocks = (max_draws + 3) >> 2;
-    unsigned long long consumed = 0ull;  // meaningful in the thread that emits the last sample
-    bool have_last = false;
-    for (unsigned long long q0 = 0; q0 < nblocks; q0 += 1024) {
-      const unsigned long long base = base_s;  // no early exit: every marked entry of first[] gets restored
-      const unsigned long long q = q0 + tid;
-      uint32_t v[4];
-      bool acc[4] = {false, false, false, false};
-      unsigned int c = 0;
-      if (q < nblocks) {
-        const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+  unsigned int t = 0;
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          const unsigned long long k = (q << 2) + l;
-          v[l] = (uint32_t)((unsigned long long)(o.w[l] >> 1) % n);
-          if (k < max_draws) {
-            acc[l] = first[v[l]] == (uint32_t)k;
-            c += acc[l] ? 1u : 0u;
-          }
-        }
-      }
-      // block exclusive scan of c
-      unsigned int incl = c;
+  for (int w = 0; w < SMP_THREADS / 32; ++w) t += sh[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(SMP_THREADS) sample_count_kernel(const SampleJob* __restrict__ jobs) {
+  const SampleJob& job = jobs[blockIdx.y];
+  if (!job.active) return;
+  __shared__ unsigned int sh[SMP_THREADS / 32];
+  __shared__ unsigned int ticket_s;
+  __shared__ unsigned long long carry_s;
+  const int tid = threadIdx.x;
+  if (job.post == 1)  // endpoint flags are rebuilt by the emit pass
+    for (int i = blockIdx.x * SMP_THREADS + tid; i < job.n_points; i += gridDim.x * SMP_THREADS) job.flags[i] = 0;
+  if (job.identity) return;
+  const uint32_t n = (uint32_t)job.n;
+  const unsigned long long max_draws = job.max_draws;
+  const unsigned long long nchunks = (max_draws + SMP_CHUNK - 1) / SMP_CHUNK;
+  const uint32_t* __restrict__ first = job.first;
+  for (unsigned long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const unsigned long long q = ch * SMP_THREADS + tid;
+    unsigned int c = 0;
+    if ((q << 2) < max_draws) {
+      const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
 #pragma unroll
-      for (int o2 = 1; o2 < 32; o2 <<= 1) {
-        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o2);
-        if (lane >= o2) incl += t;
+      for (int l = 0; l < 4; ++l) {
+        const unsigned long long k = (q << 2) + l;
+        if (k < max_draws && first[draw_value(o.w[l], n)] == (uint32_t)k) ++c;
       }
-      if (lane == 31) warp_tot[wid] = incl;
-      __syncthreads();
-      if (wid == 0) {
-        unsigned int t = warp_tot[lane];
-        unsigned int ti = t;
-#pragma unroll
-        for (int o2 = 1; o2 < 32; o2 <<= 1) {
-          unsigned int u = __shfl_up_sync(0xffffffffu, ti, o2);
-          if (lane >= o2) ti += u;
-        }
-        warp_tot[lane] = ti - t;  // exclusive
-        if (lane == 31) base_s = base + ti;
-      }
-      __syncthreads();
-      unsigned long long rank = base + warp_tot[wid] + (incl - c);
-      if (q < nblocks) {
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          const unsigned long long k = (q << 2) + l;
-          if (acc[l]) {
-            if (rank < count) {
-              out[rank] = v[l];
-              if (rank == count - 1) {
-                consumed = k + 1;
-                have_last = true;
-              }
-            }
-            ++rank;
-            first[v[l]] = 0xFFFFFFFFu;  // restore (every reader of this round passed the barrier above)
-          }
-        }
-      }
-      __syncthreads();
     }
-    if (have_last && job.status) job.status[0] = consumed;
-    __syncthreads();
-    if (tid == 0 && base_s < count && job.status) job.status[0] = 0ull;  // not enough draws
+    const unsigned int tot = block_sum_u32(c, sh);
+    if (tid == 0) job.chunk_prefix[ch] = (unsigned long long)tot;
   }
-  __syncthreads();  // out[] complete (block-scope visibility of the global writes above)
-  // ---- fused post-processing for the batch engine
-  if (job.post == 1) {
-    // src_sampled/dst_sampled = unique endpoints of the sampled line vectors (registration.cc:870-894);
-    // only the SET matters downstream (inlier counts), so it is kept as per-point flags
-    for (unsigned long long r = tid; r < count; r += 1024) {
-      const uint2 e = job.edges[out[r]];
-      job.flags[e.x] = 1;
-      job.flags[e.y] = 1;
+  // last CTA of this job: counts -> exclusive prefixes
+  __threadfence();
+  if (tid == 0) ticket_s = atomicAdd(job.ticket, 1u);
+  __syncthreads();
+  if (ticket_s != gridDim.x - 1) return;
+  __threadfence();
+  if (tid == 0) {
+    carry_s = 0ull;
+    *job.ticket = 0u;  // ready for the next use
+  }
+  __syncthreads();
+  volatile unsigned long long* pref = job.chunk_prefix;
+  for (unsigned long long c0 = 0; c0 < nchunks; c0 += SMP_THREADS) {
+    const unsigned long long ch = c0 + tid;
+    const unsigned int v = (ch < nchunks) ? (unsigned int)pref[ch] : 0u;
+    // block exclusive scan of v
+    const int lane = tid & 31, wid = tid >> 5;
+    unsigned int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh[wid] = incl;
+    __syncthreads();
+    unsigned int wbase = 0;
+#pragma unroll
+    for (int w = 0; w < SMP_THREADS / 32; ++w)
+      if (w < wid) wbase += sh[w];
+    const unsigned long long carry = carry_s;
+    if (ch < nchunks) pref[ch] = carry + wbase + (incl - v);
+    __syncthreads();
+    if (tid == SMP_THREADS - 1) carry_s = carry + wbase + incl;
+    __syncthreads();
+  }
+  if (tid == 0 && carry_s < job.count && job.status) job.status[0] = 0ull;  // draw budget too small
+}
+
+__global__ void __launch_bounds__(SMP_THREADS) sample_emit_kernel(const SampleJob* __restrict__ jobs) {
+  const SampleJob& job = jobs[blockIdx.y];
+  if (!job.active) return;
+  __shared__ unsigned int sh[SMP_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned long long count = job.count;
+  uint32_t* __restrict__ out = job.out;
+  if (job.identity) {  // registration.cc:839-847: the sample is the whole set, in order
+    for (unsigned long long r = (unsigned long long)blockIdx.x * SMP_THREADS + tid; r < count;
+         r += (unsigned long long)gridDim.x * SMP_THREADS) {
+      out[r] = (uint32_t)r;
+      if (job.post == 1) {
+        const uint2 e = job.edges[r];
+        job.flags[e.x] = 1;
+        job.flags[e.y] = 1;
+      } else if (job.post == 2) {
+        job.gathered[r] = job.edges[job.via[r]];
+      }
+    }
+    if (blockIdx.x == 0 && tid == 0 && job.status) job.status[0] = 1ull;  // nothing drawn; non-zero = success
+    return;
+  }
+  const uint32_t n = (uint32_t)job.n;
+  const unsigned long long max_draws = job.max_draws;
+  const unsigned long long nchunks = (max_draws + SMP_CHUNK - 1) / SMP_CHUNK;
+  uint32_t* __restrict__ first = job.first;
+  for (unsigned long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const unsigned long long q = ch * SMP_THREADS + tid;
+    uint32_t v[4];
+    bool acc[4] = {false, false, false, false};
+    unsigned int c = 0;
+    if ((q << 2) < max_draws) {
+      const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const unsigned long long k = (q << 2) + l;
+        v[l] = draw_value(o.w[l], n);
+        if (k < max_draws) {
+          acc[l] = first[v[l]] == (uint32_t)k;
+          c += acc[l] ? 1u : 0u;
+        }
+      }
+    }
+    unsigned int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh[wid] = incl;
+    __syncthreads();
+    unsigned int wbase = 0;
+#pragma unroll
+    for (int w = 0; w < SMP_THREADS / 32; ++w)
+      if (w < wid) wbase += sh[w];
+    unsigned long long rank = job.chunk_prefix[ch] + wbase + (incl - c);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      if (acc[l]) {
+        if (rank < count) {
+          out[rank] = v[l];
+          if (job.post == 1) {
+            // src_sampled/dst_sampled = unique endpoints of the sampled line vectors
+            // (registration.cc:870-894); only the SET matters downstream, kept as per-point flags
+            const uint2 e = job.edges[v[l]];
+            job.flags[e.x] = 1;
+            job.flags[e.y] = 1;
+          } else if (job.post == 2) {
+            // basic line vectors (registration.cc:922-925) as endpoint pairs
+            job.gathered[rank] = job.edges[job.via[v[l]]];
+          }
+          if (rank == count - 1 && job.status) job.status[0] = (q << 2) + l + 1;  // draws consumed
+        }
+        ++rank;
+        // restore the table; a rejected draw that still reads this entry sees a value != its own k either way
+        first[v[l]] = 0xFFFFFFFFu;
+      }
     }
     __syncthreads();
-    int c = 0;
-    for (int i = tid; i < job.n_points; i += 1024) c += job.flags[i] ? 1 : 0;
-    c = warp_sum_int(c);
-    if (lane == 0 && c) atomicAdd(&flag_total, c);
-    __syncthreads();
-    if (tid == 0 && job.flag_count) *job.flag_count = flag_total;
-  } else if (job.post == 2) {
-    // basic line vectors (registration.cc:922-925) as endpoint pairs
-    for (unsigned long long r = tid; r < count; r += 1024) job.gathered[r] = job.edges[job.via[out[r]]];
   }
 }
 
@@ -163,17 +221,21 @@ unsigned long long sample_default_max_draws(unsigned long long n, unsigned long 
   return sample_max_draws_formula(n, count);
 }
 
+unsigned long long sample_chunk_slots(unsigned long long max_draws) { return (max_draws + SMP_CHUNK - 1) / SMP_CHUNK + 1; }
+
 int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound) {
   if (n_jobs <= 0) return PSULVSB_OK;
-  const unsigned long long nblocks = (max_draws_bound + 3) >> 2;
-  unsigned long long gx = (nblocks + 255) / 256;
-  const unsigned long long cap = (unsigned long long)(148 * 8 / (n_jobs < 8 ? n_jobs : 8)) + 1;
+  const unsigned long long nchunks = (max_draws_bound + SMP_CHUNK - 1) / SMP_CHUNK;
+  unsigned long long gx = nchunks;
+  const unsigned long long cap = (unsigned long long)(148 * 16) / (unsigned long long)(n_jobs < 64 ? n_jobs : 64) + 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)n_jobs);
-  sample_mark_kernel<<<grid, 256, 0, st>>>(d_jobs);
+  sample_mark_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs);
   PSU_CHECK_LAUNCH("sample_mark_kernel");
-  sample_emit_kernel<<<n_jobs, 1024, 0, st>>>(d_jobs);
+  sample_count_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs);
+  PSU_CHECK_LAUNCH("sample_count_kernel");
+  sample_emit_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs);
   PSU_CHECK_LAUNCH("sample_emit_kernel");
   return PSULVSB_OK;
 }

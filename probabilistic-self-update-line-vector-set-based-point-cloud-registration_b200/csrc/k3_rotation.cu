@@ -10,9 +10,15 @@
 // r^2 = |tv - R_i sv|^2, adds w_{i-1} r^2 to the cost, updates the weight in closed form and
 // accumulates H_{i+1} += w_i sv tv^T; the 9+1 partial sums are reduced warp -> CTA -> cluster
 // through distributed shared memory in a fixed order (deterministic), and every CTA's thread 0
-// turns H into R_{i+1} with a 3x3 Jacobi SVD.  Line vectors (and weights) of a CTA live in its
-// shared memory for the whole solve; only the overflow beyond the smem capacity is recomputed
-// from the points each pass.
+// turns H into R_{i+1} with a 3x3 Jacobi SVD (warm-started from the previous iteration's V).
+// Line vectors (and weights) of a CTA live in its shared memory for the whole solve; the overflow
+// beyond the smem capacity streams from a coalesced SoA scratch in HBM/L2 (GncJob::lv), and only
+// what exceeds that too is recomputed from the points each pass.  The cluster size (1, 2, 4 or 8
+// CTAs per hypothesis) is chosen by the launcher from the batch size: few registrations ->
+// 8 SMs each (latency), many -> one SM each (throughput).
+// FP64 with explicit fma(): reduction order already differs from a sequential CPU sum, so fusing
+// adds no new class of deviation; the discrete decisions (r^2 vs th1/th2, w >= 0.5) are unaffected
+// except within an ulp of their thresholds.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
@@ -46,6 +52,44 @@ __device__ __forceinline__ void load_lv(const double* __restrict__ src, const do
     // pruned_dst_tims_ *= (1 / solution_.scale)   (registration.cc:1102)
     tv[r] = (dst[3 * (size_t)e.y + r] - dst[3 * (size_t)e.x + r]) * inv_scale;
   }
+}
+
+// line vector l of this CTA's slice (global index k): smem cache, else SoA scratch, else recompute
+struct LvSrc {
+  const double* lv_s;  // smem [7][cap]
+  size_t cap;
+  unsigned long long ncached;
+  const double* lv_g;  // global scratch [6][lv_cap]
+  unsigned long long lv_cap;
+  const double* src;
+  const double* dst;
+  const uint2* edges;
+  double inv_scale;
+};
+__device__ __forceinline__ void fetch_lv(const LvSrc& S, unsigned long long l, unsigned long long k, double sv[3],
+                                         double tv[3]) {
+  if (l < S.ncached) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      sv[r] = S.lv_s[(size_t)r * S.cap + l];
+      tv[r] = S.lv_s[(size_t)(3 + r) * S.cap + l];
+    }
+  } else if (k < S.lv_cap) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      sv[r] = S.lv_g[(size_t)r * S.lv_cap + k];
+      tv[r] = S.lv_g[(size_t)(3 + r) * S.lv_cap + k];
+    }
+  } else {
+    load_lv(S.src, S.dst, S.edges[k], S.inv_scale, sv, tv);
+  }
+}
+
+__device__ __forceinline__ double residual2(const double R[9], const double sv[3], const double tv[3]) {
+  const double d0 = fma(-R[2], sv[2], fma(-R[1], sv[1], fma(-R[0], sv[0], tv[0])));
+  const double d1 = fma(-R[5], sv[2], fma(-R[4], sv[1], fma(-R[3], sv[0], tv[1])));
+  const double d2 = fma(-R[8], sv[2], fma(-R[7], sv[1], fma(-R[6], sv[0], tv[2])));
+  return fma(d2, d2, fma(d1, d1, d0 * d0));
 }
 
 // CTA-level then cluster-level sum (or max for index MAXI) of NRED values; result in sm->total.
@@ -119,6 +163,18 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
   double acc[GNC_NRED];
 #pragma unroll
   for (int i = 0; i < GNC_NRED; ++i) acc[i] = 0.0;
+  double* __restrict__ lvg = job.lv;
+  const unsigned long long lv_cap = lvg ? job.lv_cap : 0ull;
+  LvSrc S;
+  S.lv_s = lv;
+  S.cap = cap;
+  S.ncached = ncached;
+  S.lv_g = lvg;
+  S.lv_cap = lv_cap;
+  S.src = src;
+  S.dst = dst;
+  S.edges = edges;
+  S.inv_scale = job.inv_scale;
   for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
     double sv[3], tv[3];
     load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
@@ -130,14 +186,22 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
       }
       lv[6 * cap + l] = 1.0;
     } else {
+      if (k_lo + l < lv_cap) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          lvg[(size_t)r * lv_cap + k_lo + l] = sv[r];
+          lvg[(size_t)(3 + r) * lv_cap + k_lo + l] = tv[r];
+        }
+      }
       gw[k_lo + l] = 1.0;
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc[r * 3 + c] += sv[r] * tv[c];
+      for (int c = 0; c < 3; ++c) acc[r * 3 + c] = fma(sv[r], tv[c], acc[r * 3 + c]);
   }
   int parity = 0;
+  double Vw[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // Jacobi warm start (thread 0 only)
   if (job.use_init) {
     if (tid < 9) sm->R[tid] = job.R_init[(tid % 3) * 3 + tid / 3];  // column-major -> row-major
     __syncthreads();
@@ -148,7 +212,7 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
       double H[3][3], R[3][3];
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) H[r][c] = sm->total[r * 3 + c];
-      kabsch_rotation(H, R);
+      kabsch_rotation(H, R, Vw);
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = R[r][c];
     }
@@ -170,19 +234,8 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
       for (int i = 0; i < GNC_NRED; ++i) mx[i] = 0.0;
       for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
         double sv[3], tv[3];
-        if (l < ncached) {
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            sv[r] = lv[(size_t)r * cap + l];
-            tv[r] = lv[(size_t)(3 + r) * cap + l];
-          }
-        } else {
-          load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
-        }
-        const double d0 = tv[0] - ((R[0] * sv[0] + R[1] * sv[1]) + R[2] * sv[2]);
-        const double d1 = tv[1] - ((R[3] * sv[0] + R[4] * sv[1]) + R[5] * sv[2]);
-        const double d2 = tv[2] - ((R[6] * sv[0] + R[7] * sv[1]) + R[8] * sv[2]);
-        mx[0] = fmax(mx[0], (d0 * d0 + d1 * d1) + d2 * d2);
+        fetch_lv(S, l, k_lo + l, sv, tv);
+        mx[0] = fmax(mx[0], residual2(R, sv, tv));
       }
       cluster_reduce<NC>(sm, mx, parity, 0);
       parity ^= 1;
@@ -196,24 +249,12 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
 #pragma unroll
     for (int i = 0; i < GNC_NRED; ++i) acc[i] = 0.0;
     for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
-      double sv[3], tv[3], w;
+      double sv[3], tv[3];
       const bool cached = l < ncached;
-      if (cached) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          sv[r] = lv[(size_t)r * cap + l];
-          tv[r] = lv[(size_t)(3 + r) * cap + l];
-        }
-        w = lv[6 * cap + l];
-      } else {
-        load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
-        w = gw[k_lo + l];
-      }
-      const double d0 = tv[0] - ((R[0] * sv[0] + R[1] * sv[1]) + R[2] * sv[2]);
-      const double d1 = tv[1] - ((R[3] * sv[0] + R[4] * sv[1]) + R[5] * sv[2]);
-      const double d2 = tv[2] - ((R[6] * sv[0] + R[7] * sv[1]) + R[8] * sv[2]);
-      const double r2 = (d0 * d0 + d1 * d1) + d2 * d2;
-      acc[9] += w * r2;  // cost uses the previous weights (registration.cc:1648)
+      fetch_lv(S, l, k_lo + l, sv, tv);
+      const double w = cached ? lv[6 * cap + l] : gw[k_lo + l];
+      const double r2 = residual2(R, sv, tv);
+      acc[9] = fma(w, r2, acc[9]);  // cost uses the previous weights (registration.cc:1648)
       double wn;
       if (r2 >= th1)
         wn = 0.0;
@@ -230,7 +271,7 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
         for (int r = 0; r < 3; ++r) {
           const double xs = sv[r] * wn;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) acc[r * 3 + c] += xs * tv[c];
+          for (int c = 0; c < 3; ++c) acc[r * 3 + c] = fma(xs, tv[c], acc[r * 3 + c]);
         }
       }
     }
@@ -247,7 +288,7 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
         double H[3][3], Rn[3][3];
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c) H[r][c] = sm->total[r * 3 + c];
-        kabsch_rotation(H, Rn);
+        kabsch_rotation(H, Rn, Vw);
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = Rn[r][c];
       }
@@ -350,9 +391,32 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-constexpr int GNC_CLUSTER = 8;
-
 size_t gnc_smem_bytes(int cap) { return ((sizeof(GncSmem) + 15) & ~size_t(15)) + (size_t)7 * cap * sizeof(double); }
+
+template <int NC>
+int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta) {
+  static bool attr_set = false;
+  const size_t smem = gnc_smem_bytes(cap_per_cta);
+  if (!attr_set) {
+    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)gnc_smem_bytes(gnc_default_capacity())));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NC, (unsigned)n_jobs, 1);
+  cfg.blockDim = dim3(GNC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC>, d_jobs, cap_per_cta));
+  return PSULVSB_OK;
+}
 
 }  // namespace
 
@@ -365,29 +429,25 @@ int gnc_default_capacity() {
   return cap;
 }
 
-int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta) {
+// CTAs per hypothesis for a batch of n_jobs: as many SMs per job as keeps the whole batch resident
+int gnc_cluster_for(int n_jobs) {
+  if (n_jobs * 8 <= 148) return 8;
+  if (n_jobs * 4 <= 148) return 4;
+  if (n_jobs * 2 <= 148) return 2;
+  return 1;
+}
+
+int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster) {
   if (n_jobs <= 0) return PSULVSB_OK;
-  static bool attr_set = false;
-  const size_t smem = gnc_smem_bytes(cap_per_cta);
-  if (!attr_set) {
-    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<GNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)gnc_smem_bytes(gnc_default_capacity())));
-    attr_set = true;
+  if (cap_per_cta > gnc_default_capacity()) cap_per_cta = gnc_default_capacity();
+  if (cap_per_cta < 32) cap_per_cta = 32;
+  switch (cluster) {
+    case 8: return launch_gnc_nc<8>(st, d_jobs, n_jobs, cap_per_cta);
+    case 4: return launch_gnc_nc<4>(st, d_jobs, n_jobs, cap_per_cta);
+    case 2: return launch_gnc_nc<2>(st, d_jobs, n_jobs, cap_per_cta);
+    case 1: return launch_gnc_nc<1>(st, d_jobs, n_jobs, cap_per_cta);
+    default: return fail(PSULVSB_ERR_INVALID, "launch_gnc_tls: cluster must be 1, 2, 4 or 8");
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(GNC_CLUSTER, (unsigned)n_jobs, 1);
-  cfg.blockDim = dim3(GNC_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = GNC_CLUSTER;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<GNC_CLUSTER>, d_jobs, cap_per_cta));
-  return PSULVSB_OK;
 }
 
 int launch_kabsch_batch(cudaStream_t st, const double* src, const double* dst, const uint2* edges,

@@ -97,7 +97,8 @@ def compact_edges(mask: torch.Tensor, counts: torch.Tensor, n: int, stride: int)
 
 def sample(seed: int, domain: int, event: int, n: int, count: int, max_draws: int = 0):
     out = torch.zeros(max(count, 1), dtype=torch.int32, device="cuda")
-    work = torch.empty(n, dtype=torch.int32, device="cuda")
+    nbytes = capi.lib().psulvsb_sample_workspace_bytes(n, count, max_draws)
+    work = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device="cuda")
     status = torch.zeros(1, dtype=torch.int64, device="cuda")
     capi.check(capi.lib().psulvsb_sample(_stream(), seed, domain, event, n, count, max_draws, _dev(out), _dev(work),
                                          _dev(status)))
