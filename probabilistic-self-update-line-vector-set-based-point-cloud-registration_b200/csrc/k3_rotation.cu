@@ -248,11 +248,9 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
     const double wnum = nb2 * mu * (mu + 1.0);
 #pragma unroll
     for (int i = 0; i < GNC_NRED; ++i) acc[i] = 0.0;
-    for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
-      double sv[3], tv[3];
-      const bool cached = l < ncached;
-      fetch_lv(S, l, k_lo + l, sv, tv);
-      const double w = cached ? lv[6 * cap + l] : gw[k_lo + l];
+    const double sqrt_wnum = sqrt(wnum);
+    // one line vector: cost term with the previous weight, closed-form new weight, H += w sv tv^T
+    auto body = [&](const double sv[3], const double tv[3], double w) -> double {
       const double r2 = residual2(R, sv, tv);
       acc[9] = fma(w, r2, acc[9]);  // cost uses the previous weights (registration.cc:1648)
       double wn;
@@ -261,11 +259,7 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
       else if (r2 <= th2)
         wn = 1.0;
       else
-        wn = sqrt(wnum / r2) - mu;
-      if (cached)
-        lv[6 * cap + l] = wn;
-      else
-        gw[k_lo + l] = wn;
+        wn = fma(sqrt_wnum, rsqrt(r2), -mu);  // sqrt(eps^2 mu (mu + 1) / r^2) - mu  (registration.cc:1655)
       if (wn != 0.0) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -273,6 +267,69 @@ __global__ void __launch_bounds__(GNC_THREADS) gnc_tls_kernel(const GncJob* __re
 #pragma unroll
           for (int c = 0; c < 3; ++c) acc[r * 3 + c] = fma(xs, tv[c], acc[r * 3 + c]);
         }
+      }
+      return wn;
+    };
+    // (a) shared-memory resident part
+    {
+      unsigned long long l = tid;
+      for (; l + GNC_THREADS < ncached; l += 2 * GNC_THREADS) {
+        double sa[3], ta[3], sb[3], tb[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          sa[r] = lv[(size_t)r * cap + l];
+          ta[r] = lv[(size_t)(3 + r) * cap + l];
+          sb[r] = lv[(size_t)r * cap + l + GNC_THREADS];
+          tb[r] = lv[(size_t)(3 + r) * cap + l + GNC_THREADS];
+        }
+        const double wa = lv[6 * cap + l], wb = lv[6 * cap + l + GNC_THREADS];
+        lv[6 * cap + l] = body(sa, ta, wa);
+        lv[6 * cap + l + GNC_THREADS] = body(sb, tb, wb);
+      }
+      for (; l < ncached; l += GNC_THREADS) {
+        double sa[3], ta[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          sa[r] = lv[(size_t)r * cap + l];
+          ta[r] = lv[(size_t)(3 + r) * cap + l];
+        }
+        lv[6 * cap + l] = body(sa, ta, lv[6 * cap + l]);
+      }
+    }
+    // (b) HBM/L2 scratch part: all loads of two line vectors in flight before the arithmetic
+    const unsigned long long g_hi = (k_hi < lv_cap) ? nloc : ((lv_cap > k_lo) ? lv_cap - k_lo : 0ull);  // local end
+    {
+      unsigned long long l = ncached + tid;
+      for (; l + GNC_THREADS < g_hi; l += 2 * GNC_THREADS) {
+        const unsigned long long ka = k_lo + l, kb = ka + GNC_THREADS;
+        double sa[3], ta[3], sb[3], tb[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          sa[r] = lvg[(size_t)r * lv_cap + ka];
+          ta[r] = lvg[(size_t)(3 + r) * lv_cap + ka];
+          sb[r] = lvg[(size_t)r * lv_cap + kb];
+          tb[r] = lvg[(size_t)(3 + r) * lv_cap + kb];
+        }
+        const double wa = gw[ka], wb = gw[kb];
+        gw[ka] = body(sa, ta, wa);
+        gw[kb] = body(sb, tb, wb);
+      }
+      for (; l < g_hi; l += GNC_THREADS) {
+        const unsigned long long ka = k_lo + l;
+        double sa[3], ta[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          sa[r] = lvg[(size_t)r * lv_cap + ka];
+          ta[r] = lvg[(size_t)(3 + r) * lv_cap + ka];
+        }
+        gw[ka] = body(sa, ta, gw[ka]);
+      }
+      // (c) beyond the scratch capacity: recompute from the points
+      for (; l < nloc; l += GNC_THREADS) {
+        const unsigned long long ka = k_lo + l;
+        double sa[3], ta[3];
+        load_lv(src, dst, edges[ka], job.inv_scale, sa, ta);
+        gw[ka] = body(sa, ta, gw[ka]);
       }
     }
     weights_are_unit = false;
