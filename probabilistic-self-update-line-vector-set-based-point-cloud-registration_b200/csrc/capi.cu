@@ -195,6 +195,9 @@ int psulvsb_consistency_mask_rows(void* stream, const void* d_src_f4, const void
   j.border = d_border_count;
   j.active = 1;
   if (d_row_counts) PSU_CUDA(cudaMemsetAsync(d_row_counts + row_begin, 0, sizeof(uint32_t) * (size_t)(row_end - row_begin), st));
+  // the kernel writes only the words at or right of each row's diagonal tile: define the rest as zeros
+  PSU_CUDA(cudaMemsetAsync(d_mask + (size_t)row_begin * row_stride_words, 0,
+                           sizeof(uint32_t) * (size_t)(row_end - row_begin) * row_stride_words, st));
   DeviceJob<K1Job> dj(st);
   if (int rc = dj.put(j)) return rc;
   return launch_consistency_mask(st, dj.d, 1, n, row_end - row_begin);

@@ -103,6 +103,14 @@ __device__ __forceinline__ double sqnorm3(double x, double y, double z) {
   return dadd(dadd(dmul(x, x), dmul(y, y)), dmul(z, z));
 }
 
+// centred FP64 point -> FP32 tile entry (x, y, z, |p|^2); the squared norm is taken of the ROUNDED
+// coordinates in FP64 and rounded once (K1 fast path)
+__device__ __forceinline__ float4 pack_point(double x, double y, double z) {
+  const float xf = (float)x, yf = (float)y, zf = (float)z;
+  const double n2 = (double)xf * (double)xf + (double)yf * (double)yf + (double)zf * (double)zf;
+  return make_float4(xf, yf, zf, (float)n2);
+}
+
 struct Mat3d {
   double m[3][3];  // row-major
 };

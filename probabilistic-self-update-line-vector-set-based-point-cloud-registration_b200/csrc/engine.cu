@@ -98,8 +98,7 @@ __global__ void engine_pack_kernel(const PackJob* __restrict__ jobs) {
   const PackJob& j = jobs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < j.n) {
-    j.out[i] = make_float4((float)(j.pts[3 * i] - j.c[0]), (float)(j.pts[3 * i + 1] - j.c[1]),
-                           (float)(j.pts[3 * i + 2] - j.c[2]), 0.f);
+    j.out[i] = pack_point(j.pts[3 * i] - j.c[0], j.pts[3 * i + 1] - j.c[1], j.pts[3 * i + 2] - j.c[2]);
     if (j.zero) j.zero[i] = 0u;
   }
 }

@@ -23,6 +23,8 @@ struct K1Consts {
   float kappa;      // band slope: |v - v_c| <= kappa * S
   float w_thr;      // kappa * c (+slack): pair flagged iff |v| - kappa S' <= w_thr  or  S' <= 0
   double beta;      // FP64 threshold of the exact test
+  float beta4;      // beta^4 (fast path: v = D^2 - (2 beta^2 S - beta^4))
+  float t_fast;     // fast-path sign is trusted iff |v| > t_fast (rounding band + the a + b <= beta case)
 };
 K1Consts make_k1_consts(double beta, double coord_bound);
 

@@ -13,11 +13,21 @@
 // operation order, so the emitted bits equal the FP64 reference's bit for bit; the number of
 // re-evaluated pairs is counted.
 //
+// Fast path.  A and B are formed in the "norm" form  |s_i|^2 + |s_j|^2 - 2 s_i.s_j  (the squared
+// norms travel in the .w lane of the float4 tiles, -2 s_i is pre-scaled in registers): 14 FP32-pipe
+// instructions per pair.  That form loses relative accuracy for short line vectors, so its sign is
+// trusted only when |v| exceeds ONE uniform threshold t_fast (derivation in DESIGN.md "K1 fast-path
+// threshold"; it also covers a + b <= beta, where the polynomial's sign is not the answer); a mask
+// word with any pair below it is redone with the accurate difference form above, whose own band
+// decides what goes to FP64.
+//
 // Mapping.  One thread owns R rows (its points live in registers), the CTA's column tile is staged
 // in shared memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) and read as warp-wide
 // broadcasts; a thread accumulates the 32 result bits of a mask word with a funnel shift of v's
 // sign bit, so no ballot and no divergence on the fast path.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "engine.cuh"
@@ -89,14 +99,49 @@ __device__ __forceinline__ void pair_eval(const float4 si, const float4 ti, cons
   w = fmaf(-c.kappa, sp, fabsf(v));
 }
 
+// fast path: row point as (-2 x, -2 y, -2 z, |p|^2), column point as (x, y, z, |p|^2)
+__device__ __forceinline__ float pair_fast(const float4 ms, const float4 mt, const float4 sj, const float4 tj,
+                                           const float two_beta2, const float beta4) {
+  const float A = fmaf(ms.x, sj.x, fmaf(ms.y, sj.y, fmaf(ms.z, sj.z, ms.w + sj.w)));
+  const float B = fmaf(mt.x, tj.x, fmaf(mt.y, tj.y, fmaf(mt.z, tj.z, mt.w + tj.w)));
+  const float D = A - B;
+  const float S = A + B;
+  const float r = fmaf(two_beta2, S, -beta4);
+  return fmaf(D, D, -r);
+}
+
+// Slow path (rare): the mask word of row i, columns cb .. cb+31, redone by the whole warp -- lane b
+// takes pair (i, cb + b) in the accurate difference form; what falls inside ITS rigorous band is
+// decided in FP64 with the reference's operation order; the 32 verdicts come back as one ballot.
+__device__ __noinline__ uint32_t slow_word_coop(const K1Job& job, int i, int cb, const float4 sj, const float4 tj,
+                                                unsigned int& nborder) {
+  const int lane = threadIdx.x & 31;
+  const float4 si = job.src[i];
+  const float4 ti = job.dst[i];
+  float v, w, sp;
+  pair_eval(si, ti, sj, tj, job.c, v, w, sp);
+  bool in = (__float_as_uint(v) >> 31) != 0u;
+  const int j = cb + lane;
+  if ((!(w > job.c.w_thr) || !(sp > 0.f)) && j < job.n && j > i) {
+    ++nborder;
+    in = exact_consistent(job.src64, job.dst64, i, j, job.c.beta);
+  }
+  return __ballot_sync(0xffffffffu, in);
+}
+
+// One CTA = a block of TI = 256 R rows x a chunk of `tiles_per_cta` column tiles (TJ columns each),
+// starting at the tile that holds the diagonal of the row block; the column tiles stream through a
+// two-stage shared-memory ring filled by 1-D TMA bulk copies, so the copy of tile k+1 overlaps the
+// arithmetic of tile k.  Words that lie entirely below the diagonal inside a live tile are written
+// as zeros; tiles entirely below it are not touched (callers that need them defined clear the mask
+// first -- psulvsb_consistency_mask does, the engine never reads them).
 template <int R, int TJ>
-__global__ void __launch_bounds__(K1_THREADS) k1_mask_kernel(const K1Job* __restrict__ jobs) {
+__global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 3 : (R == 2 ? 3 : 4)))
+    k1_mask_kernel(const K1Job* __restrict__ jobs, int tiles_per_cta) {
   const K1Job& job = jobs[blockIdx.z];
   if (!job.active) return;
   const float4* __restrict__ src = job.src;
   const float4* __restrict__ dst = job.dst;
-  const double* __restrict__ src64 = job.src64;
-  const double* __restrict__ dst64 = job.dst64;
   const int n = job.n, row_begin = job.row_begin, row_end = job.row_end;
   const K1Consts c = job.c;
   uint32_t* __restrict__ mask = job.mask;
@@ -105,113 +150,120 @@ __global__ void __launch_bounds__(K1_THREADS) k1_mask_kernel(const K1Job* __rest
   unsigned long long* __restrict__ border_count = job.border;
   constexpr int TI = K1_THREADS * R;
   constexpr int WORDS = TJ / 32;
-  __shared__ __align__(128) float4 cs[TJ];
-  __shared__ __align__(128) float4 ct[TJ];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(128) float4 cs[2][TJ];
+  __shared__ __align__(128) float4 ct[2][TJ];
+  __shared__ __align__(8) uint64_t bar[2];
 
-  const int col0 = blockIdx.x * TJ;
   const int row0 = row_begin + blockIdx.y * TI;
-  if (col0 >= n || row0 >= row_end) return;  // grid is sized for the largest job
-  const int ncols = min(TJ, n - col0);
-  const int tid = threadIdx.x;
-
-  // tile entirely on/below the diagonal: defined output (zeros), no work
-  if (col0 + ncols - 1 <= row0) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = row0 + tid + r * K1_THREADS;
-      if (i < row_end) {
-        for (int wj = 0; wj < WORDS; ++wj)
-          if (col0 + wj * 32 < n) mask[(size_t)i * stride + (col0 >> 5) + wj] = 0u;
-      }
-    }
-    return;
-  }
+  if (row0 >= row_end) return;  // grid is sized for the largest job
+  const int n_tiles = (n + TJ - 1) / TJ;
+  const int t_begin = row0 / TJ + blockIdx.x * tiles_per_cta;  // first live tile of the row block + chunk
+  const int t_end = min(n_tiles, t_begin + tiles_per_cta);
+  if (t_begin >= t_end) return;
+  const int nt = t_end - t_begin;
+  const int tid = threadIdx.x, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // slots past the end of the arrays hold a dummy point; their bits are masked off below
-  for (int k = ncols + tid; k < TJ; k += K1_THREADS) {
-    cs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    ct[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // slots past the end of the arrays keep a finite dummy point; their bits are masked off below
+  for (int k = tid; k < 2 * TJ; k += K1_THREADS) {
+    (&cs[0][0])[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    (&ct[0][0])[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  if (tid == 0) {
-    const uint32_t bytes = (uint32_t)ncols * (uint32_t)sizeof(float4);
-    mbar_expect_tx(&bar, 2 * bytes);
-    tma_load_1d(cs, src + col0, bytes, &bar);
-    tma_load_1d(ct, dst + col0, bytes, &bar);
-  }
+  auto issue = [&](int k) {  // thread 0: bulk copies of tile t_begin + k into stage k & 1
+    const int st = k & 1;
+    const int col0 = (t_begin + k) * TJ;
+    const uint32_t bytes = (uint32_t)min(TJ, n - col0) * (uint32_t)sizeof(float4);
+    // order the generic-proxy accesses of the stage's previous use before the async-proxy writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bar[st], 2 * bytes);
+    tma_load_1d(cs[st], src + col0, bytes, &bar[st]);
+    tma_load_1d(ct[st], dst + col0, bytes, &bar[st]);
+  };
+  if (tid == 0) issue(0);
 
-  // row points -> registers (overlaps the bulk copy)
-  float4 si[R], ti[R];
+  // row points -> registers, pre-scaled by -2 for the norm form (overlaps the bulk copy)
+  float4 ms[R], mt[R];
   int irow[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     irow[r] = row0 + tid + r * K1_THREADS;
     const bool ok = irow[r] < row_end;
-    si[r] = ok ? src[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
-    ti[r] = ok ? dst[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a = ok ? src[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b = ok ? dst[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ms[r] = make_float4(-2.f * a.x, -2.f * a.y, -2.f * a.z, a.w);
+    mt[r] = make_float4(-2.f * b.x, -2.f * b.y, -2.f * b.z, b.w);
   }
-  mbar_wait(&bar, 0);
+  const float two_beta2 = c.two_beta2, beta4 = c.beta4, t_fast = c.t_fast;
+  const int warp_row_min = row0 + (tid & ~31);  // smallest row this warp owns (r = 0)
 
   uint32_t cnt[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) cnt[r] = 0;
   unsigned int nborder = 0;
 
-  for (int wj = 0; wj < WORDS; ++wj) {
-    const int cb = col0 + wj * 32;  // first column of this word
-    if (cb >= n) break;
-    uint32_t acc[R];
-    float mw[R], ms[R];
+  for (int k = 0; k < nt; ++k) {
+    const int st = k & 1;
+    if (tid == 0 && k + 1 < nt) issue(k + 1);  // stage (k+1)&1 was released by the barrier ending iteration k-1
+    mbar_wait(&bar[st], (k >> 1) & 1);
+    const int col0 = (t_begin + k) * TJ;
+    for (int wj = 0; wj < WORDS; ++wj) {
+      const int cb = col0 + wj * 32;  // first column of this word
+      if (cb >= n) break;
+      if (cb + 31 <= warp_row_min) {  // the word is below the diagonal for every row of this warp
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      acc[r] = 0u;
-      mw[r] = 3.0e38f;
-      ms[r] = 3.0e38f;
-    }
-#pragma unroll 8
-    for (int jj = 31; jj >= 0; --jj) {
-      const float4 sj = cs[wj * 32 + jj];
-      const float4 tj = ct[wj * 32 + jj];
+        for (int r = 0; r < R; ++r)
+          if (irow[r] < row_end) mask[(size_t)irow[r] * stride + (cb >> 5)] = 0u;
+        continue;
+      }
+      uint32_t acc[R];
+      float mv[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float v, w, sp;
-        pair_eval(si[r], ti[r], sj, tj, c, v, w, sp);
-        acc[r] = __funnelshift_l(__float_as_uint(v), acc[r], 1);  // bit jj <- sign(v)
-        mw[r] = fminf(mw[r], w);
-        ms[r] = fminf(ms[r], sp);
+        acc[r] = 0u;
+        mv[r] = 3.0e38f;
       }
-    }
-    const uint32_t valid = (cb + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - cb)) - 1u);
+#pragma unroll(R >= 4 ? 2 : 4)
+      for (int jj = 31; jj >= 0; --jj) {
+        const float4 sj = cs[st][wj * 32 + jj];
+        const float4 tj = ct[st][wj * 32 + jj];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = irow[r];
-      if (i >= row_end) continue;
-      const uint32_t upper = (i < cb) ? 0xFFFFFFFFu : ((i >= cb + 31) ? 0u : (0xFFFFFFFFu << (i - cb + 1)));
-      const uint32_t live = valid & upper;
-      uint32_t word = acc[r] & live;
-      // rare: some pair of this word lies inside the FP32 error band -> exact FP64 re-evaluation
-      if (live != 0u && (!(mw[r] > c.w_thr) || !(ms[r] > 0.f))) {
-        uint32_t todo = live;
-        while (todo) {
-          const int b = __ffs(todo) - 1;
-          todo &= todo - 1;
-          float v, w, sp;
-          pair_eval(si[r], ti[r], cs[wj * 32 + b], ct[wj * 32 + b], c, v, w, sp);
-          if (!(w > c.w_thr) || !(sp > 0.f)) {
-            ++nborder;
-            const bool in = exact_consistent(src64, dst64, i, cb + b, c.beta);
-            word = in ? (word | (1u << b)) : (word & ~(1u << b));
-          }
+        for (int r = 0; r < R; ++r) {
+          const float v = pair_fast(ms[r], mt[r], sj, tj, two_beta2, beta4);
+          acc[r] = __funnelshift_l(__float_as_uint(v), acc[r], 1);  // bit jj <- sign(v)
+          mv[r] = fminf(mv[r], fabsf(v));
         }
       }
-      mask[(size_t)i * stride + (cb >> 5)] = word;
-      cnt[r] += __popc(word);
+      const uint32_t valid = (cb + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - cb)) - 1u);
+      const float4 sl = cs[st][wj * 32 + lane];  // this lane's column of the word (slow path only)
+      const float4 tl = ct[st][wj * 32 + lane];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = irow[r];
+        const bool row_ok = i < row_end;
+        const uint32_t upper = (i < cb) ? 0xFFFFFFFFu : ((i >= cb + 31) ? 0u : (0xFFFFFFFFu << (i - cb + 1)));
+        const uint32_t live = row_ok ? (valid & upper) : 0u;
+        uint32_t word = acc[r] & live;
+        // rare: some pair of this word is one the fast path cannot vouch for -> warp-cooperative redo
+        unsigned int flagged = __ballot_sync(0xffffffffu, live != 0u && !(mv[r] > t_fast));
+        while (flagged) {
+          const int owner = __ffs(flagged) - 1;
+          flagged &= flagged - 1;
+          const int oi = __shfl_sync(0xffffffffu, i, owner);
+          const uint32_t res = slow_word_coop(job, oi, cb, sl, tl, nborder);
+          if (lane == owner) word = res & live;
+        }
+        if (row_ok) {
+          mask[(size_t)i * stride + (cb >> 5)] = word;
+          cnt[r] += __popc(word);
+        }
+      }
     }
+    __syncthreads();  // every warp is done with stage st
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -226,8 +278,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_mask_kernel(const K1Job* __rest
 __global__ void pack_points_kernel(const double* __restrict__ pts, int n, double cx, double cy, double cz,
                                    float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n)
-    out[i] = make_float4((float)(pts[3 * i] - cx), (float)(pts[3 * i + 1] - cy), (float)(pts[3 * i + 2] - cz), 0.f);
+  if (i < n) out[i] = pack_point(pts[3 * i] - cx, pts[3 * i + 1] - cy, pts[3 * i + 2] - cz);
 }
 
 // mirror the upper triangle into the lower one: one warp per 32x32 bit block (bi >= bj)
@@ -344,28 +395,48 @@ K1Consts make_k1_consts(double beta, double coord_bound) {
   k.kappa = (float)(kappa * 1.0001);
   k.w_thr = (float)(kappa * cc * 1.01 + 1e-30);
   k.beta = beta;
+  // fast (norm-form) path, DESIGN.md "K1 fast-path threshold"
+  const double C2 = cmax * cmax;
+  const double E = 80.0 * mu * C2;                 // |A_c - A*|, |B_c - B*|
+  const double ED = 2.0 * E + 12.0 * mu * C2;      // |D_c - D*|
+  const double ES = 2.0 * E + 24.0 * mu * C2;      // |S_c - S*|
+  const double c0 = ED * ED + 2.0 * b2 * ES + 2.0 * mu * (48.0 * b2 * C2 + b2 * b2);
+  const double Dlim = ED + sqrt(ED * ED + 48.0 * b2 * C2 + c0);
+  const double Terr = 2.0 * Dlim * ED + c0;
+  k.beta4 = (float)(b2 * b2);
+  // a + b <= beta (where the sign of v is not the answer) implies S* <= beta^2, hence v* in
+  // [-beta^4, 2 beta^4]: one threshold on |v| covers both the rounding band and that case
+  k.t_fast = (float)((Terr + 2.0 * b2 * b2) * 1.05 + 1e-30);
   return k;
+}
+
+template <int R, int TJ>
+static int launch_k1_variant(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows) {
+  constexpr int TI = K1_THREADS * R;
+  const int n_tiles = (max_n + TJ - 1) / TJ;
+  const int row_blocks = (max_rows + TI - 1) / TI;
+  // column tiles per CTA: long-lived CTAs amortise their prologue, but keep the grid many waves deep
+  const double live_tiles = 0.55 * (double)n_tiles * row_blocks * n_jobs;
+  int tpc = (int)(live_tiles / (148.0 * 3.0 * 12.0));  // ~12 waves of resident CTAs: short tail
+  if (tpc < 1) tpc = 1;
+  if (tpc > 16) tpc = 16;
+  if (tpc > n_tiles) tpc = n_tiles;
+  dim3 grid((n_tiles + tpc - 1) / tpc, row_blocks, n_jobs);
+  k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs, tpc);
+  PSU_CHECK_LAUNCH("k1_mask_kernel");
+  return PSULVSB_OK;
 }
 
 int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows) {
   if (n_jobs <= 0 || max_n < 1 || max_rows < 1) return PSULVSB_OK;
-  // tile shape: small problems want many CTAs, large ones want register/smem reuse
-  const long long pairs = (long long)max_rows * max_n;
-  if (pairs >= (1ll << 28)) {
-    constexpr int R = 4, TJ = 256;
-    dim3 grid((max_n + TJ - 1) / TJ, (max_rows + K1_THREADS * R - 1) / (K1_THREADS * R), n_jobs);
-    k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs);
-  } else if (pairs >= (1ll << 25) || n_jobs >= 8) {
-    constexpr int R = 2, TJ = 128;
-    dim3 grid((max_n + TJ - 1) / TJ, (max_rows + K1_THREADS * R - 1) / (K1_THREADS * R), n_jobs);
-    k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs);
-  } else {
-    constexpr int R = 1, TJ = 128;
-    dim3 grid((max_n + TJ - 1) / TJ, (max_rows + K1_THREADS * R - 1) / (K1_THREADS * R), n_jobs);
-    k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs);
-  }
-  PSU_CHECK_LAUNCH("k1_mask_kernel");
-  return PSULVSB_OK;
+  // rows per thread by the amount of work: R = 4 / 2 want enough row blocks x tiles to fill the GPU
+  const double pairs = 0.5 * (double)max_rows * max_n * n_jobs;
+  static const char* force = getenv("PSULVSB_K1_VARIANT");
+  int variant = pairs >= 3.0e9 ? 4 : (pairs >= 2.0e8 ? 2 : 1);
+  if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) variant = force[0] - '0';
+  if (variant == 4) return launch_k1_variant<4, 128>(st, d_jobs, n_jobs, max_n, max_rows);
+  if (variant == 2) return launch_k1_variant<2, 128>(st, d_jobs, n_jobs, max_n, max_rows);
+  return launch_k1_variant<1, 128>(st, d_jobs, n_jobs, max_n, max_rows);
 }
 
 int launch_pack_points(cudaStream_t st, const double* pts, int n, const double center[3], float4* out) {
