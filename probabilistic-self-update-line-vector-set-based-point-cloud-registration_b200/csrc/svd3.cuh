@@ -55,80 +55,91 @@ __device__ inline void kabsch_rotation(const double Hin[3][3], double R[3][3], d
         V[i][j] = (i == j) ? 1.0 : 0.0;
       }
   }
-  const double eps = 2.220446049250313e-16;
+  // FP64 latency, not throughput, is what the single thread running this pays, so the rotation is
+  // derived with the shortest dependent chain: one rsqrt gives 1/h, from which t and c follow side
+  // by side (no sqrt(alpha beta) in the convergence test, no rsqrt(1 + t^2) after t).
+  const double eps2 = 4.930380657631324e-32;  // (2^-52)^2
   for (int sweep = 0; sweep < 30; ++sweep) {
     bool rotated = false;
 #pragma unroll
     for (int pq = 0; pq < 3; ++pq) {
       const int p = (pq == 2) ? 1 : 0;
       const int q = (pq == 0) ? 1 : 2;
-      const double alpha = A[0][p] * A[0][p] + A[1][p] * A[1][p] + A[2][p] * A[2][p];
-      const double beta = A[0][q] * A[0][q] + A[1][q] * A[1][q] + A[2][q] * A[2][q];
-      const double gamma = A[0][p] * A[0][q] + A[1][p] * A[1][q] + A[2][p] * A[2][q];
-      if (fabs(gamma) > eps * sqrt(alpha * beta) && fabs(gamma) > 1e-300) {
+      const double alpha = fma(A[2][p], A[2][p], fma(A[1][p], A[1][p], A[0][p] * A[0][p]));
+      const double beta = fma(A[2][q], A[2][q], fma(A[1][q], A[1][q], A[0][q] * A[0][q]));
+      const double gamma = fma(A[2][p], A[2][q], fma(A[1][p], A[1][q], A[0][p] * A[0][q]));
+      if (gamma * gamma > eps2 * (alpha * beta) && fabs(gamma) > 1e-300) {
         rotated = true;
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = rsqrt(1.0 + t * t);
-        const double s = c * t;
+        const double tau = beta - alpha, g = 2.0 * gamma;
+        const double h2 = fma(tau, tau, g * g);
+        const double ih = rsqrt(h2);
+        const double h = h2 * ih;
+        const double t = g / (tau + copysign(h, tau));       // smaller root of t^2 + 2 (tau / g) t - 1 = 0
+        const double c = sqrt(fma(0.5 * fabs(tau), ih, 0.5));  // cos: c^2 = (1 + |tau| / h) / 2
+        const double sn = c * t;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const double ap = A[k][p], aq = A[k][q];
-          A[k][p] = c * ap - s * aq;
-          A[k][q] = s * ap + c * aq;
+          A[k][p] = fma(c, ap, -sn * aq);
+          A[k][q] = fma(sn, ap, c * aq);
           const double vp = V[k][p], vq = V[k][q];
-          V[k][p] = c * vp - s * vq;
-          V[k][q] = s * vp + c * vq;
+          V[k][p] = fma(c, vp, -sn * vq);
+          V[k][q] = fma(sn, vp, c * vq);
         }
       }
     }
     if (!rotated) break;
   }
-  if (Vw) {
-    // keep V orthonormal over many warm-started solves (one Gram-Schmidt pass; the drift per solve is O(eps))
-    double n0 = rsqrt(V[0][0] * V[0][0] + V[1][0] * V[1][0] + V[2][0] * V[2][0]);
+  double a2[3], v2[3], ia[3], iv[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) Vw[k][0] = V[k][0] * n0;
-    double d01 = Vw[0][0] * V[0][1] + Vw[1][0] * V[1][1] + Vw[2][0] * V[2][1];
+  for (int j = 0; j < 3; ++j) {
+    a2[j] = fma(A[2][j], A[2][j], fma(A[1][j], A[1][j], A[0][j] * A[0][j]));
+    v2[j] = fma(V[2][j], V[2][j], fma(V[1][j], V[1][j], V[0][j] * V[0][j]));
+    ia[j] = a2[j] > 0.0 ? rsqrt(a2[j]) : 0.0;
+    iv[j] = rsqrt(v2[j]);
+  }
+  if (Vw) {
+    // warm start for the next solve: the normalised V (orthonormal up to rounding; re-orthogonalised
+    // by one Gram-Schmidt pass so that the drift cannot accumulate over a hundred warm-started solves)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Vw[k][0] = V[k][0] * iv[0];
+    const double d01 = (Vw[0][0] * V[0][1] + Vw[1][0] * V[1][1] + Vw[2][0] * V[2][1]) * iv[1];
     double c1[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) c1[k] = V[k][1] - d01 * Vw[k][0];
-    double n1 = rsqrt(c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2]);
+    for (int k = 0; k < 3; ++k) c1[k] = fma(V[k][1], iv[1], -d01 * Vw[k][0]);
+    const double n1 = rsqrt(c1[0] * c1[0] + c1[1] * c1[1] + c1[2] * c1[2]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) Vw[k][1] = c1[k] * n1;
-    // third column: +- cross(v0, v1), sign of the current third column
-    double cx = Vw[1][0] * Vw[2][1] - Vw[2][0] * Vw[1][1];
-    double cy = Vw[2][0] * Vw[0][1] - Vw[0][0] * Vw[2][1];
-    double cz = Vw[0][0] * Vw[1][1] - Vw[1][0] * Vw[0][1];
+    const double cx = Vw[1][0] * Vw[2][1] - Vw[2][0] * Vw[1][1];
+    const double cy = Vw[2][0] * Vw[0][1] - Vw[0][0] * Vw[2][1];
+    const double cz = Vw[0][0] * Vw[1][1] - Vw[1][0] * Vw[0][1];
     const double sg = (cx * V[0][2] + cy * V[1][2] + cz * V[2][2]) < 0.0 ? -1.0 : 1.0;
     Vw[0][2] = sg * cx;
     Vw[1][2] = sg * cy;
     Vw[2][2] = sg * cz;
   }
-  double sig[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) sig[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
-  // order the triplets by descending sigma (indices only)
+  // order the triplets by descending sigma_j = |A_j| / |V_j| (indices only, compared cross-multiplied)
   int i0 = 0, i1 = 1, i2 = 2;
-  if (sig[i0] < sig[i1]) { int t = i0; i0 = i1; i1 = t; }
-  if (sig[i1] < sig[i2]) { int t = i1; i1 = i2; i2 = t; }
-  if (sig[i0] < sig[i1]) { int t = i0; i0 = i1; i1 = t; }
+  auto less = [&](int x, int y) { return a2[x] * v2[y] < a2[y] * v2[x]; };
+  if (less(i0, i1)) { int t = i0; i0 = i1; i1 = t; }
+  if (less(i1, i2)) { int t = i1; i1 = i2; i2 = t; }
+  if (less(i0, i1)) { int t = i0; i0 = i1; i1 = t; }
   double U[3][3];  // columns: left singular vectors, in the order (i0, i1, i2)
   double Vs[3][3];
-  const double tiny = 1e-14 * sig[i0];
-  // first two columns
+  // sigma_x > 1e-14 sigma_0  <=>  a2[x] v2[i0] > 1e-28 a2[i0] v2[x]
+  const bool ok1 = a2[i1] * v2[i0] > 1e-28 * (a2[i0] * v2[i1]);
+  const bool ok2 = a2[i2] * v2[i0] > 1e-28 * (a2[i0] * v2[i2]);
   {
-    const double n0 = sig[i0];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      U[k][0] = A[k][i0] / n0;
-      Vs[k][0] = V[k][i0];
-      Vs[k][1] = V[k][i1];
-      Vs[k][2] = V[k][i2];
+      U[k][0] = A[k][i0] * ia[i0];
+      Vs[k][0] = V[k][i0] * iv[i0];
+      Vs[k][1] = V[k][i1] * iv[i1];
+      Vs[k][2] = V[k][i2] * iv[i2];
     }
-    if (sig[i1] > tiny) {
+    if (ok1) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) U[k][1] = A[k][i1] / sig[i1];
+      for (int k = 0; k < 3; ++k) U[k][1] = A[k][i1] * ia[i1];
     } else {
       // rank 1: any unit vector orthogonal to u0 (the reference's completion is arbitrary too)
       double ax = fabs(U[0][0]), ay = fabs(U[1][0]), az = fabs(U[2][0]);
@@ -140,9 +151,9 @@ __device__ inline void kabsch_rotation(const double Hin[3][3], double R[3][3], d
 #pragma unroll
       for (int k = 0; k < 3; ++k) U[k][1] = w[k] / nw;
     }
-    if (sig[i2] > tiny) {
+    if (ok2) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) U[k][2] = A[k][i2] / sig[i2];
+      for (int k = 0; k < 3; ++k) U[k][2] = A[k][i2] * ia[i2];
     } else {
       U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
       U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
