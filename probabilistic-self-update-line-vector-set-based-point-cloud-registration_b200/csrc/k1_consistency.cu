@@ -136,7 +136,7 @@ __device__ __noinline__ uint32_t slow_word_coop(const K1Job& job, int i, int cb,
 // as zeros; tiles entirely below it are not touched (callers that need them defined clear the mask
 // first -- psulvsb_consistency_mask does, the engine never reads them).
 template <int R, int TJ>
-__global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 3 : (R == 2 ? 3 : 4)))
+__global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R == 2 ? 3 : 4)))
     k1_mask_kernel(const K1Job* __restrict__ jobs, int tiles_per_cta) {
   const K1Job& job = jobs[blockIdx.z];
   if (!job.active) return;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 3 : (R == 2 ? 3 : 4)))
         acc[r] = 0u;
         mv[r] = 3.0e38f;
       }
-#pragma unroll(R >= 4 ? 2 : 4)
+#pragma unroll 4
       for (int jj = 31; jj >= 0; --jj) {
         const float4 sj = cs[st][wj * 32 + jj];
         const float4 tj = ct[st][wj * 32 + jj];
@@ -432,7 +432,9 @@ int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, in
   // rows per thread by the amount of work: R = 4 / 2 want enough row blocks x tiles to fill the GPU
   const double pairs = 0.5 * (double)max_rows * max_n * n_jobs;
   static const char* force = getenv("PSULVSB_K1_VARIANT");
-  int variant = pairs >= 3.0e9 ? 4 : (pairs >= 2.0e8 ? 2 : 1);
+  // measured on B200: R = 4 wins on long row ranges (N = 100k: 0.68 of the FP32-pipe peak vs 0.57),
+  // R = 2 on batches of 5k-point problems (0.52 vs 0.49: 1024-row blocks waste more of the diagonal)
+  int variant = (max_rows >= 16384 && pairs >= 1.0e9) ? 4 : (pairs >= 2.0e8 ? 2 : 1);
   if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) variant = force[0] - '0';
   if (variant == 4) return launch_k1_variant<4, 128>(st, d_jobs, n_jobs, max_n, max_rows);
   if (variant == 2) return launch_k1_variant<2, 128>(st, d_jobs, n_jobs, max_n, max_rows);

@@ -66,13 +66,17 @@ __global__ void __launch_bounds__(SB_THREADS)
     score_batch_kernel(const float4* __restrict__ srcf, const float4* __restrict__ dstf,
                        const double* __restrict__ src64, const double* __restrict__ dst64, int n,
                        const double* __restrict__ hyp, unsigned long long n_hyp, unsigned long long hyp_begin,
-                       ScoreArgs a, uint32_t* __restrict__ counts, unsigned long long* __restrict__ best,
+                       ScoreArgs a, int chunk_points, uint32_t* __restrict__ counts,
                        unsigned long long* __restrict__ border_count) {
   __shared__ __align__(128) float4 ps[2][SB_TP];
   __shared__ __align__(128) float4 qs[2][SB_TP];
   __shared__ __align__(8) uint64_t bar[2];
-  __shared__ unsigned long long warp_best[SB_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // this CTA's slice of the correspondences (grid.y): many short CTAs instead of a few long ones
+  const int p_lo = blockIdx.y * chunk_points;
+  const int p_hi = min(n, p_lo + chunk_points);
+  if (p_lo >= p_hi) return;
+  const int np_chunk = p_hi - p_lo;
   const unsigned long long h0 = ((unsigned long long)blockIdx.x * SB_THREADS + tid) * SB_HPT;
 
   // ---- hypotheses -> registers: Rf = s R, tf = s (R c_src + t) - c_dst  (centred coordinates)
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(SB_THREADS)
     }
   }
 
-  const int ntiles = (n + SB_TP - 1) / SB_TP;
+  const int ntiles = (np_chunk + SB_TP - 1) / SB_TP;
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -117,8 +121,9 @@ __global__ void __launch_bounds__(SB_THREADS)
   __syncthreads();
   auto issue = [&](int tile) {
     const int st = tile & 1;
-    const int p0 = tile * SB_TP;
-    const uint32_t bytes = (uint32_t)min(SB_TP, n - p0) * (uint32_t)sizeof(float4);
+    const int p0 = p_lo + tile * SB_TP;
+    const uint32_t bytes = (uint32_t)min(SB_TP, p_hi - p0) * (uint32_t)sizeof(float4);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&bar[st], 2 * bytes);
     tma_load_1d(ps[st], srcf + p0, bytes, &bar[st]);
     tma_load_1d(qs[st], dstf + p0, bytes, &bar[st]);
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(SB_THREADS)
   for (int tile = 0; tile < ntiles; ++tile) {
     const int st = tile & 1;
     mbar_wait(&bar[st], (tile >> 1) & 1);
-    const int np = min(SB_TP, n - tile * SB_TP);
+    const int np = min(SB_TP, np_chunk - tile * SB_TP);
 #pragma unroll 4
     for (int j = 0; j < np; ++j) {
       const float4 p = ps[st][j];
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(SB_THREADS)
         for (int c = 0; c < 3; ++c) R[r * 3 + c] = H[c * 3 + r];
         t[r] = H[9 + r];
       }
-      for (int j = 0; j < n; ++j) {
+      for (int j = p_lo; j < p_hi; ++j) {
         const float4 p = srcf[j];
         const float4 q = dstf[j];
         const float d0 = fmaf(Rf[k][0], p.x, fmaf(Rf[k][1], p.y, fmaf(Rf[k][2], p.z, tf[k][0] - q.x)));
@@ -178,17 +183,28 @@ __global__ void __launch_bounds__(SB_THREADS)
     }
   }
 
-  // ---- outputs: counts, then warp -> block -> grid argmax (first best hypothesis wins)
-  unsigned long long mybest = 0ull;
+  // ---- outputs: this chunk's contribution to the counts (the argmax runs once all chunks are in)
 #pragma unroll
   for (int k = 0; k < SB_HPT; ++k) {
     const unsigned long long h = h0 + k;
-    if (h < n_hyp) {
-      counts[h] = (uint32_t)cnt[k];
-      const unsigned long long key =
-          ((unsigned long long)(uint32_t)cnt[k] << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(hyp_begin + h));
-      mybest = key > mybest ? key : mybest;
-    }
+    if (h < n_hyp && cnt[k] != 0) atomicAdd(&counts[h], (uint32_t)cnt[k]);
+  }
+  const unsigned int nb = (unsigned int)warp_sum_int((int)nborder);
+  if (lane == 0 && nb && border_count) atomicAdd(border_count, (unsigned long long)nb);
+}
+
+// warp -> block -> grid argmax of (count, hypothesis) packed in 64 bits: the first best hypothesis wins
+__global__ void __launch_bounds__(256)
+    argmax_counts_kernel(const uint32_t* __restrict__ counts, unsigned long long n_hyp, unsigned long long hyp_begin,
+                         unsigned long long* __restrict__ best) {
+  __shared__ unsigned long long warp_best[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long mybest = 0ull;
+  for (unsigned long long h = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; h < n_hyp;
+       h += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long key =
+        ((unsigned long long)counts[h] << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(hyp_begin + h));
+    mybest = key > mybest ? key : mybest;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -196,13 +212,11 @@ __global__ void __launch_bounds__(SB_THREADS)
     mybest = x > mybest ? x : mybest;
   }
   if (lane == 0) warp_best[wid] = mybest;
-  const unsigned int nb = (unsigned int)warp_sum_int((int)nborder);
-  if (lane == 0 && nb && border_count) atomicAdd(border_count, (unsigned long long)nb);
   __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     unsigned long long b = warp_best[0];
-    for (int w = 1; w < SB_THREADS / 32; ++w) b = warp_best[w] > b ? warp_best[w] : b;
-    if (best) atomicMax(best, b);
+    for (int w = 1; w < 8; ++w) b = warp_best[w] > b ? warp_best[w] : b;
+    if (b) atomicMax(best, b);
   }
 }
 
@@ -292,10 +306,26 @@ int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, co
   }
   a.coord_bound = (float)(coord_bound * 1.0000002);
   const unsigned long long per_cta = (unsigned long long)SB_THREADS * SB_HPT;
-  const unsigned long long grid = (n_hyp + per_cta - 1) / per_cta;
-  score_batch_kernel<<<(unsigned)grid, SB_THREADS, 0, st>>>(src, dst, src64, dst64, n, hyp, n_hyp, hyp_begin, a, counts,
-                                                            best, border);
+  const unsigned long long gx = (n_hyp + per_cta - 1) / per_cta;
+  // slice the correspondences too until the grid is ~10 waves deep (2 CTAs per SM), >= 8 tiles per slice
+  unsigned long long chunks = (148ull * 2ull * 10ull + gx - 1) / gx;
+  const unsigned long long max_chunks = ((unsigned long long)n + 8 * SB_TP - 1) / (8 * SB_TP);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  int chunk_points = (int)(((unsigned long long)n + chunks - 1) / chunks);
+  chunk_points = (chunk_points + SB_TP - 1) / SB_TP * SB_TP;  // tile-aligned: every bulk copy stays 16-byte aligned
+  const unsigned gy = (unsigned)((n + chunk_points - 1) / chunk_points);
+  PSU_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * n_hyp, st));
+  score_batch_kernel<<<dim3((unsigned)gx, gy), SB_THREADS, 0, st>>>(src, dst, src64, dst64, n, hyp, n_hyp, hyp_begin, a,
+                                                                     chunk_points, counts, border);
   PSU_CHECK_LAUNCH("score_batch_kernel");
+  if (best) {
+    unsigned long long ga = (n_hyp + 255) / 256;
+    if (ga > 148 * 8) ga = 148 * 8;
+    argmax_counts_kernel<<<(unsigned)ga, 256, 0, st>>>(counts, n_hyp, hyp_begin, best);
+    PSU_CHECK_LAUNCH("argmax_counts_kernel");
+  }
   return PSULVSB_OK;
 }
 

@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: libpsulvsb_b200.so loads without a GPU, exports every
+symbol include/psulvsb.h declares, reports errors as codes, and the ctypes structs match the header."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import psulvsb_b200  # noqa: F401
+from psulvsb_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "psulvsb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(psulvsb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_functions()
+    assert len(names) >= 25
+    lib = C.CDLL(capi.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(capi.SYMBOLS) == names          # the Python binding covers the whole header
+
+
+def test_version_defaults_and_no_device_behaviour():
+    L = capi.lib()
+    assert L.psulvsb_version() == 100
+    p = capi.default_params()
+    # RobustRegistrationSolver::Params defaults (registration.h:383-426) and the lifted constants
+    assert p.noise_bound == 0.01 and p.cbar2 == 1 and p.estimate_scaling == 1
+    assert p.rotation_max_iterations == 100 and p.rotation_gnc_factor == 1.4 and p.rotation_cost_threshold == 1e-6
+    assert p.inloop_noise_bound == 0.05 and p.inloop_cost_threshold == 0.005 and p.host_round_limit == 5
+    assert p.tpro_host == 0.99 and p.tpro_local == 0.99 and p.local_max_iter == 10 and p.wallclock_cap_s == 60.0
+    if L.psulvsb_device_count() == 0:
+        # no CPU fallback: every compute entry point fails loudly with PSULVSB_ERR_NO_DEVICE
+        h = C.c_void_p()
+        assert L.psulvsb_create(C.byref(h), 0) == capi.ERR_NO_DEVICE
+        assert b"no CUDA device" in L.psulvsb_last_error()
+        assert L.psulvsb_philox_fill(None, 0, 1, 0, 0, 4, None) == capi.ERR_NO_DEVICE
+        with pytest.raises(capi.PsulvsbError):
+            capi.Handle(0)
+
+
+def test_struct_layouts_match_the_oracle_mirror():
+    """psulvsb_params_t / solution prefix / trace records are field-for-field the oracle's structs, so a
+    trace from either solver can be compared directly."""
+    from oracle import oracle as O
+
+    assert [f[0] for f in capi.Params._fields_] == [f[0] for f in O.Params._fields_]
+    assert C.sizeof(capi.Params) == C.sizeof(O.Params)
+    n = len(O.Solution._fields_)
+    assert [f[0] for f in capi.Solution._fields_][:n] == [f[0] for f in O.Solution._fields_]
+    assert C.sizeof(capi.LocalTrace) == C.sizeof(O.LocalTrace) == 176
+    assert C.sizeof(capi.HostTrace) == C.sizeof(O.HostTrace) == 32
+
+
+def test_host_problem_layout():
+    src = np.arange(12, dtype=np.float64).reshape(3, 4)
+    hp = capi.HostProblem(src, src + 1)
+    ps = hp.c_struct()
+    assert ps.C == 4 and ps.M == 4
+    assert [ps.src[i] for i in range(6)] == [0, 4, 8, 1, 5, 9]      # column-major 3xN, as Eigen stores it
+    assert list(hp.keep_mask) == [1, 1, 1, 1] and list(hp.reduce_map) == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        capi.HostProblem(np.zeros((4, 3)), np.zeros((4, 3)))
+    with pytest.raises(ValueError):
+        capi.HostProblem(np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((3, 9)), np.zeros((3, 9)))
+
+
+def test_mirror_params_defaults():
+    from psulvsb_b200 import RobustRegistrationSolver as S
+
+    p = S.Params()
+    assert p.noise_bound == 0.01 and p.estimate_scaling is True and p.rotation_gnc_factor == 1.4
+    assert p.rotation_estimation_algorithm == S.ROTATION_ESTIMATION_ALGORITHM.GNC_TLS
+    assert p.inlier_selection_mode == S.INLIER_SELECTION_MODE.PMC_EXACT
+    assert int(S.INLIER_SELECTION_MODE.NONE) == 3
