@@ -300,6 +300,7 @@ int psulvsb_gnc_tls_rotation(void* stream, const double* d_src64, const double* 
   if (!d_src64 || !d_dst64 || (!d_edges_uint2 && K) || !d_R || (!d_weights && K))
     return fail(PSULVSB_ERR_INVALID, "psulvsb_gnc_tls_rotation: NULL array");
   if (max_iterations < 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_gnc_tls_rotation: max_iterations < 0");
+  if (K >= 0x7FFFFFF0ull) return fail(PSULVSB_ERR_UNSUPPORTED, "psulvsb_gnc_tls_rotation: K must fit 31 bits");
   cudaStream_t st = (cudaStream_t)stream;
   GncJob j;
   std::memset(&j, 0, sizeof(j));

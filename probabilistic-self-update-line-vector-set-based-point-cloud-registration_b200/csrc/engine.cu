@@ -486,7 +486,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       }
     }
   }
-  if (max_cap >= 0xFFFFFFF0ull) return fail(PSULVSB_ERR_UNSUPPORTED, "reduced set exceeds 32-bit sampling indices");
+  if (max_cap >= 0x7FFFFFF0ull) return fail(PSULVSB_ERR_UNSUPPORTED, "reduced set exceeds the 31-bit sample / line-vector indices");
   PSU_CUDA(cudaMemcpyAsync(m.cj, cj.data(), sizeof(CompactJob) * (size_t)B, cudaMemcpyHostToDevice, st));
   PSU_CUDA(cudaMemcpyAsync(m.jobs, jobs.data(), sizeof(JobCtl) * (size_t)B, cudaMemcpyHostToDevice, st));
   if (int rc = launch_compact_edges(st, m.cj, B, maxC, false, true)) return rc;

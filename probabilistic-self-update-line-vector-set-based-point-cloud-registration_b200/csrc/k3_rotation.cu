@@ -270,66 +270,69 @@ __global__ void __launch_bounds__(GNC_THREADS, 2) gnc_tls_kernel(const GncJob* _
       }
       return wn;
     };
-    // (a) shared-memory resident part
+    // (a) shared-memory resident part (32-bit indices, one base pointer per component)
     {
-      unsigned long long l = tid;
-      for (; l + GNC_THREADS < ncached; l += 2 * GNC_THREADS) {
+      const int nc = (int)ncached;
+      double* __restrict__ ws = lv + 6 * cap;
+      int l = tid;
+      for (; l + GNC_THREADS < nc; l += 2 * GNC_THREADS) {
         double sa[3], ta[3], sb[3], tb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          sa[r] = lv[(size_t)r * cap + l];
-          ta[r] = lv[(size_t)(3 + r) * cap + l];
-          sb[r] = lv[(size_t)r * cap + l + GNC_THREADS];
-          tb[r] = lv[(size_t)(3 + r) * cap + l + GNC_THREADS];
+          sa[r] = lv[r * (int)cap + l];
+          ta[r] = lv[(3 + r) * (int)cap + l];
+          sb[r] = lv[r * (int)cap + l + GNC_THREADS];
+          tb[r] = lv[(3 + r) * (int)cap + l + GNC_THREADS];
         }
-        const double wa = lv[6 * cap + l], wb = lv[6 * cap + l + GNC_THREADS];
-        lv[6 * cap + l] = body(sa, ta, wa);
-        lv[6 * cap + l + GNC_THREADS] = body(sb, tb, wb);
+        const double wa = ws[l], wb = ws[l + GNC_THREADS];
+        ws[l] = body(sa, ta, wa);
+        ws[l + GNC_THREADS] = body(sb, tb, wb);
       }
-      for (; l < ncached; l += GNC_THREADS) {
+      for (; l < nc; l += GNC_THREADS) {
         double sa[3], ta[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          sa[r] = lv[(size_t)r * cap + l];
-          ta[r] = lv[(size_t)(3 + r) * cap + l];
+          sa[r] = lv[r * (int)cap + l];
+          ta[r] = lv[(3 + r) * (int)cap + l];
         }
-        lv[6 * cap + l] = body(sa, ta, lv[6 * cap + l]);
+        ws[l] = body(sa, ta, ws[l]);
       }
     }
     // (b) HBM/L2 scratch part: all loads of two line vectors in flight before the arithmetic
-    const unsigned long long g_hi = (k_hi < lv_cap) ? nloc : ((lv_cap > k_lo) ? lv_cap - k_lo : 0ull);  // local end
+    const unsigned long long g_hi64 = (k_hi <= lv_cap) ? nloc : ((lv_cap > k_lo) ? lv_cap - k_lo : 0ull);
     {
-      unsigned long long l = ncached + tid;
+      const int g_hi = (int)g_hi64, nl = (int)nloc;
+      const double* __restrict__ g0 = lvg + k_lo;  // component r of local line vector l: g0[r * lv_cap + l]
+      double* __restrict__ gwl = gw + k_lo;
+      const size_t st = (size_t)lv_cap;
+      int l = (int)ncached + tid;
       for (; l + GNC_THREADS < g_hi; l += 2 * GNC_THREADS) {
-        const unsigned long long ka = k_lo + l, kb = ka + GNC_THREADS;
         double sa[3], ta[3], sb[3], tb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          sa[r] = lvg[(size_t)r * lv_cap + ka];
-          ta[r] = lvg[(size_t)(3 + r) * lv_cap + ka];
-          sb[r] = lvg[(size_t)r * lv_cap + kb];
-          tb[r] = lvg[(size_t)(3 + r) * lv_cap + kb];
+          sa[r] = __ldcg(g0 + r * st + l);
+          ta[r] = __ldcg(g0 + (3 + r) * st + l);
+          sb[r] = __ldcg(g0 + r * st + l + GNC_THREADS);
+          tb[r] = __ldcg(g0 + (3 + r) * st + l + GNC_THREADS);
         }
-        const double wa = gw[ka], wb = gw[kb];
-        gw[ka] = body(sa, ta, wa);
-        gw[kb] = body(sb, tb, wb);
+        const double wa = __ldcg(gwl + l), wb = __ldcg(gwl + l + GNC_THREADS);
+        __stcg(gwl + l, body(sa, ta, wa));
+        __stcg(gwl + l + GNC_THREADS, body(sb, tb, wb));
       }
       for (; l < g_hi; l += GNC_THREADS) {
-        const unsigned long long ka = k_lo + l;
         double sa[3], ta[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          sa[r] = lvg[(size_t)r * lv_cap + ka];
-          ta[r] = lvg[(size_t)(3 + r) * lv_cap + ka];
+          sa[r] = __ldcg(g0 + r * st + l);
+          ta[r] = __ldcg(g0 + (3 + r) * st + l);
         }
-        gw[ka] = body(sa, ta, gw[ka]);
+        __stcg(gwl + l, body(sa, ta, __ldcg(gwl + l)));
       }
       // (c) beyond the scratch capacity: recompute from the points
-      for (; l < nloc; l += GNC_THREADS) {
-        const unsigned long long ka = k_lo + l;
+      for (; l < nl; l += GNC_THREADS) {
         double sa[3], ta[3];
-        load_lv(src, dst, edges[ka], job.inv_scale, sa, ta);
-        gw[ka] = body(sa, ta, gw[ka]);
+        load_lv(src, dst, edges[k_lo + l], job.inv_scale, sa, ta);
+        gwl[l] = body(sa, ta, gwl[l]);
       }
     }
     weights_are_unit = false;
