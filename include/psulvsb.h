@@ -56,7 +56,7 @@ enum {
 typedef struct psulvsb_params {
   double noise_bound;             /* registration.h:383                                         */
   double cbar2;                   /* registration.h:388                                         */
-  int estimate_scaling;           /* registration.h:396; 1 is PSULVSB_ERR_UNSUPPORTED this round */
+  int estimate_scaling;           /* registration.h:396; 1 = ratio histogram + TLS scale (:687-752, :958-983) */
   int rotation_max_iterations;    /* registration.h:416                                         */
   double rotation_gnc_factor;     /* registration.h:411                                         */
   double rotation_cost_threshold; /* registration.h:426                                         */

@@ -264,8 +264,6 @@ int Engine::solve(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb
                   psulvsb_trace_t* trace_first) {
   if (B <= 0) return fail(PSULVSB_ERR_INVALID, "solve: nothing uploaded");
   if (!params || !solutions) return fail(PSULVSB_ERR_INVALID, "solve: null params / solutions");
-  if (params->estimate_scaling)
-    return fail(PSULVSB_ERR_UNSUPPORTED, "estimate_scaling = 1 (unknown-scale path, registration.cc:958-983) is not built yet");
   if (params->host_round_limit < 0 || params->rotation_max_iterations < 0 || params->inloop_max_iterations < 0)
     return fail(PSULVSB_ERR_INVALID, "solve: negative iteration limits");
   for (int attempt = 0; attempt < 6; ++attempt) {
@@ -300,7 +298,11 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   std::vector<K1Job> k1((size_t)B);
   std::vector<CompactJob> cj((size_t)B);
   std::vector<PackJob> pj((size_t)2 * B);
+  const bool ratio = params->estimate_scaling != 0;  // unknown scale: ratio histogram instead of the bit mask
+  std::vector<RatioJob> rj(ratio ? (size_t)B : 0);
   struct Misc {
+    RatioJob* rj;
+    int* bad;
     K1Job* k1;
     CompactJob* cj;
     PackJob* pj;
@@ -328,6 +330,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       m.border = bm.take<unsigned long long>((size_t)B);
       m.n_done = bm.take<int>(4);
       m.sols = bm.take<psulvsb_solution_t>((size_t)B);
+      m.rj = bm.take<RatioJob>((size_t)B);
+      m.bad = bm.take<int>((size_t)B);
       if (pass == 0) {
         if (int rc = d_misc.ensure(bm.off)) return rc;
         bm.base = reinterpret_cast<char*>(d_misc.p);
@@ -373,6 +377,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.host_trace = bw.take<psulvsb_host_trace_t>((size_t)host_cap);
         J.local_trace_cap = local_cap;
         J.host_trace_cap = host_cap;
+        J.estimate_scaling = ratio ? 1 : 0;
         J.seed = seeds ? seeds[b] : params->seed + (uint64_t)b;
         const float a = 1 + (((float)L.C0) / (long)L.M);  // registration.cc:669 (float on purpose)
         J.tau = 2 * params->score_noise_bound * a;
@@ -388,9 +393,25 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         K.row_begin = 0;
         K.row_end = L.C0;
         K.c = make_k1_consts(2.0 * params->noise_bound * std::sqrt(params->cbar2), L.coord_bound);
-        K.mask = bk.take<uint32_t>((size_t)L.C0 * L.stride);
+        K.mask = ratio ? nullptr : bk.take<uint32_t>((size_t)L.C0 * L.stride);
         K.stride = L.stride;
         K.row_counts = bk.take<uint32_t>((size_t)L.C0);
+        if (ratio) {
+          RatioJob& Rj = rj[(size_t)b];
+          std::memset(&Rj, 0, sizeof(Rj));
+          Rj.src64 = J.src0;
+          Rj.dst64 = J.dst0;
+          Rj.n = L.C0;
+          Rj.pair_bin = bk.take<uint32_t>((size_t)L.C0 * (size_t)(L.C0 - 1) / 2 + 1);
+          Rj.hist = bk.take<unsigned int>(200000);
+          Rj.last = bk.take<unsigned long long>(200000);
+          Rj.peak = bk.take<unsigned int>(4);
+          Rj.class_counts = bk.take<unsigned int>((size_t)3 * L.C0);
+          Rj.class_offsets = bk.take<unsigned long long>((size_t)3 * L.C0 + 1);
+          Rj.n_edges = m.n_edges + b;
+          Rj.bad = m.bad + b;
+          Rj.active = 1;
+        }
         K.border = m.border + b;
         K.active = 1;
         CompactJob& Cj = cj[(size_t)b];
@@ -434,24 +455,45 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   PSU_CUDA(cudaMemcpyAsync(m.cj, cj.data(), sizeof(CompactJob) * (size_t)B, cudaMemcpyHostToDevice, st));
   PSU_CUDA(cudaMemcpyAsync(m.pj, pj.data(), sizeof(PackJob) * (size_t)2 * B, cudaMemcpyHostToDevice, st));
 
-  // ---- stage 1: float4 tiles, bit mask, row scan
-  {
-    dim3 grid((unsigned)((maxC + 255) / 256), (unsigned)(2 * B));
-    engine_pack_kernel<<<grid, 256, 0, st>>>(m.pj);
-    PSU_CHECK_LAUNCH("engine_pack_kernel");
+  // ---- stage 1: float4 tiles, bit mask, row scan  (unknown scale: ratio histogram, peak, class scan)
+  if (ratio) {
+    for (int b = 0; b < B; ++b) {
+      PSU_CUDA(cudaMemsetAsync(rj[(size_t)b].hist, 0, sizeof(unsigned int) * 200000, st));
+      PSU_CUDA(cudaMemsetAsync(rj[(size_t)b].last, 0, sizeof(unsigned long long) * 200000, st));
+    }
+    PSU_CUDA(cudaMemsetAsync(m.bad, 0, sizeof(int) * (size_t)B, st));
+    PSU_CUDA(cudaMemcpyAsync(m.rj, rj.data(), sizeof(RatioJob) * (size_t)B, cudaMemcpyHostToDevice, st));
+    PSU_CUDA(cudaEventRecord(ev_m0, st));
+    if (int rc = launch_ratio_reduced_set(st, m.rj, B, maxC, 0)) return rc;
+    PSU_CUDA(cudaEventRecord(ev_m1, st));
+    launches += 6;
+  } else {
+    {
+      dim3 grid((unsigned)((maxC + 255) / 256), (unsigned)(2 * B));
+      engine_pack_kernel<<<grid, 256, 0, st>>>(m.pj);
+      PSU_CHECK_LAUNCH("engine_pack_kernel");
+      ++launches;
+    }
+    PSU_CUDA(cudaEventRecord(ev_m0, st));
+    if (int rc = launch_consistency_mask(st, m.k1, B, maxC, maxC)) return rc;
+    PSU_CUDA(cudaEventRecord(ev_m1, st));
+    ++launches;
+    if (int rc = launch_compact_edges(st, m.cj, B, maxC, true, false)) return rc;
     ++launches;
   }
-  PSU_CUDA(cudaEventRecord(ev_m0, st));
-  if (int rc = launch_consistency_mask(st, m.k1, B, maxC, maxC)) return rc;
-  PSU_CUDA(cudaEventRecord(ev_m1, st));
-  ++launches;
-  if (int rc = launch_compact_edges(st, m.cj, B, maxC, true, false)) return rc;
-  ++launches;
-  if (int rc = h_small.ensure(sizeof(unsigned long long) * (size_t)B + 64)) return rc;
+  if (int rc = h_small.ensure((sizeof(unsigned long long) + sizeof(int)) * (size_t)B + 64)) return rc;
   unsigned long long* h_nedges = reinterpret_cast<unsigned long long*>(h_small.p);
   volatile int* h_done = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(h_small.p) + sizeof(unsigned long long) * (size_t)B);
+  int* h_bad = reinterpret_cast<int*>(reinterpret_cast<char*>(h_small.p) + sizeof(unsigned long long) * (size_t)B + 32);
   PSU_CUDA(cudaMemcpyAsync(h_nedges, m.n_edges, sizeof(unsigned long long) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (ratio) PSU_CUDA(cudaMemcpyAsync(h_bad, m.bad, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
   PSU_CUDA(cudaStreamSynchronize(st));
+  if (ratio)
+    for (int b = 0; b < B; ++b)
+      if (h_bad[b])
+        return fail(PSULVSB_ERR_UNSUPPORTED, "problem " + std::to_string(b) +
+                                                 ": a length ratio exceeds MaxScale = 10000 (registration.cc:714-718 would "
+                                                 "regrow the histogram mid-stream; coincident source points?)");
 
   // ---- edge arena, sized from the measured reduced-set sizes
   unsigned long long max_cap = 0, max_nred = 0;
@@ -475,6 +517,11 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         // covers the basic subsets up to the (0.5, 0.3) rate pair; the (1, 1) escalation recomputes the rest
         J.lv_cap = cap / 6 + 64;
         J.lv = be.take<double>((size_t)6 * J.lv_cap);
+        J.pruned_edges = ratio ? be.take<uint2>((size_t)cap) : nullptr;
+        if (ratio) {
+          rj[(size_t)b].edges = J.edges;
+          rj[(size_t)b].cap = cap;
+        }
         cj[(size_t)b].edges = J.edges;
         cj[(size_t)b].cap = cap;
         max_cap = cap > max_cap ? cap : max_cap;
@@ -487,9 +534,14 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     }
   }
   if (max_cap >= 0x7FFFFFF0ull) return fail(PSULVSB_ERR_UNSUPPORTED, "reduced set exceeds the 31-bit sample / line-vector indices");
-  PSU_CUDA(cudaMemcpyAsync(m.cj, cj.data(), sizeof(CompactJob) * (size_t)B, cudaMemcpyHostToDevice, st));
   PSU_CUDA(cudaMemcpyAsync(m.jobs, jobs.data(), sizeof(JobCtl) * (size_t)B, cudaMemcpyHostToDevice, st));
-  if (int rc = launch_compact_edges(st, m.cj, B, maxC, false, true)) return rc;
+  if (ratio) {
+    PSU_CUDA(cudaMemcpyAsync(m.rj, rj.data(), sizeof(RatioJob) * (size_t)B, cudaMemcpyHostToDevice, st));
+    if (int rc = launch_ratio_reduced_set(st, m.rj, B, maxC, 1)) return rc;
+  } else {
+    PSU_CUDA(cudaMemcpyAsync(m.cj, cj.data(), sizeof(CompactJob) * (size_t)B, cudaMemcpyHostToDevice, st));
+    if (int rc = launch_compact_edges(st, m.cj, B, maxC, false, true)) return rc;
+  }
   ++launches;
 
   EngineParams P;
@@ -532,6 +584,11 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       launches += 4;
     }
     if (int rc = launch_sample(st, m.sb, B, draws_bound)) return rc;
+    if (ratio) {
+      engine_scale_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.gj, P);
+      PSU_CHECK_LAUNCH("engine_scale_kernel");
+      ++launches;
+    }
     if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster)) return rc;
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");

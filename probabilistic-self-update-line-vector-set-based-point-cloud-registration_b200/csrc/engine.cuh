@@ -53,6 +53,24 @@ struct CompactJob {
   int active;
 };
 
+// unknown-scale stage 1 (k1_ratio.cu): ratio histogram and its three-bin reduced set
+struct RatioJob {
+  const double* src64;  // column-major 3 x n
+  const double* dst64;
+  int n;
+  uint32_t* pair_bin;                 // [n (n - 1) / 2] bin of every pair, row-major pair order
+  unsigned int* hist;                 // [200000], zero on entry
+  unsigned long long* last;           // [200000], zero on entry
+  unsigned int* peak;                 // [2]: max height, peak bin
+  unsigned int* class_counts;         // [3 n]
+  unsigned long long* class_offsets;  // [3 n + 1]
+  unsigned long long* n_edges;
+  uint2* edges;                       // NULL in phase 0
+  unsigned long long cap;
+  int* bad;                           // set to 1 when a ratio exceeds MaxScale
+  int active;
+};
+
 // ---- stage 2 --------------------------------------------------------------------------------
 struct SampleJob {
   uint64_t seed;
@@ -105,6 +123,7 @@ int launch_pack_points(cudaStream_t st, const double* pts, int n, const double c
 int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows);
 int launch_symmetrize(cudaStream_t st, uint32_t* mask, int n, int stride);
 int launch_compact_edges(cudaStream_t st, const CompactJob* d_jobs, int n_jobs, int max_n, bool scan, bool emit);
+int launch_ratio_reduced_set(cudaStream_t st, const RatioJob* d_jobs, int n_jobs, int max_n, int phase);
 
 // Draw budget for `count` distinct values out of n by rejection (mean + 8 sigma; coupon collector
 // tail for count == n).  Same formula on host and device so both agree on the stream window.

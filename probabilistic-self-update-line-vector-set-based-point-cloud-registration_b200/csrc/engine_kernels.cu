@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(BLK)
     xform_identity(J.last_best);
     J.new_corr_count = 0;
     J.inlier_map_size = 0;
+    J.scale_calls = 0;
+    J.n_pruned = 0;
+    J.cur_scale = 1.0;
     J.sample_status[0] = J.sample_status[1] = 1ull;
     J.n_local_trace = 0;
     J.n_host_trace = 0;
@@ -295,6 +298,133 @@ __global__ void __launch_bounds__(BLK)
 }
 
 // ------------------------------------------------------------------------------------------
+// unknown scale only: TLSScaleSolver on the basic subset (registration.cc:958-983 -> :397-415 ->
+// ScalarTLSEstimator::estimate, scale branch, :66-120), pruning to the scale inliers, and the
+// rotation-solve set-up that depends on the scale (registration.cc:1102-1108)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLK) engine_scale_kernel(JobCtl* __restrict__ jobs, GncJob* __restrict__ gj, EngineParams P) {
+  JobCtl& J = jobs[blockIdx.x];
+  if (J.phase != PHASE_LOCAL || !J.estimate_scaling) return;
+  __shared__ BlockScratch scratch;
+  __shared__ double est_s;
+  __shared__ int best_s, iter_s, done_s, base_s;
+  __shared__ unsigned long long k_s;
+  constexpr int G = 4;  // candidates evaluated per pass (their draws do not depend on the outcome)
+  const int tid = threadIdx.x;
+  const int K = J.basic_choose;
+  const uint2* __restrict__ edges = J.basic_edges;
+  double* __restrict__ X = J.weights;  // both arrays are dead again before the rotation solve starts
+  double* __restrict__ A = J.lv;
+  const double beta = 2.0 * J.cur.noise_bound * sqrt(J.cur.cbar2);
+  double scale = J.cur_scale;
+  int n_pruned = 0;
+  if (K > 0) {
+    for (int i = tid; i < K; i += BLK) {
+      const uint2 e = edges[i];
+      const double* sa = J.src + 3 * (size_t)e.x;
+      const double* sb = J.src + 3 * (size_t)e.y;
+      const double* ta = J.dst + 3 * (size_t)e.x;
+      const double* tb = J.dst + 3 * (size_t)e.y;
+      const double v1 = sqrt(sqnorm3(dsub(sb[0], sa[0]), dsub(sb[1], sa[1]), dsub(sb[2], sa[2])));
+      const double v2 = sqrt(sqnorm3(dsub(tb[0], ta[0]), dsub(tb[1], ta[1]), dsub(tb[2], ta[2])));
+      X[i] = v2 / v1;
+      A[i] = dmul(beta, 1.0 / v1);
+    }
+    if (tid == 0) {
+      est_s = scale;
+      best_s = 0;
+      iter_s = 0;
+      done_s = 0;
+      k_s = 0ull;
+    }
+    __syncthreads();
+    const uint32_t event = (uint32_t)J.scale_calls;
+    if (!J.first_time) {  // registration.cc:75-86: the last best scale is the first candidate
+      const double s0 = J.last_best.s;
+      int c = 0, dummy = 0;
+      for (int j = tid; j < K; j += BLK) c += (fabs(dsub(X[j], s0)) <= A[j]) ? 1 : 0;
+      block_sum_int2(&scratch, c, dummy);
+      if (tid == 0) {
+        iter_s = 1;
+        best_s = c;
+        est_s = s0;
+        const double conf = 1.0 - pow(1.0 - ((double)c / (double)K), 1);
+        done_s = conf < 0.99 ? 0 : 1;
+      }
+      __syncthreads();
+    }
+    while (!done_s) {
+      const unsigned long long k0 = k_s;
+      double xr[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) xr[g] = X[philox_rand31(J.seed, PSULVSB_DOMAIN_SCALE, event, k0 + g) % (uint32_t)K];
+      double cnt[4] = {0, 0, 0, 0};
+      for (int j = tid; j < K; j += BLK) {
+        const double xj = X[j], aj = A[j];
+#pragma unroll
+        for (int g = 0; g < G; ++g) cnt[g] += (fabs(dsub(xj, xr[g])) <= aj) ? 1.0 : 0.0;
+      }
+      block_sum<4>(&scratch, cnt);
+      if (tid == 0) {
+        int used = 0;
+        for (int g = 0; g < G && !done_s; ++g) {
+          ++used;
+          iter_s += 1;
+          const int c = (int)(cnt[g] + 0.5);
+          if (c > best_s) {
+            best_s = c;
+            est_s = xr[g];
+          }
+          const double conf = 1.0 - pow(1.0 - ((double)best_s / (double)K), iter_s);
+          if (!(conf < 0.99) || iter_s > 100000) done_s = 1;
+        }
+        k_s = k0 + (unsigned long long)used;
+      }
+      __syncthreads();
+    }
+    // refinement (registration.cc:104-119): inverse-variance weighted mean of the consensus set
+    const double est = est_s;
+    double sums[4] = {0, 0, 0, 0};
+    for (int i = tid; i < K; i += BLK)
+      if (fabs(dsub(X[i], est)) <= A[i]) {
+        const double a2 = dmul(A[i], A[i]);
+        sums[0] += 1.0 / a2;
+        sums[1] += X[i] / a2;
+      }
+    block_sum<4>(&scratch, sums);
+    scale = est;
+    if (sums[0] == sums[0] && sums[1] == sums[1]) scale = sums[1] / sums[0];
+    // pruning (registration.cc:966-983): the consensus set of the UNREFINED estimate, in order
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < K; i0 += BLK) {
+      const int i = i0 + tid;
+      const int f = (i < K && fabs(dsub(X[i], est)) <= A[i]) ? 1 : 0;
+      int ea, eb, ta, tb;
+      block_scan2(&scratch, f, 0, ea, eb, ta, tb);
+      const int base = base_s;
+      if (f) J.pruned_edges[base + ea] = edges[i];
+      __syncthreads();
+      if (tid == 0) base_s = base + ta;
+      __syncthreads();
+    }
+    n_pruned = base_s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (K > 0) J.scale_calls += 1;
+    J.scale_noise = beta;  // registration.cc:411
+    J.cur_scale = scale;
+    J.n_pruned = n_pruned;
+    GncJob& g = gj[blockIdx.x];
+    g.edges = J.pruned_edges;
+    g.K = (unsigned long long)n_pruned;
+    g.inv_scale = 1.0 / scale;                          // registration.cc:1102
+    g.noise_bound = J.cur.noise_bound * (2.0 / scale);  // registration.cc:1106-1108
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // local control: everything of one local iteration after the rotation solve
 // (registration.cc:1114-1488)
 // ------------------------------------------------------------------------------------------
@@ -338,7 +468,7 @@ __global__ void __launch_bounds__(BLK)
 
   // ---- rotation result (column-major) -> row-major
   if (tid == 0) {
-    sol_s.s = 1.0;
+    sol_s.s = J.cur_scale;
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) sol_s.R[r * 3 + c] = J.R_gnc[c * 3 + r];
     for (int r = 0; r < 3; ++r) sol_s.t[r] = J.sol.t[r];  // estimate starts from the previous value

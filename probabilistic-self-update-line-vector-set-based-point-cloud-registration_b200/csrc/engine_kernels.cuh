@@ -12,6 +12,7 @@ __global__ void engine_init_kernel(JobCtl* jobs, SampleJob* sl, SampleJob* sb, G
                                    const unsigned long long* n_edges, EngineParams P, int* n_done);
 __global__ void engine_round_start_kernel(JobCtl* jobs, SampleJob* sl, SampleJob* sb, GncJob* gj, EngineParams P,
                                           int* n_done);
+__global__ void engine_scale_kernel(JobCtl* jobs, GncJob* gj, EngineParams P);
 __global__ void engine_local_control_kernel(JobCtl* jobs, SampleJob* sl, SampleJob* sb, GncJob* gj, EngineParams P,
                                             double elapsed_s, int* n_done);
 __global__ void engine_refine_kernel(JobCtl* jobs, psulvsb_solution_t* out, const unsigned long long* border);

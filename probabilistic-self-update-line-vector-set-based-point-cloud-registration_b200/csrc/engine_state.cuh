@@ -76,6 +76,8 @@ struct JobCtl {
   double* weights;
   double* lv;  // GNC-TLS line-vector scratch, SoA [6][lv_cap]
   unsigned long long lv_cap;
+  uint2* pruned_edges;  // unknown scale: scale-inlier line vectors handed to the rotation solver
+  int estimate_scaling;
   psulvsb_local_trace_t* local_trace;
   psulvsb_host_trace_t* host_trace;
   int local_trace_cap, host_trace_cap;
@@ -94,6 +96,8 @@ struct JobCtl {
   double scale_noise, translation_noise;
   Xform sol, best_sampled, best_host, last_best;
   int new_corr_count, inlier_map_size;
+  int scale_calls, n_pruned;
+  double cur_scale;  // solution_.scale of the iteration in flight (registration.cc:958-991)
   unsigned long long sample_status[2];
   double R_gnc[9];  // column-major (GncJob::R_out)
   int gnc_info[4];

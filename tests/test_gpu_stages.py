@@ -279,7 +279,10 @@ def test_errors_are_reported_not_thrown(P):
     assert rc == capi.ERR_INVALID and b"NULL" in L.psulvsb_last_error()
     h = capi.Handle(0)
     p = capi.default_params(estimate_scaling=1)
-    prob = capi.HostProblem(np.zeros((3, 4)), np.zeros((3, 4)))
+    # coincident source points with distinct targets: the length ratio is infinite, which would regrow the
+    # reference's histogram mid-stream (registration.cc:714-718) -> reported, not guessed
+    src = np.zeros((3, 4))
+    dst = np.arange(12, dtype=np.float64).reshape(3, 4)
     with pytest.raises(capi.PsulvsbError) as ei:
-        h.solve(p, prob)
+        h.solve(p, capi.HostProblem(src, dst))
     assert ei.value.code == capi.ERR_UNSUPPORTED
