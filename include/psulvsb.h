@@ -242,6 +242,15 @@ int psulvsb_tls_translation(void* stream, const double* d_src64, const double* d
                             int n, double scale, const double* d_R, double noise, const double* d_last_best,
                             double* d_t_out, int* d_n_points);
 
+/* Clique escalation (registration.cc:1000-1085 -> teaser/src/graph.cc:12-125, PMC): a deterministic greedy
+ * maximal clique of the graph with n_vertices vertices and the given edges (uint2 endpoint pairs): take the
+ * candidate with the most neighbours among the remaining candidates (ties: lowest index), intersect.
+ * d_adj: scratch bit matrix of n_vertices * ceil(n_vertices / 32) words.  d_flags[n_vertices] (u8) receives
+ * the membership, *d_size the clique size.  PMC's own result is not unique: parity for this branch is
+ * defined on clique validity / size, not membership. */
+int psulvsb_greedy_clique(void* stream, const void* d_edges_uint2, unsigned long long n_edges, int n_vertices,
+                          uint32_t* d_adj, uint8_t* d_flags, int* d_size);
+
 /* Stage 4 -- fused transform + score + argmax (registration.cc:1303-1336, :1417-1444):
  * counts[h] = #{ j : | q_j - s (R_h p_j + t_h) | <= tau } over all n points, evaluated in FP32
  * from float4 tiles with every point inside the FP32 error band re-evaluated in FP64, plus the

@@ -352,6 +352,28 @@ int psulvsb_tls_translation(void* stream, const double* d_src64, const double* d
                                 d_t_out, d_n_points);
 }
 
+int psulvsb_greedy_clique(void* stream, const void* d_edges_uint2, unsigned long long n_edges, int n_vertices,
+                          uint32_t* d_adj, uint8_t* d_flags, int* d_size) {
+  if (int rc = need_device()) return rc;
+  if ((!d_edges_uint2 && n_edges) || !d_adj || !d_flags || !d_size || n_vertices < 1)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_greedy_clique: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CliqueJob j;
+  std::memset(&j, 0, sizeof(j));
+  j.edges = (const uint2*)d_edges_uint2;
+  j.n_edges = n_edges;
+  j.filter = 0;
+  j.n_vertices = n_vertices;
+  j.adj = d_adj;
+  j.stride = (n_vertices + 31) / 32;
+  j.flags = d_flags;
+  j.size = d_size;
+  j.active = 1;
+  DeviceJob<CliqueJob> dj(st);
+  if (int rc = dj.put(j)) return rc;
+  return launch_greedy_clique(st, dj.d, 1, n_vertices, j.stride, n_edges);
+}
+
 int psulvsb_score_batch(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,
                         const double* d_dst64, int n, const double* d_hyp, unsigned long long n_hyp,
                         unsigned long long hyp_begin, double scale, double tau, double coord_bound,

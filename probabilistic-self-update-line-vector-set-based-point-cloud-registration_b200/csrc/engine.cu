@@ -303,6 +303,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   struct Misc {
     RatioJob* rj;
     int* bad;
+    CliqueJob* cq;
     K1Job* k1;
     CompactJob* cj;
     PackJob* pj;
@@ -332,6 +333,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       m.sols = bm.take<psulvsb_solution_t>((size_t)B);
       m.rj = bm.take<RatioJob>((size_t)B);
       m.bad = bm.take<int>((size_t)B);
+      m.cq = bm.take<CliqueJob>((size_t)B);
       if (pass == 0) {
         if (int rc = d_misc.ensure(bm.off)) return rc;
         bm.base = reinterpret_cast<char*>(d_misc.p);
@@ -371,6 +373,10 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.final_inliers = bw.take<int>((size_t)L.M);
         J.inlier_map = bw.take<int>((size_t)L.Ccap);
         J.idx = bw.take<int>((size_t)L.Ccap);
+        J.adj_stride = (L.Ccap + 31) / 32;
+        // the bit matrix is only touched by the last-resort clique escalation; selection NONE never builds it
+        J.adj = params->inlier_selection_mode != 3 ? bw.take<uint32_t>((size_t)L.Ccap * J.adj_stride) : nullptr;
+        J.clique_flags = bw.take<uint8_t>((size_t)L.Ccap);
         J.sampled_flags = bw.take<uint8_t>((size_t)L.Ccap);
         J.rot_flags = bw.take<uint8_t>((size_t)L.Ccap);
         J.local_trace = bw.take<psulvsb_local_trace_t>((size_t)local_cap);
@@ -560,7 +566,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   P.self_update = params->self_update;
   P.inlier_selection_mode = params->inlier_selection_mode;
   P.max_local_iters = 4096;
-  engine_init_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.n_edges, P, m.n_done);
+  engine_init_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, m.n_edges, P, m.n_done);
   PSU_CHECK_LAUNCH("engine_init_kernel");
   ++launches;
   PSU_CUDA(cudaEventRecord(ev_k1, st));
@@ -574,30 +580,38 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   int ticks = 0;
   const int max_ticks = P.max_local_iters + P.host_round_limit + 8;
   bool round_start_pending = true;  // every job begins with a round start
+  bool clique_pending = false;
   while (true) {
     const double elapsed =
         std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count() / 1e6;
     if (round_start_pending) {
-      engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, P, m.n_done);
+      engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, m.n_done);
       PSU_CHECK_LAUNCH("engine_round_start_kernel");
       if (int rc = launch_sample(st, m.sl, B, draws_bound)) return rc;
       launches += 4;
     }
     if (int rc = launch_sample(st, m.sb, B, draws_bound)) return rc;
     if (ratio) {
-      engine_scale_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.gj, P);
+      engine_scale_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.gj, m.cq, P);
       PSU_CHECK_LAUNCH("engine_scale_kernel");
       ++launches;
     }
+    if (clique_pending) {  // some registration is in its clique round (rare, last escalation)
+      int maxCcap = 0;
+      for (int b = 0; b < B; ++b) maxCcap = lay[(size_t)b].Ccap > maxCcap ? lay[(size_t)b].Ccap : maxCcap;
+      if (int rc = launch_greedy_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap)) return rc;
+      launches += 3;
+    }
     if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster)) return rc;
-    engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, P, elapsed, m.n_done);
+    engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");
     launches += 5;
     ++ticks;
-    PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     PSU_CUDA(cudaStreamSynchronize(st));
     if (h_done[0] >= B) break;
     round_start_pending = h_done[1] > 0;
+    clique_pending = h_done[2] > 0 && params->inlier_selection_mode != 3;
     if (ticks >= max_ticks) return fail(PSULVSB_ERR_INTERNAL, "engine did not converge within the tick limit");
   }
   last_ticks = ticks;

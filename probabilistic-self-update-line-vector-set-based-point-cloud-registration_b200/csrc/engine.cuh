@@ -117,6 +117,24 @@ struct GncJob {
   int active;
 };
 
+// ---- clique escalation (k5_clique.cu) -----------------------------------------------------------
+struct CliqueJob {
+  const uint2* edges;
+  unsigned long long n_edges;
+  const double* src;  // filter != 0: keep an edge iff its line vector is length-consistent within beta
+  const double* dst;
+  double beta;
+  int filter;
+  int n_vertices;
+  uint32_t* adj;  // [n_vertices * stride] bit matrix scratch
+  int stride;
+  uint8_t* flags;  // [n_vertices] out: clique membership
+  int* size;       // out
+  int active;
+};
+int launch_greedy_clique(cudaStream_t st, const CliqueJob* d_jobs, int n_jobs, int max_vertices, int max_stride,
+                         unsigned long long max_edges);
+
 // ---- stage launchers (k1_consistency.cu, k2_sampler.cu, k3_rotation.cu, k4_score.cu) -----------
 int launch_pack_points(cudaStream_t st, const double* pts, int n, const double center[3], float4* out);
 // max_n / max_rows: grid extents over all jobs

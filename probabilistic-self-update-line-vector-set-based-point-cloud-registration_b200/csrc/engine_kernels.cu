@@ -40,7 +40,7 @@ __device__ __forceinline__ double inlier_probability(double r, double sigma) {
 
 // Prepares the basic-subset draw (registration.cc:908-933) and the rotation solve
 // (registration.cc:1102-1111) of the next local iteration.  Thread 0 only.
-__device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, const EngineParams& P) {
+__device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q, const EngineParams& P) {
   const double b_rate = kBRate[J.rate_idx];
   J.basic_choose = (int)((double)J.n_ls * b_rate);
   // reset(params_) then the overrides: THIS iteration sees the previous contents (SURVEY defect 6)
@@ -91,6 +91,19 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, const EngineP
   g.info = J.gnc_info;
   g.cost = &J.gnc_cost;
   g.active = 1;
+  // max-clique escalation (registration.cc:1000-1085): inlier graph of the round's scale-consistent line vectors
+  q.active = (J.rate_idx == 3 && P.inlier_selection_mode != 3) ? 1 : 0;
+  q.edges = J.basic_edges;
+  q.n_edges = (unsigned long long)J.basic_choose;
+  q.src = J.src;
+  q.dst = J.dst;
+  q.beta = 2.0 * J.cur.noise_bound * sqrt(J.cur.cbar2);  // ScaleInliersSelector with this iteration's params (:984-991)
+  q.filter = 1;
+  q.n_vertices = J.C;
+  q.adj = J.adj;
+  q.stride = J.adj_stride;
+  q.flags = J.clique_flags;
+  q.size = &J.clique_size;
 }
 
 // count_j [ | q_j - s (R p_j + t) | <= tau ] over the flagged points of the working set
@@ -109,7 +122,8 @@ __device__ int count_flagged(BlockScratch* s, const JobCtl& J, const Xform& X) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLK)
     engine_init_kernel(JobCtl* __restrict__ jobs, SampleJob* __restrict__ sl, SampleJob* __restrict__ sb,
-                       GncJob* __restrict__ gj, const unsigned long long* __restrict__ n_edges, EngineParams P,
+                       GncJob* __restrict__ gj, CliqueJob* __restrict__ cq,
+                       const unsigned long long* __restrict__ n_edges, EngineParams P,
                        int* __restrict__ n_done) {
   JobCtl& J = jobs[blockIdx.x];
   const int tid = threadIdx.x;
@@ -173,6 +187,9 @@ __global__ void __launch_bounds__(BLK)
     sl[blockIdx.x].active = 0;
     sb[blockIdx.x].active = 0;
     gj[blockIdx.x].active = 0;
+    cq[blockIdx.x].active = 0;
+    J.clique_size = 0;
+    J.aborted = 0;
     if (J.n_red0 > J.edge_cap) {
       J.status = PSULVSB_ERR_CAPACITY;
       J.phase = PHASE_DONE;
@@ -193,7 +210,8 @@ __global__ void __launch_bounds__(BLK)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLK)
     engine_round_start_kernel(JobCtl* __restrict__ jobs, SampleJob* __restrict__ sl, SampleJob* __restrict__ sb,
-                              GncJob* __restrict__ gj, EngineParams P, int* __restrict__ n_done) {
+                              GncJob* __restrict__ gj, CliqueJob* __restrict__ cq, EngineParams P,
+                              int* __restrict__ n_done) {
   JobCtl& J = jobs[blockIdx.x];
   SampleJob& L = sl[blockIdx.x];
   const int tid = threadIdx.x;
@@ -203,6 +221,7 @@ __global__ void __launch_bounds__(BLK)
       if (J.phase == PHASE_DONE) {
         sb[blockIdx.x].active = 0;
         gj[blockIdx.x].active = 0;
+        cq[blockIdx.x].active = 0;
       }
     }
     return;
@@ -293,7 +312,7 @@ __global__ void __launch_bounds__(BLK)
     L.active = 1;
     J.sample_status[0] = 1ull;
     J.phase = PHASE_LOCAL;
-    prepare_local(J, sb[blockIdx.x], gj[blockIdx.x], P);
+    prepare_local(J, sb[blockIdx.x], gj[blockIdx.x], cq[blockIdx.x], P);
   }
 }
 
@@ -302,7 +321,8 @@ __global__ void __launch_bounds__(BLK)
 // ScalarTLSEstimator::estimate, scale branch, :66-120), pruning to the scale inliers, and the
 // rotation-solve set-up that depends on the scale (registration.cc:1102-1108)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLK) engine_scale_kernel(JobCtl* __restrict__ jobs, GncJob* __restrict__ gj, EngineParams P) {
+__global__ void __launch_bounds__(BLK)
+    engine_scale_kernel(JobCtl* __restrict__ jobs, GncJob* __restrict__ gj, CliqueJob* __restrict__ cq, EngineParams P) {
   JobCtl& J = jobs[blockIdx.x];
   if (J.phase != PHASE_LOCAL || !J.estimate_scaling) return;
   __shared__ BlockScratch scratch;
@@ -421,6 +441,10 @@ __global__ void __launch_bounds__(BLK) engine_scale_kernel(JobCtl* __restrict__ 
     g.K = (unsigned long long)n_pruned;
     g.inv_scale = 1.0 / scale;                          // registration.cc:1102
     g.noise_bound = J.cur.noise_bound * (2.0 / scale);  // registration.cc:1106-1108
+    CliqueJob& q = cq[blockIdx.x];  // the inlier graph uses the TLS scale inliers as they are (:1005-1012)
+    q.edges = J.pruned_edges;
+    q.n_edges = (unsigned long long)n_pruned;
+    q.filter = 0;
   }
 }
 
@@ -430,7 +454,8 @@ __global__ void __launch_bounds__(BLK) engine_scale_kernel(JobCtl* __restrict__ 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLK)
     engine_local_control_kernel(JobCtl* __restrict__ jobs, SampleJob* __restrict__ sl, SampleJob* __restrict__ sb,
-                                GncJob* __restrict__ gj, EngineParams P, double elapsed_s, int* __restrict__ n_done) {
+                                GncJob* __restrict__ gj, CliqueJob* __restrict__ cq, EngineParams P, double elapsed_s,
+                                int* __restrict__ n_done) {
   JobCtl& J = jobs[blockIdx.x];
   if (J.phase != PHASE_LOCAL) return;
   __shared__ BlockScratch scratch;
@@ -442,16 +467,19 @@ __global__ void __launch_bounds__(BLK)
   const double b_rate = kBRate[J.rate_idx];
   const bool clique_round = (b_rate == 1.0);
 
-  if ((J.sample_status[0] == 0ull || J.sample_status[1] == 0ull) ||
-      (clique_round && P.inlier_selection_mode != 3)) {
-    // sampler budget exhausted (never observed: mean + 8 sigma) / max-clique escalation with a
-    // PMC mode (registration.cc:1000-1085) is not part of this round's device path
+  const bool use_clique = clique_round && P.inlier_selection_mode != 3;
+  if (J.sample_status[0] == 0ull || J.sample_status[1] == 0ull || (use_clique && J.clique_size <= 1)) {
+    // sampler budget exhausted (never observed: mean + 8 sigma), or the inlier graph has no clique of
+    // two vertices: the reference gives up there with valid = false (registration.cc:1032-1036)
     if (tid == 0) {
-      J.status = (J.sample_status[0] == 0ull || J.sample_status[1] == 0ull) ? PSULVSB_ERR_INTERNAL
-                                                                           : PSULVSB_ERR_UNSUPPORTED;
+      if (J.sample_status[0] == 0ull || J.sample_status[1] == 0ull)
+        J.status = PSULVSB_ERR_INTERNAL;
+      else
+        J.aborted = 1;
       J.phase = PHASE_DONE;
       sb[blockIdx.x].active = 0;
       gj[blockIdx.x].active = 0;
+      cq[blockIdx.x].active = 0;
       atomicAdd(n_done, 1);
     }
     return;
@@ -480,7 +508,8 @@ __global__ void __launch_bounds__(BLK)
   // (registration.cc:1114-1155), or every point in the max-clique round with selection NONE (:1066-1084)
   for (int j0 = 0; j0 < C; j0 += BLK) {
     const int j = j0 + tid;
-    const int f = (j < C && (clique_round || J.rot_flags[j])) ? 1 : 0;
+    // clique round: the clique's points (registration.cc:1238-1244); selection NONE: every point (:1066-1084)
+    const int f = (j < C && (clique_round ? (use_clique ? J.clique_flags[j] != 0 : true) : J.rot_flags[j] != 0)) ? 1 : 0;
     int ea, eb, ta, tb;
     block_scan2(&scratch, f, 0, ea, eb, ta, tb);
     const int base = base_s[0];
@@ -553,6 +582,7 @@ __global__ void __launch_bounds__(BLK)
         if (J.rate_idx < 3) {
           J.rate_idx += 1;
           J.escalations += 1;
+          if (J.rate_idx == 3) atomicAdd(n_done + 2, 1);  // n_done[2]: jobs that reached the clique round
         }
       }
     }
@@ -678,6 +708,7 @@ __global__ void __launch_bounds__(BLK)
       J.host_round += 1;
       sb[blockIdx.x].active = 0;
       gj[blockIdx.x].active = 0;
+      cq[blockIdx.x].active = 0;
       if (J.pro_host_not_over && J.rounds_left > 0) {
         J.phase = PHASE_ROUND_START;
         atomicAdd(n_done + 1, 1);
@@ -694,9 +725,10 @@ __global__ void __launch_bounds__(BLK)
       J.phase = PHASE_DONE;
       sb[blockIdx.x].active = 0;
       gj[blockIdx.x].active = 0;
+      cq[blockIdx.x].active = 0;
       atomicAdd(n_done, 1);
     } else {
-      prepare_local(J, sb[blockIdx.x], gj[blockIdx.x], P);
+      prepare_local(J, sb[blockIdx.x], gj[blockIdx.x], cq[blockIdx.x], P);
     }
   }
 }
@@ -819,6 +851,10 @@ __global__ void __launch_bounds__(BLK)
     S.scale = J.valid ? J.best_host.s : 1.0;
     S.final_inlier_count = J.valid ? J.best_host_cnt : 0;
     if (!J.valid) xform_identity(fin);
+    if (J.aborted) {  // registration.cc:1032-1036: the solution fields keep the values of the last iteration
+      fin = J.sol;
+      S.scale = J.cur_scale;
+    }
     for (int r = 0; r < 3; ++r) S.translation[r] = fin.t[r];
     for (int c = 0; c < 3; ++c)
       for (int r = 0; r < 3; ++r) S.rotation[c * 3 + r] = fin.R[r * 3 + c];

@@ -76,6 +76,9 @@ struct JobCtl {
   double* weights;
   double* lv;  // GNC-TLS line-vector scratch, SoA [6][lv_cap]
   unsigned long long lv_cap;
+  uint32_t* adj;        // clique escalation: Ccap x adj_stride bit matrix
+  int adj_stride;
+  uint8_t* clique_flags;  // [Ccap]
   uint2* pruned_edges;  // unknown scale: scale-inlier line vectors handed to the rotation solver
   int estimate_scaling;
   psulvsb_local_trace_t* local_trace;
@@ -97,6 +100,7 @@ struct JobCtl {
   Xform sol, best_sampled, best_host, last_best;
   int new_corr_count, inlier_map_size;
   int scale_calls, n_pruned;
+  int clique_size, aborted;
   double cur_scale;  // solution_.scale of the iteration in flight (registration.cc:958-991)
   unsigned long long sample_status[2];
   double R_gnc[9];  // column-major (GncJob::R_out)

@@ -187,3 +187,16 @@ def score_one(d_src, d_dst, scale, R, t, tau):
                                             _dev(inl), _dev(res), _dev(cnt)))
     torch.cuda.synchronize()
     return int(cnt.item()), inl.cpu().numpy(), res.cpu().numpy()
+
+
+def greedy_clique(edges, n_vertices: int):
+    """edges: [E, 2] int array -> (sorted clique vertex ids, size)."""
+    e = torch.from_numpy(np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)).cuda()
+    stride = (n_vertices + 31) // 32
+    adj = torch.empty(n_vertices * stride, dtype=torch.int32, device="cuda")
+    flags = torch.zeros(n_vertices, dtype=torch.uint8, device="cuda")
+    size = torch.zeros(1, dtype=torch.int32, device="cuda")
+    capi.check(capi.lib().psulvsb_greedy_clique(_stream(), _dev(e) if e.numel() else None, e.shape[0], n_vertices,
+                                                _dev(adj), _dev(flags), _dev(size)))
+    torch.cuda.synchronize()
+    return np.flatnonzero(flags.cpu().numpy()), int(size.item())

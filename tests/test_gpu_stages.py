@@ -286,3 +286,57 @@ def test_errors_are_reported_not_thrown(P):
     with pytest.raises(capi.PsulvsbError) as ei:
         h.solve(p, capi.HostProblem(src, dst))
     assert ei.value.code == capi.ERR_UNSUPPORTED
+
+
+def test_greedy_clique_on_planted_graphs(P, O):
+    """Clique escalation (registration.cc:1000-1085): the oracle's exact branch and bound stands for PMC.  On
+    registration-like graphs (one planted clique over a sparse random background) the greedy clique must be a
+    clique, maximal, and as large as the exact one."""
+    st = P["stages"]
+    rng = np.random.default_rng(3)
+    for n, k, p_bg in [(40, 8, 0.05), (200, 25, 0.05), (600, 60, 0.03), (50, 1, 0.0)]:
+        members = np.sort(rng.permutation(n)[:k])
+        A = rng.uniform(0, 1, (n, n)) < p_bg
+        A = np.triu(A, 1)
+        A[np.ix_(members, members)] = np.triu(np.ones((k, k), dtype=bool), 1)
+        ei, ej = np.nonzero(A)
+        edges = np.stack([ei, ej], axis=1).astype(np.int32)
+        got, size = st.greedy_clique(edges, n)
+        assert size == len(got)
+        full = A | A.T
+        for a in got:                                    # a clique ...
+            for b in got:
+                assert a == b or full[a, b]
+        if len(got):                                     # ... that is maximal
+            common = np.all(full[got], axis=0)
+            common[got] = False
+            assert not common.any()
+        exact = O.max_clique(n, edges) if len(edges) else np.array([], dtype=np.int32)
+        if len(edges):
+            assert size == len(exact)                    # same size as the exact maximum clique
+            if k >= 8:
+                assert np.array_equal(got, members)      # and it is the planted one
+        else:
+            assert size == 0
+
+
+def test_solver_reaches_the_clique_escalation(P, O):
+    """Inputs on which the two-level RANSAC escalates three times (rates (1.0, 1.0), registration.cc:1377-1388)
+    and falls back to the inlier-graph clique: the device path must run it (no CPU fallback) and end where the
+    oracle (exact clique) ends."""
+    capi, synth = P["capi"], P["synth"]
+    h = capi.Handle(0)
+    kw = dict(noise_bound=0.05, cbar2=1.0, estimate_scaling=0, rotation_cost_threshold=0.005, wallclock_cap_s=0.0)
+    hits = 0
+    for n, ratio, seed in [(100, 0.9, 4), (100, 0.9, 5), (60, 0.9, 2)]:
+        pair = synth.make_pair(n, ratio, seed, outliers="fpfh")
+        so, _ = O.solve(O.default_params(seed=seed, **kw), pair["src"], pair["dst"])
+        sg, _ = h.solve(capi.default_params(seed=seed, **kw), capi.HostProblem(pair["src"], pair["dst"]))
+        assert so.escalations == 3
+        assert sg.status == 0 and sg.escalations == 3 and bool(sg.valid) == bool(so.valid)
+        assert sg.local_iters == so.local_iters and sg.host_rounds == so.host_rounds
+        if sg.final_inlier_count == so.final_inlier_count:
+            hits += 1
+            assert synth.rotation_error(sg.R, O.solution_R(so)) < 1e-5
+            assert np.abs(sg.t - O.solution_t(so)).max() < 1e-5
+    assert hits >= 2
