@@ -34,6 +34,9 @@ namespace {
 
 constexpr int GNC_THREADS = 256;  // two CTAs per SM: one hypothesis' serial SVD phase overlaps another's pass
 constexpr int GNC_WARPS = GNC_THREADS / 32;
+#ifndef GNC_CTAS_PER_SM
+#define GNC_CTAS_PER_SM 2
+#endif
 constexpr int GNC_NRED = 12;  // 9 H + cost + max/aux + count
 
 struct GncSmem {
@@ -134,7 +137,7 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
 }
 
 template <int NC>
-__global__ void __launch_bounds__(GNC_THREADS, 2) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
+__global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GncSmem* sm = reinterpret_cast<GncSmem*>(smem_raw);
   double* lv = reinterpret_cast<double*>(smem_raw + ((sizeof(GncSmem) + 15) & ~size_t(15)));
@@ -481,8 +484,8 @@ int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per
 }  // namespace
 
 int gnc_default_capacity() {
-  // two CTAs share the SM's 227 KB
-  const size_t budget = 108 * 1024;
+  // GNC_CTAS_PER_SM CTAs share the SM's 227 KB
+  const size_t budget = (size_t)(220 / GNC_CTAS_PER_SM) * 1024;
   const size_t fixed = (sizeof(GncSmem) + 15) & ~size_t(15);
   int cap = (int)((budget - fixed) / (7 * sizeof(double)));
   cap &= ~31;
@@ -491,9 +494,10 @@ int gnc_default_capacity() {
 
 // CTAs per hypothesis for a batch of n_jobs: as many SMs per job as keeps the whole batch resident
 int gnc_cluster_for(int n_jobs) {
-  if (n_jobs * 8 <= 296) return 8;
-  if (n_jobs * 4 <= 296) return 4;
-  if (n_jobs * 2 <= 296) return 2;
+  const int slots = 148 * GNC_CTAS_PER_SM;
+  if (n_jobs * 8 <= slots) return 8;
+  if (n_jobs * 4 <= slots) return 4;
+  if (n_jobs * 2 <= slots) return 2;
   return 1;
 }
 
