@@ -11,6 +11,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -579,6 +580,11 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   const unsigned long long draws_bound = sample_default_max_draws(max_cap, max_cap / 8 + 1);
   int ticks = 0;
   const int max_ticks = P.max_local_iters + P.host_round_limit + 8;
+  // (measured: splitting the L-sample passes into L2-sized job groups does not pay -- 64 jobs in one group
+  // 7.9 ms/step, groups of 16: 8.2, of 4: 10.1 -- so all jobs go in one launch; PSULVSB_L_GROUP overrides)
+  static const char* lg_env = getenv("PSULVSB_L_GROUP");
+  int l_group = lg_env ? atoi(lg_env) : B;
+  if (l_group < 1 || l_group > B) l_group = B;
   bool round_start_pending = true;  // every job begins with a round start
   bool clique_pending = false;
   while (true) {
@@ -587,8 +593,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     if (round_start_pending) {
       engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, m.n_done);
       PSU_CHECK_LAUNCH("engine_round_start_kernel");
-      if (int rc = launch_sample(st, m.sl, B, draws_bound)) return rc;
-      launches += 4;
+      if (int rc = launch_sample(st, m.sl, B, draws_bound, l_group)) return rc;
+      launches += 1 + 3 * ((B + l_group - 1) / l_group);
     }
     if (int rc = launch_sample(st, m.sb, B, draws_bound)) return rc;
     if (ratio) {

@@ -164,7 +164,8 @@ __host__ __device__ inline unsigned long long sample_max_draws_formula(unsigned 
 }
 unsigned long long sample_default_max_draws(unsigned long long n, unsigned long long count);
 unsigned long long sample_chunk_slots(unsigned long long max_draws);
-int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound);
+int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound,
+                  int jobs_per_group = 0);
 int launch_philox_fill(cudaStream_t st, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long first_k,
                        unsigned long long count, uint32_t* out);
 

@@ -223,20 +223,27 @@ unsigned long long sample_default_max_draws(unsigned long long n, unsigned long 
 
 unsigned long long sample_chunk_slots(unsigned long long max_draws) { return (max_draws + SMP_CHUNK - 1) / SMP_CHUNK + 1; }
 
-int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound) {
+// jobs_per_group > 0: run the three passes group by group so that the random-access working set of a
+// group (first-occurrence tables + the edge lists the emit pass gathers from) stays L2 resident.
+int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound,
+                  int jobs_per_group) {
   if (n_jobs <= 0) return PSULVSB_OK;
+  if (jobs_per_group <= 0 || jobs_per_group > n_jobs) jobs_per_group = n_jobs;
   const unsigned long long nchunks = (max_draws_bound + SMP_CHUNK - 1) / SMP_CHUNK;
-  unsigned long long gx = nchunks;
-  const unsigned long long cap = (unsigned long long)(148 * 16) / (unsigned long long)(n_jobs < 64 ? n_jobs : 64) + 1;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)n_jobs);
-  sample_mark_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs);
-  PSU_CHECK_LAUNCH("sample_mark_kernel");
-  sample_count_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs);
-  PSU_CHECK_LAUNCH("sample_count_kernel");
-  sample_emit_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs);
-  PSU_CHECK_LAUNCH("sample_emit_kernel");
+  for (int off = 0; off < n_jobs; off += jobs_per_group) {
+    const int g = (n_jobs - off < jobs_per_group) ? n_jobs - off : jobs_per_group;
+    unsigned long long gx = nchunks;
+    const unsigned long long cap = (unsigned long long)(148 * 16) / (unsigned long long)(g < 64 ? g : 64) + 1;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)g);
+    sample_mark_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs + off);
+    PSU_CHECK_LAUNCH("sample_mark_kernel");
+    sample_count_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs + off);
+    PSU_CHECK_LAUNCH("sample_count_kernel");
+    sample_emit_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs + off);
+    PSU_CHECK_LAUNCH("sample_emit_kernel");
+  }
   return PSULVSB_OK;
 }
 
