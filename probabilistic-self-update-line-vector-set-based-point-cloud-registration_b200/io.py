@@ -1,0 +1,102 @@
+"""ctypes binding of include/psulvsb_io.h: the host-side helpers of the callers around the hot path
+(normal-angle histogram pre-filter, reduced-set builder, PLY vertices, correspondence files)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+IO_SYMBOLS = ["psulvsb_histogram_outlier_removal", "psulvsb_mask_filter", "psulvsb_ply_vertex_count",
+              "psulvsb_ply_read_xyz", "psulvsb_corr_count", "psulvsb_corr_read", "psulvsb_gtmat_read",
+              "psulvsb_gtlog_read"]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
+_llp = C.POINTER(C.c_longlong)
+_declared = False
+
+
+def _lib():
+    global _declared
+    L = capi.lib()
+    if not _declared:
+        L.psulvsb_histogram_outlier_removal.argtypes = [_dp, _dp, C.c_int, _ip, _ip]
+        L.psulvsb_mask_filter.argtypes = [_dp, _dp, _ip, C.c_int, _dp, _dp, _ip, _ip]
+        L.psulvsb_ply_vertex_count.argtypes = [C.c_char_p, _llp]
+        L.psulvsb_ply_read_xyz.argtypes = [C.c_char_p, _fp, C.c_longlong, _llp]
+        L.psulvsb_corr_count.argtypes = [C.c_char_p, _llp]
+        L.psulvsb_corr_read.argtypes = [C.c_char_p, _dp, _dp, C.c_longlong, _llp]
+        L.psulvsb_gtmat_read.argtypes = [C.c_char_p, _dp]
+        L.psulvsb_gtlog_read.argtypes = [C.c_char_p, _ip, C.c_longlong, _llp]
+        _declared = True
+    return L
+
+
+def _cm(a):
+    a = np.asfortranarray(np.asarray(a, dtype=np.float64))
+    assert a.ndim == 2 and a.shape[0] == 3
+    return a
+
+
+def histogram_outlier_removal(src_normals, tgt_normals):
+    """PSULVSB.cc:87-172 -> (keep_mask[n] in {-1,0,1}, remain_count)."""
+    a, b = _cm(src_normals), _cm(tgt_normals)
+    n = a.shape[1]
+    keep = np.zeros(n, dtype=np.int32)
+    rem = C.c_int(0)
+    capi.check(_lib().psulvsb_histogram_outlier_removal(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), n,
+                                                        keep.ctypes.data_as(_ip), C.byref(rem)))
+    return keep, rem.value
+
+
+def mask_filter(src, tgt, keep_mask):
+    """PSULVSB.cc:174-188 -> (src_reduce 3xC, tgt_reduce 3xC, dense reduce_map[n])."""
+    a, b = _cm(src), _cm(tgt)
+    n = a.shape[1]
+    keep = np.ascontiguousarray(keep_mask, dtype=np.int32)
+    sr = np.zeros((3, n), order="F")
+    tr = np.zeros((3, n), order="F")
+    rm = np.zeros(n, dtype=np.int32)
+    c = C.c_int(0)
+    capi.check(_lib().psulvsb_mask_filter(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), keep.ctypes.data_as(_ip), n,
+                                          sr.ctypes.data_as(_dp), tr.ctypes.data_as(_dp), rm.ctypes.data_as(_ip),
+                                          C.byref(c)))
+    return np.asfortranarray(sr[:, :c.value]), np.asfortranarray(tr[:, :c.value]), rm
+
+
+def read_ply_xyz(path: str) -> np.ndarray:
+    """Vertices of a PLY file as a 3xN float64 matrix (values are the file's x, y, z read as float32 like
+    teaser::PointXYZ, teaser/src/ply_io.cc:26-79)."""
+    n = C.c_longlong(0)
+    capi.check(_lib().psulvsb_ply_vertex_count(path.encode(), C.byref(n)))
+    xyz = np.zeros((max(n.value, 1), 3), dtype=np.float32)
+    capi.check(_lib().psulvsb_ply_read_xyz(path.encode(), xyz.ctypes.data_as(_fp), n.value, C.byref(n)))
+    return np.asfortranarray(xyz[:n.value].T.astype(np.float64))
+
+
+def read_correspondences(path: str):
+    """'x y z x y z' per line (optionally after a count header) -> (src 3xN, dst 3xN)."""
+    n = C.c_longlong(0)
+    capi.check(_lib().psulvsb_corr_count(path.encode(), C.byref(n)))
+    src = np.zeros((3, max(n.value, 1)), order="F")
+    dst = np.zeros((3, max(n.value, 1)), order="F")
+    capi.check(_lib().psulvsb_corr_read(path.encode(), src.ctypes.data_as(_dp), dst.ctypes.data_as(_dp), n.value,
+                                        C.byref(n)))
+    return np.asfortranarray(src[:, :n.value]), np.asfortranarray(dst[:, :n.value])
+
+
+def read_gtmat(path: str) -> np.ndarray:
+    T = np.zeros(16)
+    capi.check(_lib().psulvsb_gtmat_read(path.encode(), T.ctypes.data_as(_dp)))
+    return T.reshape(4, 4, order="F")
+
+
+def read_gtlog(path: str):
+    n = C.c_longlong(0)
+    capi.check(_lib().psulvsb_gtlog_read(path.encode(), None, 0, C.byref(n)))
+    pairs = np.zeros((max(n.value, 1), 2), dtype=np.int32)
+    capi.check(_lib().psulvsb_gtlog_read(path.encode(), pairs.ctypes.data_as(_ip), n.value, C.byref(n)))
+    return [tuple(int(v) for v in p) for p in pairs[:n.value]]

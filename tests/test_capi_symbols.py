@@ -26,6 +26,13 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(capi.SYMBOLS) == names          # the Python binding covers the whole header
+    # include/psulvsb_io.h (host-side helpers) as well
+    src = open(os.path.join(ROOT, "include", "psulvsb_io.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    io_names = sorted(set(re.findall(r"\b(psulvsb_[a-z0-9_]+)\s*\(", src)))
+    from psulvsb_b200 import io
+    assert io_names == sorted(io.IO_SYMBOLS)
+    assert not [n for n in io_names if not hasattr(lib, n)]
 
 
 def test_version_defaults_and_no_device_behaviour():
