@@ -40,6 +40,10 @@ OUTLIER_RATIO = 0.95
 PARAM_KW = dict(noise_bound=0.05, cbar2=1.0, estimate_scaling=0, rotation_max_iterations=100,
                 rotation_gnc_factor=1.4, rotation_cost_threshold=0.005, wallclock_cap_s=0.0)
 K1_SLOTS_PER_PAIR = 16
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k1_mask_kernel launch at --batch 64 from the ncu --set full
+# capture profiles/r1_ncu_k1_mask_b64.txt (79.6 MB read + 128.7 MB written; the algorithmic output is the
+# 64 x 5000 x 160-word mask = 204.8 MB incl. row padding and the untouched lower triangle, inputs 10 MB)
+K1_TRAFFIC_BYTES_B64 = 79_636_736 + 128_738_304
 
 
 def make_problems(rank: int, batch: int):
@@ -72,7 +76,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -148,7 +152,7 @@ def run_reference(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="fragment pairs per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -264,7 +268,9 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp32-pipe", "kernel": "k1_mask_kernel (line-vector length-consistency bit mask)",
                          "achieved": achieved, "peak": peak, "unit": "Gslot/s (FP32-pipe issue slots, 16 per pair)",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": K1_TRAFFIC_BYTES_B64 if B == 64 else None,
+                         "algorithmic_bytes": mask_bytes // 2 + 2 * B * N_CORR * 16,
                          "pairs_per_s": pairs_per_launch / k1_s if k1_s > 0 else None,
                          "kernel_ms": k1_ms / args.steps, "share_of_step": k1_ms / dev_ms if dev_ms > 0 else None,
                          "peak_source": f"{sms} SMs x 128 lanes x {f_mhz:.0f} MHz (nvidia-smi median under load)",

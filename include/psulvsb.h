@@ -242,6 +242,14 @@ int psulvsb_tls_translation(void* stream, const double* d_src64, const double* d
                             int n, double scale, const double* d_R, double noise, const double* d_last_best,
                             double* d_t_out, int* d_n_points);
 
+/* Surface normals by k-nearest-neighbour PCA, what the reference driver gets from PCL before its timed region
+ * (examples/teaser_cpp_ply/PSULVSB.cc:35-85: NormalEstimation, setKSearch(20), viewpoint (0,0,0)) and feeds to
+ * the histogram pre-filter (psulvsb_io.h).  d_pts / d_normals: column-major 3xn doubles on the device;
+ * 3 <= k <= 32; viewpoint may be NULL (origin).  The _host variant takes host buffers (copies inside). */
+int psulvsb_estimate_normals(void* stream, const double* d_pts, int n, int k, const double viewpoint[3],
+                             double* d_normals);
+int psulvsb_estimate_normals_host(const double* pts, int n, int k, const double viewpoint[3], double* normals);
+
 /* Clique escalation (registration.cc:1000-1085 -> teaser/src/graph.cc:12-125, PMC): a deterministic greedy
  * maximal clique of the graph with n_vertices vertices and the given edges (uint2 endpoint pairs): take the
  * candidate with the most neighbours among the remaining candidates (ties: lowest index), intersect.

@@ -79,3 +79,24 @@ def mask_filter(src, tgt, keep):
     rm = np.full(src.shape[1], -1, dtype=np.int32)
     rm[idx] = np.arange(idx.size, dtype=np.int32)
     return np.asfortranarray(src[:, idx]), np.asfortranarray(tgt[:, idx]), rm
+
+
+def knn_pca_normals(points, k=20, viewpoint=(0.0, 0.0, 0.0)):
+    """Restatement of what PSULVSB.cc:35-85 asks PCL for: for every point the k nearest neighbours (itself
+    included), the eigenvector of the smallest eigenvalue of their covariance, flipped towards the viewpoint."""
+    P = np.asarray(points, dtype=np.float64)
+    n = P.shape[1]
+    Pf = P.astype(np.float32)
+    out = np.zeros((3, n))
+    vp = np.asarray(viewpoint, dtype=np.float64)
+    for i in range(n):
+        d = ((Pf - Pf[:, i:i + 1]) ** 2).sum(axis=0)
+        idx = np.argsort(d, kind="stable")[:k]
+        nb = P[:, idx]
+        c = np.cov(nb, bias=True) * nb.shape[1]
+        w, v = np.linalg.eigh(c)
+        nv = v[:, 0]
+        if (vp - P[:, i]) @ nv < 0:
+            nv = -nv
+        out[:, i] = nv
+    return out

@@ -352,6 +352,34 @@ int psulvsb_tls_translation(void* stream, const double* d_src64, const double* d
                                 d_t_out, d_n_points);
 }
 
+int psulvsb_estimate_normals(void* stream, const double* d_pts, int n, int k, const double viewpoint[3],
+                             double* d_normals) {
+  if (int rc = need_device()) return rc;
+  if (!d_pts || !d_normals || n < 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_estimate_normals: bad argument");
+  return launch_knn_normals((cudaStream_t)stream, d_pts, n, k, viewpoint, d_normals);
+}
+
+int psulvsb_estimate_normals_host(const double* pts, int n, int k, const double viewpoint[3], double* normals) {
+  if (int rc = need_device()) return rc;
+  if (!pts || !normals || n < 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_estimate_normals_host: bad argument");
+  if (n == 0) return PSULVSB_OK;
+  double *d_p = nullptr, *d_n = nullptr;
+  const size_t bytes = sizeof(double) * 3 * (size_t)n;
+  PSU_CUDA(cudaMalloc((void**)&d_p, bytes));
+  if (cudaMalloc((void**)&d_n, bytes) != cudaSuccess) {
+    cudaFree(d_p);
+    return fail(PSULVSB_ERR_CUDA, "psulvsb_estimate_normals_host: cudaMalloc failed");
+  }
+  int rc = PSULVSB_OK;
+  if (cudaMemcpy(d_p, pts, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(PSULVSB_ERR_CUDA, "H2D copy failed");
+  if (!rc) rc = launch_knn_normals(nullptr, d_p, n, k, viewpoint, d_n);
+  if (!rc && cudaMemcpy(normals, d_n, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(PSULVSB_ERR_CUDA, std::string("normals kernel / D2H copy failed: ") + cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d_p);
+  cudaFree(d_n);
+  return rc;
+}
+
 int psulvsb_greedy_clique(void* stream, const void* d_edges_uint2, unsigned long long n_edges, int n_vertices,
                           uint32_t* d_adj, uint8_t* d_flags, int* d_size) {
   if (int rc = need_device()) return rc;

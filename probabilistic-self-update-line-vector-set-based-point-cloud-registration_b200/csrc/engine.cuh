@@ -135,6 +135,8 @@ struct CliqueJob {
 int launch_greedy_clique(cudaStream_t st, const CliqueJob* d_jobs, int n_jobs, int max_vertices, int max_stride,
                          unsigned long long max_edges);
 
+int launch_knn_normals(cudaStream_t st, const double* pts, int n, int k, const double* viewpoint, double* normals);
+
 // ---- stage launchers (k1_consistency.cu, k2_sampler.cu, k3_rotation.cu, k4_score.cu) -----------
 int launch_pack_points(cudaStream_t st, const double* pts, int n, const double center[3], float4* out);
 // max_n / max_rows: grid extents over all jobs

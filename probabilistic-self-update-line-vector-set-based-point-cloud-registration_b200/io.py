@@ -100,3 +100,13 @@ def read_gtlog(path: str):
     pairs = np.zeros((max(n.value, 1), 2), dtype=np.int32)
     capi.check(_lib().psulvsb_gtlog_read(path.encode(), pairs.ctypes.data_as(_ip), n.value, C.byref(n)))
     return [tuple(int(v) for v in p) for p in pairs[:n.value]]
+
+
+def estimate_normals(points, k: int = 20, viewpoint=(0.0, 0.0, 0.0)) -> np.ndarray:
+    """k-NN PCA normals on the GPU (psulvsb_estimate_normals_host): 3xN in, 3xN out."""
+    p = _cm(points)
+    out = np.zeros_like(p, order="F")
+    vp = (C.c_double * 3)(*[float(v) for v in viewpoint])
+    capi.check(capi.lib().psulvsb_estimate_normals_host(p.ctypes.data_as(_dp), p.shape[1], k, vp,
+                                                        out.ctypes.data_as(_dp)))
+    return out

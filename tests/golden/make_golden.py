@@ -11,6 +11,8 @@ Sources (all under /root/reference/TEASER-plusplus/test):
   teaser/data/registration_test/rotation_only_src.csv         200x3 (GNC-TLS known answer)
   teaser/data/registration_test/translation_test_v{1,2}_inliers.csv  3x34
   benchmark/data/benchmark_{1..6}/{src,dst}.ply + {R,t,s}_ref.csv + parameters.txt
+  teaser/data/registration_test/bun_zipper_res3.ply           1889 bunny vertices (config 1 of BASELINE.json;
+                                                              the full bun_zipper.ply is not in the reference tree)
 Known-answer constants:
   rotation-solver-test.cc:232-234 expected_R; translation-solver-test.cc:110 expected_t;
   registration-test.cc:229-308 expected R,t; tls-test.cc:21-86 scalar TLS answers.
@@ -102,6 +104,8 @@ def main():
              "inliers": [1, 1, 1, 0, 0, 0]},
         ],
     }
+    bunny = read_ascii_ply(os.path.join(REF, "teaser", "data", "registration_test", "bun_zipper_res3.ply"))
+    np.savez_compressed(os.path.join(OUT, "bunny_res3.npz"), vertices=bunny.astype(np.float32))
     with open(os.path.join(OUT, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("wrote", os.listdir(OUT))

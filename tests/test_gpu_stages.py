@@ -340,3 +340,27 @@ def test_solver_reaches_the_clique_escalation(P, O):
             assert synth.rotation_error(sg.R, O.solution_R(so)) < 1e-5
             assert np.abs(sg.t - O.solution_t(so)).max() < 1e-5
     assert hits >= 2
+
+
+def test_knn_pca_normals_vs_restatement(P, golden):
+    """What the reference driver asks PCL for (PSULVSB.cc:35-85: k = 20 nearest neighbours, smallest-eigenvalue
+    eigenvector, flipped towards the origin) on the reference's bunny vertices, against the numpy restatement."""
+    import os
+
+    from oracle import prefilter as OP
+    from psulvsb_b200 import io
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    v = np.load(os.path.join(root, "tests", "golden", "bunny_res3.npz"))["vertices"].astype(np.float64)
+    sub = v[:, :600]
+    got = io.estimate_normals(sub, k=20)
+    want = OP.knn_pca_normals(sub, k=20)
+    assert np.allclose(np.linalg.norm(got, axis=0), 1.0, atol=1e-9)
+    cos = np.abs((got * want).sum(axis=0))
+    assert (cos > 1 - 1e-6).mean() > 0.995          # same normal up to neighbourhood ties / degenerate planes
+    same_side = ((got * want).sum(axis=0) > 0)
+    assert same_side[cos > 1 - 1e-6].all()           # and the same orientation (flipped towards the viewpoint)
+    # a rigid motion of the cloud rotates the normals' LINES with it (orientation depends on the viewpoint)
+    R = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    moved = io.estimate_normals(R @ sub + np.array([[0.3], [0.1], [-0.2]]), k=20)
+    assert (np.abs(((R @ got) * moved).sum(axis=0)) > 1 - 1e-5).mean() > 0.97
