@@ -32,8 +32,10 @@ namespace psulvsb {
 
 namespace {
 
-constexpr int GNC_THREADS = 256;  // two CTAs per SM: one hypothesis' serial SVD phase overlaps another's pass
-constexpr int GNC_WARPS = GNC_THREADS / 32;
+// threads per CTA is a template parameter T: 256 (two CTAs per SM, so that one hypothesis' serial SVD phase
+// overlaps another's pass) for clustered launches, 512 (one CTA per SM, twice the shared-memory cache) when
+// every hypothesis runs on a single CTA (large batches)
+constexpr int GNC_MAX_WARPS = 16;
 #ifndef GNC_CTAS_PER_SM
 #define GNC_CTAS_PER_SM 2
 #endif
@@ -41,7 +43,7 @@ constexpr int GNC_NRED = 12;  // 9 H + cost + max/aux + count
 
 struct GncSmem {
   double part[2][GNC_NRED];           // this CTA's partial sums, double-buffered by iteration parity
-  double warp_part[GNC_WARPS][GNC_NRED];
+  double warp_part[GNC_MAX_WARPS][GNC_NRED];
   double R[9];                        // row-major current rotation
   double total[GNC_NRED];
   int flag;
@@ -96,7 +98,7 @@ __device__ __forceinline__ double residual2(const double R[9], const double sv[3
 }
 
 // CTA-level then cluster-level sum (or max for index MAXI) of NRED values; result in sm->total.
-template <int NC>
+template <int NC, int T>
 __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED], int parity, int max_index) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 #pragma unroll
@@ -111,7 +113,7 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
   __syncthreads();
   if (tid < GNC_NRED) {
     double acc = sm->warp_part[0][tid];
-    for (int w = 1; w < GNC_WARPS; ++w) {
+    for (int w = 1; w < T / 32; ++w) {
       const double x = sm->warp_part[w][tid];
       acc = (tid == max_index) ? fmax(acc, x) : acc + x;
     }
@@ -136,8 +138,8 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
   __syncthreads();
 }
 
-template <int NC>
-__global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
+template <int NC, int T>
+__global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GncSmem* sm = reinterpret_cast<GncSmem*>(smem_raw);
   double* lv = reinterpret_cast<double*>(smem_raw + ((sizeof(GncSmem) + 15) & ~size_t(15)));
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(c
   S.dst = dst;
   S.edges = edges;
   S.inv_scale = job.inv_scale;
-  for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+  for (unsigned long long l = tid; l < nloc; l += T) {
     double sv[3], tv[3];
     load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
     if (l < ncached) {
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(c
     if (tid < 9) sm->R[tid] = job.R_init[(tid % 3) * 3 + tid / 3];  // column-major -> row-major
     __syncthreads();
   } else {
-    cluster_reduce<NC>(sm, acc, parity, -1);
+    cluster_reduce<NC, T>(sm, acc, parity, -1);
     parity ^= 1;
     if (tid == 0) {
       double H[3][3], R[3][3];
@@ -235,12 +237,12 @@ __global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(c
       double mx[GNC_NRED];
 #pragma unroll
       for (int i = 0; i < GNC_NRED; ++i) mx[i] = 0.0;
-      for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+      for (unsigned long long l = tid; l < nloc; l += T) {
         double sv[3], tv[3];
         fetch_lv(S, l, k_lo + l, sv, tv);
         mx[0] = fmax(mx[0], residual2(R, sv, tv));
       }
-      cluster_reduce<NC>(sm, mx, parity, 0);
+      cluster_reduce<NC, T>(sm, mx, parity, 0);
       parity ^= 1;
       const double max_residual = sm->total[0];
       mu = 1.0 / (2.0 * max_residual / nb2 - 1.0);
@@ -278,20 +280,20 @@ __global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(c
       const int nc = (int)ncached;
       double* __restrict__ ws = lv + 6 * cap;
       int l = tid;
-      for (; l + GNC_THREADS < nc; l += 2 * GNC_THREADS) {
+      for (; l + T < nc; l += 2 * T) {
         double sa[3], ta[3], sb[3], tb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           sa[r] = lv[r * (int)cap + l];
           ta[r] = lv[(3 + r) * (int)cap + l];
-          sb[r] = lv[r * (int)cap + l + GNC_THREADS];
-          tb[r] = lv[(3 + r) * (int)cap + l + GNC_THREADS];
+          sb[r] = lv[r * (int)cap + l + T];
+          tb[r] = lv[(3 + r) * (int)cap + l + T];
         }
-        const double wa = ws[l], wb = ws[l + GNC_THREADS];
+        const double wa = ws[l], wb = ws[l + T];
         ws[l] = body(sa, ta, wa);
-        ws[l + GNC_THREADS] = body(sb, tb, wb);
+        ws[l + T] = body(sb, tb, wb);
       }
-      for (; l < nc; l += GNC_THREADS) {
+      for (; l < nc; l += T) {
         double sa[3], ta[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -309,20 +311,20 @@ __global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(c
       double* __restrict__ gwl = gw + k_lo;
       const size_t st = (size_t)lv_cap;
       int l = (int)ncached + tid;
-      for (; l + GNC_THREADS < g_hi; l += 2 * GNC_THREADS) {
+      for (; l + T < g_hi; l += 2 * T) {
         double sa[3], ta[3], sb[3], tb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           sa[r] = __ldcg(g0 + r * st + l);
           ta[r] = __ldcg(g0 + (3 + r) * st + l);
-          sb[r] = __ldcg(g0 + r * st + l + GNC_THREADS);
-          tb[r] = __ldcg(g0 + (3 + r) * st + l + GNC_THREADS);
+          sb[r] = __ldcg(g0 + r * st + l + T);
+          tb[r] = __ldcg(g0 + (3 + r) * st + l + T);
         }
-        const double wa = __ldcg(gwl + l), wb = __ldcg(gwl + l + GNC_THREADS);
+        const double wa = __ldcg(gwl + l), wb = __ldcg(gwl + l + T);
         __stcg(gwl + l, body(sa, ta, wa));
-        __stcg(gwl + l + GNC_THREADS, body(sb, tb, wb));
+        __stcg(gwl + l + T, body(sb, tb, wb));
       }
-      for (; l < g_hi; l += GNC_THREADS) {
+      for (; l < g_hi; l += T) {
         double sa[3], ta[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -332,14 +334,14 @@ __global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(c
         __stcg(gwl + l, body(sa, ta, __ldcg(gwl + l)));
       }
       // (c) beyond the scratch capacity: recompute from the points
-      for (; l < nl; l += GNC_THREADS) {
+      for (; l < nl; l += T) {
         double sa[3], ta[3];
         load_lv(src, dst, edges[k_lo + l], job.inv_scale, sa, ta);
         gwl[l] = body(sa, ta, gwl[l]);
       }
     }
     weights_are_unit = false;
-    cluster_reduce<NC>(sm, acc, parity, -1);
+    cluster_reduce<NC, T>(sm, acc, parity, -1);
     parity ^= 1;
     cost = sm->total[9];
     const double cost_diff = fabs(cost - prev_cost);
@@ -364,19 +366,19 @@ __global__ void __launch_bounds__(GNC_THREADS, GNC_CTAS_PER_SM) gnc_tls_kernel(c
   double cntv[GNC_NRED];
 #pragma unroll
   for (int i = 0; i < GNC_NRED; ++i) cntv[i] = 0.0;
-  for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+  for (unsigned long long l = tid; l < nloc; l += T) {
     const double w = weights_are_unit ? 1.0 : ((l < ncached) ? lv[6 * cap + l] : gw[k_lo + l]);
     cntv[0] += (w >= 0.5) ? 1.0 : 0.0;
   }
   if (job.point_flags) {
     // zero this cluster's share of the flags before anyone sets them (cluster_reduce syncs)
-    for (int i = rank * GNC_THREADS + tid; i < job.n_points; i += NC * GNC_THREADS) job.point_flags[i] = 0;
+    for (int i = rank * T + tid; i < job.n_points; i += NC * T) job.point_flags[i] = 0;
   }
-  cluster_reduce<NC>(sm, cntv, parity, -1);
+  cluster_reduce<NC, T>(sm, cntv, parity, -1);
   parity ^= 1;
   const long long gf = (long long)(sm->total[0] + 0.5);
   const bool all_in = gf <= 10;
-  for (unsigned long long l = tid; l < nloc; l += GNC_THREADS) {
+  for (unsigned long long l = tid; l < nloc; l += T) {
     const double w = weights_are_unit ? 1.0 : ((l < ncached) ? lv[6 * cap + l] : gw[k_lo + l]);
     const bool in = all_in || (w >= 0.5);
     if (job.inliers) job.inliers[k_lo + l] = in ? 1 : 0;
@@ -454,20 +456,23 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+int gnc_capacity_for(int ctas_per_sm);
 size_t gnc_smem_bytes(int cap) { return ((sizeof(GncSmem) + 15) & ~size_t(15)) + (size_t)7 * cap * sizeof(double); }
 
-template <int NC>
+template <int NC, int T>
 int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta) {
   static bool attr_set = false;
+  const int max_cap = gnc_capacity_for(T >= 512 ? 1 : GNC_CTAS_PER_SM);
+  if (cap_per_cta > max_cap) cap_per_cta = max_cap;
   const size_t smem = gnc_smem_bytes(cap_per_cta);
   if (!attr_set) {
-    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)gnc_smem_bytes(gnc_default_capacity())));
+    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<NC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)gnc_smem_bytes(max_cap)));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(NC, (unsigned)n_jobs, 1);
-  cfg.blockDim = dim3(GNC_THREADS, 1, 1);
+  cfg.blockDim = dim3(T, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -477,20 +482,24 @@ int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC>, d_jobs, cap_per_cta));
+  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T>, d_jobs, cap_per_cta));
   return PSULVSB_OK;
 }
 
 }  // namespace
 
-int gnc_default_capacity() {
-  // GNC_CTAS_PER_SM CTAs share the SM's 227 KB
-  const size_t budget = (size_t)(220 / GNC_CTAS_PER_SM) * 1024;
+namespace {
+int gnc_capacity_for(int ctas_per_sm) {
+  // the CTAs resident on an SM share its 227 KB
+  const size_t budget = (size_t)(220 / ctas_per_sm) * 1024;
   const size_t fixed = (sizeof(GncSmem) + 15) & ~size_t(15);
   int cap = (int)((budget - fixed) / (7 * sizeof(double)));
   cap &= ~31;
   return cap;
 }
+}  // namespace
+
+int gnc_default_capacity() { return gnc_capacity_for(1); }
 
 // CTAs per hypothesis for a batch of n_jobs: as many SMs per job as keeps the whole batch resident
 int gnc_cluster_for(int n_jobs) {
@@ -503,13 +512,12 @@ int gnc_cluster_for(int n_jobs) {
 
 int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster) {
   if (n_jobs <= 0) return PSULVSB_OK;
-  if (cap_per_cta > gnc_default_capacity()) cap_per_cta = gnc_default_capacity();
   if (cap_per_cta < 32) cap_per_cta = 32;
   switch (cluster) {
-    case 8: return launch_gnc_nc<8>(st, d_jobs, n_jobs, cap_per_cta);
-    case 4: return launch_gnc_nc<4>(st, d_jobs, n_jobs, cap_per_cta);
-    case 2: return launch_gnc_nc<2>(st, d_jobs, n_jobs, cap_per_cta);
-    case 1: return launch_gnc_nc<1>(st, d_jobs, n_jobs, cap_per_cta);
+    case 8: return launch_gnc_nc<8, 256>(st, d_jobs, n_jobs, cap_per_cta);
+    case 4: return launch_gnc_nc<4, 256>(st, d_jobs, n_jobs, cap_per_cta);
+    case 2: return launch_gnc_nc<2, 256>(st, d_jobs, n_jobs, cap_per_cta);
+    case 1: return launch_gnc_nc<1, 512>(st, d_jobs, n_jobs, cap_per_cta);
     default: return fail(PSULVSB_ERR_INVALID, "launch_gnc_tls: cluster must be 1, 2, 4 or 8");
   }
 }
