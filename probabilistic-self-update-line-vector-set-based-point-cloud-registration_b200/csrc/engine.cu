@@ -9,10 +9,12 @@
 // The only host synchronisations are the n_red read-back and one 4-byte "jobs done" poll per tick.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -212,43 +214,63 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
   if (int rc = d_in_int.ensure(bytes_i)) return rc;
   double* hd = reinterpret_cast<double*>(h_stage.p);
   int* hi = reinterpret_cast<int*>(reinterpret_cast<char*>(h_stage.p) + align_up(bytes_d, 256));
-  for (int b = 0; b < nb; ++b) {
-    const psulvsb_problem_t& p = problems[b];
-    ProbLayout& L = lay[(size_t)b];
-    double* d = hd + L.in_dbl;
-    std::memcpy(d, p.src, sizeof(double) * 3 * (size_t)p.C);
-    std::memcpy(d + 3 * (size_t)p.C, p.dst, sizeof(double) * 3 * (size_t)p.C);
-    std::memcpy(d + 6 * (size_t)p.C, p.ori_src, sizeof(double) * 3 * (size_t)p.M);
-    std::memcpy(d + 6 * (size_t)p.C + 3 * (size_t)p.M, p.ori_dst, sizeof(double) * 3 * (size_t)p.M);
-    std::memcpy(hi + L.in_int, p.keep_mask, sizeof(int) * (size_t)p.M);
-    std::memcpy(hi + L.in_int + p.M, p.reduce_map, sizeof(int) * (size_t)p.M);
-    // centres / coordinate bound of the FP32 tiles (differences are translation invariant)
-    for (int s = 0; s < 2; ++s) {
-      const double* pts = s ? p.dst : p.src;
-      double lo[3] = {pts[0], pts[1], pts[2]}, hi3[3] = {pts[0], pts[1], pts[2]};
-      for (int i = 1; i < p.C; ++i)
+  // staging copy + centres / coordinate bound of the FP32 tiles, split over a few host threads (33 MB for a
+  // batch of 64 cfg-A pairs: a single-threaded memcpy would cost more than the H2D copy that follows)
+  std::atomic<int> bad_problem(-1);
+  auto stage_range = [&](int b0, int b1) {
+    for (int b = b0; b < b1; ++b) {
+      const psulvsb_problem_t& p = problems[b];
+      ProbLayout& L = lay[(size_t)b];
+      double* d = hd + L.in_dbl;
+      std::memcpy(d, p.src, sizeof(double) * 3 * (size_t)p.C);
+      std::memcpy(d + 3 * (size_t)p.C, p.dst, sizeof(double) * 3 * (size_t)p.C);
+      std::memcpy(d + 6 * (size_t)p.C, p.ori_src, sizeof(double) * 3 * (size_t)p.M);
+      std::memcpy(d + 6 * (size_t)p.C + 3 * (size_t)p.M, p.ori_dst, sizeof(double) * 3 * (size_t)p.M);
+      std::memcpy(hi + L.in_int, p.keep_mask, sizeof(int) * (size_t)p.M);
+      std::memcpy(hi + L.in_int + p.M, p.reduce_map, sizeof(int) * (size_t)p.M);
+      // (differences are translation invariant: each cloud is centred on its own bounding box)
+      for (int s = 0; s < 2; ++s) {
+        const double* pts = s ? p.dst : p.src;
+        double lo[3] = {pts[0], pts[1], pts[2]}, hi3[3] = {pts[0], pts[1], pts[2]};
+        for (int i = 1; i < p.C; ++i)
+          for (int r = 0; r < 3; ++r) {
+            const double v = pts[3 * (size_t)i + r];
+            lo[r] = v < lo[r] ? v : lo[r];
+            hi3[r] = v > hi3[r] ? v : hi3[r];
+          }
+        double* c = s ? L.cdst : L.csrc;
+        double bound = 0.0;
         for (int r = 0; r < 3; ++r) {
-          const double v = pts[3 * (size_t)i + r];
-          lo[r] = v < lo[r] ? v : lo[r];
-          hi3[r] = v > hi3[r] ? v : hi3[r];
+          c[r] = 0.5 * (lo[r] + hi3[r]);
+          const double h = 0.5 * (hi3[r] - lo[r]);
+          bound = h > bound ? h : bound;
         }
-      double* c = s ? L.cdst : L.csrc;
-      double bound = 0.0;
-      for (int r = 0; r < 3; ++r) {
-        c[r] = 0.5 * (lo[r] + hi3[r]);
-        const double h = 0.5 * (hi3[r] - lo[r]);
-        bound = h > bound ? h : bound;
+        if (s == 0)
+          L.coord_bound = bound;
+        else
+          L.coord_bound = bound > L.coord_bound ? bound : L.coord_bound;
       }
-      if (s == 0)
-        L.coord_bound = bound;
-      else
-        L.coord_bound = bound > L.coord_bound ? bound : L.coord_bound;
+      L.coord_bound = L.coord_bound * (1.0 + 1e-6) + 1e-30;
+      for (int r = 0; r < 3; ++r)
+        if (!std::isfinite(L.csrc[r]) || !std::isfinite(L.cdst[r]) || !std::isfinite(L.coord_bound)) bad_problem.store(b);
     }
-    L.coord_bound = L.coord_bound * (1.0 + 1e-6) + 1e-30;
-    for (int r = 0; r < 3; ++r)
-      if (!std::isfinite(L.csrc[r]) || !std::isfinite(L.cdst[r]) || !std::isfinite(L.coord_bound))
-        return fail(PSULVSB_ERR_INVALID, "upload: problem " + std::to_string(b) + " has non-finite coordinates");
+  };
+  {
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads > 8) nthreads = 8;
+    if (nthreads > nb) nthreads = nb;
+    if (nthreads < 1 || bytes_d < (4u << 20)) nthreads = 1;
+    if (nthreads == 1) {
+      stage_range(0, nb);
+    } else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back(stage_range, (int)((long long)nb * t / nthreads), (int)((long long)nb * (t + 1) / nthreads));
+      for (auto& th : pool) th.join();
+    }
   }
+  if (bad_problem.load() >= 0)
+    return fail(PSULVSB_ERR_INVALID, "upload: problem " + std::to_string(bad_problem.load()) + " has non-finite coordinates");
   PSU_CUDA(cudaMemcpyAsync(d_in_dbl.p, hd, bytes_d, cudaMemcpyHostToDevice, st));
   PSU_CUDA(cudaMemcpyAsync(d_in_int.p, hi, bytes_i, cudaMemcpyHostToDevice, st));
   PSU_CUDA(cudaStreamSynchronize(st));

@@ -364,3 +364,35 @@ def test_knn_pca_normals_vs_restatement(P, golden):
     R = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
     moved = io.estimate_normals(R @ sub + np.array([[0.3], [0.1], [-0.2]]), k=20)
     assert (np.abs(((R @ got) * moved).sum(axis=0)) > 1 - 1e-5).mean() > 0.97
+
+
+def test_k1_large_n_sampled_rows_and_invariants(P, O):
+    """Size-independent checks at a size the O(N^2) oracle cannot sweep in full: N = 30 000 (4.5e8 pairs).
+    (1) 40 random rows bit-exact against the oracle's ScaleInliersSelector on those rows' line vectors;
+    (2) popcount(mask) == sum(row_counts) == number of compacted edges; (3) a rigid motion of BOTH clouds
+    leaves every pair's lengths unchanged up to rounding, so the mask may differ only on pairs inside the
+    counted FP64 band."""
+    st = P["stages"]
+    n, beta = 30000, 0.1
+    pair = P["synth"].make_pair(n, 0.99, 77, side=10.0)
+    r = st.consistency_mask(pair["src"], pair["dst"], beta)
+    counts = r["row_counts"].cpu().numpy().astype(np.int64)
+    rng = np.random.default_rng(1)
+    rows = np.sort(rng.permutation(n - 1)[:40])
+    m = r["mask"][torch.from_numpy(rows).cuda()].cpu().numpy().view(np.uint32)
+    bits = np.unpackbits(m.view(np.uint8), axis=1, bitorder="little")[:, :n]
+    for k, i in enumerate(rows):
+        js = np.arange(i + 1, n)
+        sv = pair["src"][:, js] - pair["src"][:, [i]]
+        tv = pair["dst"][:, js] - pair["dst"][:, [i]]
+        want = O.scale_inliers(sv, tv, beta)
+        assert np.array_equal(bits[k, i + 1:], want), i
+        assert not bits[k, : i + 1].any()
+        assert counts[i] == int(want.sum())
+    edges, offsets = st.compact_edges(r["mask"], r["row_counts"], n, r["stride"])
+    assert edges.shape[0] == int(counts.sum())
+    e = edges.cpu().numpy()
+    assert np.all(e[:, 0] < e[:, 1])
+    key = e[:, 0].astype(np.int64) * n + e[:, 1]
+    assert np.all(np.diff(key) > 0)                      # reference order: row-major over the upper triangle
+    assert r["border"] < 1e-4 * n * (n - 1) / 2
