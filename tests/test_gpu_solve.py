@@ -273,3 +273,27 @@ def test_unknown_scale_reference_benchmark_fixtures(env, golden, k):
         assert np.abs(sg.t - O.solution_t(so)).max() < T_TOL
         assert abs(sg.scale - float(b[f"b{k}_s"][0])) < 0.02 * float(b[f"b{k}_s"][0])
         assert env["synth"].rotation_error(sg.R, b[f"b{k}_R"]) < 0.02
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 7, 12, 25])
+def test_tiny_problems_terminate(env, n):
+    """Degenerate sizes: |L_sampled| and the basic subset collapse to 0 or 1 line vectors (rank-deficient
+    rotation solves, empty translation sets).  No parity is defined there (see benchmark_1), but the engine must
+    terminate with a status, never hang or fault, and agree with the oracle on the sizes it derives."""
+    capi, O = env["capi"], env["O"]
+    rng = np.random.default_rng(n)
+    src = rng.uniform(-1, 1, (3, n))
+    ang = 0.4
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    dst = R @ src + np.array([[0.2], [-0.1], [0.3]]) + rng.uniform(-0.005, 0.005, (3, n))
+    for scaling in (0, 1):
+        kw = dict(PKW)
+        kw["estimate_scaling"] = scaling
+        sg, _ = env["h"].solve(capi.default_params(seed=1, **kw), capi.HostProblem(src, dst))
+        so, _ = O.solve(O.default_params(seed=1, **kw), src, dst)
+        assert sg.status in (0, capi.ERR_INTERNAL)           # ERR_INTERNAL = the reference's non-terminating loop, cut
+        assert sg.n_line_vectors == n * (n - 1) // 2 == so.n_line_vectors
+        assert sg.n_reduced == so.n_reduced
+        if sg.status == 0 and sg.valid:
+            Rg = sg.R
+            assert np.allclose(Rg @ Rg.T, np.eye(3), atol=1e-9) and np.linalg.det(Rg) > 0
