@@ -251,6 +251,11 @@ class HostProblem:
                 self.keep_mask.nbytes + self.reduce_map.nbytes)
 
     def c_struct(self) -> Problem:
+        if getattr(self, "_cs", None) is None:  # the arrays are owned by this object: build the view once
+            self._cs = self._build_c_struct()
+        return self._cs
+
+    def _build_c_struct(self) -> Problem:
         return Problem(self.src.ctypes.data_as(_dp), self.dst.ctypes.data_as(_dp), self.src.shape[1],
                        self.ori_src.ctypes.data_as(_dp), self.ori_dst.ctypes.data_as(_dp), self.ori_src.shape[1],
                        self.keep_mask.ctypes.data_as(_ip), self.reduce_map.ctypes.data_as(_ip))

@@ -247,7 +247,8 @@ unsigned long long psulvsb_sample_default_max_draws(unsigned long long n, unsign
 unsigned long long psulvsb_sample_workspace_bytes(unsigned long long n, unsigned long long count,
                                                   unsigned long long max_draws) {
   if (max_draws == 0) max_draws = sample_default_max_draws(n, count);
-  return ((n * sizeof(uint32_t) + 15) & ~15ull) + sample_chunk_slots(max_draws) * sizeof(unsigned long long) + 16;
+  return ((sample_table_words(n, max_draws) * sizeof(uint32_t) + 15) & ~15ull) +
+         sample_chunk_slots(max_draws) * sizeof(unsigned long long) + 16;
 }
 
 int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long n,
@@ -260,9 +261,9 @@ int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event,
   if (max_draws == 0) max_draws = sample_default_max_draws(n, count);
   if (max_draws >= 0xFFFFFFFFull) return fail(PSULVSB_ERR_UNSUPPORTED, "psulvsb_sample: max_draws must be < 2^32 - 1");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t first_bytes = (n * sizeof(uint32_t) + 15) & ~15ull;
+  const size_t first_bytes = (sample_table_words(n, max_draws) * sizeof(uint32_t) + 15) & ~15ull;
   const size_t slots = sample_chunk_slots(max_draws);
-  PSU_CUDA(cudaMemsetAsync(d_work, 0xFF, n * sizeof(uint32_t), st));
+  PSU_CUDA(cudaMemsetAsync(d_work, 0, first_bytes, st));
   PSU_CUDA(cudaMemsetAsync((char*)d_work + first_bytes + slots * sizeof(unsigned long long), 0, 16, st));
   PSU_CUDA(cudaMemsetAsync(d_status, 0, sizeof(unsigned long long), st));
   if (count == 0) return PSULVSB_OK;
@@ -282,7 +283,7 @@ int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event,
   j.active = 1;
   DeviceJob<SampleJob> dj(st);
   if (int rc = dj.put(j)) return rc;
-  return launch_sample(st, dj.d, 1, max_draws);
+  return launch_sample(st, dj.d, 1, max_draws, n);
 }
 
 int psulvsb_philox_fill(void* stream, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long first_k,

@@ -536,7 +536,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         if (cap < 64) cap = 64;
         J.edge_cap = cap;
         J.edges = be.take<uint2>((size_t)cap);
-        J.first = be.take<uint32_t>((size_t)cap);
+        J.first_words = sample_table_words(cap, sample_default_max_draws(cap, cap));
+        J.first = be.take<uint32_t>((size_t)J.first_words);
         J.chunk_prefix = be.take<unsigned long long>((size_t)sample_chunk_slots(sample_default_max_draws(cap, cap)));
         J.ticket = be.take<unsigned int>(4);
         J.L_sampled = be.take<uint32_t>((size_t)cap);
@@ -602,11 +603,6 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   const unsigned long long draws_bound = sample_default_max_draws(max_cap, max_cap / 8 + 1);
   int ticks = 0;
   const int max_ticks = P.max_local_iters + P.host_round_limit + 8;
-  // (measured: splitting the L-sample passes into L2-sized job groups does not pay -- 64 jobs in one group
-  // 7.9 ms/step, groups of 16: 8.2, of 4: 10.1 -- so all jobs go in one launch; PSULVSB_L_GROUP overrides)
-  static const char* lg_env = getenv("PSULVSB_L_GROUP");
-  int l_group = lg_env ? atoi(lg_env) : B;
-  if (l_group < 1 || l_group > B) l_group = B;
   bool round_start_pending = true;  // every job begins with a round start
   bool clique_pending = false;
   while (true) {
@@ -615,10 +611,10 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     if (round_start_pending) {
       engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, m.n_done);
       PSU_CHECK_LAUNCH("engine_round_start_kernel");
-      if (int rc = launch_sample(st, m.sl, B, draws_bound, l_group)) return rc;
-      launches += 1 + 3 * ((B + l_group - 1) / l_group);
+      if (int rc = launch_sample(st, m.sl, B, draws_bound, max_cap)) return rc;
+      launches += 3;
     }
-    if (int rc = launch_sample(st, m.sb, B, draws_bound)) return rc;
+    if (int rc = launch_sample(st, m.sb, B, draws_bound, max_cap)) return rc;
     if (ratio) {
       engine_scale_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.gj, m.cq, P);
       PSU_CHECK_LAUNCH("engine_scale_kernel");
@@ -633,7 +629,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster)) return rc;
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");
-    launches += 5;
+    launches += 4;
     ++ticks;
     PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     PSU_CUDA(cudaStreamSynchronize(st));

@@ -76,9 +76,9 @@ struct SampleJob {
   uint64_t seed;
   uint32_t domain, event;
   unsigned long long n, count, max_draws;
-  uint32_t* first;               // [n] first-occurrence table, all 0xFFFFFFFF on entry and on exit
+  uint32_t* first;               // [sample_table_words(n, max_draws)] accept bitmask, all zero on entry and on exit
   unsigned long long* chunk_prefix;  // [sample_chunk_slots(max_draws)] accepted draws before each chunk
-  unsigned int* ticket;          // zero on entry and on exit (last-CTA-done counter of the count pass)
+  unsigned int* ticket;          // zero on entry and on exit (last-CTA-done counter of the bucket pass)
   uint32_t* out;                 // [count]
   unsigned long long* status;    // draws consumed (0: max_draws too small)
   int identity;                  // 1: out[r] = r (registration.cc:839-847, empty-sample fallback)
@@ -166,8 +166,9 @@ __host__ __device__ inline unsigned long long sample_max_draws_formula(unsigned 
 }
 unsigned long long sample_default_max_draws(unsigned long long n, unsigned long long count);
 unsigned long long sample_chunk_slots(unsigned long long max_draws);
+unsigned long long sample_table_words(unsigned long long n, unsigned long long max_draws);
 int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound,
-                  int jobs_per_group = 0);
+                  unsigned long long n_bound);
 int launch_philox_fill(cudaStream_t st, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long first_k,
                        unsigned long long count, uint32_t* out);
 

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(BLK)
     J.final_inliers[j] = 0;
     J.residual_history[j] = 0.0;
   }
-  for (unsigned long long i = tid; i < J.edge_cap; i += BLK) J.first[i] = 0xFFFFFFFFu;
+  for (unsigned long long i = tid; i < J.first_words; i += BLK) J.first[i] = 0u;  // sampler accept bitmask
   if (tid == 0) {
     *J.ticket = 0u;
     J.C = J.C0;

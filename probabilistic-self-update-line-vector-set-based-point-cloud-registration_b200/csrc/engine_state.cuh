@@ -67,7 +67,8 @@ struct JobCtl {
   uint8_t* rot_flags;        // [Ccap]
   uint2* edges;              // reduced set (L_reduced_set) as endpoint pairs
   unsigned long long edge_cap;
-  uint32_t* first;  // [edge_cap] sampler first-occurrence table
+  uint32_t* first;  // [first_words] sampler accept bitmask (zero between uses)
+  unsigned long long first_words;
   unsigned long long* chunk_prefix;  // sampler scratch
   unsigned int* ticket;              // sampler scratch (zero between uses)
   uint32_t* L_sampled;

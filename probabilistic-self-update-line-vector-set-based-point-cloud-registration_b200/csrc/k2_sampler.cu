@@ -4,16 +4,19 @@
 // (registration.cc:852-861, :916-932) -- inherently sequential, with a data-dependent number of
 // consumed draws.  The same index sequence is produced in parallel here: draw k (a pure function
 // of (seed, domain, event, k)) is accepted iff it is the FIRST occurrence of its value, i.e. iff
-// first[v_k] == k where first[] is built with atomicMin; the r-th accepted draw is output r.
+// first[v_k] == k where first[v] = min { k : v_k = v }; the r-th accepted draw is output r.
 // That is exactly the rejection rule, so the output equals the sequential algorithm's for the same
 // stream, and the stream position after the call (draws consumed) is reported for replay.
 //
-// Three fully parallel passes over the draw window, every one a grid of (chunks x jobs) CTAs:
-//   mark  : first[v_k] = min(first[v_k], k)
-//   count : accepted draws per 1024-draw chunk; the last CTA of a job to finish turns the chunk
-//           counts into exclusive prefixes (threadfence reduction, no CTA ever waits on another)
-//   emit  : rank = prefix[chunk] + position in chunk -> out[rank]; restores first[] on the way;
-//           optional fused post-processing for the batch engine (endpoint flags / edge gather)
+// Two passes, no global table:
+//   bucket : the value range [0, n) is cut into buckets of SMP_BW values; CTA (b, job) walks the whole draw
+//            window (Philox is cheap: the redundancy buys the removal of every random global access), keeps
+//            first[v - lo] = min k for the values of ITS bucket in SHARED memory, and sets bit k of the
+//            job's accept bitmask for every draw that is the first occurrence of its value.  The last
+//            CTA of a job to finish turns the per-1024-draw popcounts into exclusive prefixes
+//            (threadfence reduction, no CTA ever waits on another).
+//   emit   : rank = prefix[chunk] + position in chunk -> out[rank]; clears the accept words on the way;
+//            optional fused post-processing for the batch engine (endpoint flags / edge gather).
 // Kernels take device-resident SampleJob arrays (one job per registration in the batch engine,
 // whose control kernels rewrite n / count / event between ticks).
 #include <cuda_runtime.h>
@@ -25,86 +28,96 @@ namespace psulvsb {
 
 namespace {
 
-constexpr int SMP_THREADS = 256;
+constexpr int SMP_THREADS = 256;            // emit pass
 constexpr int SMP_CHUNK = SMP_THREADS * 4;  // draws per chunk (one Philox block per thread)
+constexpr int SMB_THREADS = 512;            // bucket pass (one CTA per SM: the table fills shared memory)
+constexpr int SMP_BW = 40960;               // values per bucket (160 KB of shared memory)
+constexpr int SMP_LCAP = 6144;              // matched draws a CTA remembers before it falls back to a second walk
 
 __device__ __forceinline__ uint32_t draw_value(uint32_t word, uint32_t n) { return (word >> 1) % n; }
 
-__global__ void __launch_bounds__(SMP_THREADS) sample_mark_kernel(const SampleJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const SampleJob* __restrict__ jobs) {
   const SampleJob& job = jobs[blockIdx.y];
-  if (!job.active || job.identity) return;
+  if (!job.active) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw);          // [SMP_BW]
+  uint32_t* list_k = table + SMP_BW;                                // [SMP_LCAP]
+  uint16_t* list_o = reinterpret_cast<uint16_t*>(list_k + SMP_LCAP);  // [SMP_LCAP]
+  __shared__ unsigned int cnt_s, ticket_s, sh[SMB_THREADS / 32];
+  __shared__ unsigned long long carry_s;
+  const int tid = threadIdx.x;
+  if (job.post == 1 && blockIdx.x == 0)  // endpoint flags are rebuilt by the emit pass
+    for (int i = tid; i < job.n_points; i += SMB_THREADS) job.flags[i] = 0;
+  if (job.identity) return;
   const uint32_t n = (uint32_t)job.n;
+  const unsigned int n_buckets = (n + SMP_BW - 1) / SMP_BW;
+  if (blockIdx.x >= n_buckets) return;
+  const uint32_t lo = blockIdx.x * (uint32_t)SMP_BW;
+  const uint32_t width = min((uint32_t)SMP_BW, n - lo);
   const unsigned long long max_draws = job.max_draws;
-  uint32_t* __restrict__ first = job.first;
   const unsigned long long nblocks = (max_draws + 3) >> 2;
-  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < nblocks;
-       q += (unsigned long long)gridDim.x * blockDim.x) {
+  uint32_t* __restrict__ accept = job.first;  // bit k set <=> draw k is accepted; all zero on entry and on exit
+  for (uint32_t i = tid; i < width; i += SMB_THREADS) table[i] = 0xFFFFFFFFu;
+  if (tid == 0) cnt_s = 0u;
+  __syncthreads();
+  // walk 1: first occurrence of every value of this bucket
+  for (unsigned long long q = tid; q < nblocks; q += SMB_THREADS) {
     const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       const unsigned long long k = (q << 2) + l;
-      if (k < max_draws) atomicMin(&first[draw_value(o.w[l], n)], (uint32_t)k);
+      const uint32_t off = draw_value(o.w[l], n) - lo;
+      if (k < max_draws && off < width) {
+        atomicMin(&table[off], (uint32_t)k);
+        const unsigned int slot = atomicAdd(&cnt_s, 1u);
+        if (slot < SMP_LCAP) {
+          list_k[slot] = (uint32_t)k;
+          list_o[slot] = (uint16_t)off;
+        }
+      }
     }
   }
-}
-
-__device__ __forceinline__ unsigned int block_sum_u32(unsigned int v, unsigned int* sh) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) sh[wid] = v;
   __syncthreads();
-  unsigned int t = 0;
-#pragma unroll
-  for (int w = 0; w < SMP_THREADS / 32; ++w) t += sh[w];
-  __syncthreads();
-  return t;
-}
-
-__global__ void __launch_bounds__(SMP_THREADS) sample_count_kernel(const SampleJob* __restrict__ jobs) {
-  const SampleJob& job = jobs[blockIdx.y];
-  if (!job.active) return;
-  __shared__ unsigned int sh[SMP_THREADS / 32];
-  __shared__ unsigned int ticket_s;
-  __shared__ unsigned long long carry_s;
-  const int tid = threadIdx.x;
-  if (job.post == 1)  // endpoint flags are rebuilt by the emit pass
-    for (int i = blockIdx.x * SMP_THREADS + tid; i < job.n_points; i += gridDim.x * SMP_THREADS) job.flags[i] = 0;
-  if (job.identity) return;
-  const uint32_t n = (uint32_t)job.n;
-  const unsigned long long max_draws = job.max_draws;
-  const unsigned long long nchunks = (max_draws + SMP_CHUNK - 1) / SMP_CHUNK;
-  const uint32_t* __restrict__ first = job.first;
-  for (unsigned long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const unsigned long long q = ch * SMP_THREADS + tid;
-    unsigned int c = 0;
-    if ((q << 2) < max_draws) {
+  const unsigned int matched = cnt_s;
+  if (matched <= SMP_LCAP) {
+    for (unsigned int i = tid; i < matched; i += SMB_THREADS) {
+      const uint32_t k = list_k[i];
+      if (table[list_o[i]] == k) atomicOr(&accept[k >> 5], 1u << (k & 31));
+    }
+  } else {  // walk 2 (only when the draw window is far larger than the bucket count times SMP_LCAP)
+    for (unsigned long long q = tid; q < nblocks; q += SMB_THREADS) {
       const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         const unsigned long long k = (q << 2) + l;
-        if (k < max_draws && first[draw_value(o.w[l], n)] == (uint32_t)k) ++c;
+        const uint32_t off = draw_value(o.w[l], n) - lo;
+        if (k < max_draws && off < width && table[off] == (uint32_t)k) atomicOr(&accept[k >> 5], 1u << (k & 31));
       }
     }
-    const unsigned int tot = block_sum_u32(c, sh);
-    if (tid == 0) job.chunk_prefix[ch] = (unsigned long long)tot;
   }
-  // last CTA of this job: counts -> exclusive prefixes
+  // last CTA of this job: per-chunk popcounts of the accept bitmask -> exclusive prefixes
   __threadfence();
+  __syncthreads();
   if (tid == 0) ticket_s = atomicAdd(job.ticket, 1u);
   __syncthreads();
-  if (ticket_s != gridDim.x - 1) return;
+  if (ticket_s != n_buckets - 1) return;
   __threadfence();
   if (tid == 0) {
     carry_s = 0ull;
     *job.ticket = 0u;  // ready for the next use
   }
   __syncthreads();
-  volatile unsigned long long* pref = job.chunk_prefix;
-  for (unsigned long long c0 = 0; c0 < nchunks; c0 += SMP_THREADS) {
+  const unsigned long long nchunks = (max_draws + SMP_CHUNK - 1) / SMP_CHUNK;
+  constexpr int WPC = SMP_CHUNK / 32;  // accept words per chunk
+  const unsigned long long nwords = (max_draws + 31) >> 5;
+  for (unsigned long long c0 = 0; c0 < nchunks; c0 += SMB_THREADS) {
     const unsigned long long ch = c0 + tid;
-    const unsigned int v = (ch < nchunks) ? (unsigned int)pref[ch] : 0u;
-    // block exclusive scan of v
+    unsigned int v = 0;
+    if (ch < nchunks)
+      for (int w = 0; w < WPC; ++w) {
+        const unsigned long long wi = ch * WPC + w;
+        if (wi < nwords) v += __popc(__ldcg(accept + wi));
+      }
     const int lane = tid & 31, wid = tid >> 5;
     unsigned int incl = v;
 #pragma unroll
@@ -116,12 +129,12 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_count_kernel(const SampleJ
     __syncthreads();
     unsigned int wbase = 0;
 #pragma unroll
-    for (int w = 0; w < SMP_THREADS / 32; ++w)
+    for (int w = 0; w < SMB_THREADS / 32; ++w)
       if (w < wid) wbase += sh[w];
     const unsigned long long carry = carry_s;
-    if (ch < nchunks) pref[ch] = carry + wbase + (incl - v);
+    if (ch < nchunks) job.chunk_prefix[ch] = carry + wbase + (incl - v);
     __syncthreads();
-    if (tid == SMP_THREADS - 1) carry_s = carry + wbase + incl;
+    if (tid == SMB_THREADS - 1) carry_s = carry + wbase + incl;
     __syncthreads();
   }
   if (tid == 0 && carry_s < job.count && job.status) job.status[0] = 0ull;  // draw budget too small
@@ -152,24 +165,14 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_emit_kernel(const SampleJo
   const uint32_t n = (uint32_t)job.n;
   const unsigned long long max_draws = job.max_draws;
   const unsigned long long nchunks = (max_draws + SMP_CHUNK - 1) / SMP_CHUNK;
-  uint32_t* __restrict__ first = job.first;
+  const unsigned long long nwords = (max_draws + 31) >> 5;
+  uint32_t* __restrict__ accept = job.first;
   for (unsigned long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const unsigned long long q = ch * SMP_THREADS + tid;
-    uint32_t v[4];
-    bool acc[4] = {false, false, false, false};
-    unsigned int c = 0;
-    if ((q << 2) < max_draws) {
-      const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
-#pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        const unsigned long long k = (q << 2) + l;
-        v[l] = draw_value(o.w[l], n);
-        if (k < max_draws) {
-          acc[l] = first[v[l]] == (uint32_t)k;
-          c += acc[l] ? 1u : 0u;
-        }
-      }
-    }
+    const unsigned long long q = ch * SMP_THREADS + tid;  // Philox block: draws 4q .. 4q+3, bits of ONE accept word
+    const unsigned long long wi = q >> 3;
+    const uint32_t word = (wi < nwords) ? __ldcg(accept + wi) : 0u;
+    const uint32_t bits = (word >> ((q & 7) << 2)) & 0xFu;
+    const unsigned int c = __popc(bits);
     unsigned int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -177,32 +180,35 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_emit_kernel(const SampleJo
       if (lane >= o) incl += t;
     }
     if (lane == 31) sh[wid] = incl;
-    __syncthreads();
+    __syncthreads();  // also: every thread of the chunk has read its accept word
     unsigned int wbase = 0;
 #pragma unroll
     for (int w = 0; w < SMP_THREADS / 32; ++w)
       if (w < wid) wbase += sh[w];
+    if ((q & 7) == 0 && wi < nwords && word != 0u) accept[wi] = 0u;  // leave the bitmask clear for the next use
     unsigned long long rank = job.chunk_prefix[ch] + wbase + (incl - c);
+    if (bits) {
+      const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      if (acc[l]) {
-        if (rank < count) {
-          out[rank] = v[l];
-          if (job.post == 1) {
-            // src_sampled/dst_sampled = unique endpoints of the sampled line vectors
-            // (registration.cc:870-894); only the SET matters downstream, kept as per-point flags
-            const uint2 e = job.edges[v[l]];
-            job.flags[e.x] = 1;
-            job.flags[e.y] = 1;
-          } else if (job.post == 2) {
-            // basic line vectors (registration.cc:922-925) as endpoint pairs
-            job.gathered[rank] = job.edges[job.via[v[l]]];
+      for (int l = 0; l < 4; ++l) {
+        if ((bits >> l) & 1u) {
+          if (rank < count) {
+            const uint32_t v = draw_value(o.w[l], n);
+            out[rank] = v;
+            if (job.post == 1) {
+              // src_sampled/dst_sampled = unique endpoints of the sampled line vectors
+              // (registration.cc:870-894); only the SET matters downstream, kept as per-point flags
+              const uint2 e = job.edges[v];
+              job.flags[e.x] = 1;
+              job.flags[e.y] = 1;
+            } else if (job.post == 2) {
+              // basic line vectors (registration.cc:922-925) as endpoint pairs
+              job.gathered[rank] = job.edges[job.via[v]];
+            }
+            if (rank == count - 1 && job.status) job.status[0] = (q << 2) + l + 1;  // draws consumed
           }
-          if (rank == count - 1 && job.status) job.status[0] = (q << 2) + l + 1;  // draws consumed
+          ++rank;
         }
-        ++rank;
-        // restore the table; a rejected draw that still reads this entry sees a value != its own k either way
-        first[v[l]] = 0xFFFFFFFFu;
       }
     }
     __syncthreads();
@@ -223,27 +229,34 @@ unsigned long long sample_default_max_draws(unsigned long long n, unsigned long 
 
 unsigned long long sample_chunk_slots(unsigned long long max_draws) { return (max_draws + SMP_CHUNK - 1) / SMP_CHUNK + 1; }
 
-// jobs_per_group > 0: run the three passes group by group so that the random-access working set of a
-// group (first-occurrence tables + the edge lists the emit pass gathers from) stays L2 resident.
+// 32-bit words of the accept bitmask (SampleJob::first) a job with n values / max_draws draws needs
+unsigned long long sample_table_words(unsigned long long n, unsigned long long max_draws) {
+  const unsigned long long w = (max_draws + 31) / 32 + 1;
+  return w > n ? w : n;
+}
+
+// n_bound: upper bound of SampleJob::n over the jobs (sizes the bucket grid)
 int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound,
-                  int jobs_per_group) {
+                  unsigned long long n_bound) {
   if (n_jobs <= 0) return PSULVSB_OK;
-  if (jobs_per_group <= 0 || jobs_per_group > n_jobs) jobs_per_group = n_jobs;
-  const unsigned long long nchunks = (max_draws_bound + SMP_CHUNK - 1) / SMP_CHUNK;
-  for (int off = 0; off < n_jobs; off += jobs_per_group) {
-    const int g = (n_jobs - off < jobs_per_group) ? n_jobs - off : jobs_per_group;
-    unsigned long long gx = nchunks;
-    const unsigned long long cap = (unsigned long long)(148 * 16) / (unsigned long long)(g < 64 ? g : 64) + 1;
-    if (gx > cap) gx = cap;
-    if (gx < 1) gx = 1;
-    dim3 grid((unsigned)gx, (unsigned)g);
-    sample_mark_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs + off);
-    PSU_CHECK_LAUNCH("sample_mark_kernel");
-    sample_count_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs + off);
-    PSU_CHECK_LAUNCH("sample_count_kernel");
-    sample_emit_kernel<<<grid, SMP_THREADS, 0, st>>>(d_jobs + off);
-    PSU_CHECK_LAUNCH("sample_emit_kernel");
+  static bool attr_set = false;
+  const size_t smem = (size_t)SMP_BW * 4 + (size_t)SMP_LCAP * 4 + (size_t)SMP_LCAP * 2;
+  if (!attr_set) {
+    PSU_CUDA(cudaFuncSetAttribute(sample_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
   }
+  unsigned long long nb = (n_bound + SMP_BW - 1) / SMP_BW;
+  if (nb < 1) nb = 1;
+  if (nb > 65535) return fail(PSULVSB_ERR_UNSUPPORTED, "sampler: more than 65535 value buckets");
+  sample_bucket_kernel<<<dim3((unsigned)nb, (unsigned)n_jobs), SMB_THREADS, smem, st>>>(d_jobs);
+  PSU_CHECK_LAUNCH("sample_bucket_kernel");
+  const unsigned long long nchunks = (max_draws_bound + SMP_CHUNK - 1) / SMP_CHUNK;
+  unsigned long long gx = nchunks;
+  const unsigned long long cap = (unsigned long long)(148 * 16) / (unsigned long long)(n_jobs < 64 ? n_jobs : 64) + 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  sample_emit_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), SMP_THREADS, 0, st>>>(d_jobs);
+  PSU_CHECK_LAUNCH("sample_emit_kernel");
   return PSULVSB_OK;
 }
 
