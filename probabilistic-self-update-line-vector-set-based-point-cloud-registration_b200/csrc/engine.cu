@@ -538,6 +538,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.edges = be.take<uint2>((size_t)cap);
         J.first_words = sample_table_words(cap, sample_default_max_draws(cap, cap));
         J.first = be.take<uint32_t>((size_t)J.first_words);
+        J.draws_cap = (cap + 3) & ~3ull;  // covers every rate pair below (1.0, 1.0); longer windows recompute
+        J.draws = be.take<uint32_t>((size_t)J.draws_cap);
         J.chunk_prefix = be.take<unsigned long long>((size_t)sample_chunk_slots(sample_default_max_draws(cap, cap)));
         J.ticket = be.take<unsigned int>(4);
         J.L_sampled = be.take<uint32_t>((size_t)cap);
@@ -612,7 +614,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, m.n_done);
       PSU_CHECK_LAUNCH("engine_round_start_kernel");
       if (int rc = launch_sample(st, m.sl, B, draws_bound, max_cap)) return rc;
-      launches += 3;
+      launches += 4;
     }
     if (int rc = launch_sample(st, m.sb, B, draws_bound, max_cap)) return rc;
     if (ratio) {
@@ -624,12 +626,12 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       int maxCcap = 0;
       for (int b = 0; b < B; ++b) maxCcap = lay[(size_t)b].Ccap > maxCcap ? lay[(size_t)b].Ccap : maxCcap;
       if (int rc = launch_greedy_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap)) return rc;
-      launches += 3;
+      launches += 4;
     }
     if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster)) return rc;
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");
-    launches += 4;
+    launches += 5;
     ++ticks;
     PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     PSU_CUDA(cudaStreamSynchronize(st));

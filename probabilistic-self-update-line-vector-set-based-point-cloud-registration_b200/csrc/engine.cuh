@@ -79,6 +79,8 @@ struct SampleJob {
   uint32_t* first;               // [sample_table_words(n, max_draws)] accept bitmask, all zero on entry and on exit
   unsigned long long* chunk_prefix;  // [sample_chunk_slots(max_draws)] accepted draws before each chunk
   unsigned int* ticket;          // zero on entry and on exit (last-CTA-done counter of the bucket pass)
+  uint32_t* draws;               // optional cache of the draw values [draws_cap] (16-byte aligned), or NULL
+  unsigned long long draws_cap;
   uint32_t* out;                 // [count]
   unsigned long long* status;    // draws consumed (0: max_draws too small)
   int identity;                  // 1: out[r] = r (registration.cc:839-847, empty-sample fallback)

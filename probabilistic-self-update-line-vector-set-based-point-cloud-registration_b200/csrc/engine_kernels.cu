@@ -55,6 +55,8 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   sb.first = J.first;
   sb.chunk_prefix = J.chunk_prefix;
   sb.ticket = J.ticket;
+  sb.draws = J.draws;
+  sb.draws_cap = J.draws_cap;
   sb.out = J.basic_idx;
   sb.status = &J.sample_status[1];
   sb.identity = 0;
@@ -301,6 +303,8 @@ __global__ void __launch_bounds__(BLK)
     L.first = J.first;
     L.chunk_prefix = J.chunk_prefix;
     L.ticket = J.ticket;
+    L.draws = J.draws;
+    L.draws_cap = J.draws_cap;
     L.out = J.L_sampled;
     L.status = &J.sample_status[0];
     L.post = 1;

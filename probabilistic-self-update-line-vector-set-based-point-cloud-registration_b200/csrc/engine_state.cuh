@@ -69,6 +69,8 @@ struct JobCtl {
   unsigned long long edge_cap;
   uint32_t* first;  // [first_words] sampler accept bitmask (zero between uses)
   unsigned long long first_words;
+  uint32_t* draws;  // sampler draw-value cache [draws_cap]
+  unsigned long long draws_cap;
   unsigned long long* chunk_prefix;  // sampler scratch
   unsigned int* ticket;              // sampler scratch (zero between uses)
   uint32_t* L_sampled;

@@ -31,67 +31,119 @@ namespace {
 constexpr int SMP_THREADS = 256;            // emit pass
 constexpr int SMP_CHUNK = SMP_THREADS * 4;  // draws per chunk (one Philox block per thread)
 constexpr int SMB_THREADS = 512;            // bucket pass (one CTA per SM: the table fills shared memory)
-constexpr int SMP_BW = 40960;               // values per bucket (160 KB of shared memory)
-constexpr int SMP_LCAP = 6144;              // matched draws a CTA remembers before it falls back to a second walk
+constexpr int SMP_BW = 49152;               // values per bucket (192 KB of shared memory)
 
-__device__ __forceinline__ uint32_t draw_value(uint32_t word, uint32_t n) { return (word >> 1) % n; }
+// (word >> 1) % n with the division replaced by a multiply-high: magic = ceil(2^64 / n) gives the exact
+// quotient for every 31-bit dividend (the error term v e / 2^64 < 2^-33 cannot reach the next integer,
+// which is at least 1/n > 2^-31 away)
+struct FastMod {
+  unsigned long long magic;
+  uint32_t n;
+};
+__device__ __forceinline__ FastMod make_fastmod(uint32_t n) {
+  FastMod f;
+  f.n = n;
+  f.magic = n > 1u ? (~0ull / n) + 1ull : 0ull;  // ceil(2^64 / n) (n = 1: everything maps to 0)
+  return f;
+}
+__device__ __forceinline__ uint32_t draw_value(uint32_t word, const FastMod& f) {
+  const uint32_t v = word >> 1;
+  if (f.n <= 1u) return 0u;
+  const uint32_t q = (uint32_t)__umul64hi((unsigned long long)v, f.magic);
+  return v - q * f.n;
+}
+
+// optional cache of the draw values (SampleJob::draws, one u32 per draw) so that the bucket CTAs stream
+// them instead of re-running Philox; windows longer than draws_cap fall back to recomputation
+__global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __restrict__ jobs) {
+  const SampleJob& job = jobs[blockIdx.y];
+  if (!job.active || job.identity || !job.draws || job.max_draws > job.draws_cap) return;
+  const FastMod fm = make_fastmod((uint32_t)job.n);
+  const unsigned long long nblocks = (job.max_draws + 3) >> 2;
+  uint4* __restrict__ out = reinterpret_cast<uint4*>(job.draws);
+  for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < nblocks;
+       q += (unsigned long long)gridDim.x * 256) {
+    const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+    out[q] = make_uint4(draw_value(o.w[0], fm), draw_value(o.w[1], fm), draw_value(o.w[2], fm), draw_value(o.w[3], fm));
+  }
+}
 
 __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const SampleJob* __restrict__ jobs) {
   const SampleJob& job = jobs[blockIdx.y];
   if (!job.active) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw);          // [SMP_BW]
-  uint32_t* list_k = table + SMP_BW;                                // [SMP_LCAP]
-  uint16_t* list_o = reinterpret_cast<uint16_t*>(list_k + SMP_LCAP);  // [SMP_LCAP]
-  __shared__ unsigned int cnt_s, ticket_s, sh[SMB_THREADS / 32];
+  uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw);  // [SMP_BW]
+  __shared__ unsigned int ticket_s, sh[SMB_THREADS / 32];
   __shared__ unsigned long long carry_s;
   const int tid = threadIdx.x;
   if (job.post == 1 && blockIdx.x == 0)  // endpoint flags are rebuilt by the emit pass
     for (int i = tid; i < job.n_points; i += SMB_THREADS) job.flags[i] = 0;
   if (job.identity) return;
   const uint32_t n = (uint32_t)job.n;
+  const FastMod fm = make_fastmod(n);
   const unsigned int n_buckets = (n + SMP_BW - 1) / SMP_BW;
   if (blockIdx.x >= n_buckets) return;
-  const uint32_t lo = blockIdx.x * (uint32_t)SMP_BW;
-  const uint32_t width = min((uint32_t)SMP_BW, n - lo);
+  const unsigned int n_workers = min(gridDim.x, n_buckets);  // CTAs of this job that take buckets (and a ticket)
   const unsigned long long max_draws = job.max_draws;
   const unsigned long long nblocks = (max_draws + 3) >> 2;
+  const bool cached = job.draws != nullptr && max_draws <= job.draws_cap;
+  const uint4* __restrict__ dv = reinterpret_cast<const uint4*>(job.draws);
   uint32_t* __restrict__ accept = job.first;  // bit k set <=> draw k is accepted; all zero on entry and on exit
-  for (uint32_t i = tid; i < width; i += SMB_THREADS) table[i] = 0xFFFFFFFFu;
-  if (tid == 0) cnt_s = 0u;
-  __syncthreads();
-  // walk 1: first occurrence of every value of this bucket
-  for (unsigned long long q = tid; q < nblocks; q += SMB_THREADS) {
+  auto draws_of = [&](uint32_t q) -> uint4 {
+    if (cached) return __ldcg(dv + q);
     const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+    return make_uint4(draw_value(o.w[0], fm), draw_value(o.w[1], fm), draw_value(o.w[2], fm), draw_value(o.w[3], fm));
+  };
+  for (unsigned int b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+    const uint32_t lo = b * (uint32_t)SMP_BW;
+    const uint32_t width = min((uint32_t)SMP_BW, n - lo);
+    __syncthreads();  // the previous bucket's readers are done with the table
+    for (uint32_t i = tid; i < width; i += SMB_THREADS) table[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    // walk 1: first occurrence of every value of this bucket (four 16-byte loads in flight per thread:
+    // the walk is bound by the latency of the cached draws coming from L2, not by arithmetic)
+    const uint32_t nb32 = (uint32_t)nblocks, md32 = (uint32_t)max_draws;  // max_draws < 2^32 (launcher check)
+    for (uint32_t q0 = tid; q0 < nb32; q0 += 4 * SMB_THREADS) {
+      uint4 d4[4];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const unsigned long long k = (q << 2) + l;
-      const uint32_t off = draw_value(o.w[l], n) - lo;
-      if (k < max_draws && off < width) {
-        atomicMin(&table[off], (uint32_t)k);
-        const unsigned int slot = atomicAdd(&cnt_s, 1u);
-        if (slot < SMP_LCAP) {
-          list_k[slot] = (uint32_t)k;
-          list_o[slot] = (uint16_t)off;
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t q = q0 + u * SMB_THREADS;
+        d4[u] = q < nb32 ? draws_of(q) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t q = q0 + u * SMB_THREADS;
+        const uint32_t vv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const uint32_t k = (q << 2) + l;
+          const uint32_t off = vv[l] - lo;  // 0xFFFFFFFF (no draw) never lands in the bucket: lo + width <= n < 2^31
+          if (off < width && k < md32) atomicMin(&table[off], k);
         }
       }
     }
-  }
-  __syncthreads();
-  const unsigned int matched = cnt_s;
-  if (matched <= SMP_LCAP) {
-    for (unsigned int i = tid; i < matched; i += SMB_THREADS) {
-      const uint32_t k = list_k[i];
-      if (table[list_o[i]] == k) atomicOr(&accept[k >> 5], 1u << (k & 31));
-    }
-  } else {  // walk 2 (only when the draw window is far larger than the bucket count times SMP_LCAP)
-    for (unsigned long long q = tid; q < nblocks; q += SMB_THREADS) {
-      const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+    __syncthreads();
+    // walk 2: a draw is accepted iff it is that first occurrence (the cached draw values stream from L2, so
+    // walking them twice is cheaper than remembering the matches behind a shared counter)
+    for (uint32_t q0 = tid; q0 < nb32; q0 += 4 * SMB_THREADS) {
+      uint4 d4[4];
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        const unsigned long long k = (q << 2) + l;
-        const uint32_t off = draw_value(o.w[l], n) - lo;
-        if (k < max_draws && off < width && table[off] == (uint32_t)k) atomicOr(&accept[k >> 5], 1u << (k & 31));
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t q = q0 + u * SMB_THREADS;
+        d4[u] = q < nb32 ? draws_of(q) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t q = q0 + u * SMB_THREADS;
+        const uint32_t vv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const uint32_t k = (q << 2) + l;
+          const uint32_t off = vv[l] - lo;
+          if (off < width && k < md32 && table[off] == k) bits |= 1u << l;
+        }
+        if (bits) atomicOr(&accept[q >> 3], bits << ((q & 7) << 2));
       }
     }
   }
@@ -100,7 +152,7 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
   __syncthreads();
   if (tid == 0) ticket_s = atomicAdd(job.ticket, 1u);
   __syncthreads();
-  if (ticket_s != n_buckets - 1) return;
+  if (ticket_s != n_workers - 1) return;
   __threadfence();
   if (tid == 0) {
     carry_s = 0ull;
@@ -162,10 +214,11 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_emit_kernel(const SampleJo
     if (blockIdx.x == 0 && tid == 0 && job.status) job.status[0] = 1ull;  // nothing drawn; non-zero = success
     return;
   }
-  const uint32_t n = (uint32_t)job.n;
+  const FastMod fm = make_fastmod((uint32_t)job.n);
   const unsigned long long max_draws = job.max_draws;
   const unsigned long long nchunks = (max_draws + SMP_CHUNK - 1) / SMP_CHUNK;
   const unsigned long long nwords = (max_draws + 31) >> 5;
+  const bool cached = job.draws != nullptr && max_draws <= job.draws_cap;
   uint32_t* __restrict__ accept = job.first;
   for (unsigned long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const unsigned long long q = ch * SMP_THREADS + tid;  // Philox block: draws 4q .. 4q+3, bits of ONE accept word
@@ -188,12 +241,20 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_emit_kernel(const SampleJo
     if ((q & 7) == 0 && wi < nwords && word != 0u) accept[wi] = 0u;  // leave the bitmask clear for the next use
     unsigned long long rank = job.chunk_prefix[ch] + wbase + (incl - c);
     if (bits) {
-      const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+      uint32_t vv[4];
+      if (cached) {
+        const uint4 d4 = __ldcg(reinterpret_cast<const uint4*>(job.draws) + q);
+        vv[0] = d4.x; vv[1] = d4.y; vv[2] = d4.z; vv[3] = d4.w;
+      } else {
+        const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) vv[l] = draw_value(o.w[l], fm);
+      }
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         if ((bits >> l) & 1u) {
           if (rank < count) {
-            const uint32_t v = draw_value(o.w[l], n);
+            const uint32_t v = vv[l];
             out[rank] = v;
             if (job.post == 1) {
               // src_sampled/dst_sampled = unique endpoints of the sampled line vectors
@@ -240,21 +301,26 @@ int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned
                   unsigned long long n_bound) {
   if (n_jobs <= 0) return PSULVSB_OK;
   static bool attr_set = false;
-  const size_t smem = (size_t)SMP_BW * 4 + (size_t)SMP_LCAP * 4 + (size_t)SMP_LCAP * 2;
+  const size_t smem = (size_t)SMP_BW * 4;
   if (!attr_set) {
     PSU_CUDA(cudaFuncSetAttribute(sample_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  unsigned long long nb = (n_bound + SMP_BW - 1) / SMP_BW;
-  if (nb < 1) nb = 1;
-  if (nb > 65535) return fail(PSULVSB_ERR_UNSUPPORTED, "sampler: more than 65535 value buckets");
-  sample_bucket_kernel<<<dim3((unsigned)nb, (unsigned)n_jobs), SMB_THREADS, smem, st>>>(d_jobs);
-  PSU_CHECK_LAUNCH("sample_bucket_kernel");
   const unsigned long long nchunks = (max_draws_bound + SMP_CHUNK - 1) / SMP_CHUNK;
   unsigned long long gx = nchunks;
   const unsigned long long cap = (unsigned long long)(148 * 16) / (unsigned long long)(n_jobs < 64 ? n_jobs : 64) + 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
+  sample_draws_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), 256, 0, st>>>(d_jobs);
+  PSU_CHECK_LAUNCH("sample_draws_kernel");
+  // bucket CTAs: one per SM at a time; a CTA walks several buckets when the batch alone fills the GPU
+  unsigned long long nb = (n_bound + SMP_BW - 1) / SMP_BW;
+  if (nb < 1) nb = 1;
+  unsigned long long bx = (148ull * 3ull + (unsigned long long)n_jobs - 1) / (unsigned long long)n_jobs;
+  if (bx > nb) bx = nb;
+  if (bx < 1) bx = 1;
+  sample_bucket_kernel<<<dim3((unsigned)bx, (unsigned)n_jobs), SMB_THREADS, smem, st>>>(d_jobs);
+  PSU_CHECK_LAUNCH("sample_bucket_kernel");
   sample_emit_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), SMP_THREADS, 0, st>>>(d_jobs);
   PSU_CHECK_LAUNCH("sample_emit_kernel");
   return PSULVSB_OK;
