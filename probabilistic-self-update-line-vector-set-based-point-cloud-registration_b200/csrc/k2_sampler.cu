@@ -30,7 +30,7 @@ namespace {
 
 constexpr int SMP_THREADS = 256;            // emit pass
 constexpr int SMP_CHUNK = SMP_THREADS * 4;  // draws per chunk (one Philox block per thread)
-constexpr int SMB_THREADS = 512;            // bucket pass (one CTA per SM: the table fills shared memory)
+constexpr int SMB_THREADS = 1024;           // bucket pass (one CTA per SM: the table fills shared memory)
 constexpr int SMP_BW = 49152;               // values per bucket (192 KB of shared memory)
 
 // (word >> 1) % n with the division replaced by a multiply-high: magic = ceil(2^64 / n) gives the exact
