@@ -129,6 +129,24 @@ __device__ __noinline__ uint32_t slow_word_coop(const K1Job& job, int i, int cb,
   return __ballot_sync(0xffffffffu, in);
 }
 
+// the 32 pairs (row r, columns of one mask word) for the first RL of a thread's R rows
+template <int RL, int R>
+__device__ __forceinline__ void eval_word(const float4* __restrict__ cs, const float4* __restrict__ ct,
+                                          const float4 (&ms)[R], const float4 (&mt)[R], const float two_beta2,
+                                          const float beta4, uint32_t (&acc)[R], float (&mv)[R]) {
+#pragma unroll 4
+  for (int jj = 31; jj >= 0; --jj) {
+    const float4 sj = cs[jj];
+    const float4 tj = ct[jj];
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+      const float v = pair_fast(ms[r], mt[r], sj, tj, two_beta2, beta4);
+      acc[r] = __funnelshift_l(__float_as_uint(v), acc[r], 1);  // bit jj <- sign(v)
+      mv[r] = fminf(mv[r], fabsf(v));
+    }
+  }
+}
+
 // One CTA = a block of TI = 256 R rows x a chunk of `tiles_per_cta` column tiles (TJ columns each),
 // starting at the tile that holds the diagonal of the row block; the column tiles stream through a
 // two-stage shared-memory ring filled by 1-D TMA bulk copies, so the copy of tile k+1 overlaps the
@@ -227,17 +245,23 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R == 2 ? 3 : 4)))
         acc[r] = 0u;
         mv[r] = 3.0e38f;
       }
-#pragma unroll 4
-      for (int jj = 31; jj >= 0; --jj) {
-        const float4 sj = cs[st][wj * 32 + jj];
-        const float4 tj = ct[st][wj * 32 + jj];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float v = pair_fast(ms[r], mt[r], sj, tj, two_beta2, beta4);
-          acc[r] = __funnelshift_l(__float_as_uint(v), acc[r], 1);  // bit jj <- sign(v)
-          mv[r] = fminf(mv[r], fabsf(v));
-        }
+      // row group r of this warp (rows warp_row_min + 256 r ..) still has live columns in this word iff
+      // cb + 31 > its smallest row; the groups die in the order R-1, ..., 0 along the diagonal tile
+      int n_live = R;
+      if (R > 1) {
+        n_live = (cb + 31 - warp_row_min + K1_THREADS - 1) / K1_THREADS;  // >= 1 here
+        n_live = n_live > R ? R : n_live;
       }
+      const float4* cw = &cs[st][wj * 32];
+      const float4* tw = &ct[st][wj * 32];
+      if (n_live == R)
+        eval_word<R, R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
+      else if (R > 1 && n_live == 1)
+        eval_word<1, R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
+      else if (R > 2 && n_live == 2)
+        eval_word<(R > 2 ? 2 : 1), R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
+      else
+        eval_word<(R > 3 ? 3 : 1), R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
       const uint32_t valid = (cb + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - cb)) - 1u);
       const float4 sl = cs[st][wj * 32 + lane];  // this lane's column of the word (slow path only)
       const float4 tl = ct[st][wj * 32 + lane];
@@ -436,6 +460,18 @@ int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, in
   // R = 2 on batches of 5k-point problems (0.52 vs 0.49: 1024-row blocks waste more of the diagonal)
   int variant = (max_rows >= 16384 && pairs >= 1.0e9) ? 4 : (pairs >= 2.0e8 ? 2 : 1);
   if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) variant = force[0] - '0';
+  static const char* tj_env = getenv("PSULVSB_K1_TJ");  // '1': 128-column tiles, '5': 512; default 256
+  if (tj_env && tj_env[0] == '5') {
+    if (variant == 4) return launch_k1_variant<4, 512>(st, d_jobs, n_jobs, max_n, max_rows);
+    if (variant == 2) return launch_k1_variant<2, 512>(st, d_jobs, n_jobs, max_n, max_rows);
+    return launch_k1_variant<1, 512>(st, d_jobs, n_jobs, max_n, max_rows);
+  }
+  const bool wide = tj_env ? (tj_env[0] != '1') : true;  // measured: 256-column tiles halve the barrier stalls
+  if (wide) {
+    if (variant == 4) return launch_k1_variant<4, 256>(st, d_jobs, n_jobs, max_n, max_rows);
+    if (variant == 2) return launch_k1_variant<2, 256>(st, d_jobs, n_jobs, max_n, max_rows);
+    return launch_k1_variant<1, 256>(st, d_jobs, n_jobs, max_n, max_rows);
+  }
   if (variant == 4) return launch_k1_variant<4, 128>(st, d_jobs, n_jobs, max_n, max_rows);
   if (variant == 2) return launch_k1_variant<2, 128>(st, d_jobs, n_jobs, max_n, max_rows);
   return launch_k1_variant<1, 128>(st, d_jobs, n_jobs, max_n, max_rows);
