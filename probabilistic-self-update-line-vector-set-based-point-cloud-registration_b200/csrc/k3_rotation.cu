@@ -35,7 +35,7 @@ namespace {
 // threads per CTA is a template parameter T: 256 (two CTAs per SM, so that one hypothesis' serial SVD phase
 // overlaps another's pass) for clustered launches, 512 (one CTA per SM, twice the shared-memory cache) when
 // every hypothesis runs on a single CTA (large batches)
-constexpr int GNC_MAX_WARPS = 16;
+constexpr int GNC_MAX_WARPS = 32;
 #ifndef GNC_CTAS_PER_SM
 #define GNC_CTAS_PER_SM 2
 #endif
@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_k
 
   double mu = 1.0, prev_cost = INFINITY, cost = INFINITY;
   int it_done = 0;
+  long long t_svd = 0;               // cycles thread 0 spends in the 3x3 SVDs (diagnostic, info[2])
+  const long long t_start = clock64();
   bool weights_are_unit = true;
   for (int it = 0; it < job.max_iterations; ++it) {
     it_done = it + 1;
@@ -353,7 +355,9 @@ __global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_k
         double H[3][3], Rn[3][3];
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c) H[r][c] = sm->total[r * 3 + c];
+        const long long c0 = clock64();
         kabsch_rotation(H, Rn, Vw);
+        t_svd += clock64() - c0;
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = Rn[r][c];
       }
@@ -396,8 +400,8 @@ __global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_k
     if (job.info) {
       job.info[0] = it_done;
       job.info[1] = (int)(all_in ? (long long)K : gf);
-      job.info[2] = 0;
-      job.info[3] = 0;
+      job.info[2] = (int)(t_svd >> 4);                   // SVD cycles / 16
+      job.info[3] = (int)((clock64() - t_start) >> 4);  // GNC loop cycles / 16
     }
     if (job.cost) job.cost[0] = cost;
   }
@@ -514,6 +518,7 @@ int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_pe
   if (n_jobs <= 0) return PSULVSB_OK;
   if (cap_per_cta < 32) cap_per_cta = 32;
   switch (cluster) {
+    // (measured: 512 threads x 2 CTAs per SM = 64 registers spills 1.3 KB per thread and loses 25 %)
     case 8: return launch_gnc_nc<8, 256>(st, d_jobs, n_jobs, cap_per_cta);
     case 4: return launch_gnc_nc<4, 256>(st, d_jobs, n_jobs, cap_per_cta);
     case 2: return launch_gnc_nc<2, 256>(st, d_jobs, n_jobs, cap_per_cta);
