@@ -20,6 +20,7 @@
 // adds no new class of deviation; the discrete decisions (r^2 vs th1/th2, w >= 0.5) are unaffected
 // except within an ulp of their thresholds.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -46,6 +47,7 @@ struct GncSmem {
   double warp_part[GNC_MAX_WARPS][GNC_NRED];
   double R[9];                        // row-major current rotation
   double total[GNC_NRED];
+  double Vw[9];  // Jacobi warm start (right singular vectors of the previous solve), row-major
   int flag;
 };
 
@@ -97,6 +99,28 @@ __device__ __forceinline__ double residual2(const double R[9], const double sv[3
   return fma(d2, d2, fma(d1, d1, d0 * d0));
 }
 
+// H = sm->total[0..8] -> sm->R, warm-started from / updating sm->Vw.  Out of line on purpose: one thread
+// runs it, and inlining its ~600 instructions would set the register budget of the streaming loops
+// around it; its operands travel through shared memory, not through local-memory arrays.
+__device__ __noinline__ void svd_from_smem(GncSmem* sm) {
+  double H[3][3], R[3][3], V[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      H[r][c] = sm->total[r * 3 + c];
+      V[r][c] = sm->Vw[r * 3 + c];
+    }
+  kabsch_rotation(H, R, V);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      sm->R[r * 3 + c] = R[r][c];
+      sm->Vw[r * 3 + c] = V[r][c];
+    }
+}
+
 // CTA-level then cluster-level sum (or max for index MAXI) of NRED values; result in sm->total.
 template <int NC, int T>
 __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED], int parity, int max_index) {
@@ -138,8 +162,8 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
   __syncthreads();
 }
 
-template <int NC, int T>
-__global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
+template <int NC, int T, int CPS>
+__global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GncSmem* sm = reinterpret_cast<GncSmem*>(smem_raw);
   double* lv = reinterpret_cast<double*>(smem_raw + ((sizeof(GncSmem) + 15) & ~size_t(15)));
@@ -206,21 +230,14 @@ __global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_k
       for (int c = 0; c < 3; ++c) acc[r * 3 + c] = fma(sv[r], tv[c], acc[r * 3 + c]);
   }
   int parity = 0;
-  double Vw[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};  // Jacobi warm start (thread 0 only)
+  if (tid < 9) sm->Vw[tid] = (tid % 4 == 0) ? 1.0 : 0.0;
   if (job.use_init) {
     if (tid < 9) sm->R[tid] = job.R_init[(tid % 3) * 3 + tid / 3];  // column-major -> row-major
     __syncthreads();
   } else {
     cluster_reduce<NC, T>(sm, acc, parity, -1);
     parity ^= 1;
-    if (tid == 0) {
-      double H[3][3], R[3][3];
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) H[r][c] = sm->total[r * 3 + c];
-      kabsch_rotation(H, R, Vw);
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = R[r][c];
-    }
+    if (tid == 0) svd_from_smem(sm);
     __syncthreads();
   }
 
@@ -282,7 +299,7 @@ __global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_k
       const int nc = (int)ncached;
       double* __restrict__ ws = lv + 6 * cap;
       int l = tid;
-      for (; l + T < nc; l += 2 * T) {
+      for (; CPS < 3 && l + T < nc; l += 2 * T) {
         double sa[3], ta[3], sb[3], tb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -313,7 +330,7 @@ __global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_k
       double* __restrict__ gwl = gw + k_lo;
       const size_t st = (size_t)lv_cap;
       int l = (int)ncached + tid;
-      for (; l + T < g_hi; l += 2 * T) {
+      for (; CPS < 3 && l + T < g_hi; l += 2 * T) {
         double sa[3], ta[3], sb[3], tb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -352,14 +369,9 @@ __global__ void __launch_bounds__(T, (T >= 512 ? 1 : GNC_CTAS_PER_SM)) gnc_tls_k
     if (cost_diff < job.cost_threshold) break;
     if (it + 1 < job.max_iterations) {
       if (tid == 0) {
-        double H[3][3], Rn[3][3];
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) H[r][c] = sm->total[r * 3 + c];
         const long long c0 = clock64();
-        kabsch_rotation(H, Rn, Vw);
+        svd_from_smem(sm);
         t_svd += clock64() - c0;
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = Rn[r][c];
       }
       __syncthreads();
     }
@@ -463,14 +475,14 @@ __global__ void __launch_bounds__(256)
 int gnc_capacity_for(int ctas_per_sm);
 size_t gnc_smem_bytes(int cap) { return ((sizeof(GncSmem) + 15) & ~size_t(15)) + (size_t)7 * cap * sizeof(double); }
 
-template <int NC, int T>
+template <int NC, int T, int CPS>
 int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta) {
   static bool attr_set = false;
-  const int max_cap = gnc_capacity_for(T >= 512 ? 1 : GNC_CTAS_PER_SM);
+  const int max_cap = gnc_capacity_for(CPS);
   if (cap_per_cta > max_cap) cap_per_cta = max_cap;
   const size_t smem = gnc_smem_bytes(cap_per_cta);
   if (!attr_set) {
-    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<NC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<NC, T, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)gnc_smem_bytes(max_cap)));
     attr_set = true;
   }
@@ -486,7 +498,7 @@ int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T>, d_jobs, cap_per_cta));
+  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T, CPS>, d_jobs, cap_per_cta));
   return PSULVSB_OK;
 }
 
@@ -507,7 +519,8 @@ int gnc_default_capacity() { return gnc_capacity_for(1); }
 
 // CTAs per hypothesis for a batch of n_jobs: as many SMs per job as keeps the whole batch resident
 int gnc_cluster_for(int n_jobs) {
-  const int slots = 148 * GNC_CTAS_PER_SM;
+  static const char* lean_env = getenv("PSULVSB_GNC_LEAN");
+  const int slots = 148 * ((lean_env && lean_env[0] == '1') ? 4 : GNC_CTAS_PER_SM);
   if (n_jobs * 8 <= slots) return 8;
   if (n_jobs * 4 <= slots) return 4;
   if (n_jobs * 2 <= slots) return 2;
@@ -517,12 +530,14 @@ int gnc_cluster_for(int n_jobs) {
 int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster) {
   if (n_jobs <= 0) return PSULVSB_OK;
   if (cap_per_cta < 32) cap_per_cta = 32;
+  static const char* lean_env = getenv("PSULVSB_GNC_LEAN");
+  const bool lean = lean_env && lean_env[0] == '1';
   switch (cluster) {
     // (measured: 512 threads x 2 CTAs per SM = 64 registers spills 1.3 KB per thread and loses 25 %)
-    case 8: return launch_gnc_nc<8, 256>(st, d_jobs, n_jobs, cap_per_cta);
-    case 4: return launch_gnc_nc<4, 256>(st, d_jobs, n_jobs, cap_per_cta);
-    case 2: return launch_gnc_nc<2, 256>(st, d_jobs, n_jobs, cap_per_cta);
-    case 1: return launch_gnc_nc<1, 512>(st, d_jobs, n_jobs, cap_per_cta);
+    case 8: return lean ? launch_gnc_nc<8, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<8, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
+    case 4: return lean ? launch_gnc_nc<4, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<4, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
+    case 2: return lean ? launch_gnc_nc<2, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<2, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
+    case 1: return lean ? launch_gnc_nc<1, 512, 2>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<1, 512, 1>(st, d_jobs, n_jobs, cap_per_cta);
     default: return fail(PSULVSB_ERR_INVALID, "launch_gnc_tls: cluster must be 1, 2, 4 or 8");
   }
 }
