@@ -534,7 +534,11 @@ int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_pe
   const bool lean = lean_env && lean_env[0] == '1';
   switch (cluster) {
     // (measured: 512 threads x 2 CTAs per SM = 64 registers spills 1.3 KB per thread and loses 25 %)
-    case 8: return lean ? launch_gnc_nc<8, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<8, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
+    case 8:
+      // few registrations (8 CTAs each still leave SMs idle): 512 threads, one CTA per SM -- half the line
+      // vectors per thread in the latency-bound pass
+      if (!lean && n_jobs * 8 <= 148) return launch_gnc_nc<8, 512, 1>(st, d_jobs, n_jobs, cap_per_cta);
+      return lean ? launch_gnc_nc<8, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<8, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
     case 4: return lean ? launch_gnc_nc<4, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<4, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
     case 2: return lean ? launch_gnc_nc<2, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<2, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
     case 1: return lean ? launch_gnc_nc<1, 512, 2>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<1, 512, 1>(st, d_jobs, n_jobs, cap_per_cta);
