@@ -89,3 +89,25 @@ def test_example_driver_registers_the_bunny(tmp_path):
     rot = [float(x) for x in re.findall(r"rot_err_deg=([0-9.]+) trans", r.stdout)][:4]
     tra = [float(x) for x in re.findall(r"trans_err=([0-9.]+) time", r.stdout)][:4]
     assert len(rot) == 4 and sorted(rot)[2] < 3.0 and sorted(tra)[2] < 0.1
+
+
+def test_cmake_package_provides_the_reference_targets(tmp_path):
+    """find_package(teaserpp) + teaserpp::teaser_registration / teaserpp::teaser_io, the names the reference's
+    examples/teaser_cpp_ply/CMakeLists.txt links, resolve to this library."""
+    import shutil
+
+    if shutil.which("cmake") is None:
+        pytest.skip("cmake not available")
+    src = tmp_path / "proj"
+    src.mkdir()
+    (src / "CMakeLists.txt").write_text(
+        "cmake_minimum_required(VERSION 3.10)\nproject(consumer CXX)\nset(CMAKE_CXX_STANDARD 17)\n"
+        "find_package(teaserpp REQUIRED)\n"
+        f"add_executable(driver {os.path.join(ROOT, 'tests', 'cpp', 'driver_snippet.cc')})\n"
+        f"target_include_directories(driver PRIVATE {os.path.join(ROOT, 'tests', 'shim')})\n"
+        "target_link_libraries(driver teaserpp::teaser_registration teaserpp::teaser_io)\n")
+    bld = tmp_path / "build"
+    subprocess.check_call(["cmake", "-S", str(src), "-B", str(bld), f"-Dteaserpp_DIR={os.path.join(ROOT, 'cmake')}"],
+                          stdout=subprocess.DEVNULL)
+    subprocess.check_call(["cmake", "--build", str(bld)], stdout=subprocess.DEVNULL)
+    assert os.path.exists(bld / "driver")
