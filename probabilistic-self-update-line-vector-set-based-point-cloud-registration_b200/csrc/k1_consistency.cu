@@ -456,9 +456,9 @@ int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, in
   // rows per thread by the amount of work: R = 4 / 2 want enough row blocks x tiles to fill the GPU
   const double pairs = 0.5 * (double)max_rows * max_n * n_jobs;
   static const char* force = getenv("PSULVSB_K1_VARIANT");
-  // measured on B200: R = 4 wins on long row ranges (N = 100k: 0.68 of the FP32-pipe peak vs 0.57),
-  // R = 2 on batches of 5k-point problems (0.52 vs 0.49: 1024-row blocks waste more of the diagonal)
-  int variant = (max_rows >= 16384 && pairs >= 1.0e9) ? 4 : (pairs >= 2.0e8 ? 2 : 1);
+  // measured on B200 (256-column tiles, dead row groups skipped): R = 4 wins once there is enough work
+  // (N = 100k: 0.68-0.72 of the FP32-pipe peak vs 0.63; 256 x 5k-point problems: 0.59 vs 0.57; 64: 0.56 vs 0.55)
+  int variant = pairs >= 5.0e8 ? 4 : (pairs >= 1.0e8 ? 2 : 1);
   if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) variant = force[0] - '0';
   static const char* tj_env = getenv("PSULVSB_K1_TJ");  // '1': 128-column tiles, '5': 512; default 256
   if (tj_env && tj_env[0] == '5') {
