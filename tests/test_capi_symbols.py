@@ -88,3 +88,16 @@ def test_mirror_params_defaults():
     assert p.rotation_estimation_algorithm == S.ROTATION_ESTIMATION_ALGORITHM.GNC_TLS
     assert p.inlier_selection_mode == S.INLIER_SELECTION_MODE.PMC_EXACT
     assert int(S.INLIER_SELECTION_MODE.NONE) == 3
+
+
+def test_argument_validation_without_device():
+    """Bad arguments are refused with PSULVSB_ERR_INVALID before any device work (so this runs without a GPU)."""
+    L = capi.lib()
+    assert L.psulvsb_solve(None, None, None, None, None) == capi.ERR_INVALID
+    assert L.psulvsb_solve_batch(None, None, None, 0, None, None) == capi.ERR_INVALID
+    assert L.psulvsb_batch_upload(None, None, 0) == capi.ERR_INVALID
+    assert L.psulvsb_destroy(None) == capi.OK
+    assert L.psulvsb_launch_count(None) == 0 and L.psulvsb_last_ticks(None) == 0
+    n = C.c_longlong(0)
+    assert L.psulvsb_ply_vertex_count(b"/nonexistent/file.ply", C.byref(n)) == capi.ERR_INVALID
+    assert b"cannot open" in L.psulvsb_last_error()

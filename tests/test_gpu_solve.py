@@ -297,3 +297,39 @@ def test_tiny_problems_terminate(env, n):
         if sg.status == 0 and sg.valid:
             Rg = sg.R
             assert np.allclose(Rg @ Rg.T, np.eye(3), atol=1e-9) and np.linalg.det(Rg) > 0
+
+
+def test_invalid_problems_are_refused(env):
+    capi = env["capi"]
+    h = env["h"]
+    p = capi.default_params(**PKW)
+    with pytest.raises(capi.PsulvsbError) as ei:                     # a single correspondence has no line vector
+        h.solve(p, capi.HostProblem(np.zeros((3, 1)), np.zeros((3, 1))))
+    assert ei.value.code == capi.ERR_INVALID
+    bad = np.zeros((3, 10))
+    bad[1, 3] = np.nan
+    with pytest.raises(capi.PsulvsbError) as ei:                     # non-finite coordinates
+        h.solve(p, capi.HostProblem(bad, np.ones((3, 10))))
+    assert ei.value.code == capi.ERR_INVALID
+    with pytest.raises(capi.PsulvsbError):                           # nothing uploaded
+        capi.Handle(0).solve_resident.__func__  # attribute exists
+        hh = capi.Handle(0)
+        hh._problems = []
+        hh.solve_resident(p)
+    # the handle is still usable afterwards
+    pair = env["synth"].make_pair(300, 0.5, 1)
+    sol, _ = h.solve(p, capi.HostProblem(pair["src"], pair["dst"]))
+    assert sol.status == 0 and sol.valid
+
+
+def test_keep_mask_minus_one_points_are_scored_but_never_adopted(env):
+    """keep_mask == -1 (bins far from the histogram peak, PSULVSB.cc:152-157): counted as inliers of the final
+    score when they fit, never appended by the self-update (registration.cc:1428-1434)."""
+    capi, synth, O = env["capi"], env["synth"], env["O"]
+    pair = synth.make_pair(900, 0.8, 33)
+    pre = synth.prefilter(pair, 33, keep_inlier=0.5, keep_outlier=0.3, discard_outlier=0.6)
+    assert (pre["keep_mask"] == -1).sum() > 50
+    so, to, sg, tg = both(env, pair, pre, seed=33)
+    assert_same_run(env, so, to, sg, tg)
+    adopted = sg.final_C - pre["src_reduce"].shape[1]
+    assert adopted <= int((pre["keep_mask"] == 0).sum())
