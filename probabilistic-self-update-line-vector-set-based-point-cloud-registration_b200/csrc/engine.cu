@@ -232,12 +232,17 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       for (int s = 0; s < 2; ++s) {
         const double* pts = s ? p.dst : p.src;
         double lo[3] = {pts[0], pts[1], pts[2]}, hi3[3] = {pts[0], pts[1], pts[2]};
-        for (int i = 1; i < p.C; ++i)
+        bool finite = true;
+        for (int i = 0; i < p.C; ++i)
           for (int r = 0; r < 3; ++r) {
             const double v = pts[3 * (size_t)i + r];
+            finite &= std::isfinite(v);
             lo[r] = v < lo[r] ? v : lo[r];
             hi3[r] = v > hi3[r] ? v : hi3[r];
           }
+        const double* ori = s ? p.ori_dst : p.ori_src;
+        for (size_t i = 0; i < (size_t)3 * p.M; ++i) finite &= std::isfinite(ori[i]);
+        if (!finite) bad_problem.store(b);
         double* c = s ? L.cdst : L.csrc;
         double bound = 0.0;
         for (int r = 0; r < 3; ++r) {
