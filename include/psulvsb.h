@@ -209,8 +209,10 @@ int psulvsb_compact_edges(void* stream, const uint32_t* d_mask, int n, int row_s
 
 /* Stage 2 -- replayable sampling without replacement (registration.cc:852-861, :916-932):
  * d_out[r] = r-th distinct value of rand31(seed, domain, event, k) % n, k = 0,1,2,...
- * d_work: >= psulvsb_sample_workspace_bytes(n, count) bytes.  d_status[0] = draws consumed
- * (0 if max_draws was too small: call again with a larger max_draws). */
+ * max_draws = 0 selects psulvsb_sample_default_max_draws(n, count) (mean + 8 sigma of the rejection loop).
+ * d_work: >= psulvsb_sample_workspace_bytes(n, count, max_draws) bytes of scratch (16-byte aligned).
+ * d_status[0] = draws consumed, i.e. the stream position the sequential loop would be at
+ * (0 if max_draws was too small: call again with a larger max_draws).  n < 2^31, max_draws < 2^32. */
 unsigned long long psulvsb_sample_workspace_bytes(unsigned long long n, unsigned long long count,
                                                   unsigned long long max_draws);
 unsigned long long psulvsb_sample_default_max_draws(unsigned long long n, unsigned long long count);
