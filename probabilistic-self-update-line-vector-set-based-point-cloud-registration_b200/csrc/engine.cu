@@ -604,6 +604,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
 
   // ---- ticks
   const int gnc_cluster = gnc_cluster_for(B);
+  int max_ccap = 0;
+  for (int b = 0; b < B; ++b) max_ccap = lay[(size_t)b].Ccap > max_ccap ? lay[(size_t)b].Ccap : max_ccap;
   int gnc_cap = (int)((0.03 * (double)max_nred) / (double)gnc_cluster) + 64;
   gnc_cap = (gnc_cap + 31) & ~31;
   if (gnc_cap > gnc_default_capacity()) gnc_cap = gnc_default_capacity();
@@ -633,7 +635,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       if (int rc = launch_greedy_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap)) return rc;
       launches += 4;
     }
-    if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster)) return rc;
+    if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster, max_ccap)) return rc;
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");
     launches += 5;

@@ -61,6 +61,42 @@ __device__ __forceinline__ void load_lv(const double* __restrict__ src, const do
   }
 }
 
+// point-cache mode (one CTA per hypothesis, large batches): the CTA keeps the POINTS (48 B each, as many as
+// fit) in shared memory and re-forms every line vector from its endpoint pair each pass -- 8 + 16 bytes of
+// HBM traffic per line vector and pass (edge, old and new weight) instead of 48 + 16
+__device__ __forceinline__ void load_lv_pc(const double* __restrict__ pc, unsigned p_cap, const double* __restrict__ src,
+                                           const double* __restrict__ dst, uint2 e, double inv_scale, double sv[3],
+                                           double tv[3]) {
+  double sa[3], ta[3], sb[3], tb[3];
+  if (e.x < p_cap) {
+    const double2* p = reinterpret_cast<const double2*>(pc + 6 * (size_t)e.x);
+    const double2 p0 = p[0], p1 = p[1], p2 = p[2];
+    sa[0] = p0.x; sa[1] = p0.y; sa[2] = p1.x; ta[0] = p1.y; ta[1] = p2.x; ta[2] = p2.y;
+  } else {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      sa[r] = src[3 * (size_t)e.x + r];
+      ta[r] = dst[3 * (size_t)e.x + r];
+    }
+  }
+  if (e.y < p_cap) {
+    const double2* p = reinterpret_cast<const double2*>(pc + 6 * (size_t)e.y);
+    const double2 p0 = p[0], p1 = p[1], p2 = p[2];
+    sb[0] = p0.x; sb[1] = p0.y; sb[2] = p1.x; tb[0] = p1.y; tb[1] = p2.x; tb[2] = p2.y;
+  } else {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      sb[r] = src[3 * (size_t)e.y + r];
+      tb[r] = dst[3 * (size_t)e.y + r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    sv[r] = sb[r] - sa[r];
+    tv[r] = (tb[r] - ta[r]) * inv_scale;  // pruned_dst_tims_ *= (1 / solution_.scale)   (registration.cc:1102)
+  }
+}
+
 // line vector l of this CTA's slice (global index k): smem cache, else SoA scratch, else recompute
 struct LvSrc {
   const double* lv_s;  // smem [7][cap]
@@ -162,7 +198,7 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
   __syncthreads();
 }
 
-template <int NC, int T, int CPS>
+template <int NC, int T, int CPS, bool PC>
 __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GncSmem* sm = reinterpret_cast<GncSmem*>(smem_raw);
@@ -178,7 +214,10 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   const unsigned long long k_lo = (per * rank < K) ? per * rank : K;
   const unsigned long long k_hi = (k_lo + per < K) ? k_lo + per : K;
   const unsigned long long nloc = k_hi - k_lo;
-  const unsigned long long ncached = nloc < (unsigned long long)cap_per_cta ? nloc : (unsigned long long)cap_per_cta;
+  // PC: cap_per_cta counts cached POINTS and no line vector is cached
+  const unsigned long long ncached =
+      PC ? 0ull : (nloc < (unsigned long long)cap_per_cta ? nloc : (unsigned long long)cap_per_cta);
+  const unsigned p_cap = PC ? (unsigned)min(cap_per_cta, job.n_points) : 0u;
   const double* __restrict__ src = job.src;
   const double* __restrict__ dst = job.dst;
   const uint2* __restrict__ edges = job.edges;
@@ -192,8 +231,18 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   double acc[GNC_NRED];
 #pragma unroll
   for (int i = 0; i < GNC_NRED; ++i) acc[i] = 0.0;
-  double* __restrict__ lvg = job.lv;
+  double* __restrict__ lvg = PC ? nullptr : job.lv;
   const unsigned long long lv_cap = lvg ? job.lv_cap : 0ull;
+  if (PC) {  // stage the points: (sx, sy, sz, tx, ty, tz) per point
+    for (unsigned i = tid; i < p_cap; i += T) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        lv[6 * (size_t)i + r] = src[3 * (size_t)i + r];
+        lv[6 * (size_t)i + 3 + r] = dst[3 * (size_t)i + r];
+      }
+    }
+    __syncthreads();
+  }
   LvSrc S;
   S.lv_s = lv;
   S.cap = cap;
@@ -206,7 +255,10 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   S.inv_scale = job.inv_scale;
   for (unsigned long long l = tid; l < nloc; l += T) {
     double sv[3], tv[3];
-    load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
+    if (PC)
+      load_lv_pc(lv, p_cap, src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
+    else
+      load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
     if (l < ncached) {
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
@@ -258,7 +310,10 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
       for (int i = 0; i < GNC_NRED; ++i) mx[i] = 0.0;
       for (unsigned long long l = tid; l < nloc; l += T) {
         double sv[3], tv[3];
-        fetch_lv(S, l, k_lo + l, sv, tv);
+        if (PC)
+          load_lv_pc(lv, p_cap, src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
+        else
+          fetch_lv(S, l, k_lo + l, sv, tv);
         mx[0] = fmax(mx[0], residual2(R, sv, tv));
       }
       cluster_reduce<NC, T>(sm, mx, parity, 0);
@@ -352,10 +407,25 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
         }
         __stcg(gwl + l, body(sa, ta, __ldcg(gwl + l)));
       }
-      // (c) beyond the scratch capacity: recompute from the points
+      // (c) beyond the scratch capacity / point-cache mode: re-form the line vectors from the points
+      if (PC) {
+        const uint2* __restrict__ el = edges + k_lo;
+        for (; l + T < nl; l += 2 * T) {  // two line vectors in flight: edges and weights stream from HBM
+          const uint2 ea = el[l], eb = el[l + T];
+          const double wa = __ldcg(gwl + l), wb = __ldcg(gwl + l + T);
+          double sa[3], ta[3], sb[3], tb[3];
+          load_lv_pc(lv, p_cap, src, dst, ea, job.inv_scale, sa, ta);
+          load_lv_pc(lv, p_cap, src, dst, eb, job.inv_scale, sb, tb);
+          __stcg(gwl + l, body(sa, ta, wa));
+          __stcg(gwl + l + T, body(sb, tb, wb));
+        }
+      }
       for (; l < nl; l += T) {
         double sa[3], ta[3];
-        load_lv(src, dst, edges[k_lo + l], job.inv_scale, sa, ta);
+        if (PC)
+          load_lv_pc(lv, p_cap, src, dst, edges[k_lo + l], job.inv_scale, sa, ta);
+        else
+          load_lv(src, dst, edges[k_lo + l], job.inv_scale, sa, ta);
         gwl[l] = body(sa, ta, gwl[l]);
       }
     }
@@ -475,15 +545,16 @@ __global__ void __launch_bounds__(256)
 int gnc_capacity_for(int ctas_per_sm);
 size_t gnc_smem_bytes(int cap) { return ((sizeof(GncSmem) + 15) & ~size_t(15)) + (size_t)7 * cap * sizeof(double); }
 
-template <int NC, int T, int CPS>
+template <int NC, int T, int CPS, bool PC>
 int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta) {
   static bool attr_set = false;
-  const int max_cap = gnc_capacity_for(CPS);
+  // shared-memory payload: 7 doubles per cached line vector, or (PC) 6 doubles per cached point
+  const int max_cap = PC ? gnc_capacity_for(CPS) * 7 / 6 - 2 : gnc_capacity_for(CPS);
   if (cap_per_cta > max_cap) cap_per_cta = max_cap;
-  const size_t smem = gnc_smem_bytes(cap_per_cta);
+  const size_t smem = PC ? gnc_smem_bytes((cap_per_cta * 6 + 6) / 7 + 1) : gnc_smem_bytes(cap_per_cta);
   if (!attr_set) {
-    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<NC, T, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)gnc_smem_bytes(max_cap)));
+    PSU_CUDA(cudaFuncSetAttribute(gnc_tls_kernel<NC, T, CPS, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)gnc_smem_bytes(gnc_capacity_for(CPS))));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -498,7 +569,7 @@ int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T, CPS>, d_jobs, cap_per_cta));
+  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T, CPS, PC>, d_jobs, cap_per_cta));
   return PSULVSB_OK;
 }
 
@@ -527,8 +598,11 @@ int gnc_cluster_for(int n_jobs) {
   return 1;
 }
 
-int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster) {
+int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster, int max_points) {
   if (n_jobs <= 0) return PSULVSB_OK;
+  static const char* pc_env = getenv("PSULVSB_GNC_POINT_CACHE");
+  // opt-in only: measured on B200 it does not pay (B = 256: 29.9 vs 28.1 ms per step, B = 512: 55.4 vs 54.7)
+  const bool point_cache = max_points > 0 && pc_env && pc_env[0] == '1';
   if (cap_per_cta < 32) cap_per_cta = 32;
   static const char* lean_env = getenv("PSULVSB_GNC_LEAN");
   const bool lean = lean_env && lean_env[0] == '1';
@@ -537,11 +611,15 @@ int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_pe
     case 8:
       // few registrations (8 CTAs each still leave SMs idle): 512 threads, one CTA per SM -- half the line
       // vectors per thread in the latency-bound pass
-      if (!lean && n_jobs * 8 <= 148) return launch_gnc_nc<8, 512, 1>(st, d_jobs, n_jobs, cap_per_cta);
-      return lean ? launch_gnc_nc<8, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<8, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
-    case 4: return lean ? launch_gnc_nc<4, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<4, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
-    case 2: return lean ? launch_gnc_nc<2, 256, 4>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<2, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
-    case 1: return lean ? launch_gnc_nc<1, 512, 2>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<1, 512, 1>(st, d_jobs, n_jobs, cap_per_cta);
+      if (!lean && n_jobs * 8 <= 148) return launch_gnc_nc<8, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+      return lean ? launch_gnc_nc<8, 256, 4, false>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<8, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
+    case 4: return lean ? launch_gnc_nc<4, 256, 4, false>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<4, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
+    case 2: return lean ? launch_gnc_nc<2, 256, 4, false>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<2, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
+    case 1:
+      if (lean) return launch_gnc_nc<1, 512, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
+      // one CTA per hypothesis (large batches); PSULVSB_GNC_POINT_CACHE=1 caches the points instead of line vectors
+      if (point_cache) return launch_gnc_nc<1, 512, 1, true>(st, d_jobs, n_jobs, max_points);
+      return launch_gnc_nc<1, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
     default: return fail(PSULVSB_ERR_INVALID, "launch_gnc_tls: cluster must be 1, 2, 4 or 8");
   }
 }
