@@ -409,15 +409,33 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
       }
       // (c) beyond the scratch capacity / point-cache mode: re-form the line vectors from the points
       if (PC) {
+        // software pipeline: the (edge, weight) pairs of the NEXT two line vectors are already in flight from
+        // HBM while the current two are re-formed from the cached points and processed
         const uint2* __restrict__ el = edges + k_lo;
-        for (; l + T < nl; l += 2 * T) {  // two line vectors in flight: edges and weights stream from HBM
-          const uint2 ea = el[l], eb = el[l + T];
-          const double wa = __ldcg(gwl + l), wb = __ldcg(gwl + l + T);
-          double sa[3], ta[3], sb[3], tb[3];
-          load_lv_pc(lv, p_cap, src, dst, ea, job.inv_scale, sa, ta);
-          load_lv_pc(lv, p_cap, src, dst, eb, job.inv_scale, sb, tb);
-          __stcg(gwl + l, body(sa, ta, wa));
-          __stcg(gwl + l + T, body(sb, tb, wb));
+        if (l + T < nl) {
+          uint2 ea = el[l], eb = el[l + T];
+          double wa = __ldcg(gwl + l), wb = __ldcg(gwl + l + T);
+          for (; l + T < nl; l += 2 * T) {
+            const int ln = l + 2 * T;
+            const bool more = ln + T < nl;
+            uint2 na = ea, nb = eb;
+            double nwa = 0.0, nwb = 0.0;
+            if (more) {
+              na = el[ln];
+              nb = el[ln + T];
+              nwa = __ldcg(gwl + ln);
+              nwb = __ldcg(gwl + ln + T);
+            }
+            double sa[3], ta[3], sb[3], tb[3];
+            load_lv_pc(lv, p_cap, src, dst, ea, job.inv_scale, sa, ta);
+            load_lv_pc(lv, p_cap, src, dst, eb, job.inv_scale, sb, tb);
+            __stcg(gwl + l, body(sa, ta, wa));
+            __stcg(gwl + l + T, body(sb, tb, wb));
+            ea = na;
+            eb = nb;
+            wa = nwa;
+            wb = nwb;
+          }
         }
       }
       for (; l < nl; l += T) {
