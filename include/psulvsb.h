@@ -252,14 +252,18 @@ int psulvsb_estimate_normals(void* stream, const double* d_pts, int n, int k, co
                              double* d_normals);
 int psulvsb_estimate_normals_host(const double* pts, int n, int k, const double viewpoint[3], double* normals);
 
-/* Clique escalation (registration.cc:1000-1085 -> teaser/src/graph.cc:12-125, PMC): a deterministic greedy
- * maximal clique of the graph with n_vertices vertices and the given edges (uint2 endpoint pairs): take the
- * candidate with the most neighbours among the remaining candidates (ties: lowest index), intersect.
- * d_adj: scratch bit matrix of n_vertices * ceil(n_vertices / 32) words.  d_flags[n_vertices] (u8) receives
- * the membership, *d_size the clique size.  PMC's own result is not unique: parity for this branch is
- * defined on clique validity / size, not membership. */
-int psulvsb_greedy_clique(void* stream, const void* d_edges_uint2, unsigned long long n_edges, int n_vertices,
-                          uint32_t* d_adj, uint8_t* d_flags, int* d_size);
+/* Clique escalation (registration.cc:1000-1085 -> teaser/src/graph.cc:12-125, PMC exact maximum clique) of the
+ * graph with n_vertices vertices and the given edges (uint2 endpoint pairs).  A deterministic greedy maximal
+ * clique (most neighbours among the remaining candidates first, ties: lowest index) gives the lower bound;
+ * exact != 0 then runs a branch and bound from every vertex of sufficient degree (one warp per root, local
+ * bit matrix in shared memory) and keeps the largest clique (ties: lowest root).
+ * d_adj: scratch of psulvsb_max_clique_scratch_words(n_vertices) 32-bit words.  d_flags[n_vertices] (u8)
+ * receives the membership, d_size[0] the clique size, d_size[1] = 1 when the size is proven maximum (0: a
+ * neighbourhood above 512 vertices or the node budget stopped the search; the greedy answer stands).
+ * Which maximum clique PMC returns is not unique: parity for this branch is defined on the size. */
+unsigned long long psulvsb_max_clique_scratch_words(int n_vertices);
+int psulvsb_max_clique(void* stream, const void* d_edges_uint2, unsigned long long n_edges, int n_vertices,
+                       uint32_t* d_adj, uint8_t* d_flags, int* d_size, int exact);
 
 /* Stage 4 -- fused transform + score + argmax (registration.cc:1303-1336, :1417-1444):
  * counts[h] = #{ j : | q_j - s (R_h p_j + t_h) | <= tau } over all n points, evaluated in FP32

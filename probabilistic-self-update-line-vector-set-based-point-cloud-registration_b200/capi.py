@@ -25,7 +25,7 @@ SYMBOLS = [
     "psulvsb_mask_symmetrize", "psulvsb_compact_edges", "psulvsb_sample_workspace_bytes",
     "psulvsb_sample_default_max_draws", "psulvsb_sample", "psulvsb_philox_fill", "psulvsb_gnc_tls_rotation",
     "psulvsb_kabsch_batch", "psulvsb_tls_translation", "psulvsb_score_batch", "psulvsb_score_one",
-    "psulvsb_greedy_clique", "psulvsb_estimate_normals", "psulvsb_estimate_normals_host",
+    "psulvsb_max_clique", "psulvsb_max_clique_scratch_words", "psulvsb_estimate_normals", "psulvsb_estimate_normals_host",
 ]
 
 
@@ -190,7 +190,9 @@ def _declare(L: C.CDLL) -> None:
     L.psulvsb_estimate_normals.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_double), _vp]
     L.psulvsb_estimate_normals_host.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double),
                                                 C.POINTER(C.c_double)]
-    L.psulvsb_greedy_clique.argtypes = [_vp, _vp, _ull, C.c_int, _vp, _vp, _vp]
+    L.psulvsb_max_clique.argtypes = [_vp, _vp, _ull, C.c_int, _vp, _vp, _vp, C.c_int]
+    L.psulvsb_max_clique_scratch_words.argtypes = [C.c_int]
+    L.psulvsb_max_clique_scratch_words.restype = _ull
     L.psulvsb_score_one.argtypes = [_vp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, C.c_double, _vp, _vp, _vp]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here = the library does not export what the header declares

@@ -381,11 +381,15 @@ int psulvsb_estimate_normals_host(const double* pts, int n, int k, const double 
   return rc;
 }
 
-int psulvsb_greedy_clique(void* stream, const void* d_edges_uint2, unsigned long long n_edges, int n_vertices,
-                          uint32_t* d_adj, uint8_t* d_flags, int* d_size) {
+unsigned long long psulvsb_max_clique_scratch_words(int n_vertices) {
+  return n_vertices < 1 ? 0ull : (unsigned long long)clique_scratch_words(n_vertices);
+}
+
+int psulvsb_max_clique(void* stream, const void* d_edges_uint2, unsigned long long n_edges, int n_vertices,
+                       uint32_t* d_adj, uint8_t* d_flags, int* d_size, int exact) {
   if (int rc = need_device()) return rc;
   if ((!d_edges_uint2 && n_edges) || !d_adj || !d_flags || !d_size || n_vertices < 1)
-    return fail(PSULVSB_ERR_INVALID, "psulvsb_greedy_clique: bad argument");
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_max_clique: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CliqueJob j;
   std::memset(&j, 0, sizeof(j));
@@ -397,10 +401,11 @@ int psulvsb_greedy_clique(void* stream, const void* d_edges_uint2, unsigned long
   j.stride = (n_vertices + 31) / 32;
   j.flags = d_flags;
   j.size = d_size;
+  j.proven = d_size + 1;
   j.active = 1;
   DeviceJob<CliqueJob> dj(st);
   if (int rc = dj.put(j)) return rc;
-  return launch_greedy_clique(st, dj.d, 1, n_vertices, j.stride, n_edges);
+  return launch_max_clique(st, dj.d, 1, n_vertices, j.stride, n_edges, exact != 0);
 }
 
 int psulvsb_score_batch(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,

@@ -126,7 +126,7 @@ class Engine {
   std::vector<ProbLayout> lay;
   std::vector<unsigned long long> reserve;  // self-update edge head-room per job
   size_t in_dbl_total = 0, in_int_total = 0;
-  DevBuf d_in_dbl, d_in_int, d_work, d_mask, d_edge, d_jobs, d_misc;
+  DevBuf d_in_dbl, d_in_int, d_work, d_mask, d_edge, d_jobs, d_misc, d_hist;
   PinBuf h_stage, h_small;
   long long launches = 0;
   double last_ms = 0.0;
@@ -142,6 +142,7 @@ class Engine {
     d_edge.release();
     d_jobs.release();
     d_misc.release();
+    d_hist.release();
     h_stage.release();
     h_small.release();
     if (ev_begin) cudaEventDestroy(ev_begin);
@@ -403,7 +404,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.idx = bw.take<int>((size_t)L.Ccap);
         J.adj_stride = (L.Ccap + 31) / 32;
         // the bit matrix is only touched by the last-resort clique escalation; selection NONE never builds it
-        J.adj = params->inlier_selection_mode != 3 ? bw.take<uint32_t>((size_t)L.Ccap * J.adj_stride) : nullptr;
+        J.adj = params->inlier_selection_mode != 3 ? bw.take<uint32_t>(clique_scratch_words(L.Ccap)) : nullptr;
         J.clique_flags = bw.take<uint8_t>((size_t)L.Ccap);
         J.sampled_flags = bw.take<uint8_t>((size_t)L.Ccap);
         J.rot_flags = bw.take<uint8_t>((size_t)L.Ccap);
@@ -437,8 +438,13 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
           Rj.dst64 = J.dst0;
           Rj.n = L.C0;
           Rj.pair_bin = bk.take<uint32_t>((size_t)L.C0 * (size_t)(L.C0 - 1) / 2 + 1);
-          Rj.hist = bk.take<unsigned int>(200000);
-          Rj.last = bk.take<unsigned long long>(200000);
+          Rj.exceed_idx = bk.take<unsigned long long>(RATIO_EXCEED_CAP);
+          Rj.exceed_x = bk.take<double>(RATIO_EXCEED_CAP);
+          Rj.bp_idx = bk.take<unsigned long long>(RATIO_EXCEED_CAP);
+          Rj.bp_scale = bk.take<double>(RATIO_EXCEED_CAP);
+          Rj.exceed_n = bk.take<unsigned int>(2);
+          Rj.bp_n = Rj.exceed_n + 1;
+          Rj.final_scale = bk.take<double>(1);
           Rj.peak = bk.take<unsigned int>(4);
           Rj.class_counts = bk.take<unsigned int>((size_t)3 * L.C0);
           Rj.class_offsets = bk.take<unsigned long long>((size_t)3 * L.C0 + 1);
@@ -491,14 +497,48 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
 
   // ---- stage 1: float4 tiles, bit mask, row scan  (unknown scale: ratio histogram, peak, class scan)
   if (ratio) {
-    for (int b = 0; b < B; ++b) {
-      PSU_CUDA(cudaMemsetAsync(rj[(size_t)b].hist, 0, sizeof(unsigned int) * 200000, st));
-      PSU_CUDA(cudaMemsetAsync(rj[(size_t)b].last, 0, sizeof(unsigned long long) * 200000, st));
-    }
+    // phase 0: does the histogram grow (a ratio above MaxScale = 10000)?  final MaxScale[B] -> host: sizes it
+    for (int b = 0; b < B; ++b) PSU_CUDA(cudaMemsetAsync(rj[(size_t)b].exceed_n, 0, 2 * sizeof(unsigned int), st));
     PSU_CUDA(cudaMemsetAsync(m.bad, 0, sizeof(int) * (size_t)B, st));
     PSU_CUDA(cudaMemcpyAsync(m.rj, rj.data(), sizeof(RatioJob) * (size_t)B, cudaMemcpyHostToDevice, st));
-    PSU_CUDA(cudaEventRecord(ev_m0, st));
     if (int rc = launch_ratio_reduced_set(st, m.rj, B, maxC, 0)) return rc;
+    launches += 2;
+    std::vector<double> fscale((size_t)B);
+    std::vector<int> badv((size_t)B);
+    for (int b = 0; b < B; ++b)
+      PSU_CUDA(cudaMemcpyAsync(&fscale[(size_t)b], rj[(size_t)b].final_scale, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PSU_CUDA(cudaMemcpyAsync(badv.data(), m.bad, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    PSU_CUDA(cudaStreamSynchronize(st));
+    size_t hist_total = 0;
+    for (int b = 0; b < B; ++b) {
+      if (badv[(size_t)b])
+        return fail(PSULVSB_ERR_UNSUPPORTED,
+                    "problem " + std::to_string(b) +
+                        (badv[(size_t)b] == 1 ? ": an infinite length ratio (coincident source points with distinct targets; "
+                                                "registration.cc:714-718 is undefined there)"
+                                              : ": the ratio histogram would outgrow the supported MaxScale "
+                                                "(registration.cc:714-718)"));
+      hist_total += (size_t)(fscale[(size_t)b] * 20.0) + 64;
+    }
+    if (int rc = d_hist.ensure(hist_total * (sizeof(unsigned int) + sizeof(unsigned long long)))) return rc;
+    {
+      char* hb = reinterpret_cast<char*>(d_hist.p);
+      size_t off = 0;
+      for (int b = 0; b < B; ++b) {
+        const size_t bins = (size_t)(fscale[(size_t)b] * 20.0) + 64;
+        rj[(size_t)b].last = reinterpret_cast<unsigned long long*>(hb + off);
+        off += bins * sizeof(unsigned long long);
+      }
+      for (int b = 0; b < B; ++b) {
+        const size_t bins = (size_t)(fscale[(size_t)b] * 20.0) + 64;
+        rj[(size_t)b].hist = reinterpret_cast<unsigned int*>(hb + off);
+        off += bins * sizeof(unsigned int);
+      }
+      PSU_CUDA(cudaMemsetAsync(d_hist.p, 0, off, st));
+    }
+    PSU_CUDA(cudaMemcpyAsync(m.rj, rj.data(), sizeof(RatioJob) * (size_t)B, cudaMemcpyHostToDevice, st));
+    PSU_CUDA(cudaEventRecord(ev_m0, st));
+    if (int rc = launch_ratio_reduced_set(st, m.rj, B, maxC, 1)) return rc;
     PSU_CUDA(cudaEventRecord(ev_m1, st));
     launches += 6;
   } else {
@@ -518,16 +558,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   if (int rc = h_small.ensure((sizeof(unsigned long long) + sizeof(int)) * (size_t)B + 64)) return rc;
   unsigned long long* h_nedges = reinterpret_cast<unsigned long long*>(h_small.p);
   volatile int* h_done = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(h_small.p) + sizeof(unsigned long long) * (size_t)B);
-  int* h_bad = reinterpret_cast<int*>(reinterpret_cast<char*>(h_small.p) + sizeof(unsigned long long) * (size_t)B + 32);
   PSU_CUDA(cudaMemcpyAsync(h_nedges, m.n_edges, sizeof(unsigned long long) * (size_t)B, cudaMemcpyDeviceToHost, st));
-  if (ratio) PSU_CUDA(cudaMemcpyAsync(h_bad, m.bad, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
   PSU_CUDA(cudaStreamSynchronize(st));
-  if (ratio)
-    for (int b = 0; b < B; ++b)
-      if (h_bad[b])
-        return fail(PSULVSB_ERR_UNSUPPORTED, "problem " + std::to_string(b) +
-                                                 ": a length ratio exceeds MaxScale = 10000 (registration.cc:714-718 would "
-                                                 "regrow the histogram mid-stream; coincident source points?)");
 
   // ---- edge arena, sized from the measured reduced-set sizes
   unsigned long long max_cap = 0, max_nred = 0;
@@ -574,7 +606,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   PSU_CUDA(cudaMemcpyAsync(m.jobs, jobs.data(), sizeof(JobCtl) * (size_t)B, cudaMemcpyHostToDevice, st));
   if (ratio) {
     PSU_CUDA(cudaMemcpyAsync(m.rj, rj.data(), sizeof(RatioJob) * (size_t)B, cudaMemcpyHostToDevice, st));
-    if (int rc = launch_ratio_reduced_set(st, m.rj, B, maxC, 1)) return rc;
+    if (int rc = launch_ratio_reduced_set(st, m.rj, B, maxC, 2)) return rc;
   } else {
     PSU_CUDA(cudaMemcpyAsync(m.cj, cj.data(), sizeof(CompactJob) * (size_t)B, cudaMemcpyHostToDevice, st));
     if (int rc = launch_compact_edges(st, m.cj, B, maxC, false, true)) return rc;
@@ -632,8 +664,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     if (clique_pending) {  // some registration is in its clique round (rare, last escalation)
       int maxCcap = 0;
       for (int b = 0; b < B; ++b) maxCcap = lay[(size_t)b].Ccap > maxCcap ? lay[(size_t)b].Ccap : maxCcap;
-      if (int rc = launch_greedy_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap)) return rc;
-      launches += 4;
+      if (int rc = launch_max_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap, true)) return rc;
+      launches += 6;
     }
     if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster, max_ccap)) return rc;
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);

@@ -54,20 +54,29 @@ struct CompactJob {
 };
 
 // unknown-scale stage 1 (k1_ratio.cu): ratio histogram and its three-bin reduced set
+constexpr unsigned int RATIO_EXCEED_CAP = 1024;  // growth candidates kept per job
+constexpr double RATIO_MAX_SCALE = 2.0e6;        // largest MaxScale served (a 40 M-bin histogram)
 struct RatioJob {
   const double* src64;  // column-major 3 x n
   const double* dst64;
   int n;
   uint32_t* pair_bin;                 // [n (n - 1) / 2] bin of every pair, row-major pair order
-  unsigned int* hist;                 // [200000], zero on entry
-  unsigned long long* last;           // [200000], zero on entry
+  unsigned int* hist;                 // [final MaxScale * 20], zero on entry (sized after phase 0)
+  unsigned long long* last;           // same length, zero on entry
+  unsigned long long* exceed_idx;     // [RATIO_EXCEED_CAP] pairs with X > 10000 (growth candidates)
+  double* exceed_x;
+  unsigned int* exceed_n;             // zero on entry
+  unsigned long long* bp_idx;         // [RATIO_EXCEED_CAP] growth break points: from pair bp_idx[k] on ...
+  double* bp_scale;                   // ... MaxScale == bp_scale[k]
+  unsigned int* bp_n;
+  double* final_scale;                // MaxScale after the last pair
   unsigned int* peak;                 // [2]: max height, peak bin
   unsigned int* class_counts;         // [3 n]
   unsigned long long* class_offsets;  // [3 n + 1]
   unsigned long long* n_edges;
   uint2* edges;                       // NULL in phase 0
   unsigned long long cap;
-  int* bad;                           // set to 1 when a ratio exceeds MaxScale
+  int* bad;                           // 1: infinite ratio, 2: too many growth candidates, 3: histogram too large
   int active;
 };
 
@@ -128,14 +137,19 @@ struct CliqueJob {
   double beta;
   int filter;
   int n_vertices;
-  uint32_t* adj;  // [n_vertices * stride] bit matrix scratch
+  uint32_t* adj;  // [clique_scratch_words(n_vertices)] bit matrix scratch + the exact search's work area
   int stride;
   uint8_t* flags;  // [n_vertices] out: clique membership
   int* size;       // out
+  int* proven;     // out: 1 = the size is the exact maximum, 0 = the search gave up (greedy answer kept)
   int active;
 };
-int launch_greedy_clique(cudaStream_t st, const CliqueJob* d_jobs, int n_jobs, int max_vertices, int max_stride,
-                         unsigned long long max_edges);
+inline size_t clique_scratch_words(int n_vertices) {
+  return (((size_t)n_vertices * (size_t)((n_vertices + 31) / 32) + 3) & ~(size_t)3) + 8;
+}
+// exact = false: the greedy maximal clique only
+int launch_max_clique(cudaStream_t st, const CliqueJob* d_jobs, int n_jobs, int max_vertices, int max_stride,
+                      unsigned long long max_edges, bool exact);
 
 int launch_knn_normals(cudaStream_t st, const double* pts, int n, int k, const double* viewpoint, double* normals);
 

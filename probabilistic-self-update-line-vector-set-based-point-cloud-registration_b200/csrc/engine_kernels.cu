@@ -106,6 +106,7 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   q.stride = J.adj_stride;
   q.flags = J.clique_flags;
   q.size = &J.clique_size;
+  q.proven = &J.clique_proven;
 }
 
 // count_j [ | q_j - s (R p_j + t) | <= tau ] over the flagged points of the working set

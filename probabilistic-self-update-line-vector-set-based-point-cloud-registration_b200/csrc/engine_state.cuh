@@ -103,7 +103,7 @@ struct JobCtl {
   Xform sol, best_sampled, best_host, last_best;
   int new_corr_count, inlier_map_size;
   int scale_calls, n_pruned;
-  int clique_size, aborted;
+  int clique_size, clique_proven, aborted;
   double cur_scale;  // solution_.scale of the iteration in flight (registration.cc:958-991)
   unsigned long long sample_status[2];
   double R_gnc[9];  // column-major (GncJob::R_out)

@@ -189,14 +189,20 @@ def score_one(d_src, d_dst, scale, R, t, tau):
     return int(cnt.item()), inl.cpu().numpy(), res.cpu().numpy()
 
 
-def greedy_clique(edges, n_vertices: int):
-    """edges: [E, 2] int array -> (sorted clique vertex ids, size)."""
+def max_clique(edges, n_vertices: int, exact: bool = True):
+    """edges: [E, 2] int array -> (sorted clique vertex ids, size, proven).  exact=False: greedy lower bound only."""
+    L = capi.lib()
     e = torch.from_numpy(np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)).cuda()
-    stride = (n_vertices + 31) // 32
-    adj = torch.empty(n_vertices * stride, dtype=torch.int32, device="cuda")
+    adj = torch.empty(int(L.psulvsb_max_clique_scratch_words(n_vertices)), dtype=torch.int32, device="cuda")
     flags = torch.zeros(n_vertices, dtype=torch.uint8, device="cuda")
-    size = torch.zeros(1, dtype=torch.int32, device="cuda")
-    capi.check(capi.lib().psulvsb_greedy_clique(_stream(), _dev(e) if e.numel() else None, e.shape[0], n_vertices,
-                                                _dev(adj), _dev(flags), _dev(size)))
+    size = torch.zeros(2, dtype=torch.int32, device="cuda")
+    capi.check(L.psulvsb_max_clique(_stream(), _dev(e) if e.numel() else None, e.shape[0], n_vertices, _dev(adj),
+                                    _dev(flags), _dev(size), 1 if exact else 0))
     torch.cuda.synchronize()
-    return np.flatnonzero(flags.cpu().numpy()), int(size.item())
+    sz = size.cpu().numpy()
+    return np.flatnonzero(flags.cpu().numpy()), int(sz[0]), bool(sz[1]) if exact else False
+
+
+def greedy_clique(edges, n_vertices: int):
+    got, size, _ = max_clique(edges, n_vertices, exact=False)
+    return got, size

@@ -237,6 +237,28 @@ def test_unknown_scale_matches_oracle(env, n, ratio, seed, scale):
     assert abs(sg.scale - scale) < 0.02 * scale and env["synth"].rotation_error(sg.R, pair["R"]) < 0.05
 
 
+def test_unknown_scale_histogram_growth_matches_oracle(env):
+    """A length ratio above MaxScale = 10000 makes the reference grow MaxScale and its histogram in the middle of
+    the pair loop (registration.cc:714-718): every LATER pair is binned on the new, coarser grid.  Two nearly
+    coincident source pairs (ratios ~1e4 and ~1e5, the second later in pair order) exercise two growth steps."""
+    pair = scaled_pair(env["synth"], 800, 0.8, 31, 1.3)
+    out = np.flatnonzero(~pair["inlier_mask"])
+    src = pair["src"].copy()
+    src[:, out[40]] = src[:, out[3]] + np.array([3e-4, 0, 0])
+    src[:, out[90]] = src[:, out[70]] + np.array([0, 3e-5, 0])
+    pair["src"] = np.asfortranarray(src)
+    so, to, sg, tg = both(env, pair, seed=5, estimate_scaling=1)
+    assert sg.status == 0
+    assert sg.n_reduced == so.n_reduced and len(tg["local"]) == len(to["local"])
+    for a, b in zip(tg["local"], to["local"]):
+        for f in ["n_sampled_lines", "n_sampled_points", "basic_choose", "gnc_iterations", "rot_inliers",
+                  "n_rot_points", "similar", "curr_count", "best_count", "local_r"]:
+            assert getattr(a, f) == getattr(b, f), (f, a.local_iter, getattr(a, f), getattr(b, f))
+    assert np.array_equal(tg["final_inliers"], to["final_inliers"])
+    assert abs(sg.scale - so.scale) <= 1e-12 * abs(so.scale)
+    assert env["synth"].rotation_error(sg.R, env["O"].solution_R(so)) < R_TOL
+
+
 def test_unknown_scale_benchmark_1_rank_deficient(env, golden):
     """benchmark_1 has 10 points: |L_sampled| = 4 and the basic subset is ONE line vector, so H = sv tv^T has
     rank 1 and R = V U^T is not unique (any SVD completes the null space differently -- Eigen's, the oracle's

@@ -192,6 +192,30 @@ def test_kabsch_batch_vs_oracle(P, O):
         assert P["synth"].rotation_error(Rg, Rw) < 1e-7
 
 
+def test_kabsch_rank2_is_unique_and_matches_oracle(P, O):
+    """Two line vectors: H has rank 2, sigma_3 = 0, and R = V diag(1, 1, +-1) U^T is still unique (the third
+    singular pair is fixed by orthogonality and the determinant rule, utils.h:131-133).  Basic subsets of two
+    line vectors occur on small reduced sets, so this must agree with the oracle like the full-rank case."""
+    st = P["stages"]
+    pair, e = _edges_for(P, O, 400, 5, frac=0.2)
+    rng = np.random.default_rng(1)
+    k, H = 2, 400
+    sets = np.stack([rng.permutation(len(e))[:k] for _ in range(H)]).astype(np.int32)
+    R, _ = st.kabsch_batch(st.to_device_points(pair["src"]), st.to_device_points(pair["dst"]),
+                           torch.from_numpy(e).cuda(), torch.from_numpy(sets).cuda(), k)
+    R = R.cpu().numpy()
+    worst = 0.0
+    for h in range(H):
+        ee = e[sets[h]]
+        sv = pair["src"][:, ee[:, 1]] - pair["src"][:, ee[:, 0]]
+        tv = pair["dst"][:, ee[:, 1]] - pair["dst"][:, ee[:, 0]]
+        Rw = O.svd_rot(sv, tv, np.ones(k))
+        Rg = R[h].reshape(3, 3, order="F")
+        assert np.allclose(Rg @ Rg.T, np.eye(3), atol=1e-12) and np.linalg.det(Rg) > 0
+        worst = max(worst, float(np.abs(Rg - Rw).max()))
+    assert worst < 1e-9, worst
+
+
 @pytest.mark.parametrize("n,with_last", [(34, False), (300, False), (300, True), (2500, True)])
 def test_tls_translation_vs_oracle(P, O, n, with_last):
     st = P["stages"]
@@ -303,6 +327,9 @@ def test_greedy_clique_on_planted_graphs(P, O):
         edges = np.stack([ei, ej], axis=1).astype(np.int32)
         got, size = st.greedy_clique(edges, n)
         assert size == len(got)
+        if len(edges):
+            got_x, size_x, proven = st.max_clique(edges, n)   # the exact search confirms it
+            assert proven and size_x == size and np.array_equal(got_x, got)
         full = A | A.T
         for a in got:                                    # a clique ...
             for b in got:
@@ -318,6 +345,47 @@ def test_greedy_clique_on_planted_graphs(P, O):
                 assert np.array_equal(got, members)      # and it is the planted one
         else:
             assert size == 0
+
+
+def _is_clique(edges, n, got):
+    full = np.zeros((n, n), dtype=bool)
+    full[edges[:, 0], edges[:, 1]] = True
+    full |= full.T
+    return all(a == b or full[a, b] for a in got for b in got)
+
+
+@pytest.mark.parametrize("n,p_edge,seed", [(60, 0.15, 1), (300, 0.05, 2), (1000, 0.02, 3), (2500, 0.02, 4),
+                                           (400, 0.2, 5), (150, 0.5, 6)])
+def test_exact_clique_on_random_graphs(P, O, n, p_edge, seed):
+    """No-consensus inlier graphs (what the (1.0, 1.0) round sees when a registration is failing) are sparse random
+    graphs where a greedy clique is often one vertex short of the maximum.  The exact improvement search must
+    reach the size of the oracle's exact branch and bound (PMC's stand-in) and say so (proven)."""
+    st = P["stages"]
+    rng = np.random.default_rng(seed)
+    A = np.triu(rng.uniform(0, 1, (n, n)) < p_edge, 1)
+    ei, ej = np.nonzero(A)
+    edges = np.stack([ei, ej], axis=1).astype(np.int32)
+    exact = O.max_clique(n, edges)
+    got, size, proven = st.max_clique(edges, n)
+    assert size == len(got) and _is_clique(edges, n, got)
+    assert proven and size == len(exact)
+    g_got, g_size = st.greedy_clique(edges, n)
+    assert g_size == len(g_got) <= size and _is_clique(edges, n, g_got)
+    got2, size2, _ = st.max_clique(edges, n)            # deterministic: same members on a second run
+    assert np.array_equal(got, got2) and size2 == size
+
+
+def test_exact_clique_reports_unproven_on_wide_neighbourhoods(P, O):
+    """A dense graph whose neighbourhoods exceed the 512-vertex local matrix: the search declines (proven = 0) and the
+    greedy clique stands -- still a valid maximal clique."""
+    st = P["stages"]
+    rng = np.random.default_rng(9)
+    n = 1600
+    A = np.triu(rng.uniform(0, 1, (n, n)) < 0.8, 1)
+    ei, ej = np.nonzero(A)
+    edges = np.stack([ei, ej], axis=1).astype(np.int32)
+    got, size, proven = st.max_clique(edges, n)
+    assert not proven and size == len(got) >= 10 and _is_clique(edges, n, got)
 
 
 def test_solver_reaches_the_clique_escalation(P, O):

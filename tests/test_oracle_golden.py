@@ -299,3 +299,25 @@ def test_end_to_end_object_scene(golden):
         ours = (np.linalg.norm(dst - (R @ src + t[:, None]), axis=0) <= tau).sum()
         assert ours >= exp_inl
         assert sol.n_reduced > 0 and sol.host_rounds >= 1
+
+
+def test_rank_one_rotation_is_roundoff_determined_in_the_reference_algorithm():
+    """Why no parity is defined when a basic subset is ONE line vector (tiny reduced sets, benchmark_1): H = x y^T
+    has rank 1, and the null-space completion of Eigen's two-sided Jacobi sweep (restated in the oracle's svd3) is
+    decided by entries of size ~ 1 ulp crossing the 2 eps threshold.  Moving the inputs by one ulp flips R = V U^T by
+    O(1) in a large share of cases -- the reference's own answer changes with the compiler's FMA / vector flags
+    there.  With two line vectors (rank 2) the rotation is unique and stable."""
+    rng = np.random.default_rng(0)
+
+    def flipped(k, trials=400):
+        bad = 0
+        for _ in range(trials):
+            x, y = rng.normal(size=(3, k)), rng.normal(size=(3, k))
+            r0 = O.svd_rot(x, y, np.ones(k))
+            x2 = np.nextafter(x, x + rng.choice([-1.0, 1.0], x.shape))
+            y2 = np.nextafter(y, y + rng.choice([-1.0, 1.0], y.shape))
+            bad += int(np.abs(r0 - O.svd_rot(x2, y2, np.ones(k))).max() > 1e-6)
+        return bad / trials
+
+    assert flipped(1) > 0.2
+    assert flipped(2) == 0.0 and flipped(3) == 0.0
