@@ -132,6 +132,9 @@ typedef struct psulvsb_trace {
   int host_cap, host_n;
   int* final_inliers;  /* optional [M]                                                          */
   int* inlier_counter; /* optional [M]                                                          */
+  int* reduce_map_out; /* optional [M]: reduce_map after self-update (column of each original
+                          correspondence in the grown working set, -1 = absent): entries >= C are the
+                          columns the reference appends to the caller's src / dst (registration.cc:800-806) */
 } psulvsb_trace_t;
 
 typedef struct psulvsb_handle_s* psulvsb_handle_t;
@@ -243,6 +246,38 @@ int psulvsb_kabsch_batch(void* stream, const double* d_src64, const double* d_ds
 int psulvsb_tls_translation(void* stream, const double* d_src64, const double* d_dst64, const uint8_t* d_point_flags,
                             int n, double scale, const double* d_R, double noise, const double* d_last_best,
                             double* d_t_out, int* d_n_points);
+
+/* ---- The reference's public sub-solver calls on HOST buffers --------------------------------------------
+ * (teaser/include/teaser/registration.h:107-317; what rotation-solver-test.cc, scale-solver-test.cc,
+ * translation-solver-test.cc, tls-test.cc and RobustRegistrationSolver::solveForScale / solveForRotation /
+ * solveForTranslation / computeTIMs call).  Column-major 3 x n doubles in, results out; each call stages its
+ * arrays on the device and runs the kernels the engine runs.  include/teaser/registration.h wraps them in the
+ * reference's class names. */
+
+/* RobustRegistrationSolver::computeTIMs (registration.cc:471-505): tims[3 x n(n-1)/2], column
+ * i*n - i(i+1)/2 + (j-i-1) = v_j - v_i; map (2 x L ints: i, j) may be NULL. */
+int psulvsb_compute_tims_host(const double* pts, int n, double* tims, int* map);
+/* ScaleInliersSelector::solveForScale (registration.cc:418-434): inliers[l] = | |src_l| - |dst_l| | <= 2 noise_bound
+ * sqrt(cbar2); the scale it reports is 1. */
+int psulvsb_scale_inliers_host(const double* src_tims, const double* dst_tims, unsigned long long n, double noise_bound,
+                               double cbar2, unsigned char* inliers);
+/* TLSScaleSolver::solveForScale (registration.cc:397-415 -> ScalarTLSEstimator::estimate :66-120).  The reference
+ * draws candidates with rand(); here draw k of the call is philox(seed; PSULVSB_DOMAIN_SCALE, event, k).
+ * last_best_scale: NULL on the first call (first_time), else the reference's scale_last_best. */
+int psulvsb_tls_scale_host(const double* src_tims, const double* dst_tims, int n, double noise_bound, double cbar2,
+                           uint64_t seed, uint32_t event, const double* last_best_scale, double* scale,
+                           unsigned char* inliers);
+/* GNCTLSRotationSolver::solveForRotation (registration.cc:1563-1692 + utils.h:121-136).  R_last_best: NULL on the
+ * first call, else the warm start (column-major).  R[9] column-major; inliers / cost / iterations may be NULL. */
+int psulvsb_gnc_tls_rotation_host(const double* src_tims, const double* dst_tims, unsigned long long n,
+                                  double noise_bound, int max_iterations, double gnc_factor, double cost_threshold,
+                                  const double* R_last_best, double* R, unsigned char* inliers, double* cost,
+                                  int* iterations);
+/* TLSTranslationSolver::solveForTranslation (registration.cc:436-463 -> :121-203): per-axis max-stabbing of
+ * (dst - src) +- noise_bound sqrt(cbar2); inliers = within the bound of the estimate on all three axes.
+ * t_last_best: NULL on the first call, else the pseudo-measurement of :136-161. */
+int psulvsb_tls_translation_host(const double* src, const double* dst, int n, double noise_bound, double cbar2,
+                                 const double* t_last_best, double* t, unsigned char* inliers);
 
 /* Surface normals by k-nearest-neighbour PCA, what the reference driver gets from PCL before its timed region
  * (examples/teaser_cpp_ply/PSULVSB.cc:35-85: NormalEstimation, setKSearch(20), viewpoint (0,0,0)) and feeds to

@@ -8,8 +8,14 @@
 // getSolution() (:553), getParams() (:548), reset() (:747).  The reference's drivers
 // (examples/teaser_cpp_ply/PSULVSB.cc:291-331) compile against it unchanged; see INTEGRATION.md.
 //
-// Not carried over (outside the PSULVSB path): the abstract sub-solver classes,
-// set*Estimator, the TIM / mask getters, computeTIMs, the certifier.
+// Also declared, with the reference's names and signatures, because the reference's own unit tests and
+// solveForScale / solveForRotation / solveForTranslation call them: the abstract sub-solver interfaces (:47-101),
+// ScaleInliersSelector (:203-215), TLSScaleSolver (:180-198), TLSTranslationSolver (:221-239), GNCRotationSolver /
+// GNCTLSRotationSolver (:244-290) and computeTIMs (:523) -- each one call into the C ABI (CUDA).
+//
+// Not carried over (outside the PSULVSB path): FastGlobalRegistrationSolver,
+// ScalarTLSEstimator::estimate_tiled, set*Estimator, the TIM / mask getters of the upstream pipeline (the fork's
+// solve() no longer maintains them), the certifier.
 #pragma once
 
 #include <Eigen/Core>
@@ -30,6 +36,178 @@ struct RegistrationSolution {
   int final_inlier_count;
   Eigen::Vector3d translation;
   Eigen::Matrix3d rotation;
+};
+
+// ---- sub-solvers (registration.h:47-317) ------------------------------------------------------
+namespace detail {
+template <typename Mask>
+inline void fill_mask(Mask* inliers, const std::vector<unsigned char>& m) {
+  if (!inliers) return;
+  inliers->resize(1, static_cast<long>(m.size()));
+  for (size_t i = 0; i < m.size(); ++i) (*inliers)(0, static_cast<long>(i)) = m[i] != 0;
+}
+} // namespace detail
+
+class AbstractScaleSolver { // registration.h:47-61
+public:
+  virtual ~AbstractScaleSolver() {}
+  virtual void solveForScale(const Eigen::Matrix<double, 3, Eigen::Dynamic>& src,
+                             const Eigen::Matrix<double, 3, Eigen::Dynamic>& dst, double* scale,
+                             Eigen::Matrix<bool, 1, Eigen::Dynamic>* inliers) = 0;
+};
+
+class AbstractRotationSolver { // registration.h:66-81
+public:
+  virtual ~AbstractRotationSolver() {}
+  virtual void solveForRotation(const Eigen::Matrix<double, 3, Eigen::Dynamic>& src,
+                                const Eigen::Matrix<double, 3, Eigen::Dynamic>& dst, Eigen::Matrix3d* rotation,
+                                Eigen::Matrix<bool, 1, Eigen::Dynamic>* inliers) = 0;
+};
+
+class AbstractTranslationSolver { // registration.h:86-101
+public:
+  virtual ~AbstractTranslationSolver() {}
+  virtual void solveForTranslation(const Eigen::Matrix<double, 3, Eigen::Dynamic>& src,
+                                   const Eigen::Matrix<double, 3, Eigen::Dynamic>& dst, Eigen::Vector3d* translation,
+                                   Eigen::Matrix<bool, 1, Eigen::Dynamic>* inliers) = 0;
+};
+
+/// registration.cc:418-434: known scale; inliers = line vectors whose lengths agree within 2 noise_bound sqrt(cbar2)
+class ScaleInliersSelector : public AbstractScaleSolver {
+public:
+  ScaleInliersSelector() = delete;
+  explicit ScaleInliersSelector(double noise_bound, double cbar2) : noise_bound_(noise_bound), cbar2_(cbar2) {}
+  void solveForScale(const Eigen::Matrix<double, 3, Eigen::Dynamic>& src,
+                     const Eigen::Matrix<double, 3, Eigen::Dynamic>& dst, double* scale,
+                     Eigen::Matrix<bool, 1, Eigen::Dynamic>* inliers) override {
+    std::vector<unsigned char> m(static_cast<size_t>(src.cols()), 0);
+    status_ = psulvsb_scale_inliers_host(src.data(), dst.data(), static_cast<unsigned long long>(src.cols()),
+                                         noise_bound_, cbar2_, m.data());
+    if (scale) *scale = 1;
+    detail::fill_mask(inliers, m);
+  }
+  int lastStatus() const { return status_; }
+
+private:
+  double noise_bound_;
+  double cbar2_;
+  int status_ = PSULVSB_OK;
+};
+
+/// registration.cc:397-415 -> :66-120.  The reference draws its RANSAC candidates with rand() seeded by time();
+/// here draw k of call e comes from philox(seed; PSULVSB_DOMAIN_SCALE, e, k).  setLastBest() supplies the
+/// reference's file-scope scale_last_best (first candidate of later calls, :75-86).
+class TLSScaleSolver : public AbstractScaleSolver {
+public:
+  TLSScaleSolver() = delete;
+  explicit TLSScaleSolver(double noise_bound, double cbar2, uint64_t seed = 0)
+      : noise_bound_(noise_bound), cbar2_(cbar2), seed_(seed) {}
+  void setLastBest(double scale) {
+    last_best_ = scale;
+    have_last_ = true;
+  }
+  void solveForScale(const Eigen::Matrix<double, 3, Eigen::Dynamic>& src,
+                     const Eigen::Matrix<double, 3, Eigen::Dynamic>& dst, double* scale,
+                     Eigen::Matrix<bool, 1, Eigen::Dynamic>* inliers) override {
+    std::vector<unsigned char> m(static_cast<size_t>(src.cols()), 0);
+    double s = 1;
+    status_ = psulvsb_tls_scale_host(src.data(), dst.data(), static_cast<int>(src.cols()), noise_bound_, cbar2_, seed_,
+                                     calls_++, have_last_ ? &last_best_ : nullptr, &s, m.data());
+    if (scale) *scale = s;
+    detail::fill_mask(inliers, m);
+  }
+  int lastStatus() const { return status_; }
+
+private:
+  double noise_bound_;
+  double cbar2_;
+  uint64_t seed_;
+  uint32_t calls_ = 0;
+  double last_best_ = 1;
+  bool have_last_ = false;
+  int status_ = PSULVSB_OK;
+};
+
+/// registration.cc:436-463 -> :121-203: per-axis max-stabbing.  setLastBest(): translation_last_best (:136-161).
+class TLSTranslationSolver : public AbstractTranslationSolver {
+public:
+  TLSTranslationSolver() = delete;
+  explicit TLSTranslationSolver(double noise_bound, double cbar2) : noise_bound_(noise_bound), cbar2_(cbar2) {}
+  void setLastBest(const Eigen::Vector3d& t) {
+    for (int r = 0; r < 3; ++r) last_best_[r] = t(r, 0);
+    have_last_ = true;
+  }
+  void solveForTranslation(const Eigen::Matrix<double, 3, Eigen::Dynamic>& src,
+                           const Eigen::Matrix<double, 3, Eigen::Dynamic>& dst, Eigen::Vector3d* translation,
+                           Eigen::Matrix<bool, 1, Eigen::Dynamic>* inliers) override {
+    std::vector<unsigned char> m(static_cast<size_t>(src.cols()), 0);
+    double t[3] = {0, 0, 0};
+    status_ = psulvsb_tls_translation_host(src.data(), dst.data(), static_cast<int>(src.cols()), noise_bound_, cbar2_,
+                                           have_last_ ? last_best_ : nullptr, t, m.data());
+    if (translation)
+      for (int r = 0; r < 3; ++r) (*translation)(r, 0) = t[r];
+    detail::fill_mask(inliers, m);
+  }
+  int lastStatus() const { return status_; }
+
+private:
+  double noise_bound_;
+  double cbar2_;
+  double last_best_[3] = {0, 0, 0};
+  bool have_last_ = false;
+  int status_ = PSULVSB_OK;
+};
+
+class GNCRotationSolver : public AbstractRotationSolver { // registration.h:244-262
+public:
+  struct Params {
+    size_t max_iterations;
+    double cost_threshold;
+    double gnc_factor;
+    double noise_bound;
+  };
+  GNCRotationSolver(Params params) : params_(params) {}
+  Params getParams() { return params_; }
+  void setParams(Params params) { params_ = params; }
+  double getCostAtTermination() { return cost_; }
+
+protected:
+  Params params_;
+  double cost_ = 0;
+};
+
+/// registration.cc:1563-1692 + utils.h:121-136.  setLastBest(): rotation_last_best, the warm start of later calls.
+class GNCTLSRotationSolver : public GNCRotationSolver {
+public:
+  GNCTLSRotationSolver() = delete;
+  explicit GNCTLSRotationSolver(Params params) : GNCRotationSolver(params) {}
+  void setLastBest(const Eigen::Matrix3d& R) {
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) last_best_[c * 3 + r] = R(r, c);
+    have_last_ = true;
+  }
+  void solveForRotation(const Eigen::Matrix<double, 3, Eigen::Dynamic>& src,
+                        const Eigen::Matrix<double, 3, Eigen::Dynamic>& dst, Eigen::Matrix3d* rotation,
+                        Eigen::Matrix<bool, 1, Eigen::Dynamic>* inliers) override {
+    std::vector<unsigned char> m(static_cast<size_t>(src.cols()), 0);
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    status_ = psulvsb_gnc_tls_rotation_host(src.data(), dst.data(), static_cast<unsigned long long>(src.cols()),
+                                            params_.noise_bound, static_cast<int>(params_.max_iterations),
+                                            params_.gnc_factor, params_.cost_threshold,
+                                            have_last_ ? last_best_ : nullptr, R, m.data(), &cost_, &iterations_);
+    if (rotation)
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) (*rotation)(r, c) = R[c * 3 + r];
+    detail::fill_mask(inliers, m);
+  }
+  int getIterations() const { return iterations_; }
+  int lastStatus() const { return status_; }
+
+private:
+  double last_best_[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  bool have_last_ = false;
+  int iterations_ = 0;
+  int status_ = PSULVSB_OK;
 };
 
 class RobustRegistrationSolver {
@@ -146,9 +324,10 @@ public:
     prob.M = M;
     prob.keep_mask = keep.data();
     prob.reduce_map = dense.data();
-    std::vector<int> final_inliers(static_cast<size_t>(M), 0);
+    std::vector<int> final_inliers(static_cast<size_t>(M), 0), map_out(static_cast<size_t>(M), -1);
     psulvsb_trace_t trace = {};
     trace.final_inliers = final_inliers.data();
+    trace.reduce_map_out = map_out.data();
     last_status_ = psulvsb_solve(handle_, &p, &prob, &raw_, &trace);
     if (last_status_ != PSULVSB_OK) return solution_;
     if (raw_.status != PSULVSB_OK) {
@@ -163,12 +342,71 @@ public:
       for (int c = 0; c < 3; ++c) solution_.rotation(r, c) = raw_.rotation[c * 3 + r];
     }
     final_inliers_ = final_inliers;
-    if (raw_.final_C > C) {  // the working set grew: keep the caller's matrices in step with the reference
-      src.conservativeResize(3, raw_.final_C);
+    if (raw_.final_C > C && have_ori) {  // self-update grew the working set: append the adopted correspondences to the
+      src.conservativeResize(3, raw_.final_C);  // caller's matrices, as the reference does (registration.cc:800-806)
       dst.conservativeResize(3, raw_.final_C);
+      for (int j = 0; j < M; ++j) {
+        const int col = map_out[static_cast<size_t>(j)];
+        if (col < C || col >= raw_.final_C) continue;
+        for (int r = 0; r < 3; ++r) {
+          src(r, col) = params_.ori_src(r, j);
+          dst(r, col) = params_.ori_dst(r, j);
+        }
+      }
     }
     return solution_;
   }
+
+  /// registration.cc:471-505: all pairwise differences v_j - v_i (i < j), column i*N - i(i+1)/2 + (j-i-1); map = (i, j)
+  Eigen::Matrix<double, 3, Eigen::Dynamic> computeTIMs(const Eigen::Matrix<double, 3, Eigen::Dynamic>& v,
+                                                      Eigen::Matrix<int, 2, Eigen::Dynamic>* map) {
+    const long N = static_cast<long>(v.cols());
+    const long L = N * (N - 1) / 2;
+    Eigen::Matrix<double, 3, Eigen::Dynamic> vtilde;
+    vtilde.resize(3, L);
+    if (map) map->resize(2, L);
+    last_status_ = psulvsb_compute_tims_host(v.data(), static_cast<int>(N), vtilde.data(), map ? map->data() : nullptr);
+    return vtilde;
+  }
+
+  /// registration.cc:1537-1560: the configured sub-solvers on explicit line vectors / points
+  double solveForScale(const Eigen::Matrix<double, 3, Eigen::Dynamic>& v1,
+                       const Eigen::Matrix<double, 3, Eigen::Dynamic>& v2) {
+    Eigen::Matrix<bool, 1, Eigen::Dynamic>& mask = scale_inliers_mask_;
+    double s = 1;
+    if (params_.estimate_scaling) {
+      TLSScaleSolver solver(params_.noise_bound, params_.cbar2, params_.seed);
+      solver.solveForScale(v1, v2, &s, &mask);
+      last_status_ = solver.lastStatus();
+    } else {
+      ScaleInliersSelector solver(params_.noise_bound, params_.cbar2);
+      solver.solveForScale(v1, v2, &s, &mask);
+      last_status_ = solver.lastStatus();
+    }
+    solution_.scale = s;
+    return s;
+  }
+  Eigen::Matrix3d solveForRotation(const Eigen::Matrix<double, 3, Eigen::Dynamic>& v1,
+                                   const Eigen::Matrix<double, 3, Eigen::Dynamic>& v2) {
+    GNCRotationSolver::Params gp = {params_.rotation_max_iterations, params_.rotation_cost_threshold,
+                                    params_.rotation_gnc_factor, params_.noise_bound};
+    GNCTLSRotationSolver solver(gp);
+    solver.solveForRotation(v1, v2, &solution_.rotation, &rotation_inliers_mask_);
+    last_status_ = solver.lastStatus();
+    return solution_.rotation;
+  }
+  Eigen::Vector3d solveForTranslation(const Eigen::Matrix<double, 3, Eigen::Dynamic>& v1,
+                                      const Eigen::Matrix<double, 3, Eigen::Dynamic>& v2) {
+    TLSTranslationSolver solver(params_.noise_bound, params_.cbar2);
+    solver.solveForTranslation(v1, v2, &solution_.translation, &translation_inliers_mask_);
+    last_status_ = solver.lastStatus();
+    return solution_.translation;
+  }
+
+  /// masks of the last solveForScale / solveForRotation / solveForTranslation call (registration.h:588-613)
+  Eigen::Matrix<bool, 1, Eigen::Dynamic> getScaleInliersMask() { return scale_inliers_mask_; }
+  Eigen::Matrix<bool, 1, Eigen::Dynamic> getRotationInliersMask() { return rotation_inliers_mask_; }
+  Eigen::Matrix<bool, 1, Eigen::Dynamic> getTranslationInliersMask() { return translation_inliers_mask_; }
 
   /// 1 for the original correspondences the solver ended with as inliers (final_inliers, registration.cc:1427)
   const std::vector<int>& getFinalInliers() const { return final_inliers_; }
@@ -180,6 +418,7 @@ private:
   psulvsb_solution_t raw_ = {};
   int last_status_ = PSULVSB_OK;
   std::vector<int> final_inliers_;
+  Eigen::Matrix<bool, 1, Eigen::Dynamic> scale_inliers_mask_, rotation_inliers_mask_, translation_inliers_mask_;
 };
 
 } // namespace teaser

@@ -25,7 +25,9 @@ SYMBOLS = [
     "psulvsb_mask_symmetrize", "psulvsb_compact_edges", "psulvsb_sample_workspace_bytes",
     "psulvsb_sample_default_max_draws", "psulvsb_sample", "psulvsb_philox_fill", "psulvsb_gnc_tls_rotation",
     "psulvsb_kabsch_batch", "psulvsb_tls_translation", "psulvsb_score_batch", "psulvsb_score_one",
-    "psulvsb_max_clique", "psulvsb_max_clique_scratch_words", "psulvsb_estimate_normals", "psulvsb_estimate_normals_host",
+    "psulvsb_max_clique", "psulvsb_max_clique_scratch_words",
+    "psulvsb_compute_tims_host", "psulvsb_scale_inliers_host", "psulvsb_tls_scale_host",
+    "psulvsb_gnc_tls_rotation_host", "psulvsb_tls_translation_host", "psulvsb_estimate_normals", "psulvsb_estimate_normals_host",
 ]
 
 
@@ -126,6 +128,7 @@ class Trace(C.Structure):
         ("local", C.POINTER(LocalTrace)), ("local_cap", C.c_int), ("local_n", C.c_int),
         ("host", C.POINTER(HostTrace)), ("host_cap", C.c_int), ("host_n", C.c_int),
         ("final_inliers", C.POINTER(C.c_int)), ("inlier_counter", C.POINTER(C.c_int)),
+        ("reduce_map_out", C.POINTER(C.c_int)),
     ]
 
 
@@ -192,6 +195,12 @@ def _declare(L: C.CDLL) -> None:
                                                 C.POINTER(C.c_double)]
     L.psulvsb_max_clique.argtypes = [_vp, _vp, _ull, C.c_int, _vp, _vp, _vp, C.c_int]
     L.psulvsb_max_clique_scratch_words.argtypes = [C.c_int]
+    L.psulvsb_compute_tims_host.argtypes = [_vp, C.c_int, _vp, _vp]
+    L.psulvsb_scale_inliers_host.argtypes = [_vp, _vp, _ull, C.c_double, C.c_double, _vp]
+    L.psulvsb_tls_scale_host.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint32, _vp, _vp, _vp]
+    L.psulvsb_gnc_tls_rotation_host.argtypes = [_vp, _vp, _ull, C.c_double, C.c_int, C.c_double, C.c_double, _vp, _vp,
+                                                _vp, _vp, _vp]
+    L.psulvsb_tls_translation_host.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp]
     L.psulvsb_max_clique_scratch_words.restype = _ull
     L.psulvsb_score_one.argtypes = [_vp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, C.c_double, _vp, _vp, _vp]
     for name in SYMBOLS:
@@ -290,12 +299,13 @@ class Handle:
             hst = (HostTrace * trace_cap)()
             fin = np.zeros(M, dtype=np.int32)
             cnt = np.zeros(M, dtype=np.int32)
+            rmap = np.zeros(M, dtype=np.int32)
             tr = Trace(C.cast(loc, C.POINTER(LocalTrace)), trace_cap, 0, C.cast(hst, C.POINTER(HostTrace)), trace_cap,
-                       0, fin.ctypes.data_as(_ip), cnt.ctypes.data_as(_ip))
+                       0, fin.ctypes.data_as(_ip), cnt.ctypes.data_as(_ip), rmap.ctypes.data_as(_ip))
             ps = problem.c_struct()
             check(lib().psulvsb_solve(self._h, C.byref(params), C.byref(ps), C.byref(sol), C.byref(tr)))
             trace = {"local": [loc[i] for i in range(tr.local_n)], "host": [hst[i] for i in range(tr.host_n)],
-                     "final_inliers": fin, "inlier_counter": cnt}
+                     "final_inliers": fin, "inlier_counter": cnt, "reduce_map": rmap}
             return sol, trace
         ps = problem.c_struct()
         check(lib().psulvsb_solve(self._h, C.byref(params), C.byref(ps), C.byref(sol), None))

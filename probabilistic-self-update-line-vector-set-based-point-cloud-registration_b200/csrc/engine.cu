@@ -723,6 +723,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       PSU_CUDA(cudaMemcpy(trace_first->final_inliers, j0.final_inliers, sizeof(int) * (size_t)j0.M, cudaMemcpyDeviceToHost));
     if (trace_first->inlier_counter)
       PSU_CUDA(cudaMemcpy(trace_first->inlier_counter, j0.inlier_counter, sizeof(int) * (size_t)j0.M, cudaMemcpyDeviceToHost));
+    if (trace_first->reduce_map_out)
+      PSU_CUDA(cudaMemcpy(trace_first->reduce_map_out, j0.reduce_map, sizeof(int) * (size_t)j0.M, cudaMemcpyDeviceToHost));
   }
   return PSULVSB_OK;
 }

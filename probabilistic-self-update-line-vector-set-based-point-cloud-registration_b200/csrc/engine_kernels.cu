@@ -331,10 +331,8 @@ __global__ void __launch_bounds__(BLK)
   JobCtl& J = jobs[blockIdx.x];
   if (J.phase != PHASE_LOCAL || !J.estimate_scaling) return;
   __shared__ BlockScratch scratch;
-  __shared__ double est_s;
-  __shared__ int best_s, iter_s, done_s, base_s;
-  __shared__ unsigned long long k_s;
-  constexpr int G = 4;  // candidates evaluated per pass (their draws do not depend on the outcome)
+  __shared__ double est_s, scale_s;
+  __shared__ int base_s;
   const int tid = threadIdx.x;
   const int K = J.basic_choose;
   const uint2* __restrict__ edges = J.basic_edges;
@@ -355,70 +353,10 @@ __global__ void __launch_bounds__(BLK)
       X[i] = v2 / v1;
       A[i] = dmul(beta, 1.0 / v1);
     }
-    if (tid == 0) {
-      est_s = scale;
-      best_s = 0;
-      iter_s = 0;
-      done_s = 0;
-      k_s = 0ull;
-    }
-    __syncthreads();
-    const uint32_t event = (uint32_t)J.scale_calls;
-    if (!J.first_time) {  // registration.cc:75-86: the last best scale is the first candidate
-      const double s0 = J.last_best.s;
-      int c = 0, dummy = 0;
-      for (int j = tid; j < K; j += BLK) c += (fabs(dsub(X[j], s0)) <= A[j]) ? 1 : 0;
-      block_sum_int2(&scratch, c, dummy);
-      if (tid == 0) {
-        iter_s = 1;
-        best_s = c;
-        est_s = s0;
-        const double conf = 1.0 - pow(1.0 - ((double)c / (double)K), 1);
-        done_s = conf < 0.99 ? 0 : 1;
-      }
-      __syncthreads();
-    }
-    while (!done_s) {
-      const unsigned long long k0 = k_s;
-      double xr[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) xr[g] = X[philox_rand31(J.seed, PSULVSB_DOMAIN_SCALE, event, k0 + g) % (uint32_t)K];
-      double cnt[4] = {0, 0, 0, 0};
-      for (int j = tid; j < K; j += BLK) {
-        const double xj = X[j], aj = A[j];
-#pragma unroll
-        for (int g = 0; g < G; ++g) cnt[g] += (fabs(dsub(xj, xr[g])) <= aj) ? 1.0 : 0.0;
-      }
-      block_sum<4>(&scratch, cnt);
-      if (tid == 0) {
-        int used = 0;
-        for (int g = 0; g < G && !done_s; ++g) {
-          ++used;
-          iter_s += 1;
-          const int c = (int)(cnt[g] + 0.5);
-          if (c > best_s) {
-            best_s = c;
-            est_s = xr[g];
-          }
-          const double conf = 1.0 - pow(1.0 - ((double)best_s / (double)K), iter_s);
-          if (!(conf < 0.99) || iter_s > 100000) done_s = 1;
-        }
-        k_s = k0 + (unsigned long long)used;
-      }
-      __syncthreads();
-    }
-    // refinement (registration.cc:104-119): inverse-variance weighted mean of the consensus set
+    block_tls_scale(&scratch, X, A, K, J.seed, (uint32_t)J.scale_calls, !J.first_time, J.last_best.s, scale, &est_s,
+                    &scale_s);
     const double est = est_s;
-    double sums[4] = {0, 0, 0, 0};
-    for (int i = tid; i < K; i += BLK)
-      if (fabs(dsub(X[i], est)) <= A[i]) {
-        const double a2 = dmul(A[i], A[i]);
-        sums[0] += 1.0 / a2;
-        sums[1] += X[i] / a2;
-      }
-    block_sum<4>(&scratch, sums);
-    scale = est;
-    if (sums[0] == sums[0] && sums[1] == sums[1]) scale = sums[1] / sums[0];
+    scale = scale_s;
     // pruning (registration.cc:966-983): the consensus set of the UNREFINED estimate, in order
     if (tid == 0) base_s = 0;
     __syncthreads();

@@ -127,6 +127,92 @@ struct StabBest {
   int k;
 };
 
+// TLSScaleSolver::solveForScale -> ScalarTLSEstimator::estimate, scale branch (registration.cc:397-415, :66-120) on
+// K ratios X with per-item bounds A: 1-D RANSAC (candidate = X[rand % K], consensus = |X_j - X_ran| <= A_j, stop when
+// 1 - (1 - best / K)^it >= 0.99), four candidates evaluated per pass (their draws do not depend on the outcome; the
+// confidence rule is then applied in order), then the inverse-variance weighted mean of the consensus set (:104-119).
+// use_last: the last best scale is the first candidate (:75-86).  *est_out: the unrefined estimate (the pruning of
+// :966-983 uses it), *scale_out: the refined one (fallback: init_scale semantics of the caller are kept by passing
+// the value to keep when K == 0 -- not reached here, K > 0).  The draws are philox (seed; DOMAIN_SCALE, event, k).
+__device__ inline void block_tls_scale(BlockScratch* scratch, const double* __restrict__ X, const double* __restrict__ A,
+                                       int K, uint64_t seed, uint32_t event, bool use_last, double last_s,
+                                       double init_scale, double* est_out, double* scale_out) {
+  __shared__ double est_s;
+  __shared__ int best_s, iter_s, done_s;
+  __shared__ unsigned long long k_s;
+  constexpr int G = 4;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    est_s = init_scale;
+    best_s = 0;
+    iter_s = 0;
+    done_s = 0;
+    k_s = 0ull;
+  }
+  __syncthreads();
+  if (use_last) {
+    const double s0 = last_s;
+    int c = 0, dummy = 0;
+    for (int j = tid; j < K; j += BLK) c += (fabs(dsub(X[j], s0)) <= A[j]) ? 1 : 0;
+    block_sum_int2(scratch, c, dummy);
+    if (tid == 0) {
+      iter_s = 1;
+      best_s = c;
+      est_s = s0;
+      const double conf = 1.0 - pow(1.0 - ((double)c / (double)K), 1);
+      done_s = conf < 0.99 ? 0 : 1;
+    }
+    __syncthreads();
+  }
+  while (!done_s) {
+    const unsigned long long k0 = k_s;
+    double xr[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) xr[g] = X[philox_rand31(seed, PSULVSB_DOMAIN_SCALE, event, k0 + g) % (uint32_t)K];
+    double cnt[4] = {0, 0, 0, 0};
+    for (int j = tid; j < K; j += BLK) {
+      const double xj = X[j], aj = A[j];
+#pragma unroll
+      for (int g = 0; g < G; ++g) cnt[g] += (fabs(dsub(xj, xr[g])) <= aj) ? 1.0 : 0.0;
+    }
+    block_sum<4>(scratch, cnt);
+    if (tid == 0) {
+      int used = 0;
+      for (int g = 0; g < G && !done_s; ++g) {
+        ++used;
+        iter_s += 1;
+        const int c = (int)(cnt[g] + 0.5);
+        if (c > best_s) {
+          best_s = c;
+          est_s = xr[g];
+        }
+        const double conf = 1.0 - pow(1.0 - ((double)best_s / (double)K), iter_s);
+        if (!(conf < 0.99) || iter_s > 100000) done_s = 1;
+      }
+      k_s = k0 + (unsigned long long)used;
+    }
+    __syncthreads();
+  }
+  const double est = est_s;
+  double sums[4] = {0, 0, 0, 0};
+  for (int i = tid; i < K; i += BLK)
+    if (fabs(dsub(X[i], est)) <= A[i]) {
+      const double a2 = dmul(A[i], A[i]);
+      sums[0] += 1.0 / a2;
+      sums[1] += X[i] / a2;
+    }
+  block_sum<4>(scratch, sums);
+  double scale = est;
+  if (sums[0] == sums[0] && sums[1] == sums[1]) scale = sums[1] / sums[0];
+  __syncthreads();
+  if (tid == 0) {
+    *est_out = est;
+    *scale_out = scale;
+  }
+  __syncthreads();
+}
+
+
 __device__ inline void block_translation(BlockScratch* s, const double* __restrict__ src,
                                          const double* __restrict__ dst, const int* __restrict__ idx, int P,
                                          double scale, const double R[9], double sigma, const double* last_best,

@@ -39,6 +39,34 @@ def test_facade_registers_synthetic_pair(tmp_path):
     assert "valid=1" in r.stdout
 
 
+def build_subsolver_snippet(tmp_path):
+    exe = str(tmp_path / "subsolver_snippet")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "tests", "shim"), os.path.join(ROOT, "tests", "cpp", "subsolver_snippet.cc"),
+           "-o", exe, "-L", libdir, "-l:libpsulvsb_b200.so", "-Wl,-rpath," + libdir]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_subsolver_classes_compile_and_fail_loudly_without_gpu(tmp_path):
+    """ScaleInliersSelector / TLSScaleSolver / GNCTLSRotationSolver / TLSTranslationSolver / computeTIMs with the
+    reference's signatures (registration.h:107-317, :523)."""
+    exe = build_subsolver_snippet(tmp_path)
+    if capi.lib().psulvsb_device_count() > 0:
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "no CUDA device" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_subsolver_classes_pass_the_reference_unit_test_sequences(tmp_path):
+    exe = build_subsolver_snippet(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0 and "FAIL" not in r.stdout and r.stdout.count(" ok") >= 10, r.stdout + r.stderr
+
+
 def build_example(tmp_path):
     exe = str(tmp_path / "psulvsb_ply")
     libdir = os.path.dirname(capi.LIB_PATH)
