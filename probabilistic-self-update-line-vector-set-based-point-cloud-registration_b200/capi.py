@@ -25,7 +25,7 @@ SYMBOLS = [
     "psulvsb_mask_symmetrize", "psulvsb_compact_edges", "psulvsb_sample_workspace_bytes",
     "psulvsb_sample_default_max_draws", "psulvsb_sample", "psulvsb_philox_fill", "psulvsb_gnc_tls_rotation",
     "psulvsb_kabsch_batch", "psulvsb_tls_translation", "psulvsb_score_batch", "psulvsb_score_one",
-    "psulvsb_max_clique", "psulvsb_max_clique_scratch_words",
+    "psulvsb_max_clique", "psulvsb_max_clique_scratch_words", "psulvsb_gnc_tls_rotation_batch",
     "psulvsb_compute_tims_host", "psulvsb_scale_inliers_host", "psulvsb_tls_scale_host",
     "psulvsb_gnc_tls_rotation_host", "psulvsb_tls_translation_host", "psulvsb_estimate_normals", "psulvsb_estimate_normals_host",
 ]
@@ -195,6 +195,8 @@ def _declare(L: C.CDLL) -> None:
                                                 C.POINTER(C.c_double)]
     L.psulvsb_max_clique.argtypes = [_vp, _vp, _ull, C.c_int, _vp, _vp, _vp, C.c_int]
     L.psulvsb_max_clique_scratch_words.argtypes = [C.c_int]
+    L.psulvsb_gnc_tls_rotation_batch.argtypes = [_vp, _vp, _vp, C.c_int, _vp, _ull, C.c_int, C.c_double, C.c_int,
+                                                 C.c_double, C.c_double, C.c_int, _vp, _vp, _ull, _vp, _vp, _vp]
     L.psulvsb_compute_tims_host.argtypes = [_vp, C.c_int, _vp, _vp]
     L.psulvsb_scale_inliers_host.argtypes = [_vp, _vp, _ull, C.c_double, C.c_double, _vp]
     L.psulvsb_tls_scale_host.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint32, _vp, _vp, _vp]
@@ -258,8 +260,12 @@ class HostProblem:
 
     @property
     def nbytes(self) -> int:
-        return (self.src.nbytes + self.dst.nbytes + self.ori_src.nbytes + self.ori_dst.nbytes +
-                self.keep_mask.nbytes + self.reduce_map.nbytes)
+        """Bytes the library copies to the device for this problem (ori_* passed as the very same arrays as src / dst
+        -- no pre-filter -- are uploaded once)."""
+        aliased = (self.ori_src.ctypes.data == self.src.ctypes.data and self.ori_dst.ctypes.data == self.dst.ctypes.data
+                   and self.ori_src.shape == self.src.shape)
+        ori = 0 if aliased else self.ori_src.nbytes + self.ori_dst.nbytes
+        return self.src.nbytes + self.dst.nbytes + ori + self.keep_mask.nbytes + self.reduce_map.nbytes
 
     def c_struct(self) -> Problem:
         if getattr(self, "_cs", None) is None:  # the arrays are owned by this object: build the view once

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "engine.cuh"
@@ -332,6 +333,50 @@ int psulvsb_gnc_tls_rotation(void* stream, const double* d_src64, const double* 
   int cap = (int)((K + 7) / 8) + 32;
   cap = (cap + 31) & ~31;
   return launch_gnc_tls(st, dj.d, 1, cap, 8);
+}
+
+int psulvsb_gnc_tls_rotation_batch(void* stream, const double* d_src64, const double* d_dst64, int n_points,
+                                   const void* d_edges_uint2, unsigned long long K, int n_jobs, double noise_bound,
+                                   int max_iterations, double gnc_factor, double cost_threshold, int cluster,
+                                   double* d_weights, double* d_lv, unsigned long long lv_cap, double* d_R,
+                                   int* d_info, long long* d_prof) {
+  if (int rc = need_device()) return rc;
+  if (!d_src64 || !d_dst64 || !d_edges_uint2 || !d_R || !d_weights || n_jobs < 1 || K < 1)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_gnc_tls_rotation_batch: bad argument");
+  if (K >= 0x7FFFFFF0ull) return fail(PSULVSB_ERR_UNSUPPORTED, "psulvsb_gnc_tls_rotation_batch: K must fit 31 bits");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<GncJob> jobs((size_t)n_jobs);
+  for (int b = 0; b < n_jobs; ++b) {
+    GncJob& j = jobs[(size_t)b];
+    std::memset(&j, 0, sizeof(j));
+    j.src = d_src64;
+    j.dst = d_dst64;
+    j.edges = (const uint2*)d_edges_uint2 + (size_t)b * K;
+    j.K = K;
+    j.inv_scale = 1.0;
+    j.noise_bound = noise_bound;
+    j.gnc_factor = gnc_factor;
+    j.cost_threshold = cost_threshold;
+    j.max_iterations = max_iterations;
+    j.weights = d_weights + (size_t)b * K;
+    j.lv = d_lv ? d_lv + (size_t)b * 6 * lv_cap : nullptr;
+    j.lv_cap = d_lv ? lv_cap : 0;
+    j.R_out = d_R + (size_t)b * 9;
+    j.n_points = n_points;
+    j.info = d_info ? d_info + (size_t)b * 4 : nullptr;
+    j.prof = d_prof ? d_prof + (size_t)b * 8 : nullptr;
+    j.active = 1;
+  }
+  GncJob* d_jobs = nullptr;
+  PSU_CUDA(cudaMallocAsync((void**)&d_jobs, sizeof(GncJob) * (size_t)n_jobs, st));
+  PSU_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(GncJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, st));
+  PSU_CUDA(cudaStreamSynchronize(st));  // jobs is pageable host memory
+  if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = gnc_cluster_for(n_jobs);
+  int cap = (int)((K + (unsigned long long)cluster - 1) / (unsigned long long)cluster) + 32;
+  cap = (cap + 31) & ~31;
+  const int rc = launch_gnc_tls(st, d_jobs, n_jobs, cap, cluster, 0);
+  cudaFreeAsync(d_jobs, st);
+  return rc;
 }
 
 int psulvsb_kabsch_batch(void* stream, const double* d_src64, const double* d_dst64, const void* d_edges_uint2,

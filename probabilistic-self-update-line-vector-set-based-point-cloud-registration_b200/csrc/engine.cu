@@ -109,6 +109,7 @@ __global__ void engine_pack_kernel(const PackJob* __restrict__ jobs) {
 struct ProbLayout {
   int C0, M, Ccap;
   size_t in_dbl;   // offset (doubles) of src0 in the input arena: src0, dst0, ori_src, ori_dst
+  bool alias_ori;  // the caller passed the same arrays as ori_src / ori_dst (no pre-filter): uploaded once
   size_t in_int;   // offset (ints): keep_mask0, reduce_map0
   double csrc[3], cdst[3];
   double coord_bound;
@@ -202,7 +203,8 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
     L.stride = (int)align_up((size_t)(p.C + 31) / 32, 4);
     od = align_up(od, 16);
     L.in_dbl = od;
-    od += (size_t)6 * p.C + (size_t)6 * p.M;
+    L.alias_ori = (p.ori_src == p.src && p.ori_dst == p.dst && p.M == p.C);
+    od += (size_t)6 * p.C + (L.alias_ori ? 0 : (size_t)6 * p.M);
     oi = align_up(oi, 32);
     L.in_int = oi;
     oi += (size_t)2 * p.M;
@@ -225,8 +227,10 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       double* d = hd + L.in_dbl;
       std::memcpy(d, p.src, sizeof(double) * 3 * (size_t)p.C);
       std::memcpy(d + 3 * (size_t)p.C, p.dst, sizeof(double) * 3 * (size_t)p.C);
-      std::memcpy(d + 6 * (size_t)p.C, p.ori_src, sizeof(double) * 3 * (size_t)p.M);
-      std::memcpy(d + 6 * (size_t)p.C + 3 * (size_t)p.M, p.ori_dst, sizeof(double) * 3 * (size_t)p.M);
+      if (!L.alias_ori) {
+        std::memcpy(d + 6 * (size_t)p.C, p.ori_src, sizeof(double) * 3 * (size_t)p.M);
+        std::memcpy(d + 6 * (size_t)p.C + 3 * (size_t)p.M, p.ori_dst, sizeof(double) * 3 * (size_t)p.M);
+      }
       std::memcpy(hi + L.in_int, p.keep_mask, sizeof(int) * (size_t)p.M);
       std::memcpy(hi + L.in_int + p.M, p.reduce_map, sizeof(int) * (size_t)p.M);
       // (differences are translation invariant: each cloud is centred on its own bounding box)
@@ -241,8 +245,10 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
             lo[r] = v < lo[r] ? v : lo[r];
             hi3[r] = v > hi3[r] ? v : hi3[r];
           }
-        const double* ori = s ? p.ori_dst : p.ori_src;
-        for (size_t i = 0; i < (size_t)3 * p.M; ++i) finite &= std::isfinite(ori[i]);
+        if (!L.alias_ori) {
+          const double* ori = s ? p.ori_dst : p.ori_src;
+          for (size_t i = 0; i < (size_t)3 * p.M; ++i) finite &= std::isfinite(ori[i]);
+        }
         if (!finite) bad_problem.store(b);
         double* c = s ? L.cdst : L.csrc;
         double bound = 0.0;
@@ -386,8 +392,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.Ccap = L.Ccap;
         J.src0 = in_dbl + L.in_dbl;
         J.dst0 = J.src0 + 3 * (size_t)L.C0;
-        J.ori_src = J.src0 + 6 * (size_t)L.C0;
-        J.ori_dst = J.ori_src + 3 * (size_t)L.M;
+        J.ori_src = L.alias_ori ? J.src0 : J.src0 + 6 * (size_t)L.C0;  // read-only on the device
+        J.ori_dst = L.alias_ori ? J.dst0 : J.ori_src + 3 * (size_t)L.M;
         J.keep_mask0 = in_int + L.in_int;
         J.reduce_map0 = J.keep_mask0 + L.M;
         J.src = bw.take<double>((size_t)3 * L.Ccap);

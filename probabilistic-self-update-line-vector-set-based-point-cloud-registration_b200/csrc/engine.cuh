@@ -125,6 +125,7 @@ struct GncJob {
   int n_points;
   int* info;             // [4]: iterations, inlier count
   double* cost;
+  long long* prof;       // optional [8] diagnostics: pass / loop / SVD cycles, cached count, prologue / epilogue cycles
   int active;
 };
 

@@ -91,6 +91,7 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   g.point_flags = J.rot_flags;
   g.n_points = J.C;
   g.info = J.gnc_info;
+  g.prof = nullptr;
   g.cost = &J.gnc_cost;
   g.active = 1;
   // max-clique escalation (registration.cc:1000-1085): inlier graph of the round's scale-consistent line vectors

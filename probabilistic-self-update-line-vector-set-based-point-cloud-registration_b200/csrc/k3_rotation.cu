@@ -157,6 +157,26 @@ __device__ __noinline__ void svd_from_smem(GncSmem* sm) {
     }
 }
 
+// Inside the GNC loop: Newton update from the previous iteration's rotation, Jacobi SVD when it declines.
+__device__ __noinline__ void rotation_from_smem(GncSmem* sm) {
+  double H[3][3], R[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      H[r][c] = sm->total[r * 3 + c];
+      R[r][c] = sm->R[r * 3 + c];
+    }
+  if (rotation_newton(H, R)) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = R[r][c];
+    return;
+  }
+  svd_from_smem(sm);
+}
+
 // CTA-level then cluster-level sum (or max for index MAXI) of NRED values; result in sm->total.
 template <int NC, int T>
 __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED], int parity, int max_index) {
@@ -206,6 +226,7 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   // layout: lv[0..5][cap] = sv.xyz, tv.xyz ; lv[6][cap] = weight
   const GncJob job = jobs[blockIdx.y];
   if (!job.active) return;  // uniform over the cluster
+  const long long t_kernel0 = clock64();
   const int tid = threadIdx.x;
   const unsigned rank = (NC > 1) ? cg::this_cluster().block_rank() : 0u;
   const unsigned long long K = job.K;
@@ -253,12 +274,8 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   S.dst = dst;
   S.edges = edges;
   S.inv_scale = job.inv_scale;
-  for (unsigned long long l = tid; l < nloc; l += T) {
-    double sv[3], tv[3];
-    if (PC)
-      load_lv_pc(lv, p_cap, src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
-    else
-      load_lv(src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
+  // one line vector into its home (shared-memory cache / global SoA scratch), unit weight, H_0 += sv tv^T
+  auto stage = [&](unsigned long long l, const double sv[3], const double tv[3]) {
     if (l < ncached) {
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
@@ -270,16 +287,53 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
       if (k_lo + l < lv_cap) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          lvg[(size_t)r * lv_cap + k_lo + l] = sv[r];
-          lvg[(size_t)(3 + r) * lv_cap + k_lo + l] = tv[r];
+          __stcg(lvg + (size_t)r * lv_cap + k_lo + l, sv[r]);
+          __stcg(lvg + (size_t)(3 + r) * lv_cap + k_lo + l, tv[r]);
         }
       }
-      gw[k_lo + l] = 1.0;
+      __stcg(gw + k_lo + l, 1.0);
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int c = 0; c < 3; ++c) acc[r * 3 + c] = fma(sv[r], tv[c], acc[r * 3 + c]);
+  };
+  {
+    // the endpoint gathers are dependent loads (edge -> 4 points): two line vectors per step, and the edges of the
+    // next step already in flight while this step's points arrive
+    const uint2* __restrict__ el = edges + k_lo;
+    unsigned long long l = tid;
+    if (l + T < nloc) {
+      uint2 ea = el[l], eb = el[l + T];
+      for (; l + T < nloc; l += 2 * T) {
+        const unsigned long long ln = l + 2 * T;
+        uint2 na = ea, nb = eb;
+        if (ln + T < nloc) {
+          na = el[ln];
+          nb = el[ln + T];
+        }
+        double sa[3], ta[3], sb[3], tb[3];
+        if (PC) {
+          load_lv_pc(lv, p_cap, src, dst, ea, job.inv_scale, sa, ta);
+          load_lv_pc(lv, p_cap, src, dst, eb, job.inv_scale, sb, tb);
+        } else {
+          load_lv(src, dst, ea, job.inv_scale, sa, ta);
+          load_lv(src, dst, eb, job.inv_scale, sb, tb);
+        }
+        stage(l, sa, ta);
+        stage(l + T, sb, tb);
+        ea = na;
+        eb = nb;
+      }
+    }
+    for (; l < nloc; l += T) {
+      double sv[3], tv[3];
+      if (PC)
+        load_lv_pc(lv, p_cap, src, dst, el[l], job.inv_scale, sv, tv);
+      else
+        load_lv(src, dst, el[l], job.inv_scale, sv, tv);
+      stage(l, sv, tv);
+    }
   }
   int parity = 0;
   if (tid < 9) sm->Vw[tid] = (tid % 4 == 0) ? 1.0 : 0.0;
@@ -296,6 +350,7 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   double mu = 1.0, prev_cost = INFINITY, cost = INFINITY;
   int it_done = 0;
   long long t_svd = 0;               // cycles thread 0 spends in the 3x3 SVDs (diagnostic, info[2])
+  long long t_stream = 0;            // cycles thread 0 spends in the line-vector passes (diagnostic, prof[0])
   const long long t_start = clock64();
   bool weights_are_unit = true;
   for (int it = 0; it < job.max_iterations; ++it) {
@@ -349,6 +404,7 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
       }
       return wn;
     };
+    const long long c_stream0 = clock64();
     // (a) shared-memory resident part (32-bit indices, one base pointer per component)
     {
       const int nc = (int)ncached;
@@ -448,6 +504,7 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
       }
     }
     weights_are_unit = false;
+    t_stream += clock64() - c_stream0;
     cluster_reduce<NC, T>(sm, acc, parity, -1);
     parity ^= 1;
     cost = sm->total[9];
@@ -458,13 +515,14 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
     if (it + 1 < job.max_iterations) {
       if (tid == 0) {
         const long long c0 = clock64();
-        svd_from_smem(sm);
+        rotation_from_smem(sm);
         t_svd += clock64() - c0;
       }
       __syncthreads();
     }
   }
 
+  const long long t_loop_end = clock64();
   // ---- epilogue: inlier mask w >= 0.5 (all when <= 10), endpoint flags (registration.cc:1676-1691,
   // :1114-1155).  The stale-bit defect of the reference is resolved as "zero then set".
   double cntv[GNC_NRED];
@@ -504,6 +562,14 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
       job.info[3] = (int)((clock64() - t_start) >> 4);  // GNC loop cycles / 16
     }
     if (job.cost) job.cost[0] = cost;
+    if (job.prof) {
+      job.prof[0] = t_stream;
+      job.prof[1] = t_loop_end - t_start;
+      job.prof[2] = t_svd;
+      job.prof[3] = (long long)ncached;
+      job.prof[4] = t_start - t_kernel0;     // prologue: line vectors from the points, H_0, first SVD
+      job.prof[5] = clock64() - t_loop_end;  // epilogue: inlier mask, endpoint flags
+    }
   }
   if (NC > 1) cg::this_cluster().sync();  // peers may still be reading this CTA's partial sums
 }
