@@ -592,6 +592,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         // covers the basic subsets up to the (0.5, 0.3) rate pair; the (1, 1) escalation recomputes the rest
         J.lv_cap = cap / 6 + 64;
         J.lv = be.take<double>((size_t)6 * J.lv_cap);
+        J.gnc_perm = be.take<uint32_t>((size_t)2 * J.lv_cap);
         J.pruned_edges = ratio ? be.take<uint2>((size_t)cap) : nullptr;
         if (ratio) {
           rj[(size_t)b].edges = J.edges;

@@ -119,6 +119,7 @@ struct GncJob {
   double* weights;       // K doubles of scratch (overflow beyond the shared-memory capacity)
   double* lv;            // optional SoA scratch [6][lv_cap] for the line vectors beyond that capacity
   unsigned long long lv_cap;
+  uint32_t* perm;        // optional [2][lv_cap] index scratch: enables parking sleeping line vectors (k3_rotation.cu)
   double* R_out;         // column-major
   uint8_t* inliers;      // [K] or NULL
   uint8_t* point_flags;  // [n_points] or NULL: endpoints of inlier line vectors

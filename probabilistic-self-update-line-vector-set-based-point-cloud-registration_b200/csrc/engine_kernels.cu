@@ -86,6 +86,7 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   g.weights = J.weights;
   g.lv = J.lv;
   g.lv_cap = J.lv_cap;
+  g.perm = J.gnc_perm;
   g.R_out = J.R_gnc;
   g.inliers = nullptr;
   g.point_flags = J.rot_flags;

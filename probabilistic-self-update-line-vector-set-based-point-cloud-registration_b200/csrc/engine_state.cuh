@@ -79,6 +79,7 @@ struct JobCtl {
   double* weights;
   double* lv;  // GNC-TLS line-vector scratch, SoA [6][lv_cap]
   unsigned long long lv_cap;
+  uint32_t* gnc_perm;  // [2][lv_cap] index scratch of the GNC kernel's line-vector parking
   uint32_t* adj;        // clique escalation: Ccap x adj_stride bit matrix
   int adj_stride;
   uint8_t* clique_flags;  // [Ccap]

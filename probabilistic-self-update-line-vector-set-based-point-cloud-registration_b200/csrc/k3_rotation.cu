@@ -16,6 +16,18 @@
 // what exceeds that too is recomputed from the points each pass.  The cluster size (1, 2, 4 or 8
 // CTAs per hypothesis) is chosen by the launcher from the batch size: few registrations ->
 // 8 SMs each (latency), many -> one SM each (throughput).
+//
+// Sleeping line vectors.  Once mu has grown, most outliers sit at weight 0 and stay there: w = 0 iff
+// r >= sqrt(th1), th1 only shrinks (mu grows), and a rotation change moves a residual by at most
+// |R_new - R_old|_2 |sv|.  A line vector found with w = 0 and margin m = (r - sqrt(th1)) / |sv| therefore keeps
+// w = 0 -- contributing nothing to the cost (its previous weight is 0) nor to H -- until the accumulated
+// drift sum |R_{i+1} - R_i|_F has grown by m.  Its weight slot then stores -(drift + m) ("asleep until the
+// drift reaches this") and the pass skips it exactly; nothing is approximated.  When half of a CTA's active
+// positions sleep deeply (remaining margin >= 0.02 rad) the CTA swaps them behind the active range
+// [0, n_act) (a deterministic permutation, kept in GncJob::perm for the epilogue), so that later passes
+// touch only the survivors, which by then fit in shared memory.  If the drift ever reaches the smallest
+// parked wake-up value, the range is reopened to the whole slice.  On cfg-A (K = 22 000, 95 % outliers)
+// 62 % of the line-vector evaluations of a solve disappear.
 // FP64 with explicit fma(): reduction order already differs from a sequential CPU sum, so fusing
 // adds no new class of deviation; the discrete decisions (r^2 vs th1/th2, w >= 0.5) are unaffected
 // except within an ulp of their thresholds.
@@ -41,6 +53,7 @@ constexpr int GNC_MAX_WARPS = 32;
 #define GNC_CTAS_PER_SM 2
 #endif
 constexpr int GNC_NRED = 12;  // 9 H + cost + max/aux + count
+constexpr double GNC_DEEP_MARGIN = 0.005;  // remaining margin (rad) from which a sleeping line vector is parked
 
 struct GncSmem {
   double part[2][GNC_NRED];           // this CTA's partial sums, double-buffered by iteration parity
@@ -48,6 +61,12 @@ struct GncSmem {
   double R[9];                        // row-major current rotation
   double total[GNC_NRED];
   double Vw[9];  // Jacobi warm start (right singular vectors of the previous solve), row-major
+  // sleeping line vectors (see the kernel's header comment)
+  double drift;     // sum of |R_new - R_old|_F over the rotation updates so far
+  double min_wake;  // smallest wake-up drift among the line vectors parked behind n_act
+  int wcnt2[2][4][GNC_MAX_WARPS];
+  int n_act;        // this CTA's passes cover positions [0, n_act) of its slice
+  int permuted;     // positions no longer are original indices: job.perm holds the map
   int flag;
 };
 
@@ -167,14 +186,28 @@ __device__ __noinline__ void rotation_from_smem(GncSmem* sm) {
       H[r][c] = sm->total[r * 3 + c];
       R[r][c] = sm->R[r * 3 + c];
     }
+  double d2 = 0.0;
   if (rotation_newton(H, R)) {
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) sm->R[r * 3 + c] = R[r][c];
-    return;
+      for (int c = 0; c < 3; ++c) {
+        const double d = R[r][c] - sm->R[r * 3 + c];
+        d2 = fma(d, d, d2);
+        sm->R[r * 3 + c] = R[r][c];
+      }
+  } else {
+    svd_from_smem(sm);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double d = R[r][c] - sm->R[r * 3 + c];
+        d2 = fma(d, d, d2);
+      }
   }
-  svd_from_smem(sm);
+  // |R_new - R_old|_2 <= |.|_F, rounded up: every residual moved by at most this much times |sv|
+  sm->drift += sqrt(d2) * (1.0 + 1e-9) + 1e-15;
 }
 
 // CTA-level then cluster-level sum (or max for index MAXI) of NRED values; result in sm->total.
@@ -337,6 +370,16 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   }
   int parity = 0;
   if (tid < 9) sm->Vw[tid] = (tid % 4 == 0) ? 1.0 : 0.0;
+  if (tid == 0) {
+    sm->drift = 0.0;
+    sm->min_wake = INFINITY;
+    sm->n_act = (int)nloc;
+    sm->permuted = 0;
+  }
+  // compaction needs every position's line vector in storage (no re-formed tail) and the index scratch
+  uint32_t* __restrict__ perm = job.perm;
+  const bool can_compact = !PC && perm != nullptr && k_hi <= lv_cap && nloc < 0x7FFFFFFFull;
+  const bool can_sleep = can_compact && job.gnc_factor > 1.0;  // th1 must not grow; pointless without parking
   if (job.use_init) {
     if (tid < 9) sm->R[tid] = job.R_init[(tid % 3) * 3 + tid / 3];  // column-major -> row-major
     __syncthreads();
@@ -351,6 +394,7 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   int it_done = 0;
   long long t_svd = 0;               // cycles thread 0 spends in the 3x3 SVDs (diagnostic, info[2])
   long long t_stream = 0;            // cycles thread 0 spends in the line-vector passes (diagnostic, prof[0])
+  long long sum_act = 0, n_compactions = 0, first_compaction = -1, t_compact = 0;  // diagnostics, prof[6..7]
   const long long t_start = clock64();
   bool weights_are_unit = true;
   for (int it = 0; it < job.max_iterations; ++it) {
@@ -382,11 +426,18 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
     const double wnum = nb2 * mu * (mu + 1.0);
 #pragma unroll
     for (int i = 0; i < GNC_NRED; ++i) acc[i] = 0.0;
+    acc[10] = -INFINITY;  // reduced with max: this CTA's -(smallest wake-up drift among its deep sleepers)
     const double sqrt_wnum = sqrt(wnum);
-    // one line vector: cost term with the previous weight, closed-form new weight, H += w sv tv^T
-    auto body = [&](const double sv[3], const double tv[3], double w) -> double {
+    const double drift = sm->drift;
+    const float sqrt_th1_up = sqrtf((float)th1) * 1.000001f;  // rounded up
+    const int n_act = sm->n_act;
+    sum_act += n_act;
+    // one line vector: cost term with the previous weight, closed-form new weight, H += w sv tv^T.
+    // slot >= 0: the previous weight; slot < 0: weight 0, asleep until the drift reaches -slot.  Positions inside
+    // the active range are simply evaluated (a sleeper's weight comes out 0 again and its margin is refreshed).
+    auto body = [&](const double sv[3], const double tv[3], double slot) -> double {
       const double r2 = residual2(R, sv, tv);
-      acc[9] = fma(w, r2, acc[9]);  // cost uses the previous weights (registration.cc:1648)
+      acc[9] = fma(fmax(slot, 0.0), r2, acc[9]);  // cost uses the previous weights (registration.cc:1648)
       double wn;
       if (r2 >= th1)
         wn = 0.0;
@@ -402,12 +453,28 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
           for (int c = 0; c < 3; ++c) acc[r * 3 + c] = fma(xs, tv[c], acc[r * 3 + c]);
         }
       }
+      if (wn == 0.0 && can_sleep) {
+        double out = slot;
+        if (!(slot < 0.0 && (-slot - drift) >= GNC_DEEP_MARGIN)) {
+          // not (or no longer) a deep sleeper: (re)compute the margin in units of rotation change.  A LOWER bound
+          // is all that is needed, so it is formed in FP32 (two MUFU operations) and shaved by far more than the
+          // FP32 rounding of r, sqrt(th1) and |sv|.  Early iterations have no zero weight and never enter here.
+          const float s2f = (float)fma(sv[2], sv[2], fma(sv[1], sv[1], sv[0] * sv[0]));
+          const float mf = (sqrtf((float)r2) - sqrt_th1_up) * rsqrtf(s2f) * 0.999f - 1e-6f;
+          out = (mf > 0.0f && mf < 1e30f) ? -(drift + (double)mf) : 0.0;
+        }
+        if (out < 0.0 && (-out - drift) >= GNC_DEEP_MARGIN) {
+          acc[11] += 1.0;
+          acc[10] = fmax(acc[10], out);  // max of the negated wake-up drifts = -(the smallest one)
+        }
+        return out;
+      }
       return wn;
     };
     const long long c_stream0 = clock64();
     // (a) shared-memory resident part (32-bit indices, one base pointer per component)
     {
-      const int nc = (int)ncached;
+      const int nc = n_act < (int)ncached ? n_act : (int)ncached;
       double* __restrict__ ws = lv + 6 * cap;
       int l = tid;
       for (; CPS < 3 && l + T < nc; l += 2 * T) {
@@ -436,7 +503,8 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
     // (b) HBM/L2 scratch part: all loads of two line vectors in flight before the arithmetic
     const unsigned long long g_hi64 = (k_hi <= lv_cap) ? nloc : ((lv_cap > k_lo) ? lv_cap - k_lo : 0ull);
     {
-      const int g_hi = (int)g_hi64, nl = (int)nloc;
+      // (n_act < nloc only after a compaction, which requires g_hi64 == nloc)
+      const int g_hi = n_act < (int)g_hi64 ? n_act : (int)g_hi64, nl = n_act < (int)nloc ? n_act : (int)nloc;
       const double* __restrict__ g0 = lvg + k_lo;  // component r of local line vector l: g0[r * lv_cap + l]
       double* __restrict__ gwl = gw + k_lo;
       const size_t st = (size_t)lv_cap;
@@ -505,17 +573,120 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
     }
     weights_are_unit = false;
     t_stream += clock64() - c_stream0;
-    cluster_reduce<NC, T>(sm, acc, parity, -1);
+    cluster_reduce<NC, T>(sm, acc, parity, 10);
     parity ^= 1;
     cost = sm->total[9];
     const double cost_diff = fabs(cost - prev_cost);
     mu *= job.gnc_factor;
     prev_cost = cost;
     if (cost_diff < job.cost_threshold) break;
+    // ---- park the deep sleepers behind the active range (see the header comment).  The pass counted them
+    // (acc[11]) and took their smallest wake-up drift (acc[10]) with the predicate used again below, so this CTA's
+    // own partial sums (before the cluster combined them) are exact.
+    if (can_compact && n_act >= 512) {
+      const int deep_total = (int)(sm->part[parity ^ 1][11] + 0.5);
+      if (2 * deep_total >= n_act) {
+        const long long c_comp0 = clock64();
+        ++n_compactions;
+        if (first_compaction < 0) first_compaction = it;
+        const int lane = tid & 31, wid = tid >> 5;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        double* __restrict__ ws = lv + 6 * cap;
+        auto slot_at = [&](int l) -> double { return (l < (int)ncached) ? ws[l] : __ldcg(gw + k_lo + l); };
+        auto is_deep = [&](double slot) -> bool { return slot < 0.0 && (-slot - drift) >= GNC_DEEP_MARGIN; };
+        if (!sm->permuted)
+          for (int l = tid; l < (int)nloc; l += T) perm[k_lo + l] = (uint32_t)l;
+        const int new_act = n_act - deep_total;
+        uint32_t* __restrict__ holes = perm + lv_cap + k_lo;
+        uint32_t* __restrict__ movers = holes + (nloc + 1) / 2;
+        int base_h = 0, base_m = 0;
+        constexpr int E = 4;  // positions per thread and round: a quarter of the barriers
+        for (int base = 0; base < n_act; base += E * T) {
+          bool hole[E], mover[E];
+          int nh = 0, nm = 0;
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            const int l = base + j * T + tid;
+            const bool deep = (l < n_act) && is_deep(slot_at(l));
+            hole[j] = deep && l < new_act;
+            mover[j] = !deep && l >= new_act && l < n_act;
+          }
+          // rank order: round j before round j + 1, positions ascending inside a round
+          unsigned bh[E], bm[E];
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            bh[j] = __ballot_sync(0xffffffffu, hole[j]);
+            bm[j] = __ballot_sync(0xffffffffu, mover[j]);
+            nh += __popc(bh[j]);
+            nm += __popc(bm[j]);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+              sm->wcnt2[0][j][wid] = __popc(bh[j]);
+              sm->wcnt2[1][j][wid] = __popc(bm[j]);
+            }
+          }
+          __syncthreads();
+          int off_h = base_h, off_m = base_m;
+#pragma unroll
+          for (int j = 0; j < E; ++j) {
+            int ph = 0, pm = 0, th = 0, tm = 0;
+            for (int w = 0; w < T / 32; ++w) {
+              const int c0 = sm->wcnt2[0][j][w], c1 = sm->wcnt2[1][j][w];
+              if (w < wid) {
+                ph += c0;
+                pm += c1;
+              }
+              th += c0;
+              tm += c1;
+            }
+            const int l = base + j * T + tid;
+            if (hole[j]) holes[off_h + ph + __popc(bh[j] & lt_mask)] = (uint32_t)l;
+            if (mover[j]) movers[off_m + pm + __popc(bm[j] & lt_mask)] = (uint32_t)l;
+            off_h += th;
+            off_m += tm;
+          }
+          base_h = off_h;
+          base_m = off_m;
+          __syncthreads();
+        }
+        // the i-th deep sleeper inside the new range trades places with the i-th survivor behind it
+        const int n_swap = base_h < base_m ? base_h : base_m;  // (equal by construction)
+        for (int i = tid; i < n_swap; i += T) {
+          const int a = (int)holes[i], b = (int)movers[i];
+#pragma unroll
+          for (int c = 0; c < 7; ++c) {
+            // (shared-memory cache, or the L2-level scratch the passes read with ld.cg / write with st.cg)
+            double* ga = (c < 6 ? lvg + (size_t)c * lv_cap : gw) + k_lo + a;
+            double* gb = (c < 6 ? lvg + (size_t)c * lv_cap : gw) + k_lo + b;
+            const double va = (a < (int)ncached) ? lv[(size_t)c * cap + a] : __ldcg(ga);
+            const double vb = (b < (int)ncached) ? lv[(size_t)c * cap + b] : __ldcg(gb);
+            if (a < (int)ncached) lv[(size_t)c * cap + a] = vb; else __stcg(ga, vb);
+            if (b < (int)ncached) lv[(size_t)c * cap + b] = va; else __stcg(gb, va);
+          }
+          const uint32_t qa = perm[k_lo + a], qb = perm[k_lo + b];
+          perm[k_lo + a] = qb;
+          perm[k_lo + b] = qa;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          sm->min_wake = fmin(sm->min_wake, -sm->part[parity ^ 1][10]);
+          sm->n_act = new_act;
+          sm->permuted = 1;
+        }
+        __syncthreads();
+        t_compact += clock64() - c_comp0;
+      }
+    }
     if (it + 1 < job.max_iterations) {
       if (tid == 0) {
         const long long c0 = clock64();
         rotation_from_smem(sm);
+        if (sm->min_wake <= sm->drift) {  // a parked line vector may wake under the new rotation: reopen the range
+          sm->n_act = (int)nloc;
+          sm->min_wake = INFINITY;
+        }
         t_svd += clock64() - c0;
       }
       __syncthreads();
@@ -529,7 +700,7 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
 #pragma unroll
   for (int i = 0; i < GNC_NRED; ++i) cntv[i] = 0.0;
   for (unsigned long long l = tid; l < nloc; l += T) {
-    const double w = weights_are_unit ? 1.0 : ((l < ncached) ? lv[6 * cap + l] : gw[k_lo + l]);
+    const double w = weights_are_unit ? 1.0 : ((l < ncached) ? lv[6 * cap + l] : gw[k_lo + l]);  // < 0: asleep, weight 0
     cntv[0] += (w >= 0.5) ? 1.0 : 0.0;
   }
   if (job.point_flags) {
@@ -540,12 +711,14 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   parity ^= 1;
   const long long gf = (long long)(sm->total[0] + 0.5);
   const bool all_in = gf <= 10;
+  const bool permuted = sm->permuted != 0;
   for (unsigned long long l = tid; l < nloc; l += T) {
     const double w = weights_are_unit ? 1.0 : ((l < ncached) ? lv[6 * cap + l] : gw[k_lo + l]);
     const bool in = all_in || (w >= 0.5);
-    if (job.inliers) job.inliers[k_lo + l] = in ? 1 : 0;
+    const unsigned long long k = k_lo + (permuted ? (unsigned long long)perm[k_lo + l] : l);  // original index
+    if (job.inliers) job.inliers[k] = in ? 1 : 0;
     if (in && job.point_flags) {
-      const uint2 e = edges[k_lo + l];
+      const uint2 e = edges[k];
       job.point_flags[e.x] = 1;
       job.point_flags[e.y] = 1;
     }
@@ -569,6 +742,8 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
       job.prof[3] = (long long)ncached;
       job.prof[4] = t_start - t_kernel0;     // prologue: line vectors from the points, H_0, first SVD
       job.prof[5] = clock64() - t_loop_end;  // epilogue: inlier mask, endpoint flags
+      job.prof[6] = sum_act;                  // active positions of this CTA summed over the iterations
+      job.prof[7] = n_compactions + 100 * (first_compaction + 1) + 10000 * t_compact;
     }
   }
   if (NC > 1) cg::this_cluster().sync();  // peers may still be reading this CTA's partial sums

@@ -17,6 +17,7 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 22000
     use_lv = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
+    use_perm = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
     pair = synth.make_pair(5000, 0.95, 3, outliers="fpfh")
     pi, pj = O.reduced_set(pair["src"], pair["dst"], 0.1)
     rng = np.random.default_rng(0)
@@ -29,11 +30,13 @@ def main():
     w = torch.zeros(B * K, dtype=torch.float64, device="cuda")
     lv_cap = K
     lv = torch.zeros(B * 6 * lv_cap, dtype=torch.float64, device="cuda") if use_lv else None
+    perm = torch.zeros(B * 2 * lv_cap, dtype=torch.int32, device="cuda") if (use_lv and use_perm) else None
     R = torch.zeros(B * 9, dtype=torch.float64, device="cuda")
     info = torch.zeros(B * 4, dtype=torch.int32, device="cuda")
     prof = torch.zeros(B * 8, dtype=torch.int64, device="cuda")
     L = capi.lib()
-    print(f"B={B} K={K} reduced set {len(pi)} lv scratch {'on' if use_lv else 'off'}")
+    print(f"B={B} K={K} reduced set {len(pi)} lv scratch {'on' if use_lv else 'off'} parking {'on' if perm is not None else 'off'}")
+    Rs = {}
     for cluster in (0, 1, 2, 4, 8):
         if cluster * B > 148 * 2 and cluster > 1:
             continue
@@ -42,7 +45,8 @@ def main():
             capi.check(L.psulvsb_gnc_tls_rotation_batch(torch.cuda.current_stream().cuda_stream, d_src.data_ptr(),
                                                         d_dst.data_ptr(), 5000, e.data_ptr(), K, B, 0.1, 100, 1.4, 0.005,
                                                         cluster, w.data_ptr(), lv.data_ptr() if use_lv else None, lv_cap,
-                                                        R.data_ptr(), info.data_ptr(), prof.data_ptr()))
+                                                        perm.data_ptr() if perm is not None else None, R.data_ptr(),
+                                                        info.data_ptr(), prof.data_ptr()))
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -56,10 +60,18 @@ def main():
         i = info.cpu().numpy().reshape(B, 4)
         p = prof.cpu().numpy().reshape(B, 8)
         its = i[:, 0].mean()
+        Rs[cluster] = (R.cpu().numpy().copy(), i[:, :2].copy())
         print(f"cluster={cluster}: {ms * 1000:8.1f} us/launch  its {its:.1f}  per iteration: loop {p[:, 1].mean() / its:8.0f} "
               f"cycles = line-vector pass {p[:, 0].mean() / its:8.0f} + svd {p[:, 2].mean() / its:6.0f} + rest "
               f"{(p[:, 1] - p[:, 0] - p[:, 2]).mean() / its:6.0f};  cached {int(p[0, 3])} per CTA; whole kernel: prologue "
-              f"{p[:, 4].mean():8.0f} + loop {p[:, 1].mean():8.0f} + epilogue {p[:, 5].mean():8.0f} cycles")
+              f"{p[:, 4].mean():8.0f} + loop {p[:, 1].mean():8.0f} + epilogue {p[:, 5].mean():8.0f} cycles; parking: "
+              f"{(p[:, 7] % 100).mean():.1f} compactions (first after iteration {((p[:, 7] // 100) % 100).mean() - 1:.1f}, "
+              f"{(p[:, 7] // 10000).mean():.0f} cycles), mean active positions per pass {p[:, 6].mean() / its:.0f}")
+    # every configuration must end at the same rotations, iteration counts and inlier counts
+    ref = Rs[1]
+    for c, (r, ii) in Rs.items():
+        print(f"cluster={c}: max |R - R(cluster=1)| = {np.abs(r - ref[0]).max():.2e}, iterations/inliers equal: "
+              f"{np.array_equal(ii, ref[1])}")
 
 
 if __name__ == "__main__":
