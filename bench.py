@@ -44,6 +44,10 @@ K1_SLOTS_PER_PAIR = 16
 # capture profiles/r1_ncu_k1_mask_b64.txt (79.6 MB read + 128.7 MB written; the algorithmic output is the
 # 64 x 5000 x 160-word mask = 204.8 MB incl. row padding and the untouched lower triangle, inputs 10 MB)
 K1_TRAFFIC_BYTES_B64 = 79_636_736 + 128_738_304
+# the same at --batch 256 (profiles/r1_ncu_k1_mask_b256_final.txt: 336.4 MB read + 692.0 MB written; algorithmic
+# output 4 x 204.8 MB): the default batch
+K1_TRAFFIC_BYTES = {64: K1_TRAFFIC_BYTES_B64, 256: 336_378_368 + 691_986_688}
+# (other batch sizes, incl. the default 296: scaled from the 256 capture -- the kernel's traffic is per registration)
 
 
 def make_problems(rank: int, batch: int):
@@ -179,7 +183,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="fragment pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=296,
+                    help="fragment pairs per GPU per step (default: two per SM of a 148-SM B200 -- the GNC-TLS kernel runs "
+                         "one CTA per registration, so multiples of the SM count leave no partial wave)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -294,7 +300,7 @@ def main():
             "roofline": {"bound": "fp32-pipe", "kernel": "k1_mask_kernel (line-vector length-consistency bit mask)",
                          "achieved": achieved, "peak": peak, "unit": "Gslot/s (FP32-pipe issue slots, 16 per pair)",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": K1_TRAFFIC_BYTES_B64 if B == 64 else None,
+                         "traffic": K1_TRAFFIC_BYTES.get(B, int(K1_TRAFFIC_BYTES[256] * B / 256) if B > 64 else None),
                          "algorithmic_bytes": mask_bytes // 2 + 2 * B * N_CORR * 16,
                          "pairs_per_s": pairs_per_launch / k1_s if k1_s > 0 else None,
                          "kernel_ms": k1_ms / args.steps, "share_of_step": k1_ms / dev_ms if dev_ms > 0 else None,

@@ -398,6 +398,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.reduce_map0 = J.keep_mask0 + L.M;
         J.src = bw.take<double>((size_t)3 * L.Ccap);
         J.dst = bw.take<double>((size_t)3 * L.Ccap);
+        J.pts8 = bw.take<double>((size_t)8 * L.Ccap);
         J.residual_history = bw.take<double>((size_t)L.M);
         J.xs = bw.take<double>((size_t)3 * (L.Ccap + 1));
         J.keep_mask = bw.take<int>((size_t)L.M);

@@ -107,6 +107,7 @@ struct SampleJob {
 struct GncJob {
   const double* src;     // column-major 3 x n_points
   const double* dst;
+  const double* pts8;    // optional [n_points][8]: the same points as 64-byte records (sx sy sz tx ty tz 0 0)
   const uint2* edges;    // K endpoint pairs (a, b): sv = s[b] - s[a], tv = (t[b] - t[a]) * inv_scale
   unsigned long long K;
   double inv_scale;

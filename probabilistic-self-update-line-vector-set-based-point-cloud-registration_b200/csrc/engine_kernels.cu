@@ -87,6 +87,7 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   g.lv = J.lv;
   g.lv_cap = J.lv_cap;
   g.perm = J.gnc_perm;
+  g.pts8 = J.pts8;
   g.R_out = J.R_gnc;
   g.inliers = nullptr;
   g.point_flags = J.rot_flags;
@@ -135,6 +136,17 @@ __global__ void __launch_bounds__(BLK)
   for (int i = tid; i < 3 * J.C0; i += BLK) {
     J.src[i] = J.src0[i];
     J.dst[i] = J.dst0[i];
+  }
+  // 64-byte point records (sx sy sz tx ty tz 0 0): the GNC prologue forms each line vector from two of them with
+  // six 16-byte loads instead of twelve scattered 8-byte ones
+  for (int i = tid; i < J.C0; i += BLK) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      J.pts8[8 * (size_t)i + r] = J.src0[3 * (size_t)i + r];
+      J.pts8[8 * (size_t)i + 3 + r] = J.dst0[3 * (size_t)i + r];
+    }
+    J.pts8[8 * (size_t)i + 6] = 0.0;
+    J.pts8[8 * (size_t)i + 7] = 0.0;
   }
   for (int j = tid; j < J.M; j += BLK) {
     J.keep_mask[j] = J.keep_mask0[j];
@@ -261,7 +273,11 @@ __global__ void __launch_bounds__(BLK)
       for (int r = 0; r < 3; ++r) {
         J.src[3 * (size_t)(C + i) + r] = J.ori_src[3 * (size_t)o + r];
         J.dst[3 * (size_t)(C + i) + r] = J.ori_dst[3 * (size_t)o + r];
+        J.pts8[8 * (size_t)(C + i) + r] = J.ori_src[3 * (size_t)o + r];
+        J.pts8[8 * (size_t)(C + i) + 3 + r] = J.ori_dst[3 * (size_t)o + r];
       }
+      J.pts8[8 * (size_t)(C + i) + 6] = 0.0;
+      J.pts8[8 * (size_t)(C + i) + 7] = 0.0;
       J.keep_mask[o] = 1;
       J.reduce_map[o] = C + i;
     }

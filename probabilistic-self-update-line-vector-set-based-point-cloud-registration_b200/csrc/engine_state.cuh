@@ -79,6 +79,7 @@ struct JobCtl {
   double* weights;
   double* lv;  // GNC-TLS line-vector scratch, SoA [6][lv_cap]
   unsigned long long lv_cap;
+  double* pts8;        // [Ccap][8] working points as 64-byte records (sx sy sz tx ty tz 0 0) for the GNC prologue
   uint32_t* gnc_perm;  // [2][lv_cap] index scratch of the GNC kernel's line-vector parking
   uint32_t* adj;        // clique escalation: Ccap x adj_stride bit matrix
   int adj_stride;

@@ -80,6 +80,21 @@ __device__ __forceinline__ void load_lv(const double* __restrict__ src, const do
   }
 }
 
+// the same from 64-byte point records: six 16-byte read-only loads, four sectors
+__device__ __forceinline__ void load_lv8(const double* __restrict__ pts8, uint2 e, double inv_scale, double sv[3],
+                                         double tv[3]) {
+  const double2* pa = reinterpret_cast<const double2*>(pts8 + 8 * (size_t)e.x);
+  const double2* pb = reinterpret_cast<const double2*>(pts8 + 8 * (size_t)e.y);
+  const double2 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+  const double2 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+  sv[0] = b0.x - a0.x;
+  sv[1] = b0.y - a0.y;
+  sv[2] = b1.x - a1.x;
+  tv[0] = (b1.y - a1.y) * inv_scale;  // pruned_dst_tims_ *= (1 / solution_.scale)   (registration.cc:1102)
+  tv[1] = (b2.x - a2.x) * inv_scale;
+  tv[2] = (b2.y - a2.y) * inv_scale;
+}
+
 // point-cache mode (one CTA per hypothesis, large batches): the CTA keeps the POINTS (48 B each, as many as
 // fit) in shared memory and re-forms every line vector from its endpoint pair each pass -- 8 + 16 bytes of
 // HBM traffic per line vector and pass (edge, old and new weight) instead of 48 + 16
@@ -275,6 +290,7 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
   const double* __restrict__ src = job.src;
   const double* __restrict__ dst = job.dst;
   const uint2* __restrict__ edges = job.edges;
+  const double* __restrict__ pts8 = job.pts8;
   double* __restrict__ gw = job.weights;  // weights of the overflow part live in global memory
   const size_t cap = (size_t)cap_per_cta;
 
@@ -349,6 +365,9 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
         if (PC) {
           load_lv_pc(lv, p_cap, src, dst, ea, job.inv_scale, sa, ta);
           load_lv_pc(lv, p_cap, src, dst, eb, job.inv_scale, sb, tb);
+        } else if (pts8) {
+          load_lv8(pts8, ea, job.inv_scale, sa, ta);
+          load_lv8(pts8, eb, job.inv_scale, sb, tb);
         } else {
           load_lv(src, dst, ea, job.inv_scale, sa, ta);
           load_lv(src, dst, eb, job.inv_scale, sb, tb);
@@ -363,6 +382,8 @@ __global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restric
       double sv[3], tv[3];
       if (PC)
         load_lv_pc(lv, p_cap, src, dst, el[l], job.inv_scale, sv, tv);
+      else if (pts8)
+        load_lv8(pts8, el[l], job.inv_scale, sv, tv);
       else
         load_lv(src, dst, el[l], job.inv_scale, sv, tv);
       stage(l, sv, tv);
