@@ -187,6 +187,10 @@ class Engine {
 
 int Engine::upload(const psulvsb_problem_t* problems, int nb) {
   if (!problems || nb <= 0) return fail(PSULVSB_ERR_INVALID, "upload: no problems");
+  static const bool prof = getenv("PSULVSB_UPLOAD_PROF") != nullptr;
+  const auto t_up0 = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up0).count(); };
+  double t_layout = 0, t_staged = 0;
   PSU_CUDA(cudaSetDevice(device));
   lay.assign((size_t)nb, ProbLayout());
   size_t od = 0, oi = 0;
@@ -197,9 +201,7 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
     ProbLayout& L = lay[(size_t)b];
     L.C0 = p.C;
     L.M = p.M;
-    int zeros = 0;
-    for (int j = 0; j < p.M; ++j) zeros += (p.keep_mask[j] == 0) ? 1 : 0;
-    L.Ccap = p.C + zeros;  // every original correspondence can be appended at most once (registration.cc:828)
+    L.Ccap = p.C;  // + the keep_mask zeros, counted by the staging threads below
     L.stride = (int)align_up((size_t)(p.C + 31) / 32, 4);
     od = align_up(od, 16);
     L.in_dbl = od;
@@ -219,8 +221,21 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
   int* hi = reinterpret_cast<int*>(reinterpret_cast<char*>(h_stage.p) + align_up(bytes_d, 256));
   // staging copy + centres / coordinate bound of the FP32 tiles, split over a few host threads (33 MB for a
   // batch of 64 cfg-A pairs: a single-threaded memcpy would cost more than the H2D copy that follows)
-  std::atomic<int> bad_problem(-1);
+  t_layout = since();
+  std::atomic<int> bad_problem(-1), copy_error(0);
+  // a staged group of problems goes to the device at once (its H2D copy overlaps the staging of the next group)
+  auto push_group = [&](int g0, int g1) {
+    const size_t d0 = lay[(size_t)g0].in_dbl, d1 = (g1 < nb) ? lay[(size_t)g1].in_dbl : od;
+    const size_t i0 = lay[(size_t)g0].in_int, i1 = (g1 < nb) ? lay[(size_t)g1].in_int : oi;
+    if (cudaMemcpyAsync(reinterpret_cast<double*>(d_in_dbl.p) + d0, hd + d0, (d1 - d0) * sizeof(double),
+                        cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(reinterpret_cast<int*>(d_in_int.p) + i0, hi + i0, (i1 - i0) * sizeof(int), cudaMemcpyHostToDevice,
+                        st) != cudaSuccess)
+      copy_error.store(1);
+  };
   auto stage_range = [&](int b0, int b1) {
+    if (cudaSetDevice(device) != cudaSuccess) copy_error.store(1);
+    int group_begin = b0;
     for (int b = b0; b < b1; ++b) {
       const psulvsb_problem_t& p = problems[b];
       ProbLayout& L = lay[(size_t)b];
@@ -233,22 +248,46 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       }
       std::memcpy(hi + L.in_int, p.keep_mask, sizeof(int) * (size_t)p.M);
       std::memcpy(hi + L.in_int + p.M, p.reduce_map, sizeof(int) * (size_t)p.M);
+      {
+        int zeros = 0;
+        for (int j = 0; j < p.M; ++j) zeros += (p.keep_mask[j] == 0) ? 1 : 0;
+        L.Ccap = p.C + zeros;  // every original correspondence can be appended at most once (registration.cc:828)
+      }
       // (differences are translation invariant: each cloud is centred on its own bounding box)
       for (int s = 0; s < 2; ++s) {
         const double* pts = s ? p.dst : p.src;
-        double lo[3] = {pts[0], pts[1], pts[2]}, hi3[3] = {pts[0], pts[1], pts[2]};
-        bool finite = true;
-        for (int i = 0; i < p.C; ++i)
-          for (int r = 0; r < 3; ++r) {
-            const double v = pts[3 * (size_t)i + r];
-            finite &= std::isfinite(v);
-            lo[r] = v < lo[r] ? v : lo[r];
-            hi3[r] = v > hi3[r] ? v : hi3[r];
+        // bounding box + finiteness in one flat pass the compiler can vectorise: two points (six doubles) per step,
+        // v * 0 is NaN exactly when v is NaN or infinite
+        double lo6[6], hi6[6], poison6[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < 6; ++k) lo6[k] = hi6[k] = pts[k % 3];
+        const size_t n6 = ((size_t)p.C / 2) * 6;
+        for (size_t i = 0; i < n6; i += 6)
+          for (int k = 0; k < 6; ++k) {
+            const double v = pts[i + k];
+            lo6[k] = v < lo6[k] ? v : lo6[k];
+            hi6[k] = v > hi6[k] ? v : hi6[k];
+            poison6[k] += v * 0.0;
           }
+        for (size_t i = n6; i < (size_t)3 * p.C; ++i) {
+          const double v = pts[i];
+          const int k = (int)(i % 3);
+          lo6[k] = v < lo6[k] ? v : lo6[k];
+          hi6[k] = v > hi6[k] ? v : hi6[k];
+          poison6[k] += v * 0.0;
+        }
+        double lo[3], hi3[3];
+        for (int r = 0; r < 3; ++r) {
+          lo[r] = lo6[r] < lo6[r + 3] ? lo6[r] : lo6[r + 3];
+          hi3[r] = hi6[r] > hi6[r + 3] ? hi6[r] : hi6[r + 3];
+        }
         if (!L.alias_ori) {
           const double* ori = s ? p.ori_dst : p.ori_src;
-          for (size_t i = 0; i < (size_t)3 * p.M; ++i) finite &= std::isfinite(ori[i]);
+          const size_t n_ori = (size_t)3 * p.M;
+          for (size_t i = 0; i + 6 <= n_ori; i += 6)
+            for (int k = 0; k < 6; ++k) poison6[k] += ori[i + k] * 0.0;
+          for (size_t i = n_ori - n_ori % 6; i < n_ori; ++i) poison6[0] += ori[i] * 0.0;
         }
+        const bool finite = (poison6[0] + poison6[1] + poison6[2] + poison6[3] + poison6[4] + poison6[5] == 0.0);
         if (!finite) bad_problem.store(b);
         double* c = s ? L.cdst : L.csrc;
         double bound = 0.0;
@@ -265,11 +304,15 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       L.coord_bound = L.coord_bound * (1.0 + 1e-6) + 1e-30;
       for (int r = 0; r < 3; ++r)
         if (!std::isfinite(L.csrc[r]) || !std::isfinite(L.cdst[r]) || !std::isfinite(L.coord_bound)) bad_problem.store(b);
+      if (b + 1 - group_begin >= 8 || b + 1 == b1) {
+        push_group(group_begin, b + 1);
+        group_begin = b + 1;
+      }
     }
   };
   {
     int nthreads = (int)std::thread::hardware_concurrency();
-    if (nthreads > 8) nthreads = 8;
+    if (nthreads > 12) nthreads = 12;
     if (nthreads > nb) nthreads = nb;
     if (nthreads < 1 || bytes_d < (4u << 20)) nthreads = 1;
     if (nthreads == 1) {
@@ -281,11 +324,15 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       for (auto& th : pool) th.join();
     }
   }
-  if (bad_problem.load() >= 0)
-    return fail(PSULVSB_ERR_INVALID, "upload: problem " + std::to_string(bad_problem.load()) + " has non-finite coordinates");
-  PSU_CUDA(cudaMemcpyAsync(d_in_dbl.p, hd, bytes_d, cudaMemcpyHostToDevice, st));
-  PSU_CUDA(cudaMemcpyAsync(d_in_int.p, hi, bytes_i, cudaMemcpyHostToDevice, st));
-  PSU_CUDA(cudaStreamSynchronize(st));
+  t_staged = since();
+  {
+    const cudaError_t e = cudaStreamSynchronize(st);  // (also before an error return: copies may still read h_stage)
+    if (prof) fprintf(stderr, "upload: layout %.3f ms, staged+issued %.3f ms, copies done %.3f ms\n", t_layout, t_staged, since());
+    if (bad_problem.load() >= 0)
+      return fail(PSULVSB_ERR_INVALID,
+                  "upload: problem " + std::to_string(bad_problem.load()) + " has non-finite coordinates");
+    if (copy_error.load() || e != cudaSuccess) return fail(PSULVSB_ERR_CUDA, "upload: host-to-device copy failed");
+  }
   B = nb;
   reserve.assign((size_t)nb, 0ull);
   for (int b = 0; b < nb; ++b) {

@@ -3,7 +3,7 @@ sys.path.insert(0,'/root/repo')
 import psulvsb_b200
 from psulvsb_b200 import capi, synth
 import bench
-B=64
+B=int(sys.argv[1]) if len(sys.argv) > 1 else 64
 pairs = bench.make_problems(0, B)
 probs = [capi.HostProblem(p["src"], p["dst"]) for p in pairs]
 seeds = list(range(B))
