@@ -241,14 +241,14 @@ int psulvsb_gnc_tls_rotation(void* stream, const double* d_src64, const double* 
  * choice for n_jobs).  d_weights: n_jobs*K doubles of scratch; d_lv: optional n_jobs*6*lv_cap doubles of scratch
  * for the line vectors beyond the shared-memory capacity (NULL: they are re-formed from the points); d_perm:
  * optional n_jobs*2*lv_cap uint32 of scratch (with d_lv: lets the kernel park sleeping line vectors).
- * Outputs: d_R[n_jobs*9] column-major, d_info[n_jobs*4] (iterations, inliers, SVD cycles/16, loop cycles/16),
+ * Outputs: d_R[n_jobs*9] column-major, d_inliers[n_jobs*K] (u8, optional), d_info[n_jobs*4] (iterations, inliers, SVD cycles/16, loop cycles/16),
  * d_prof[n_jobs*8] optional diagnostics (cycles of thread 0: line-vector passes, iteration loop, SVDs; cached line
  * vectors per CTA; prologue and epilogue cycles). */
 int psulvsb_gnc_tls_rotation_batch(void* stream, const double* d_src64, const double* d_dst64, int n_points,
                                    const void* d_edges_uint2, unsigned long long K, int n_jobs, double noise_bound,
                                    int max_iterations, double gnc_factor, double cost_threshold, int cluster,
                                    double* d_weights, double* d_lv, unsigned long long lv_cap, uint32_t* d_perm,
-                                   double* d_R, int* d_info, long long* d_prof);
+                                   double* d_R, uint8_t* d_inliers, int* d_info, long long* d_prof);
 /* Stage 3b -- batched closed-form Kabsch, one warp per hypothesis (utils.h:121-136): hypothesis h
  * uses the k line vectors d_sets[h*k .. h*k+k) (indices into d_edges).  Outputs d_R[h*9..]
  * (column-major) and, if d_t != NULL, the translation of the centroid of the sampled endpoints. */

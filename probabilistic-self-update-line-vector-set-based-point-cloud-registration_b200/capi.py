@@ -196,7 +196,7 @@ def _declare(L: C.CDLL) -> None:
     L.psulvsb_max_clique.argtypes = [_vp, _vp, _ull, C.c_int, _vp, _vp, _vp, C.c_int]
     L.psulvsb_max_clique_scratch_words.argtypes = [C.c_int]
     L.psulvsb_gnc_tls_rotation_batch.argtypes = [_vp, _vp, _vp, C.c_int, _vp, _ull, C.c_int, C.c_double, C.c_int,
-                                                 C.c_double, C.c_double, C.c_int, _vp, _vp, _ull, _vp, _vp, _vp, _vp]
+                                                 C.c_double, C.c_double, C.c_int, _vp, _vp, _ull, _vp, _vp, _vp, _vp, _vp]
     L.psulvsb_compute_tims_host.argtypes = [_vp, C.c_int, _vp, _vp]
     L.psulvsb_scale_inliers_host.argtypes = [_vp, _vp, _ull, C.c_double, C.c_double, _vp]
     L.psulvsb_tls_scale_host.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint32, _vp, _vp, _vp]

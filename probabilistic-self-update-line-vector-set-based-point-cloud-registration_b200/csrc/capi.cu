@@ -339,7 +339,7 @@ int psulvsb_gnc_tls_rotation_batch(void* stream, const double* d_src64, const do
                                    const void* d_edges_uint2, unsigned long long K, int n_jobs, double noise_bound,
                                    int max_iterations, double gnc_factor, double cost_threshold, int cluster,
                                    double* d_weights, double* d_lv, unsigned long long lv_cap, uint32_t* d_perm,
-                                   double* d_R, int* d_info, long long* d_prof) {
+                                   double* d_R, uint8_t* d_inliers, int* d_info, long long* d_prof) {
   if (int rc = need_device()) return rc;
   if (!d_src64 || !d_dst64 || !d_edges_uint2 || !d_R || !d_weights || n_jobs < 1 || K < 1)
     return fail(PSULVSB_ERR_INVALID, "psulvsb_gnc_tls_rotation_batch: bad argument");
@@ -363,6 +363,7 @@ int psulvsb_gnc_tls_rotation_batch(void* stream, const double* d_src64, const do
     j.lv_cap = d_lv ? lv_cap : 0;
     j.perm = (d_lv && d_perm) ? d_perm + (size_t)b * 2 * lv_cap : nullptr;
     j.R_out = d_R + (size_t)b * 9;
+    j.inliers = d_inliers ? d_inliers + (size_t)b * K : nullptr;
     j.n_points = n_points;
     j.info = d_info ? d_info + (size_t)b * 4 : nullptr;
     j.prof = d_prof ? d_prof + (size_t)b * 8 : nullptr;

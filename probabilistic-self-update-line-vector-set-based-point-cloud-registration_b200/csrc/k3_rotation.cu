@@ -899,6 +899,12 @@ int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_pe
       if (lean) return launch_gnc_nc<1, 512, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
       // one CTA per hypothesis (large batches); PSULVSB_GNC_POINT_CACHE=1 caches the points instead of line vectors
       if (point_cache) return launch_gnc_nc<1, 512, 1, true>(st, d_jobs, n_jobs, max_points);
+      {
+        static const char* v_env = getenv("PSULVSB_GNC_NC1");
+        if (v_env && v_env[0] == '2') return launch_gnc_nc<1, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
+        if (v_env && v_env[0] == '3') return launch_gnc_nc<1, 768, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+        if (v_env && v_env[0] == '4') return launch_gnc_nc<1, 640, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+      }
       return launch_gnc_nc<1, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
     default: return fail(PSULVSB_ERR_INVALID, "launch_gnc_tls: cluster must be 1, 2, 4 or 8");
   }

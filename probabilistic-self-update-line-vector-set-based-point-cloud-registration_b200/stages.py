@@ -133,6 +133,27 @@ def gnc_tls_rotation(d_src, d_dst, d_edges, noise_bound, max_iterations=100, gnc
     return (R.cpu().numpy().reshape(3, 3, order="F"), inl[:K].cpu().numpy(), int(i[0]), float(cost.item()), int(i[1]))
 
 
+def gnc_tls_rotation_batch(d_src, d_dst, d_edges, noise_bound, max_iterations=100, gnc_factor=1.4, cost_threshold=0.005,
+                           cluster: int = 0, lv_scratch: bool = True, parking: bool = True):
+    """d_edges: [B, K, 2] int32 on the device, one basic subset per job over the shared points ->
+    (R [B, 3, 3], inlier masks [B, K], iterations [B], inlier counts [B])."""
+    B, K = int(d_edges.shape[0]), int(d_edges.shape[1])
+    w = torch.zeros(B * K, dtype=torch.float64, device="cuda")
+    lv = torch.zeros(B * 6 * K, dtype=torch.float64, device="cuda") if lv_scratch else None
+    perm = torch.zeros(B * 2 * K, dtype=torch.int32, device="cuda") if (lv_scratch and parking) else None
+    R = torch.zeros(B * 9, dtype=torch.float64, device="cuda")
+    inl = torch.zeros(B * K, dtype=torch.uint8, device="cuda")
+    info = torch.zeros(B * 4, dtype=torch.int32, device="cuda")
+    capi.check(capi.lib().psulvsb_gnc_tls_rotation_batch(
+        _stream(), _dev(d_src), _dev(d_dst), int(d_src.shape[0]), _dev(d_edges), K, B, noise_bound, max_iterations,
+        gnc_factor, cost_threshold, cluster, _dev(w), _dev(lv) if lv is not None else None, K,
+        _dev(perm) if perm is not None else None, _dev(R), _dev(inl), _dev(info), None))
+    torch.cuda.synchronize()
+    i = info.cpu().numpy().reshape(B, 4)
+    Rn = R.cpu().numpy().reshape(B, 3, 3).transpose(0, 2, 1)  # column-major -> [b][r][c]
+    return Rn, inl.cpu().numpy().reshape(B, K), i[:, 0].copy(), i[:, 1].copy()
+
+
 def kabsch_batch(d_src, d_dst, d_edges, d_sets, k: int, want_t: bool = True):
     n_hyp = d_sets.numel() // k
     R = torch.zeros((n_hyp, 9), dtype=torch.float64, device="cuda")

@@ -46,7 +46,7 @@ def main():
                                                         d_dst.data_ptr(), 5000, e.data_ptr(), K, B, 0.1, 100, 1.4, 0.005,
                                                         cluster, w.data_ptr(), lv.data_ptr() if use_lv else None, lv_cap,
                                                         perm.data_ptr() if perm is not None else None, R.data_ptr(),
-                                                        info.data_ptr(), prof.data_ptr()))
+                                                        None, info.data_ptr(), prof.data_ptr()))
         for _ in range(3):
             run()
         torch.cuda.synchronize()

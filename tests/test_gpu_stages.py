@@ -173,6 +173,35 @@ def test_gnc_tls_golden_rotation_only(P, O, golden):
     assert P["synth"].rotation_error(Rg, Rexp) < 1e-5
 
 
+@pytest.mark.parametrize("cluster,parking", [(1, True), (4, True), (8, True), (4, False)])
+def test_gnc_batch_parks_sleeping_line_vectors_exactly(P, O, cluster, parking):
+    """The shape of one engine tick of cfg-A (K = 22 000 line vectors, 95 % FPFH-style outliers per job).  From the
+    tenth iteration on most line vectors sit at weight 0 with a margin the remaining rotation drift cannot consume;
+    the kernel parks them behind the active range (k3_rotation.cu).  Nothing is approximated: rotation, iteration
+    count and the inlier mask -- reported by ORIGINAL index although the positions were permuted -- must match
+    the oracle's plain loop."""
+    st, synth = P["stages"], P["synth"]
+    pair = synth.make_pair(5000, 0.95, 3, outliers="fpfh")
+    pi, pj = O.reduced_set(pair["src"], pair["dst"], 0.1)
+    rng = np.random.default_rng(cluster)
+    B, K = 3, 22000
+    edges = np.empty((B, K, 2), dtype=np.int32)
+    for b in range(B):
+        sel = rng.permutation(len(pi))[:K]
+        edges[b, :, 0], edges[b, :, 1] = pi[sel], pj[sel]
+    Rg, inl, its, n_inl = st.gnc_tls_rotation_batch(st.to_device_points(pair["src"]), st.to_device_points(pair["dst"]),
+                                                    torch.from_numpy(edges).cuda(), 0.1, 100, 1.4, 0.005, cluster=cluster,
+                                                    parking=parking)
+    for b in range(B):
+        sv = pair["src"][:, edges[b, :, 1]] - pair["src"][:, edges[b, :, 0]]
+        tv = pair["dst"][:, edges[b, :, 1]] - pair["dst"][:, edges[b, :, 0]]
+        Rw, inl_w, its_w, _ = O.gnc_tls(sv, tv, 0.1, 100, 1.4, 0.005)
+        assert its[b] == its_w and its_w > 20
+        assert np.abs(Rg[b] - Rw).max() < 1e-9
+        assert np.array_equal(inl[b], inl_w) and n_inl[b] == int(inl_w.sum())
+        assert P["synth"].rotation_error(Rg[b], pair["R"]) < 0.02
+
+
 def test_kabsch_batch_vs_oracle(P, O):
     st = P["stages"]
     pair, e = _edges_for(P, O, 800, 4, frac=0.2)
