@@ -46,8 +46,10 @@ K1_SLOTS_PER_PAIR = 16
 K1_TRAFFIC_BYTES_B64 = 79_636_736 + 128_738_304
 # the same at --batch 256 (profiles/r1_ncu_k1_mask_b256_final.txt: 336.4 MB read + 692.0 MB written; algorithmic
 # output 4 x 204.8 MB): the default batch
-K1_TRAFFIC_BYTES = {64: K1_TRAFFIC_BYTES_B64, 256: 336_378_368 + 691_986_688}
-# (other batch sizes, incl. the default 296: scaled from the 256 capture -- the kernel's traffic is per registration)
+# and at the default --batch 296 (profiles/r1_ncu_k1_mask_b296_final.txt: 472.2 MB read + 898.9 MB written; the
+# algorithmic output is 296 x 5000 x 160 words = 947 MB incl. row padding and the untouched lower triangle)
+K1_TRAFFIC_BYTES = {64: K1_TRAFFIC_BYTES_B64, 256: 336_378_368 + 691_986_688, 296: 472_242_176 + 898_935_296}
+# (other batch sizes: scaled from the 296 capture -- the kernel's traffic is per registration)
 
 
 def make_problems(rank: int, batch: int):
@@ -255,8 +257,8 @@ def main():
         sols_e2e = h.solve_batch(params, probs, seeds)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1000.0
-    h2d = sum(p.nbytes for p in probs)
-    d2h = B * __import__("ctypes").sizeof(capi.Solution)
+    h2d = world * sum(p.nbytes for p in probs)  # whole job, like `value`
+    d2h = world * B * __import__("ctypes").sizeof(capi.Solution)
 
     # max over ranks (device-timed value, wall-timed e2e)
     t = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
@@ -300,7 +302,7 @@ def main():
             "roofline": {"bound": "fp32-pipe", "kernel": "k1_mask_kernel (line-vector length-consistency bit mask)",
                          "achieved": achieved, "peak": peak, "unit": "Gslot/s (FP32-pipe issue slots, 16 per pair)",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": K1_TRAFFIC_BYTES.get(B, int(K1_TRAFFIC_BYTES[256] * B / 256) if B > 64 else None),
+                         "traffic": K1_TRAFFIC_BYTES.get(B, int(K1_TRAFFIC_BYTES[296] * B / 296) if B > 64 else None),
                          "algorithmic_bytes": mask_bytes // 2 + 2 * B * N_CORR * 16,
                          "pairs_per_s": pairs_per_launch / k1_s if k1_s > 0 else None,
                          "kernel_ms": k1_ms / args.steps, "share_of_step": k1_ms / dev_ms if dev_ms > 0 else None,
