@@ -249,7 +249,8 @@ unsigned long long psulvsb_sample_workspace_bytes(unsigned long long n, unsigned
                                                   unsigned long long max_draws) {
   if (max_draws == 0) max_draws = sample_default_max_draws(n, count);
   return ((sample_table_words(n, max_draws) * sizeof(uint32_t) + 15) & ~15ull) +
-         sample_chunk_slots(max_draws) * sizeof(unsigned long long) + 16;
+         sample_chunk_slots(max_draws) * sizeof(unsigned long long) + 16 +
+         sample_list_counters() * sizeof(unsigned int) + sample_list_entries(n, max_draws) * sizeof(uint32_t);
 }
 
 int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long n,
@@ -279,6 +280,14 @@ int psulvsb_sample(void* stream, uint64_t seed, uint32_t domain, uint32_t event,
   j.first = (uint32_t*)d_work;
   j.chunk_prefix = (unsigned long long*)((char*)d_work + first_bytes);
   j.ticket = (unsigned int*)((char*)d_work + first_bytes + slots * sizeof(unsigned long long));
+  {
+    // bucket-list scratch behind the ticket: counters (zeroed), then the lists
+    char* p = (char*)d_work + first_bytes + slots * sizeof(unsigned long long) + 16;
+    j.bcount = (unsigned int*)p;
+    PSU_CUDA(cudaMemsetAsync(p, 0, sample_list_counters() * sizeof(unsigned int), st));
+    j.blist_cap = sample_list_entries(n, max_draws);
+    j.blist = j.blist_cap ? (uint32_t*)(p + sample_list_counters() * sizeof(unsigned int)) : nullptr;
+  }
   j.out = d_out;
   j.status = d_status;
   j.active = 1;

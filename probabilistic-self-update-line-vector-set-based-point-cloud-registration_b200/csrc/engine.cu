@@ -633,6 +633,10 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.draws = be.take<uint32_t>((size_t)J.draws_cap);
         J.chunk_prefix = be.take<unsigned long long>((size_t)sample_chunk_slots(sample_default_max_draws(cap, cap)));
         J.ticket = be.take<unsigned int>(4);
+        // bucket lists of the sampler: sized for the L sample at the largest rate below 1.0 (0.5 -> ~0.7 cap draws)
+        J.blist_cap = sample_list_entries(cap, cap) ? sample_list_entries(cap, cap) : 0ull;
+        J.blist = J.blist_cap ? be.take<uint32_t>((size_t)J.blist_cap) : nullptr;
+        J.bcount = be.take<unsigned int>((size_t)sample_list_counters());
         J.L_sampled = be.take<uint32_t>((size_t)cap);
         J.basic_idx = be.take<uint32_t>((size_t)cap);
         J.basic_edges = be.take<uint2>((size_t)cap);

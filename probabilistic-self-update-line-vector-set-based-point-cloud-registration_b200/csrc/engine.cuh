@@ -90,6 +90,9 @@ struct SampleJob {
   unsigned int* ticket;          // zero on entry and on exit (last-CTA-done counter of the bucket pass)
   uint32_t* draws;               // optional cache of the draw values [draws_cap] (16-byte aligned), or NULL
   unsigned long long draws_cap;
+  uint32_t* blist;               // optional bucket-list scratch [blist_cap] (k2_sampler.cu), or NULL
+  unsigned long long blist_cap;
+  unsigned int* bcount;          // [sample_list_counters()] list fill counters + overflow flag, zero on entry and on exit
   uint32_t* out;                 // [count]
   unsigned long long* status;    // draws consumed (0: max_draws too small)
   int identity;                  // 1: out[r] = r (registration.cc:839-847, empty-sample fallback)
@@ -185,6 +188,8 @@ __host__ __device__ inline unsigned long long sample_max_draws_formula(unsigned 
 }
 unsigned long long sample_default_max_draws(unsigned long long n, unsigned long long count);
 unsigned long long sample_chunk_slots(unsigned long long max_draws);
+unsigned long long sample_list_entries(unsigned long long n, unsigned long long max_draws);  // 0: lists not applicable
+unsigned long long sample_list_counters();
 unsigned long long sample_table_words(unsigned long long n, unsigned long long max_draws);
 int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound,
                   unsigned long long n_bound);

@@ -57,6 +57,9 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   sb.ticket = J.ticket;
   sb.draws = J.draws;
   sb.draws_cap = J.draws_cap;
+  sb.blist = J.blist;
+  sb.blist_cap = J.blist_cap;
+  sb.bcount = J.bcount;
   sb.out = J.basic_idx;
   sb.status = &J.sample_status[1];
   sb.identity = 0;
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(BLK)
     J.residual_history[j] = 0.0;
   }
   for (unsigned long long i = tid; i < J.first_words; i += BLK) J.first[i] = 0u;  // sampler accept bitmask
+  for (int i = tid; i < 260; i += BLK) J.bcount[i] = 0u;  // sampler list counters (sample_list_counters())
   if (tid == 0) {
     *J.ticket = 0u;
     J.C = J.C0;
@@ -324,6 +328,9 @@ __global__ void __launch_bounds__(BLK)
     L.ticket = J.ticket;
     L.draws = J.draws;
     L.draws_cap = J.draws_cap;
+    L.blist = J.blist;
+    L.blist_cap = J.blist_cap;
+    L.bcount = J.bcount;
     L.out = J.L_sampled;
     L.status = &J.sample_status[0];
     L.post = 1;

@@ -67,6 +67,9 @@ struct JobCtl {
   uint8_t* rot_flags;        // [Ccap]
   uint2* edges;              // reduced set (L_reduced_set) as endpoint pairs
   unsigned long long edge_cap;
+  uint32_t* blist;            // sampler bucket lists [blist_cap]
+  unsigned long long blist_cap;
+  unsigned int* bcount;       // [sample_list_counters()] zero between uses
   uint32_t* first;  // [first_words] sampler accept bitmask (zero between uses)
   unsigned long long first_words;
   uint32_t* draws;  // sampler draw-value cache [draws_cap]

@@ -8,6 +8,12 @@
 // That is exactly the rejection rule, so the output equals the sequential algorithm's for the same
 // stream, and the stream position after the call (draws consumed) is reported for replay.
 //
+// Long value ranges (three buckets or more) first sort the draws by bucket: the draw kernel appends (k, v - lo) to
+// its bucket's list (shared-memory histogram per 1024 draws, one global atomicAdd per bucket and step), so that a
+// bucket CTA reads only its own ~max_draws / n_buckets draws instead of walking the whole window once per bucket
+// (16 buckets on cfg-A: 10 MB -> 1.5 MB of L2 traffic per registration and sample).  The order inside a list is
+// arbitrary, the result is not: first[v] is a minimum and the accept bits are indexed by k.
+//
 // Two passes, no global table:
 //   bucket : the value range [0, n) is cut into buckets of SMP_BW values; CTA (b, job) walks the whole draw
 //            window (Philox is cheap: the redundancy buys the removal of every random global access), keeps
@@ -32,6 +38,39 @@ constexpr int SMP_THREADS = 256;            // emit pass
 constexpr int SMP_CHUNK = SMP_THREADS * 4;  // draws per chunk (one Philox block per thread)
 constexpr int SMB_THREADS = 1024;           // bucket pass (one CTA per SM: the table fills shared memory)
 constexpr int SMP_BW = 49152;               // values per bucket (192 KB of shared memory)
+constexpr int SMP_MAX_LIST_BUCKETS = 256;   // bucket lists are used for 3 .. 256 buckets
+
+// layout of the bucket lists for (n, max_draws).  An entry is ONE 32-bit word, (k << w_bits) | (v - lo): the draw
+// index takes the bits it needs and the rest addresses the value inside its bucket, so the bucket width shrinks
+// from SMP_BW to a power of two when the draw window is long (2^17 draws -> 32 768 values per bucket).  n_buckets
+// regions of cap_b entries (mean + 10 sigma + 64 of the uniform draws).  false: lists not applicable / scratch too
+// small -> every bucket CTA walks the whole window.
+struct ListPlan {
+  unsigned int n_buckets, w_bits, width;
+  unsigned long long cap_b;
+};
+__host__ __device__ inline bool sample_list_plan(unsigned long long n, unsigned long long max_draws,
+                                                 unsigned long long blist_cap, ListPlan& p) {
+  p.n_buckets = 0;
+  p.cap_b = 0;
+  if (max_draws < 2 || n < 3ull * SMP_BW) return false;
+  unsigned int k_bits = 1;
+  while (((max_draws - 1) >> k_bits) != 0ull) ++k_bits;
+  if (k_bits > 24) return false;  // buckets of fewer than 256 values: not worth it
+  p.w_bits = 32u - k_bits;
+  p.width = (p.w_bits >= 16u) ? (unsigned int)SMP_BW : (1u << p.w_bits);
+  const unsigned long long nb = (n + p.width - 1) / p.width;
+  if (nb < 3 || nb > (unsigned long long)SMP_MAX_LIST_BUCKETS) return false;
+  p.n_buckets = (unsigned int)nb;
+  const unsigned long long mean = (max_draws * (unsigned long long)p.width + n - 1) / n + 1;
+  unsigned long long s = 1;
+  while (s * s < mean) ++s;  // ceil(sqrt(mean)), integer: identical on host and device
+  p.cap_b = (mean + 10 * s + 64 + 3) & ~3ull;
+  return nb * p.cap_b <= blist_cap;
+}
+__device__ __forceinline__ uint32_t list_bucket(uint32_t v, const ListPlan& p) {
+  return (p.w_bits >= 16u) ? v / (uint32_t)SMP_BW : v >> p.w_bits;
+}
 
 // (word >> 1) % n with the division replaced by a multiply-high: magic = ceil(2^64 / n) gives the exact
 // quotient for every 31-bit dividend (the error term v e / 2^64 < 2^-33 cannot reach the next integer,
@@ -57,14 +96,104 @@ __device__ __forceinline__ uint32_t draw_value(uint32_t word, const FastMod& f) 
 // them instead of re-running Philox; windows longer than draws_cap fall back to recomputation
 __global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __restrict__ jobs) {
   const SampleJob& job = jobs[blockIdx.y];
-  if (!job.active || job.identity || !job.draws || job.max_draws > job.draws_cap) return;
+  if (!job.active || job.identity) return;
+  const bool cache = job.draws != nullptr && job.max_draws <= job.draws_cap;
+  __shared__ ListPlan plan_s;
+  __shared__ int lists_s;
+  if (threadIdx.x == 0)  // (the plan has two short loops: once per CTA, not per thread)
+    lists_s = (job.blist != nullptr && sample_list_plan(job.n, job.max_draws, job.blist_cap, plan_s)) ? 1 : 0;
+  __syncthreads();
+  const ListPlan plan = plan_s;
+  const bool lists = lists_s != 0;
+  const unsigned int n_buckets = plan.n_buckets;
+  const unsigned long long cap_b = plan.cap_b;
+  if (!cache && !lists) return;
   const FastMod fm = make_fastmod((uint32_t)job.n);
   const unsigned long long nblocks = (job.max_draws + 3) >> 2;
   uint4* __restrict__ out = reinterpret_cast<uint4*>(job.draws);
-  for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < nblocks;
-       q += (unsigned long long)gridDim.x * 256) {
-    const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
-    out[q] = make_uint4(draw_value(o.w[0], fm), draw_value(o.w[1], fm), draw_value(o.w[2], fm), draw_value(o.w[3], fm));
+  if (!lists) {
+    for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < nblocks;
+         q += (unsigned long long)gridDim.x * 256) {
+      const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+      out[q] = make_uint4(draw_value(o.w[0], fm), draw_value(o.w[1], fm), draw_value(o.w[2], fm), draw_value(o.w[3], fm));
+    }
+    return;
+  }
+  constexpr int QPT = 4;  // Philox blocks per thread and step: 4096 draws share one round of barriers / global atomics
+  // ranks inside a step without shared-memory atomics (a handful of buckets would serialise them): lanes of a warp
+  // that hit the same bucket find each other with match.any, the warp keeps private running counts per bucket
+  __shared__ unsigned int wh[8][SMP_MAX_LIST_BUCKETS];  // per warp: draws of the step that fell into each bucket
+  __shared__ unsigned int base[SMP_MAX_LIST_BUCKETS];   // per bucket: reserved start in the global list
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  const unsigned long long max_draws = job.max_draws;
+  for (unsigned long long q0 = (unsigned long long)blockIdx.x * (256 * QPT); q0 < nblocks;
+       q0 += (unsigned long long)gridDim.x * (256 * QPT)) {
+    uint32_t vv[QPT][4];
+    unsigned int rk[QPT][4];
+    for (int b = lane; b < (int)n_buckets; b += 32) wh[wid][b] = 0u;
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+      const unsigned long long q = q0 + (unsigned long long)u * 256 + tid;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) vv[u][l] = 0xFFFFFFFFu;  // no draw
+      if (q < nblocks) {
+        const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
+        uint32_t v4[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) v4[l] = draw_value(o.w[l], fm);
+        if (cache) out[q] = make_uint4(v4[0], v4[1], v4[2], v4[3]);  // (the emit pass reads the values back)
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if ((q << 2) + l < max_draws) vv[u][l] = v4[l];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < QPT; ++u)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const uint32_t b = (vv[u][l] != 0xFFFFFFFFu) ? list_bucket(vv[u][l], plan) : 0xFFFFFFFFu;
+        const unsigned int peers = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(peers) - 1;
+        unsigned int start = 0u;
+        if (lane == leader && b != 0xFFFFFFFFu) {
+          start = wh[wid][b];
+          wh[wid][b] = start + __popc(peers);
+        }
+        start = __shfl_sync(0xffffffffu, start, leader);
+        rk[u][l] = start + __popc(peers & lt_mask);
+        __syncwarp();
+      }
+    __syncthreads();
+    // per bucket: total of the step -> one global reservation; per warp: exclusive offset inside it
+    if (tid < (int)n_buckets) {
+      unsigned int run = 0u;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const unsigned int c = wh[w][tid];
+        wh[w][tid] = run;
+        run += c;
+      }
+      if (run != 0u) base[tid] = atomicAdd(&job.bcount[tid], run);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+      const unsigned long long q = q0 + (unsigned long long)u * 256 + tid;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        if (vv[u][l] == 0xFFFFFFFFu) continue;
+        const uint32_t b = list_bucket(vv[u][l], plan);
+        const unsigned long long pos = (unsigned long long)base[b] + wh[wid][b] + rk[u][l];
+        if (pos < cap_b)
+          job.blist[(unsigned long long)b * cap_b + pos] =
+              (uint32_t)((((q << 2) + l) << plan.w_bits) | (unsigned long long)(vv[u][l] - b * plan.width));
+        else
+          atomicExch(&job.bcount[SMP_MAX_LIST_BUCKETS], 1u);  // a list overflowed (10 sigma): the bucket pass walks instead
+      }
+    }
+    __syncthreads();  // wh / base are rewritten by the next step
   }
 }
 
@@ -81,7 +210,10 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
   if (job.identity) return;
   const uint32_t n = (uint32_t)job.n;
   const FastMod fm = make_fastmod(n);
-  const unsigned int n_buckets = (n + SMP_BW - 1) / SMP_BW;
+  ListPlan plan;
+  const bool list_mode = job.blist != nullptr && sample_list_plan(job.n, job.max_draws, job.blist_cap, plan);
+  const bool lists = list_mode && __ldcg(job.bcount + SMP_MAX_LIST_BUCKETS) == 0u;  // (no list overflowed)
+  const unsigned int n_buckets = lists ? plan.n_buckets : (n + SMP_BW - 1) / SMP_BW;
   if (blockIdx.x >= n_buckets) return;
   const unsigned int n_workers = min(gridDim.x, n_buckets);  // CTAs of this job that take buckets (and a ticket)
   const unsigned long long max_draws = job.max_draws;
@@ -94,6 +226,63 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
     const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
     return make_uint4(draw_value(o.w[0], fm), draw_value(o.w[1], fm), draw_value(o.w[2], fm), draw_value(o.w[3], fm));
   };
+  if (lists) {
+    // every draw of bucket b sits in its list as (k << w_bits | v - lo).  A thread keeps its entries of the bucket in
+    // registers for the three short walks (first occurrence, accept, clean the table) and already has the next
+    // bucket's entries in flight while it works: one exposed HBM latency per CTA instead of three per bucket.
+    const unsigned int wb = plan.w_bits, wmask = (1u << wb) - 1u;
+    for (uint32_t i = tid; i < plan.width; i += SMB_THREADS) table[i] = 0xFFFFFFFFu;
+    constexpr int EPT = 8;
+    uint32_t cur[EPT], nxt[EPT];
+    uint32_t cnt_cur = 0u, cnt_nxt = 0u;
+    auto fetch = [&](unsigned int b, uint32_t (&e)[EPT], uint32_t& cnt) {
+      const uint32_t* __restrict__ list = job.blist + (unsigned long long)b * plan.cap_b;
+      cnt = __ldcg(job.bcount + b);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const uint32_t i = tid + j * SMB_THREADS;
+        e[j] = (i < cnt) ? __ldcg(list + i) : 0u;
+      }
+    };
+    unsigned int b = blockIdx.x;
+    if (b < n_buckets) fetch(b, cur, cnt_cur);
+    for (; b < n_buckets; b += gridDim.x) {
+      const unsigned int bn = b + gridDim.x;
+      if (bn < n_buckets) fetch(bn, nxt, cnt_nxt);
+      const uint32_t* __restrict__ list = job.blist + (unsigned long long)b * plan.cap_b;
+      __syncthreads();  // the table is clean (initialisation / the previous bucket's third walk)
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+        if (tid + j * SMB_THREADS < cnt_cur) atomicMin(&table[cur[j] & wmask], cur[j] >> wb);
+      for (uint32_t i = tid + EPT * SMB_THREADS; i < cnt_cur; i += SMB_THREADS) {  // (lists longer than 8192 entries)
+        const uint32_t e = __ldcg(list + i);
+        atomicMin(&table[e & wmask], e >> wb);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+        if (tid + j * SMB_THREADS < cnt_cur) {
+          const uint32_t k = cur[j] >> wb;
+          if (table[cur[j] & wmask] == k) atomicOr(&accept[k >> 5], 1u << (k & 31));
+        }
+      for (uint32_t i = tid + EPT * SMB_THREADS; i < cnt_cur; i += SMB_THREADS) {
+        const uint32_t e = __ldcg(list + i);
+        const uint32_t k = e >> wb;
+        if (table[e & wmask] == k) atomicOr(&accept[k >> 5], 1u << (k & 31));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+        if (tid + j * SMB_THREADS < cnt_cur) table[cur[j] & wmask] = 0xFFFFFFFFu;
+      for (uint32_t i = tid + EPT * SMB_THREADS; i < cnt_cur; i += SMB_THREADS) table[__ldcg(list + i) & wmask] = 0xFFFFFFFFu;
+      if (tid == 0) job.bcount[b] = 0u;  // zero on exit, like the accept bitmask
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) cur[j] = nxt[j];
+      cnt_cur = cnt_nxt;
+    }
+  } else {
+  if (list_mode && blockIdx.x == 0)  // a list overflowed: drop them all (zero on exit), walk the window instead
+    for (int i = tid; i < SMP_MAX_LIST_BUCKETS; i += SMB_THREADS) job.bcount[i] = 0u;
   for (unsigned int b = blockIdx.x; b < n_buckets; b += gridDim.x) {
     const uint32_t lo = b * (uint32_t)SMP_BW;
     const uint32_t width = min((uint32_t)SMP_BW, n - lo);
@@ -147,6 +336,7 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
       }
     }
   }
+  }
   // last CTA of this job: per-chunk popcounts of the accept bitmask -> exclusive prefixes
   __threadfence();
   __syncthreads();
@@ -157,6 +347,7 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
   if (tid == 0) {
     carry_s = 0ull;
     *job.ticket = 0u;  // ready for the next use
+    if (job.blist != nullptr) job.bcount[SMP_MAX_LIST_BUCKETS] = 0u;  // every CTA of the job has read the overflow flag
   }
   __syncthreads();
   const unsigned long long nchunks = (max_draws + SMP_CHUNK - 1) / SMP_CHUNK;
@@ -287,6 +478,14 @@ __global__ void philox_fill_kernel(uint64_t seed, uint32_t domain, uint32_t even
 unsigned long long sample_default_max_draws(unsigned long long n, unsigned long long count) {
   return sample_max_draws_formula(n, count);
 }
+
+// entries of bucket-list scratch (SampleJob::blist) that make the lists usable for (n, max_draws); 0: not applicable
+unsigned long long sample_list_entries(unsigned long long n, unsigned long long max_draws) {
+  ListPlan p;
+  if (!sample_list_plan(n, max_draws, ~0ull, p)) return 0;
+  return (unsigned long long)p.n_buckets * p.cap_b;
+}
+unsigned long long sample_list_counters() { return SMP_MAX_LIST_BUCKETS + 4; }
 
 unsigned long long sample_chunk_slots(unsigned long long max_draws) { return (max_draws + SMP_CHUNK - 1) / SMP_CHUNK + 1; }
 

@@ -36,7 +36,8 @@ def test_philox_stream_matches_oracle(P, O):
         assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("n,count", [(10, 10), (1000, 100), (1000, 1000), (65536, 20000), (627562, 62756), (7, 1)])
+@pytest.mark.parametrize("n,count", [(10, 10), (1000, 100), (1000, 1000), (65536, 20000), (627562, 62756), (7, 1),
+                                     (147457, 14000), (150000, 75000), (2000000, 200000), (98304, 30000)])
 def test_sampler_replays_rejection_sampling(P, O, n, count):
     st = P["stages"]
     for seed, dom, ev in [(1, 1, 0), (99, 2, 13)]:
