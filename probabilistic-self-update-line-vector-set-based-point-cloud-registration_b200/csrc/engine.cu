@@ -637,6 +637,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.blist_cap = sample_list_entries(cap, cap) ? sample_list_entries(cap, cap) : 0ull;
         J.blist = J.blist_cap ? be.take<uint32_t>((size_t)J.blist_cap) : nullptr;
         J.bcount = be.take<unsigned int>((size_t)sample_list_counters());
+        J.vbits = be.take<uint32_t>((size_t)((cap + 31) / 32 + 32));
         J.L_sampled = be.take<uint32_t>((size_t)cap);
         J.basic_idx = be.take<uint32_t>((size_t)cap);
         J.basic_edges = be.take<uint2>((size_t)cap);
@@ -711,8 +712,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     if (round_start_pending) {
       engine_round_start_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, m.n_done);
       PSU_CHECK_LAUNCH("engine_round_start_kernel");
-      if (int rc = launch_sample(st, m.sl, B, draws_bound, max_cap)) return rc;
-      launches += 4;
+      if (int rc = launch_sample(st, m.sl, B, draws_bound, max_cap, true)) return rc;
+      launches += 5;
     }
     if (int rc = launch_sample(st, m.sb, B, draws_bound, max_cap)) return rc;
     if (ratio) {

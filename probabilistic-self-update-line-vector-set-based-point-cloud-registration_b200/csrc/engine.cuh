@@ -102,6 +102,8 @@ struct SampleJob {
   const uint32_t* via;           // post 2: L_sampled (out[r] indexes it)
   uint2* gathered;               // post 2: gathered[r] = edges[via[out[r]]]
   uint8_t* flags;                // post 1: [n_points] endpoint flags
+  uint32_t* vbits;               // post 1, optional: [ceil(n / 32)] value bitmap, zero on entry and on exit -- the flags
+                                 // then come from a streaming pass over the edge list (launch_sample(flag_pass = true))
   int n_points;
   int active;
 };
@@ -192,7 +194,7 @@ unsigned long long sample_list_entries(unsigned long long n, unsigned long long 
 unsigned long long sample_list_counters();
 unsigned long long sample_table_words(unsigned long long n, unsigned long long max_draws);
 int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound,
-                  unsigned long long n_bound);
+                  unsigned long long n_bound, bool flag_pass = false);
 int launch_philox_fill(cudaStream_t st, uint64_t seed, uint32_t domain, uint32_t event, unsigned long long first_k,
                        unsigned long long count, uint32_t* out);
 

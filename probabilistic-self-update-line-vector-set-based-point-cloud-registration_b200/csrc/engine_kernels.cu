@@ -64,6 +64,7 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   sb.status = &J.sample_status[1];
   sb.identity = 0;
   sb.post = 2;
+  sb.vbits = nullptr;
   sb.edges = J.edges;
   sb.via = J.L_sampled;
   sb.gathered = J.basic_edges;
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(BLK)
   }
   for (unsigned long long i = tid; i < J.first_words; i += BLK) J.first[i] = 0u;  // sampler accept bitmask
   for (int i = tid; i < 260; i += BLK) J.bcount[i] = 0u;  // sampler list counters (sample_list_counters())
+  for (unsigned long long i = tid; i < (J.edge_cap + 31) / 32 + 32; i += BLK) J.vbits[i] = 0u;
   if (tid == 0) {
     *J.ticket = 0u;
     J.C = J.C0;
@@ -334,6 +336,7 @@ __global__ void __launch_bounds__(BLK)
     L.out = J.L_sampled;
     L.status = &J.sample_status[0];
     L.post = 1;
+    L.vbits = J.vbits;
     L.edges = J.edges;
     L.via = nullptr;
     L.gathered = nullptr;

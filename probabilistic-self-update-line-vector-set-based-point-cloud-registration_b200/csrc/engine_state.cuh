@@ -67,6 +67,7 @@ struct JobCtl {
   uint8_t* rot_flags;        // [Ccap]
   uint2* edges;              // reduced set (L_reduced_set) as endpoint pairs
   unsigned long long edge_cap;
+  uint32_t* vbits;            // sampler value bitmap of the L sample [ceil(edge_cap / 32)], zero between uses
   uint32_t* blist;            // sampler bucket lists [blist_cap]
   unsigned long long blist_cap;
   unsigned int* bcount;       // [sample_list_counters()] zero between uses

@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
   if (!job.active) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw);  // [SMP_BW]
+  uint32_t* wbm = table + SMP_BW;                            // [SMP_BW / 32] value bitmap of the current bucket
   __shared__ unsigned int ticket_s, sh[SMB_THREADS / 32];
   __shared__ unsigned long long carry_s;
   const int tid = threadIdx.x;
@@ -221,6 +222,8 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
   const bool cached = job.draws != nullptr && max_draws <= job.draws_cap;
   const uint4* __restrict__ dv = reinterpret_cast<const uint4*>(job.draws);
   uint32_t* __restrict__ accept = job.first;  // bit k set <=> draw k is accepted; all zero on entry and on exit
+  // post 1 with a value bitmap: bit v set <=> value v is in the sample; the flag pass streams the edge list by it
+  uint32_t* __restrict__ vbits = (job.post == 1) ? job.vbits : nullptr;
   auto draws_of = [&](uint32_t q) -> uint4 {
     if (cached) return __ldcg(dv + q);
     const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
@@ -250,6 +253,8 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
       const unsigned int bn = b + gridDim.x;
       if (bn < n_buckets) fetch(bn, nxt, cnt_nxt);
       const uint32_t* __restrict__ list = job.blist + (unsigned long long)b * plan.cap_b;
+      if (vbits)
+        for (uint32_t i = tid; i < (plan.width >> 5); i += SMB_THREADS) wbm[i] = 0u;
       __syncthreads();  // the table is clean (initialisation / the previous bucket's third walk)
 #pragma unroll
       for (int j = 0; j < EPT; ++j)
@@ -259,18 +264,28 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
         atomicMin(&table[e & wmask], e >> wb);
       }
       __syncthreads();
+      const uint32_t lo_b = b * plan.width;  // (vbits: which values were drawn; the emit pass removes the few beyond `count`)
 #pragma unroll
       for (int j = 0; j < EPT; ++j)
         if (tid + j * SMB_THREADS < cnt_cur) {
           const uint32_t k = cur[j] >> wb;
-          if (table[cur[j] & wmask] == k) atomicOr(&accept[k >> 5], 1u << (k & 31));
+          if (table[cur[j] & wmask] == k) {
+            atomicOr(&accept[k >> 5], 1u << (k & 31));
+            if (vbits) atomicOr(&wbm[(cur[j] & wmask) >> 5], 1u << (cur[j] & 31u));
+          }
         }
       for (uint32_t i = tid + EPT * SMB_THREADS; i < cnt_cur; i += SMB_THREADS) {
         const uint32_t e = __ldcg(list + i);
         const uint32_t k = e >> wb;
-        if (table[e & wmask] == k) atomicOr(&accept[k >> 5], 1u << (k & 31));
+        if (table[e & wmask] == k) {
+          atomicOr(&accept[k >> 5], 1u << (k & 31));
+          if (vbits) atomicOr(&wbm[(e & wmask) >> 5], 1u << (e & 31u));
+        }
       }
       __syncthreads();
+      if (vbits)  // the bucket's slice of the value bitmap, written once and coalesced (width is a multiple of 32)
+        for (uint32_t i = tid; i < (plan.width >> 5); i += SMB_THREADS)
+          if (wbm[i] && ((unsigned long long)lo_b + 32ull * i) < job.n) vbits[(lo_b >> 5) + i] = wbm[i];
 #pragma unroll
       for (int j = 0; j < EPT; ++j)
         if (tid + j * SMB_THREADS < cnt_cur) table[cur[j] & wmask] = 0xFFFFFFFFu;
@@ -288,6 +303,8 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
     const uint32_t width = min((uint32_t)SMP_BW, n - lo);
     __syncthreads();  // the previous bucket's readers are done with the table
     for (uint32_t i = tid; i < width; i += SMB_THREADS) table[i] = 0xFFFFFFFFu;
+    if (vbits)
+      for (uint32_t i = tid; i < (uint32_t)(SMP_BW / 32); i += SMB_THREADS) wbm[i] = 0u;
     __syncthreads();
     // walk 1: first occurrence of every value of this bucket (four 16-byte loads in flight per thread:
     // the walk is bound by the latency of the cached draws coming from L2, not by arithmetic)
@@ -330,10 +347,18 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
         for (int l = 0; l < 4; ++l) {
           const uint32_t k = (q << 2) + l;
           const uint32_t off = vv[l] - lo;
-          if (off < width && k < md32 && table[off] == k) bits |= 1u << l;
+          if (off < width && k < md32 && table[off] == k) {
+            bits |= 1u << l;
+            if (vbits) atomicOr(&wbm[off >> 5], 1u << (off & 31u));
+          }
         }
         if (bits) atomicOr(&accept[q >> 3], bits << ((q & 7) << 2));
       }
+    }
+    if (vbits) {
+      __syncthreads();
+      for (uint32_t i = tid; i < ((width + 31u) >> 5); i += SMB_THREADS)
+        if (wbm[i]) vbits[(lo >> 5) + i] = wbm[i];
     }
   }
   }
@@ -447,7 +472,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_emit_kernel(const SampleJo
           if (rank < count) {
             const uint32_t v = vv[l];
             out[rank] = v;
-            if (job.post == 1) {
+            if (job.post == 1 && !job.vbits) {
               // src_sampled/dst_sampled = unique endpoints of the sampled line vectors
               // (registration.cc:870-894); only the SET matters downstream, kept as per-point flags
               const uint2 e = job.edges[v];
@@ -458,12 +483,52 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_emit_kernel(const SampleJo
               job.gathered[rank] = job.edges[job.via[v]];
             }
             if (rank == count - 1 && job.status) job.status[0] = (q << 2) + l + 1;  // draws consumed
+          } else if (job.post == 1 && job.vbits) {
+            // a first occurrence beyond the count-th accepted draw: not part of the sample
+            atomicAnd(&job.vbits[vv[l] >> 5], ~(1u << (vv[l] & 31u)));
           }
           ++rank;
         }
       }
     }
     __syncthreads();
+  }
+}
+
+// post 1 with a value bitmap: endpoint flags of the sampled edges (registration.cc:870-894) by STREAMING the edge list in
+// value order -- a warp takes 1024 consecutive values, skips the 32-value rows without a sampled one and reads the
+// others coalesced -- instead of one random 8-byte gather (a 64-byte HBM atom) per sampled edge.  Clears the bitmap.
+__global__ void __launch_bounds__(256) sample_flag_kernel(const SampleJob* __restrict__ jobs) {
+  const SampleJob& job = jobs[blockIdx.y];
+  if (!job.active || job.identity || job.post != 1 || !job.vbits) return;
+  const unsigned long long nwords = (job.n + 31) >> 5;
+  const unsigned long long threads = (unsigned long long)gridDim.x * 256;
+  const uint2* __restrict__ edges = job.edges;
+  // a lane owns one 32-value row (its bitmap word) per step and walks the set bits four at a time, loads first
+  for (unsigned long long wi = (unsigned long long)blockIdx.x * 256 + threadIdx.x; wi < nwords; wi += threads) {
+    uint32_t word = __ldcg(job.vbits + wi);
+    if (!word) continue;
+    job.vbits[wi] = 0u;  // zero on exit
+    const uint2* __restrict__ row = edges + wi * 32;
+    while (word) {
+      uint2 e[4];
+      int m = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (word) {
+          const int bit = __ffs(word) - 1;
+          word &= word - 1;
+          e[j] = row[bit];
+          m = j + 1;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < m) {
+          job.flags[e[j].x] = 1;
+          job.flags[e[j].y] = 1;
+        }
+    }
   }
 }
 
@@ -497,10 +562,10 @@ unsigned long long sample_table_words(unsigned long long n, unsigned long long m
 
 // n_bound: upper bound of SampleJob::n over the jobs (sizes the bucket grid)
 int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned long long max_draws_bound,
-                  unsigned long long n_bound) {
+                  unsigned long long n_bound, bool flag_pass) {
   if (n_jobs <= 0) return PSULVSB_OK;
   static bool attr_set = false;
-  const size_t smem = (size_t)SMP_BW * 4;
+  const size_t smem = (size_t)SMP_BW * 4 + (size_t)SMP_BW / 8;  // first-occurrence table + the bucket's value bitmap
   if (!attr_set) {
     PSU_CUDA(cudaFuncSetAttribute(sample_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -522,6 +587,14 @@ int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned
   PSU_CHECK_LAUNCH("sample_bucket_kernel");
   sample_emit_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), SMP_THREADS, 0, st>>>(d_jobs);
   PSU_CHECK_LAUNCH("sample_emit_kernel");
+  if (flag_pass) {
+    unsigned long long fx = (n_bound + 32ull * 256 - 1) / (32ull * 256);  // CTAs of 256 lanes x one 32-value row each
+    const unsigned long long fcap = (148ull * 16 + (unsigned long long)n_jobs - 1) / (unsigned long long)n_jobs;
+    if (fx > fcap) fx = fcap;
+    if (fx < 1) fx = 1;
+    sample_flag_kernel<<<dim3((unsigned)fx, (unsigned)n_jobs), 256, 0, st>>>(d_jobs);
+    PSU_CHECK_LAUNCH("sample_flag_kernel");
+  }
   return PSULVSB_OK;
 }
 
