@@ -128,6 +128,8 @@ class Engine {
   std::vector<unsigned long long> reserve;  // self-update edge head-room per job
   size_t in_dbl_total = 0, in_int_total = 0;
   DevBuf d_in_dbl, d_in_int, d_work, d_mask, d_edge, d_jobs, d_misc, d_hist;
+  unsigned long long sampler_scratch_sig = 0;  // arena layout of the sampler scratch at the last solve
+  bool sampler_scratch_clean = false;          // ... and whether that solve ran to completion
   PinBuf h_stage, h_small;
   long long launches = 0;
   double last_ms = 0.0;
@@ -627,6 +629,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         if (cap < 64) cap = 64;
         J.edge_cap = cap;
         J.edges = be.take<uint2>((size_t)cap);
+        // (the (1.0, 1.0) rate pair draws ALL n values by rejection -- a random order, ~n (ln n + 10.6) draws)
         J.first_words = sample_table_words(cap, sample_default_max_draws(cap, cap));
         J.first = be.take<uint32_t>((size_t)J.first_words);
         J.draws_cap = (cap + 3) & ~3ull;  // covers every rate pair below (1.0, 1.0); longer windows recompute
@@ -689,6 +692,23 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   P.self_update = params->self_update;
   P.inlier_selection_mode = params->inlier_selection_mode;
   P.max_local_iters = 4096;
+  {
+    // The sampler leaves its accept bitmask and value bitmap zeroed after every use.  They are cleared here only when
+    // that cannot be relied on: a new arena layout (other pointers / sizes than the last COMPLETED solve) or a
+    // previous solve that ended early.  Saves a ~2.5 MB memset per registration and solve.
+    unsigned long long sig = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
+    for (int b = 0; b < B; ++b) {
+      const JobCtl& J = jobs[(size_t)b];
+      mix((unsigned long long)(uintptr_t)J.first);
+      mix(J.first_words);
+      mix((unsigned long long)(uintptr_t)J.vbits);
+      mix(J.edge_cap);
+    }
+    P.zero_sampler_scratch = (sampler_scratch_sig == sig && sampler_scratch_clean) ? 0 : 1;
+    sampler_scratch_sig = sig;
+    sampler_scratch_clean = false;  // until this solve completes
+  }
   engine_init_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, m.n_edges, P, m.n_done);
   PSU_CHECK_LAUNCH("engine_init_kernel");
   ++launches;
@@ -747,6 +767,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   PSU_CUDA(cudaMemcpyAsync(solutions, m.sols, sizeof(psulvsb_solution_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
   PSU_CUDA(cudaEventRecord(ev_end, st));
   PSU_CUDA(cudaStreamSynchronize(st));
+  sampler_scratch_clean = true;  // every sample of this solve ran all its passes
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev_begin, ev_end);
   last_ms = ms;

@@ -161,9 +161,13 @@ __global__ void __launch_bounds__(BLK)
     J.final_inliers[j] = 0;
     J.residual_history[j] = 0.0;
   }
-  for (unsigned long long i = tid; i < J.first_words; i += BLK) J.first[i] = 0u;  // sampler accept bitmask
+  // sampler scratch that every use leaves zeroed: only cleared when the host cannot vouch for it (first solve on this
+  // arena layout, or the previous solve did not complete)
+  if (P.zero_sampler_scratch)
+    for (unsigned long long i = tid; i < J.first_words; i += BLK) J.first[i] = 0u;  // sampler accept bitmask
   for (int i = tid; i < 260; i += BLK) J.bcount[i] = 0u;  // sampler list counters (sample_list_counters())
-  for (unsigned long long i = tid; i < (J.edge_cap + 31) / 32 + 32; i += BLK) J.vbits[i] = 0u;
+  if (P.zero_sampler_scratch)
+    for (unsigned long long i = tid; i < (J.edge_cap + 31) / 32 + 32; i += BLK) J.vbits[i] = 0u;
   if (tid == 0) {
     *J.ticket = 0u;
     J.C = J.C0;

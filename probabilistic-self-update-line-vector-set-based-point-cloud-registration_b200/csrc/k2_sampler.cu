@@ -556,8 +556,8 @@ unsigned long long sample_chunk_slots(unsigned long long max_draws) { return (ma
 
 // 32-bit words of the accept bitmask (SampleJob::first) a job with n values / max_draws draws needs
 unsigned long long sample_table_words(unsigned long long n, unsigned long long max_draws) {
-  const unsigned long long w = (max_draws + 31) / 32 + 1;
-  return w > n ? w : n;
+  (void)n;  // (it once was a per-value table)
+  return (max_draws + 31) / 32 + 8;
 }
 
 // n_bound: upper bound of SampleJob::n over the jobs (sizes the bucket grid)
