@@ -11,6 +11,9 @@
 
 #include <atomic>
 #include <chrono>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -187,6 +190,52 @@ class Engine {
                  psulvsb_trace_t* trace_first);
 };
 
+namespace {
+// Staging copy of one 3 x C point array fused with its bounding box and finiteness check: the source is read once,
+// the pinned destination is written with streaming stores (no read-for-ownership traffic on the host memory bus the
+// H2D copies of the previous group are reading from at the same time).  lo6 / hi6: per-lane extrema of the period-6
+// pattern (x y z x y z), poison: sum of v * 0 (NaN iff some v is NaN or infinite).  dst must be 16-byte aligned.
+inline void stage_points(double* dst, const double* src, size_t n_doubles, double lo6[6], double hi6[6], double& poison) {
+  for (int k = 0; k < 6; ++k) lo6[k] = hi6[k] = src[k % 3];
+  size_t i = 0;
+#if defined(__SSE2__)
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    __m128d l0 = _mm_set_pd(src[1], src[0]), l1 = _mm_set_pd(src[0], src[2]), l2 = _mm_set_pd(src[2], src[1]);
+    __m128d h0 = l0, h1 = l1, h2 = l2;
+    __m128d p0 = _mm_setzero_pd(), p1 = p0, p2 = p0;
+    const __m128d zero = _mm_setzero_pd();
+    for (; i + 6 <= n_doubles; i += 6) {
+      const __m128d a = _mm_loadu_pd(src + i), b = _mm_loadu_pd(src + i + 2), c = _mm_loadu_pd(src + i + 4);
+      _mm_stream_pd(dst + i, a);
+      _mm_stream_pd(dst + i + 2, b);
+      _mm_stream_pd(dst + i + 4, c);
+      l0 = _mm_min_pd(l0, a); h0 = _mm_max_pd(h0, a); p0 = _mm_add_pd(p0, _mm_mul_pd(a, zero));
+      l1 = _mm_min_pd(l1, b); h1 = _mm_max_pd(h1, b); p1 = _mm_add_pd(p1, _mm_mul_pd(b, zero));
+      l2 = _mm_min_pd(l2, c); h2 = _mm_max_pd(h2, c); p2 = _mm_add_pd(p2, _mm_mul_pd(c, zero));
+    }
+    _mm_sfence();
+    double t[2];
+    _mm_storeu_pd(t, l0); lo6[0] = t[0]; lo6[1] = t[1];
+    _mm_storeu_pd(t, l1); lo6[2] = t[0]; lo6[3] = t[1];
+    _mm_storeu_pd(t, l2); lo6[4] = t[0]; lo6[5] = t[1];
+    _mm_storeu_pd(t, h0); hi6[0] = t[0]; hi6[1] = t[1];
+    _mm_storeu_pd(t, h1); hi6[2] = t[0]; hi6[3] = t[1];
+    _mm_storeu_pd(t, h2); hi6[4] = t[0]; hi6[5] = t[1];
+    _mm_storeu_pd(t, _mm_add_pd(p0, _mm_add_pd(p1, p2)));
+    poison += t[0] + t[1];
+  }
+#endif
+  for (; i < n_doubles; ++i) {  // tail (and the whole array without SSE2)
+    const double v = src[i];
+    dst[i] = v;
+    const int k = (int)(i % 6);
+    lo6[k] = v < lo6[k] ? v : lo6[k];
+    hi6[k] = v > hi6[k] ? v : hi6[k];
+    poison += v * 0.0;
+  }
+}
+}  // namespace
+
 int Engine::upload(const psulvsb_problem_t* problems, int nb) {
   if (!problems || nb <= 0) return fail(PSULVSB_ERR_INVALID, "upload: no problems");
   static const bool prof = getenv("PSULVSB_UPLOAD_PROF") != nullptr;
@@ -242,8 +291,6 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       const psulvsb_problem_t& p = problems[b];
       ProbLayout& L = lay[(size_t)b];
       double* d = hd + L.in_dbl;
-      std::memcpy(d, p.src, sizeof(double) * 3 * (size_t)p.C);
-      std::memcpy(d + 3 * (size_t)p.C, p.dst, sizeof(double) * 3 * (size_t)p.C);
       if (!L.alias_ori) {
         std::memcpy(d + 6 * (size_t)p.C, p.ori_src, sizeof(double) * 3 * (size_t)p.M);
         std::memcpy(d + 6 * (size_t)p.C + 3 * (size_t)p.M, p.ori_dst, sizeof(double) * 3 * (size_t)p.M);
@@ -258,25 +305,8 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       // (differences are translation invariant: each cloud is centred on its own bounding box)
       for (int s = 0; s < 2; ++s) {
         const double* pts = s ? p.dst : p.src;
-        // bounding box + finiteness in one flat pass the compiler can vectorise: two points (six doubles) per step,
-        // v * 0 is NaN exactly when v is NaN or infinite
-        double lo6[6], hi6[6], poison6[6] = {0, 0, 0, 0, 0, 0};
-        for (int k = 0; k < 6; ++k) lo6[k] = hi6[k] = pts[k % 3];
-        const size_t n6 = ((size_t)p.C / 2) * 6;
-        for (size_t i = 0; i < n6; i += 6)
-          for (int k = 0; k < 6; ++k) {
-            const double v = pts[i + k];
-            lo6[k] = v < lo6[k] ? v : lo6[k];
-            hi6[k] = v > hi6[k] ? v : hi6[k];
-            poison6[k] += v * 0.0;
-          }
-        for (size_t i = n6; i < (size_t)3 * p.C; ++i) {
-          const double v = pts[i];
-          const int k = (int)(i % 3);
-          lo6[k] = v < lo6[k] ? v : lo6[k];
-          hi6[k] = v > hi6[k] ? v : hi6[k];
-          poison6[k] += v * 0.0;
-        }
+        double lo6[6], hi6[6], poison = 0.0;
+        stage_points(d + (s ? 3 * (size_t)p.C : 0), pts, (size_t)3 * p.C, lo6, hi6, poison);
         double lo[3], hi3[3];
         for (int r = 0; r < 3; ++r) {
           lo[r] = lo6[r] < lo6[r + 3] ? lo6[r] : lo6[r + 3];
@@ -284,12 +314,14 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
         }
         if (!L.alias_ori) {
           const double* ori = s ? p.ori_dst : p.ori_src;
+          double p6[6] = {0, 0, 0, 0, 0, 0};
           const size_t n_ori = (size_t)3 * p.M;
           for (size_t i = 0; i + 6 <= n_ori; i += 6)
-            for (int k = 0; k < 6; ++k) poison6[k] += ori[i + k] * 0.0;
-          for (size_t i = n_ori - n_ori % 6; i < n_ori; ++i) poison6[0] += ori[i] * 0.0;
+            for (int k = 0; k < 6; ++k) p6[k] += ori[i + k] * 0.0;
+          for (size_t i = n_ori - n_ori % 6; i < n_ori; ++i) p6[0] += ori[i] * 0.0;
+          poison += p6[0] + p6[1] + p6[2] + p6[3] + p6[4] + p6[5];
         }
-        const bool finite = (poison6[0] + poison6[1] + poison6[2] + poison6[3] + poison6[4] + poison6[5] == 0.0);
+        const bool finite = (poison == 0.0);
         if (!finite) bad_problem.store(b);
         double* c = s ? L.cdst : L.csrc;
         double bound = 0.0;
