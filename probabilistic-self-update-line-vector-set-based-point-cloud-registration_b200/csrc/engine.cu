@@ -238,6 +238,7 @@ inline void stage_points(double* dst, const double* src, size_t n_doubles, doubl
 
 int Engine::upload(const psulvsb_problem_t* problems, int nb) {
   if (!problems || nb <= 0) return fail(PSULVSB_ERR_INVALID, "upload: no problems");
+  if (st) cudaStreamSynchronize(st);  // earlier copies out of the staging buffer (and solves on its contents) are done
   static const bool prof = getenv("PSULVSB_UPLOAD_PROF") != nullptr;
   const auto t_up0 = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up0).count(); };
@@ -359,13 +360,22 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
     }
   }
   t_staged = since();
-  {
-    const cudaError_t e = cudaStreamSynchronize(st);  // (also before an error return: copies may still read h_stage)
-    if (prof) fprintf(stderr, "upload: layout %.3f ms, staged+issued %.3f ms, copies done %.3f ms\n", t_layout, t_staged, since());
-    if (bad_problem.load() >= 0)
-      return fail(PSULVSB_ERR_INVALID,
-                  "upload: problem " + std::to_string(bad_problem.load()) + " has non-finite coordinates");
-    if (copy_error.load() || e != cudaSuccess) return fail(PSULVSB_ERR_CUDA, "upload: host-to-device copy failed");
+  // The tail of the H2D copies is NOT waited for: everything that consumes the inputs is launched on the same stream,
+  // and the host-side set-up of the solve overlaps it.  (The staging buffer is reused by the next upload only, which
+  // begins with a stream synchronisation.)
+  if (prof) {
+    const double t_issue = since();
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "upload: layout %.3f ms, staged+issued %.3f ms (%.3f), copies done %.3f ms\n", t_layout, t_staged,
+            t_issue, since());
+  }
+  if (bad_problem.load() >= 0) {
+    cudaStreamSynchronize(st);
+    return fail(PSULVSB_ERR_INVALID, "upload: problem " + std::to_string(bad_problem.load()) + " has non-finite coordinates");
+  }
+  if (copy_error.load()) {
+    cudaStreamSynchronize(st);
+    return fail(PSULVSB_ERR_CUDA, "upload: host-to-device copy failed");
   }
   B = nb;
   reserve.assign((size_t)nb, 0ull);
