@@ -53,7 +53,7 @@ constexpr int GNC_MAX_WARPS = 32;
 #define GNC_CTAS_PER_SM 2
 #endif
 constexpr int GNC_NRED = 12;  // 9 H + cost + max/aux + count
-constexpr double GNC_DEEP_MARGIN = 0.005;  // remaining margin (rad) from which a sleeping line vector is parked
+constexpr double GNC_DEEP_MARGIN_DEFAULT = 0.005;  // remaining margin (rad) from which a sleeping line vector is parked
 
 struct GncSmem {
   double part[2][GNC_NRED];           // this CTA's partial sums, double-buffered by iteration parity
@@ -267,7 +267,8 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
 }
 
 template <int NC, int T, int CPS, bool PC>
-__global__ void __launch_bounds__(T, CPS) gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta) {
+__global__ void __launch_bounds__(T, CPS)
+    gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta, const double GNC_DEEP_MARGIN) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GncSmem* sm = reinterpret_cast<GncSmem*>(smem_raw);
   double* lv = reinterpret_cast<double*>(smem_raw + ((sizeof(GncSmem) + 15) & ~size_t(15)));
@@ -849,7 +850,13 @@ int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T, CPS, PC>, d_jobs, cap_per_cta));
+  // (a performance knob only -- any value gives the same results; the tests shrink it to force wake-ups)
+  double deep_margin = GNC_DEEP_MARGIN_DEFAULT;
+  if (const char* e = getenv("PSULVSB_GNC_DEEP_MARGIN")) {
+    const double v = atof(e);
+    if (v > 0.0) deep_margin = v;
+  }
+  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T, CPS, PC>, d_jobs, cap_per_cta, deep_margin));
   return PSULVSB_OK;
 }
 

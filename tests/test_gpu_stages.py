@@ -203,6 +203,34 @@ def test_gnc_batch_parks_sleeping_line_vectors_exactly(P, O, cluster, parking):
         assert P["synth"].rotation_error(Rg[b], pair["R"]) < 0.02
 
 
+@pytest.mark.parametrize("margin", ["1e-9", "1e-4"])
+def test_gnc_parking_wakes_line_vectors_up_again(P, O, margin, monkeypatch):
+    """The parking threshold is a performance knob: with a tiny one, line vectors are parked with almost no margin,
+    the rotation drift reaches their wake-up values within an iteration or two and the active range is reopened
+    again and again.  The result must not change."""
+    monkeypatch.setenv("PSULVSB_GNC_DEEP_MARGIN", margin)
+    st, synth = P["stages"], P["synth"]
+    pair = synth.make_pair(5000, 0.95, 11, outliers="fpfh")
+    pi, pj = O.reduced_set(pair["src"], pair["dst"], 0.1)
+    rng = np.random.default_rng(5)
+    B, K = 2, 16000
+    edges = np.empty((B, K, 2), dtype=np.int32)
+    for b in range(B):
+        sel = rng.permutation(len(pi))[:K]
+        edges[b, :, 0], edges[b, :, 1] = pi[sel], pj[sel]
+    for cluster in (1, 4):
+        Rg, inl, its, n_inl = st.gnc_tls_rotation_batch(st.to_device_points(pair["src"]), st.to_device_points(pair["dst"]),
+                                                        torch.from_numpy(edges).cuda(), 0.1, 100, 1.4, 0.005,
+                                                        cluster=cluster)
+        for b in range(B):
+            sv = pair["src"][:, edges[b, :, 1]] - pair["src"][:, edges[b, :, 0]]
+            tv = pair["dst"][:, edges[b, :, 1]] - pair["dst"][:, edges[b, :, 0]]
+            Rw, inl_w, its_w, _ = O.gnc_tls(sv, tv, 0.1, 100, 1.4, 0.005)
+            assert its[b] == its_w
+            assert np.abs(Rg[b] - Rw).max() < 1e-9
+            assert np.array_equal(inl[b], inl_w)
+
+
 def test_kabsch_batch_vs_oracle(P, O):
     st = P["stages"]
     pair, e = _edges_for(P, O, 800, 4, frac=0.2)
