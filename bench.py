@@ -234,19 +234,22 @@ def main():
     sampler.start()
     barrier()
     l0 = h.launch_count
-    dev_ms, k1_ms, ticks = 0.0, 0.0, 0
+    dev_ms, k1_ms, gnc_ms, ticks = 0.0, 0.0, 0.0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         sols = h.solve_resident(params, seeds)
         dev_ms += h.last_device_ms
         k1_ms += h.last_stage_ms(2)
+        gnc_ms += h.last_stage_ms(3)
         ticks += h.last_ticks
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1000.0
     launches = h.launch_count - l0
     clocks = sampler.stop()
     stage = {"stage1_ms": h.last_stage_ms(0), "ticks_ms": h.last_stage_ms(1), "k1_kernel_ms": h.last_stage_ms(2),
-             "refine_ms": h.last_stage_ms(4), "ticks": h.last_ticks}
+             "gnc_kernels_ms": h.last_stage_ms(3), "refine_ms": h.last_stage_ms(4), "ticks": h.last_ticks}
+    # mean basic-subset size of the step (line vectors handed to one GNC-TLS solve): the algorithmic input of that kernel
+    gnc_k_mean = float(np.mean([s.n_reduced for s in sols])) * 0.1 * 0.3
 
     # ---------------- end to end through the C ABI with host buffers (e2e) ----------------
     for _ in range(2):
@@ -307,6 +310,23 @@ def main():
                          "pairs_per_s": pairs_per_launch / k1_s if k1_s > 0 else None,
                          "kernel_ms": k1_ms / args.steps, "share_of_step": k1_ms / dev_ms if dev_ms > 0 else None,
                          "peak_source": f"{sms} SMs x 128 lanes x {f_mhz:.0f} MHz (nvidia-smi median under load)",
+                         # the kernel with the largest share of the step is not an FP32-pipe kernel and has no per-unit
+                         # figure in SURVEY 8(d); reported beside K1: algorithmic bytes = every line vector of every
+                         # GNC-TLS solve read once (48 B) -- what a launch would move if the whole solve stayed on chip
+                         "largest_kernel": {
+                             "kernel": "gnc_tls_kernel (GNC-TLS rotation, FP64; one launch per tick)",
+                             "share_of_step": gnc_ms / dev_ms if dev_ms > 0 else None,
+                             "ms_per_launch": gnc_ms / ticks if ticks else None, "bound": "hbm",
+                             "algorithmic_bytes": int(B * gnc_k_mean * 48),
+                             "achieved": (B * gnc_k_mean * 48) / (gnc_ms / ticks / 1e3) / 1e9 if ticks and gnc_ms > 0 else None,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": ((B * gnc_k_mean * 48) / (gnc_ms / ticks / 1e3) / 1e9 / hbm_peak)
+                             if ticks and gnc_ms > 0 else None,
+                             "traffic": int((2_416_580_000 + 866_402_560) * B / 296) if B >= 148 else None,
+                             "note": "traffic = dram read + write of one launch at B = 296 "
+                                     "(profiles/r1_ncu_gnc_b296_final.txt): 10x the algorithmic bytes -- the line vectors "
+                                     "beyond the shared-memory cache are re-read every GNC iteration until they are "
+                                     "parked; FP64 pipe 14 % busy, long-scoreboard bound"},
                          "hbm_mask_write": {"achieved": mask_bytes / k1_s / 1e9 if k1_s > 0 else None,
                                             "peak": hbm_peak, "unit": "GB/s",
                                             "frac": (mask_bytes / k1_s / 1e9 / hbm_peak) if k1_s > 0 else None,

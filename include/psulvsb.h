@@ -175,7 +175,7 @@ double psulvsb_last_device_ms(psulvsb_handle_t h);
 /* Device time (ms), CUDA events on the handle's stream, of part `which` of the last solve call:
  * 0 stage 1 in full (float4 packing, mask, row scan, n_red read-back, edge compaction, state init),
  * 1 the tick loop (sampling, GNC-TLS, translation, scoring, control), 2 the consistency-mask kernel
- * alone (one launch over the whole batch), 3 reserved, 4 refinement + solution copy. */
+ * alone (one launch over the whole batch), 3 the GNC-TLS launches of all ticks, 4 refinement + solution copy. */
 double psulvsb_last_stage_ms(psulvsb_handle_t h, int which);
 /* Engine ticks (lock-step local iterations over the whole batch) of the last solve call. */
 int psulvsb_last_ticks(psulvsb_handle_t h);

@@ -126,6 +126,7 @@ class Engine {
   int device = 0;
   cudaStream_t st = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k1 = nullptr, ev_loop = nullptr, ev_m0 = nullptr, ev_m1 = nullptr;
+  cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;  // around the GNC-TLS launch of a tick
   int B = 0;
   std::vector<ProbLayout> lay;
   std::vector<unsigned long long> reserve;  // self-update edge head-room per job
@@ -157,6 +158,8 @@ class Engine {
     if (ev_loop) cudaEventDestroy(ev_loop);
     if (ev_m0) cudaEventDestroy(ev_m0);
     if (ev_m1) cudaEventDestroy(ev_m1);
+    if (ev_g0) cudaEventDestroy(ev_g0);
+    if (ev_g1) cudaEventDestroy(ev_g1);
     if (st) cudaStreamDestroy(st);
   }
 
@@ -178,6 +181,8 @@ class Engine {
     PSU_CUDA(cudaEventCreate(&ev_loop));
     PSU_CUDA(cudaEventCreate(&ev_m0));
     PSU_CUDA(cudaEventCreate(&ev_m1));
+    PSU_CUDA(cudaEventCreate(&ev_g0));
+    PSU_CUDA(cudaEventCreate(&ev_g1));
     return PSULVSB_OK;
   }
 
@@ -765,6 +770,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   if (gnc_cap > gnc_default_capacity()) gnc_cap = gnc_default_capacity();
   const unsigned long long draws_bound = sample_default_max_draws(max_cap, max_cap / 8 + 1);
   int ticks = 0;
+  double gnc_ms = 0.0;
   const int max_ticks = P.max_local_iters + P.host_round_limit + 8;
   bool round_start_pending = true;  // every job begins with a round start
   bool clique_pending = false;
@@ -789,13 +795,19 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       if (int rc = launch_max_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap, true)) return rc;
       launches += 6;
     }
+    PSU_CUDA(cudaEventRecord(ev_g0, st));
     if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster, max_ccap)) return rc;
+    PSU_CUDA(cudaEventRecord(ev_g1, st));
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");
     launches += 5;
     ++ticks;
     PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     PSU_CUDA(cudaStreamSynchronize(st));
+    {
+      float g = 0.f;
+      if (cudaEventElapsedTime(&g, ev_g0, ev_g1) == cudaSuccess) gnc_ms += g;  // (the tick's poll already synchronised)
+    }
     if (h_done[0] >= B) break;
     round_start_pending = h_done[1] > 0;
     clique_pending = h_done[2] > 0 && params->inlier_selection_mode != 3;
@@ -821,7 +833,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   stage_ms[4] = ms;
   cudaEventElapsedTime(&ms, ev_m0, ev_m1);
   stage_ms[2] = ms;  // the consistency-mask kernel alone (one launch over the whole batch)
-  stage_ms[3] = 0.0;
+  stage_ms[3] = gnc_ms;  // the GNC-TLS launches of all ticks
 
   if (trace_first) {
     JobCtl j0;
