@@ -268,7 +268,7 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
 
 template <int NC, int T, int CPS, bool PC>
 __global__ void __launch_bounds__(T, CPS)
-    gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta, const double GNC_DEEP_MARGIN) {
+    gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta, const double GNC_DEEP_MARGIN, const int pf_steps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GncSmem* sm = reinterpret_cast<GncSmem*>(smem_raw);
   double* lv = reinterpret_cast<double*>(smem_raw + ((sizeof(GncSmem) + 15) & ~size_t(15)));
@@ -531,7 +531,20 @@ __global__ void __launch_bounds__(T, CPS)
       double* __restrict__ gwl = gw + k_lo;
       const size_t st = (size_t)lv_cap;
       int l = (int)ncached + tid;
+      // register-free look-ahead: the sectors this thread group reads `pf_ahead` steps from now are pulled into L2
+      // (one lane per 32-byte sector issues the prefetch), so that the loads below see L2 latency instead of HBM's
+      static_assert(T % 4 == 0, "");
+      const int pf_ahead = pf_steps * (2 * T);
       for (; CPS < 3 && l + T < g_hi; l += 2 * T) {
+        if (pf_steps > 0 && (tid & 3) == 0 && l + pf_ahead + T < g_hi) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g0 + r * st + l + pf_ahead));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(g0 + r * st + l + pf_ahead + T));
+          }
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gwl + l + pf_ahead));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gwl + l + pf_ahead + T));
+        }
         double sa[3], ta[3], sb[3], tb[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -856,7 +869,9 @@ int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per
     const double v = atof(e);
     if (v > 0.0) deep_margin = v;
   }
-  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T, CPS, PC>, d_jobs, cap_per_cta, deep_margin));
+  int pf_steps = 1;  // look-ahead of the L2 prefetch in the streamed pass, in double-steps (0 = off; measured: 1 is best)
+  if (const char* e = getenv("PSULVSB_GNC_PREFETCH")) pf_steps = atoi(e);
+  PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T, CPS, PC>, d_jobs, cap_per_cta, deep_margin, pf_steps));
   return PSULVSB_OK;
 }
 
