@@ -98,18 +98,22 @@ __global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __re
   const SampleJob& job = jobs[blockIdx.y];
   if (!job.active || job.identity) return;
   const bool cache = job.draws != nullptr && job.max_draws <= job.draws_cap;
+  const unsigned long long nblocks = (job.max_draws + 3) >> 2;
+  if ((unsigned long long)blockIdx.x * 256 >= nblocks) return;  // the grid is sized for the longest window of the batch
   __shared__ ListPlan plan_s;
+  __shared__ FastMod fm_s;
   __shared__ int lists_s;
-  if (threadIdx.x == 0)  // (the plan has two short loops: once per CTA, not per thread)
+  if (threadIdx.x == 0) {  // (a 64-bit division and two short loops: once per CTA, not per thread)
     lists_s = (job.blist != nullptr && sample_list_plan(job.n, job.max_draws, job.blist_cap, plan_s)) ? 1 : 0;
+    fm_s = make_fastmod((uint32_t)job.n);
+  }
   __syncthreads();
   const ListPlan plan = plan_s;
   const bool lists = lists_s != 0;
   const unsigned int n_buckets = plan.n_buckets;
   const unsigned long long cap_b = plan.cap_b;
   if (!cache && !lists) return;
-  const FastMod fm = make_fastmod((uint32_t)job.n);
-  const unsigned long long nblocks = (job.max_draws + 3) >> 2;
+  const FastMod fm = fm_s;
   uint4* __restrict__ out = reinterpret_cast<uint4*>(job.draws);
   if (!lists) {
     for (unsigned long long q = (unsigned long long)blockIdx.x * 256 + threadIdx.x; q < nblocks;
