@@ -431,6 +431,13 @@ __global__ void __launch_bounds__(T, CPS)
       for (int i = 0; i < GNC_NRED; ++i) mx[i] = 0.0;
       for (unsigned long long l = tid; l < nloc; l += T) {
         double sv[3], tv[3];
+        if (!PC && pf_steps > 0 && (tid & 3) == 0) {  // same register-free look-ahead as in the streamed pass below
+          const unsigned long long la = l + 2 * T;
+          if (la >= ncached && la < nloc && k_lo + la < lv_cap) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(lvg + (size_t)r * lv_cap + k_lo + la));
+          }
+        }
         if (PC)
           load_lv_pc(lv, p_cap, src, dst, edges[k_lo + l], job.inv_scale, sv, tv);
         else
