@@ -101,6 +101,9 @@ struct SampleJob {
   const uint2* edges;            // post 1/2: the reduced set
   const uint32_t* via;           // post 2: L_sampled (out[r] indexes it)
   uint2* gathered;               // post 2: gathered[r] = edges[via[out[r]]]
+  const double* pts8;            // post 2, optional: 64-byte point records (sx sy sz tx ty tz 0 0) ...
+  double* lv_out;                // ... then the line vector of gathered[r] goes to lv_out[c * lv_cap + r], c = 0..5
+  unsigned long long lv_cap;     //     (r < lv_cap): the GNC-TLS kernel finds its line vectors already formed
   uint8_t* flags;                // post 1: [n_points] endpoint flags
   uint32_t* vbits;               // post 1, optional: [ceil(n / 32)] value bitmap, zero on entry and on exit -- the flags
                                  // then come from a streaming pass over the edge list (launch_sample(flag_pass = true))
@@ -126,6 +129,7 @@ struct GncJob {
   double* lv;            // optional SoA scratch [6][lv_cap] for the line vectors beyond that capacity
   unsigned long long lv_cap;
   uint32_t* perm;        // optional [2][lv_cap] index scratch: enables parking sleeping line vectors (k3_rotation.cu)
+  int lv_ready;          // 1: lv[c * lv_cap + k], k < min(K, lv_cap), already hold the line vectors (sampler emit pass)
   double* R_out;         // column-major
   uint8_t* inliers;      // [K] or NULL
   uint8_t* point_flags;  // [n_points] or NULL: endpoints of inlier line vectors

@@ -68,6 +68,9 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   sb.edges = J.edges;
   sb.via = J.L_sampled;
   sb.gathered = J.basic_edges;
+  sb.pts8 = J.pts8;
+  sb.lv_out = J.estimate_scaling ? nullptr : J.lv;  // known scale: the emit pass forms the GNC-TLS line vectors
+  sb.lv_cap = J.lv_cap;
   sb.flags = nullptr;
   sb.n_points = 0;
   sb.active = (J.basic_choose > 0) ? 1 : 0;
@@ -92,6 +95,7 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   g.lv_cap = J.lv_cap;
   g.perm = J.gnc_perm;
   g.pts8 = J.pts8;
+  g.lv_ready = (J.estimate_scaling || sb.identity) ? 0 : 1;  // (unknown scale: pruned subset, rescaled -- formed in the kernel)
   g.R_out = J.R_gnc;
   g.inliers = nullptr;
   g.point_flags = J.rot_flags;

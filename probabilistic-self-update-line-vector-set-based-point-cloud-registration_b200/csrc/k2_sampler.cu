@@ -484,7 +484,24 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_emit_kernel(const SampleJo
               job.flags[e.y] = 1;
             } else if (job.post == 2) {
               // basic line vectors (registration.cc:922-925) as endpoint pairs
-              job.gathered[rank] = job.edges[job.via[v]];
+              const uint2 e = job.edges[job.via[v]];
+              job.gathered[rank] = e;
+              if (job.lv_out && rank < job.lv_cap) {
+                // the line vector itself, formed here (many warps in flight hide the dependent gathers) instead of in
+                // the prologue of the latency-bound GNC-TLS kernel; same operations as its load_lv8
+                const double2* pa = reinterpret_cast<const double2*>(job.pts8 + 8 * (size_t)e.x);
+                const double2* pb = reinterpret_cast<const double2*>(job.pts8 + 8 * (size_t)e.y);
+                const double2 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+                const double2 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+                double* __restrict__ o = job.lv_out + rank;
+                const size_t st = (size_t)job.lv_cap;
+                __stcg(o, b0.x - a0.x);
+                __stcg(o + st, b0.y - a0.y);
+                __stcg(o + 2 * st, b1.x - a1.x);
+                __stcg(o + 3 * st, b1.y - a1.y);
+                __stcg(o + 4 * st, b2.x - a2.x);
+                __stcg(o + 5 * st, b2.y - a2.y);
+              }
             }
             if (rank == count - 1 && job.status) job.status[0] = (q << 2) + l + 1;  // draws consumed
           } else if (job.post == 1 && job.vbits) {

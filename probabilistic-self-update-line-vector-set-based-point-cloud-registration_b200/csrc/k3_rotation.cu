@@ -324,6 +324,8 @@ __global__ void __launch_bounds__(T, CPS)
   S.dst = dst;
   S.edges = edges;
   S.inv_scale = job.inv_scale;
+  // lv_ready: the sampler's emit pass already formed the line vectors k < lv_cap (inv_scale == 1 there)
+  const unsigned long long n_ready = (!PC && job.lv_ready && lvg) ? ((k_hi <= lv_cap) ? nloc : (lv_cap > k_lo ? lv_cap - k_lo : 0ull)) : 0ull;
   // one line vector into its home (shared-memory cache / global SoA scratch), unit weight, H_0 += sv tv^T
   auto stage = [&](unsigned long long l, const double sv[3], const double tv[3]) {
     if (l < ncached) {
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(T, CPS)
       }
       lv[6 * cap + l] = 1.0;
     } else {
-      if (k_lo + l < lv_cap) {
+      if (k_lo + l < lv_cap && l >= n_ready) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           __stcg(lvg + (size_t)r * lv_cap + k_lo + l, sv[r]);
@@ -352,7 +354,21 @@ __global__ void __launch_bounds__(T, CPS)
     // the endpoint gathers are dependent loads (edge -> 4 points): two line vectors per step, and the edges of the
     // next step already in flight while this step's points arrive
     const uint2* __restrict__ el = edges + k_lo;
-    unsigned long long l = tid;
+    // already formed: one coalesced read (two line vectors in flight, register-free look-ahead like the passes)
+    for (unsigned long long l = tid; l < n_ready; l += T) {
+      if ((tid & 3) == 0 && l + 2 * T < n_ready) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(lvg + (size_t)r * lv_cap + k_lo + l + 2 * T));
+      }
+      double sv[3], tv[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        sv[r] = __ldcg(lvg + (size_t)r * lv_cap + k_lo + l);
+        tv[r] = __ldcg(lvg + (size_t)(3 + r) * lv_cap + k_lo + l);
+      }
+      stage(l, sv, tv);
+    }
+    unsigned long long l = n_ready + tid;
     if (l + T < nloc) {
       uint2 ea = el[l], eb = el[l + T];
       for (; l + T < nloc; l += 2 * T) {
