@@ -322,11 +322,11 @@ def main():
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": ((B * gnc_k_mean * 48) / (gnc_ms / ticks / 1e3) / 1e9 / hbm_peak)
                              if ticks and gnc_ms > 0 else None,
-                             "traffic": int((2_416_580_000 + 866_402_560) * B / 296) if B >= 148 else None,
+                             "traffic": int((2_878_978_000 + 694_162_944) * B / 296) if B >= 148 else None,
                              "note": "traffic = dram read + write of one launch at B = 296 "
-                                     "(profiles/r1_ncu_gnc_b296_final.txt): 10x the algorithmic bytes -- the line vectors "
+                                     "(profiles/r1_ncu_gnc_b296_final.txt): 12x the algorithmic bytes -- the line vectors "
                                      "beyond the shared-memory cache are re-read every GNC iteration until they are "
-                                     "parked; FP64 pipe 14 % busy, long-scoreboard bound"},
+                                     "parked; FP64 pipe 18 % busy, long-scoreboard bound"},
                          "hbm_mask_write": {"achieved": mask_bytes / k1_s / 1e9 if k1_s > 0 else None,
                                             "peak": hbm_peak, "unit": "GB/s",
                                             "frac": (mask_bytes / k1_s / 1e9 / hbm_peak) if k1_s > 0 else None,
