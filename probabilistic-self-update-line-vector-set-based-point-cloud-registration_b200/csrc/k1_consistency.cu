@@ -154,7 +154,7 @@ __device__ __forceinline__ void eval_word(const float4* __restrict__ cs, const f
 // as zeros; tiles entirely below it are not touched (callers that need them defined clear the mask
 // first -- psulvsb_consistency_mask does, the engine never reads them).
 template <int R, int TJ>
-__global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R == 2 ? 3 : 4)))
+__global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
     k1_mask_kernel(const K1Job* __restrict__ jobs, int tiles_per_cta) {
   const K1Job& job = jobs[blockIdx.z];
   if (!job.active) return;
@@ -459,7 +459,7 @@ int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, in
   // measured on B200 (256-column tiles, dead row groups skipped): R = 4 wins once there is enough work
   // (N = 100k: 0.68-0.72 of the FP32-pipe peak vs 0.63; 256 x 5k-point problems: 0.59 vs 0.57; 64: 0.56 vs 0.55)
   int variant = pairs >= 5.0e8 ? 4 : (pairs >= 1.0e8 ? 2 : 1);
-  if (force && (force[0] == '1' || force[0] == '2' || force[0] == '4')) variant = force[0] - '0';
+  if (force && (force[0] == '1' || force[0] == '2' || force[0] == '3' || force[0] == '4')) variant = force[0] - '0';
   static const char* tj_env = getenv("PSULVSB_K1_TJ");  // '1': 128-column tiles, '5': 512; default 256
   if (tj_env && tj_env[0] == '5') {
     if (variant == 4) return launch_k1_variant<4, 512>(st, d_jobs, n_jobs, max_n, max_rows);
@@ -468,6 +468,7 @@ int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, in
   }
   const bool wide = tj_env ? (tj_env[0] != '1') : true;  // measured: 256-column tiles halve the barrier stalls
   if (wide) {
+    if (variant == 3) return launch_k1_variant<3, 256>(st, d_jobs, n_jobs, max_n, max_rows);
     if (variant == 4) return launch_k1_variant<4, 256>(st, d_jobs, n_jobs, max_n, max_rows);
     if (variant == 2) return launch_k1_variant<2, 256>(st, d_jobs, n_jobs, max_n, max_rows);
     return launch_k1_variant<1, 256>(st, d_jobs, n_jobs, max_n, max_rows);
