@@ -134,7 +134,8 @@ template <int RL, int R>
 __device__ __forceinline__ void eval_word(const float4* __restrict__ cs, const float4* __restrict__ ct,
                                           const float4 (&ms)[R], const float4 (&mt)[R], const float two_beta2,
                                           const float beta4, uint32_t (&acc)[R], float (&mv)[R]) {
-#pragma unroll 4
+  constexpr int kUnroll = 8;  // measured: 4 -> 0.593, 8 -> 0.602, 16 -> 0.438 (instruction cache) of the FP32-pipe peak on cfg-A batches
+#pragma unroll kUnroll
   for (int jj = 31; jj >= 0; --jj) {
     const float4 sj = cs[jj];
     const float4 tj = ct[jj];
