@@ -99,15 +99,25 @@ __device__ __forceinline__ void pair_eval(const float4 si, const float4 ti, cons
   w = fmaf(-c.kappa, sp, fabsf(v));
 }
 
-// fast path: row point as (-2 x, -2 y, -2 z, |p|^2), column point as (x, y, z, |p|^2)
+// fast path, norm form: with a = |s_i - s_j|^2 and b = |t_i - t_j|^2 the pair is consistent iff
+//   v = (a - b)^2 - (2 beta^2 (a + b) - beta^4) = (a - b - beta^2)^2 - 4 beta^2 b <= 0   (and a + b > beta, see t_fast).
+// Column point as (x, y, z, |p|^2).  Row registers: ms = (-2 x, -2 y, -2 z, c1), mt = (-2 x, -2 y, -2 z, c2) with the
+// per-row constants c1 = |s_i|^2 - |t_i|^2 - beta^2 and c2 = -4 beta^2 |t_i|^2 folded in, so that with
+//   A = |s_j|^2 - 2 s_i.s_j,  B = |t_j|^2 - 2 t_i.t_j   (3 FMA each)
+//   u = (A - B) + c1 = a - b - beta^2   (2 FADD),   w = -4 beta^2 B + c2 = -4 beta^2 b   (1 FMA),   v = u u + w   (1 FMA):
+// 8 FMA + 2 FADD per pair (adding the row norms per pair and forming a + b cost two more).  Every partial sum stays
+// below 9 Cmax^2 and the constants carry two more float roundings of 6 Cmax^2: inside the E, ED, ES of
+// make_k1_consts (80 / 172 / 184 mu Cmax^2 against ~41 / ~120 needed; the w term errs by 4 beta^2 E + 60 mu beta^2
+// Cmax^2, less than the 2 beta^2 ES + 2 mu (48 beta^2 Cmax^2 + beta^4) budgeted for r); |u| <= |a - b| + beta^2 is
+// accounted for in Dlim.
 __device__ __forceinline__ float pair_fast(const float4 ms, const float4 mt, const float4 sj, const float4 tj,
-                                           const float two_beta2, const float beta4) {
-  const float A = fmaf(ms.x, sj.x, fmaf(ms.y, sj.y, fmaf(ms.z, sj.z, ms.w + sj.w)));
-  const float B = fmaf(mt.x, tj.x, fmaf(mt.y, tj.y, fmaf(mt.z, tj.z, mt.w + tj.w)));
-  const float D = A - B;
-  const float S = A + B;
-  const float r = fmaf(two_beta2, S, -beta4);
-  return fmaf(D, D, -r);
+                                           const float neg_four_beta2, const float beta4) {
+  (void)beta4;
+  const float A = fmaf(ms.x, sj.x, fmaf(ms.y, sj.y, fmaf(ms.z, sj.z, sj.w)));
+  const float B = fmaf(mt.x, tj.x, fmaf(mt.y, tj.y, fmaf(mt.z, tj.z, tj.w)));
+  const float u = (A - B) + ms.w;
+  const float w = fmaf(neg_four_beta2, B, mt.w);
+  return fmaf(u, u, w);
 }
 
 // Slow path (rare): the mask word of row i, columns cb .. cb+31, redone by the whole warp -- lane b
@@ -214,10 +224,11 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
     const bool ok = irow[r] < row_end;
     const float4 a = ok ? src[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 b = ok ? dst[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
-    ms[r] = make_float4(-2.f * a.x, -2.f * a.y, -2.f * a.z, a.w);
-    mt[r] = make_float4(-2.f * b.x, -2.f * b.y, -2.f * b.z, b.w);
+    const float beta2 = 0.5f * c.two_beta2;
+    ms[r] = make_float4(-2.f * a.x, -2.f * a.y, -2.f * a.z, (a.w - b.w) - beta2);        // .w = c1
+    mt[r] = make_float4(-2.f * b.x, -2.f * b.y, -2.f * b.z, -2.f * c.two_beta2 * b.w);  // .w = c2
   }
-  const float two_beta2 = c.two_beta2, beta4 = c.beta4, t_fast = c.t_fast;
+  const float two_beta2 = -2.f * c.two_beta2, beta4 = c.beta4, t_fast = c.t_fast;  // (pair_fast takes -4 beta^2)
   const int warp_row_min = row0 + (tid & ~31);  // smallest row this warp owns (r = 0)
 
   uint32_t cnt[R];
@@ -426,7 +437,7 @@ K1Consts make_k1_consts(double beta, double coord_bound) {
   const double ED = 2.0 * E + 12.0 * mu * C2;      // |D_c - D*|
   const double ES = 2.0 * E + 24.0 * mu * C2;      // |S_c - S*|
   const double c0 = ED * ED + 2.0 * b2 * ES + 2.0 * mu * (48.0 * b2 * C2 + b2 * b2);
-  const double Dlim = ED + sqrt(ED * ED + 48.0 * b2 * C2 + c0);
+  const double Dlim = ED + sqrt(ED * ED + 48.0 * b2 * C2 + c0) + b2;  // (+ beta^2: the squared term is a - b - beta^2)
   const double Terr = 2.0 * Dlim * ED + c0;
   k.beta4 = (float)(b2 * b2);
   // a + b <= beta (where the sign of v is not the answer) implies S* <= beta^2, hence v* in
