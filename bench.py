@@ -46,9 +46,9 @@ K1_SLOTS_PER_PAIR = 16
 K1_TRAFFIC_BYTES_B64 = 79_636_736 + 128_738_304
 # the same at --batch 256 (profiles/r1_ncu_k1_mask_b256_final.txt: 336.4 MB read + 692.0 MB written; algorithmic
 # output 4 x 204.8 MB): the default batch
-# and at the default --batch 296 (profiles/r1_ncu_k1_mask_b296_final.txt: 472.2 MB read + 898.9 MB written; the
+# and at the default --batch 296 (profiles/r1_ncu_k1_mask_b296_final.txt: 473.5 MB read + 901.7 MB written; the
 # algorithmic output is 296 x 5000 x 160 words = 947 MB incl. row padding and the untouched lower triangle)
-K1_TRAFFIC_BYTES = {64: K1_TRAFFIC_BYTES_B64, 256: 336_378_368 + 691_986_688, 296: 472_242_176 + 898_935_296}
+K1_TRAFFIC_BYTES = {64: K1_TRAFFIC_BYTES_B64, 256: 336_378_368 + 691_986_688, 296: 473_451_264 + 901_693_952}
 # (other batch sizes: scaled from the 296 capture -- the kernel's traffic is per registration)
 
 
