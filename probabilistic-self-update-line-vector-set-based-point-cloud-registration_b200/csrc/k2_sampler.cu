@@ -25,6 +25,7 @@
 //            optional fused post-processing for the batch engine (endpoint flags / edge gather).
 // Kernels take device-resident SampleJob arrays (one job per registration in the batch engine,
 // whose control kernels rewrite n / count / event between ticks).
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -94,7 +95,8 @@ __device__ __forceinline__ uint32_t draw_value(uint32_t word, const FastMod& f) 
 
 // optional cache of the draw values (SampleJob::draws, one u32 per draw) so that the bucket CTAs stream
 // them instead of re-running Philox; windows longer than draws_cap fall back to recomputation
-__global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __restrict__ jobs) {
+// list_cap_test: 0, or (tests only) a smaller capacity the lists are filled to, which forces the overflow fallback
+__global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __restrict__ jobs, unsigned int list_cap_test) {
   const SampleJob& job = jobs[blockIdx.y];
   if (!job.active || job.identity) return;
   const bool cache = job.draws != nullptr && job.max_draws <= job.draws_cap;
@@ -111,7 +113,8 @@ __global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __re
   const ListPlan plan = plan_s;
   const bool lists = lists_s != 0;
   const unsigned int n_buckets = plan.n_buckets;
-  const unsigned long long cap_b = plan.cap_b;
+  const unsigned long long cap_b = plan.cap_b;  // region stride; cap_fill: how far a region may be filled
+  const unsigned long long cap_fill = (list_cap_test != 0u && list_cap_test < plan.cap_b) ? list_cap_test : plan.cap_b;
   if (!cache && !lists) return;
   const FastMod fm = fm_s;
   uint4* __restrict__ out = reinterpret_cast<uint4*>(job.draws);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __re
         if (vv[u][l] == 0xFFFFFFFFu) continue;
         const uint32_t b = list_bucket(vv[u][l], plan);
         const unsigned long long pos = (unsigned long long)base[b] + wh[wid][b] + rk[u][l];
-        if (pos < cap_b)
+        if (pos < cap_fill)
           job.blist[(unsigned long long)b * cap_b + pos] =
               (uint32_t)((((q << 2) + l) << plan.w_bits) | (unsigned long long)(vv[u][l] - b * plan.width));
         else
@@ -596,7 +599,9 @@ int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned
   const unsigned long long cap = (unsigned long long)(148 * 16) / (unsigned long long)(n_jobs < 64 ? n_jobs : 64) + 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  sample_draws_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), 256, 0, st>>>(d_jobs);
+  unsigned int list_cap_test = 0u;  // PSULVSB_SAMPLE_LIST_CAP_TEST: exercise the list-overflow fallback (tests only)
+  if (const char* e = getenv("PSULVSB_SAMPLE_LIST_CAP_TEST")) list_cap_test = (unsigned int)atoi(e);
+  sample_draws_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), 256, 0, st>>>(d_jobs, list_cap_test);
   PSU_CHECK_LAUNCH("sample_draws_kernel");
   // bucket CTAs: one per SM at a time; a CTA walks several buckets when the batch alone fills the GPU
   unsigned long long nb = (n_bound + SMP_BW - 1) / SMP_BW;

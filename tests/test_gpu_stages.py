@@ -47,6 +47,21 @@ def test_sampler_replays_rejection_sampling(P, O, n, count):
         assert consumed == want_consumed          # same stream position afterwards
 
 
+def test_sampler_list_overflow_falls_back_to_the_walk(P, O, monkeypatch):
+    """The per-bucket draw lists have room for the mean + 10 sigma of the uniform draws; should one ever overflow, the
+    bucket pass walks the whole window instead.  Forced here by filling the lists only to 100 entries."""
+    monkeypatch.setenv("PSULVSB_SAMPLE_LIST_CAP_TEST", "100")
+    st = P["stages"]
+    for n, count in [(627562, 62756), (150000, 75000)]:
+        got, consumed = st.sample(7, 1, 3, n, count)
+        want, want_consumed = O.sample_without_replacement(7, 1, 3, n, count)
+        assert np.array_equal(got, want) and consumed == want_consumed
+    monkeypatch.delenv("PSULVSB_SAMPLE_LIST_CAP_TEST")
+    got, consumed = st.sample(7, 1, 3, 627562, 62756)          # and the lists work again afterwards (counters were reset)
+    want, want_consumed = O.sample_without_replacement(7, 1, 3, 627562, 62756)
+    assert np.array_equal(got, want) and consumed == want_consumed
+
+
 def test_sampler_small_budget_reports_failure(P):
     got, consumed = P["stages"].sample(5, 1, 0, 1000, 1000, max_draws=1200)
     assert consumed == 0
