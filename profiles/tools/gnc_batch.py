@@ -9,7 +9,6 @@ import torch
 
 sys.path.insert(0, ".")
 import psulvsb_b200  # noqa: E402,F401
-from oracle import oracle as O  # noqa: E402
 from psulvsb_b200 import capi, stages, synth  # noqa: E402
 
 
@@ -19,7 +18,10 @@ def main():
     use_lv = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
     use_perm = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
     pair = synth.make_pair(5000, 0.95, 3, outliers="fpfh")
-    pi, pj = O.reduced_set(pair["src"], pair["dst"], 0.1)
+    r = stages.consistency_mask(pair["src"], pair["dst"], 0.1)  # the reduced set from the product's own stage 1
+    e_all, _ = stages.compact_edges(r["mask"], r["row_counts"], r["n"], r["stride"])
+    e_all = e_all.cpu().numpy()
+    pi, pj = e_all[:, 0], e_all[:, 1]
     rng = np.random.default_rng(0)
     d_src, d_dst = stages.to_device_points(pair["src"]), stages.to_device_points(pair["dst"])
     edges = np.empty((B, K, 2), dtype=np.int32)

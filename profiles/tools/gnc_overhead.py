@@ -2,9 +2,11 @@ import sys, numpy as np, torch
 sys.path.insert(0,'/root/repo')
 import psulvsb_b200
 from psulvsb_b200 import capi, stages, synth
-from oracle import oracle as O
 pair = synth.make_pair(5000, 0.95, 3)
-pi, pj = O.reduced_set(pair['src'], pair['dst'], 0.1)
+r = stages.consistency_mask(pair['src'], pair['dst'], 0.1)  # the reduced set from the product's own stage 1
+e_all, _ = stages.compact_edges(r['mask'], r['row_counts'], r['n'], r['stride'])
+e_all = e_all.cpu().numpy()
+pi, pj = e_all[:, 0], e_all[:, 1]
 rng = np.random.default_rng(0)
 d_src, d_dst = stages.to_device_points(pair['src']), stages.to_device_points(pair['dst'])
 L = capi.lib()

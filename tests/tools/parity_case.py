@@ -1,5 +1,5 @@
-"""Dump the local traces (GPU vs oracle) of single problems of parity_sweep.py around their first difference.
-    python profiles/tools/parity_case.py 183 55 ..."""
+"""TEST INFRASTRUCTURE (imports the CPU oracle as the checker).  Dump the local traces (GPU vs oracle) of single problems of parity_sweep.py around their first difference.
+    python tests/tools/parity_case.py 183 55 ..."""
 import sys
 
 import numpy as np
@@ -8,7 +8,8 @@ sys.path.insert(0, ".")
 import psulvsb_b200  # noqa: E402,F401
 from oracle import oracle as O  # noqa: E402
 from psulvsb_b200 import capi, synth  # noqa: E402
-from profiles.tools.parity_sweep import first_difference  # noqa: E402
+sys.path.insert(0, "tests/tools")
+from parity_sweep import first_difference  # noqa: E402
 
 
 def main():

@@ -1,4 +1,4 @@
-"""Parity sweep: the CUDA solver (C ABI) vs the CPU oracle on many random problems with the same replayed
+"""TEST INFRASTRUCTURE (imports the CPU oracle as the checker).  Parity sweep: the CUDA solver (C ABI) vs the CPU oracle on many random problems with the same replayed
 sample stream.  A run is IDENTICAL when every integer field of every local / host trace record, the final
 inlier set, and R / t / scale of every local iteration agree (R within 1e-5 rad, t within 1e-5).
 
@@ -9,7 +9,7 @@ Runs are reported in three groups:
                 and the (1.0, 1.0) round's clique is one of many maximum cliques -- no parity is defined there,
                 the sweep only reports how often the runs coincide anyway;
   refused       PSULVSB_ERR_UNSUPPORTED.
-Run on a GPU box:   python profiles/tools/parity_sweep.py [n_problems]
+Run on a GPU box:   python tests/tools/parity_sweep.py [n_problems]
 """
 import sys
 
