@@ -63,6 +63,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -120,21 +123,30 @@ __device__ __forceinline__ float pair_fast(const float4 ms, const float4 mt, con
   return fmaf(u, u, w);
 }
 
+// What the slow path needs, staged once per CTA in shared memory: the path is rare per pair but a cfg-A batch
+// takes it for 1.7 % of the mask words, and reading these through the job record (pointer -> point: two
+// dependent global loads per call) made it 19 % of the kernel's warp time (ncu source page, long scoreboard).
+struct K1Slow {
+  K1Consts c;
+  const double* src64;
+  const double* dst64;
+  int n;
+};
+
 // Slow path (rare): the mask word of row i, columns cb .. cb+31, redone by the whole warp -- lane b
 // takes pair (i, cb + b) in the accurate difference form; what falls inside ITS rigorous band is
 // decided in FP64 with the reference's operation order; the 32 verdicts come back as one ballot.
-__device__ __noinline__ uint32_t slow_word_coop(const K1Job& job, int i, int cb, const float4 sj, const float4 tj,
-                                                unsigned int& nborder) {
+// (si, ti) = the row's packed point, broadcast from its owner lane's registers (.w unused here).
+__device__ __noinline__ uint32_t slow_word_coop(const K1Slow& sl, int i, int cb, const float4 si, const float4 ti,
+                                                const float4 sj, const float4 tj, unsigned int& nborder) {
   const int lane = threadIdx.x & 31;
-  const float4 si = job.src[i];
-  const float4 ti = job.dst[i];
   float v, w, sp;
-  pair_eval(si, ti, sj, tj, job.c, v, w, sp);
+  pair_eval(si, ti, sj, tj, sl.c, v, w, sp);
   bool in = (__float_as_uint(v) >> 31) != 0u;
   const int j = cb + lane;
-  if ((!(w > job.c.w_thr) || !(sp > 0.f)) && j < job.n && j > i) {
+  if ((!(w > sl.c.w_thr) || !(sp > 0.f)) && j < sl.n && j > i) {
     ++nborder;
-    in = exact_consistent(job.src64, job.dst64, i, j, job.c.beta);
+    in = exact_consistent(sl.src64, sl.dst64, i, j, sl.c.beta);
   }
   return __ballot_sync(0xffffffffu, in);
 }
@@ -158,12 +170,35 @@ __device__ __forceinline__ void eval_word(const float4* __restrict__ cs, const f
   }
 }
 
+// Position (in units of 32 rows) of warp w's rows inside row group r of the CTA's row block.  Along the
+// diagonal a warp's work in the tile where group r is partially live is 8 - pos words per tile, so the
+// positions are permuted per group to give every warp (nearly) the same total over the diagonal tiles of a
+// chunk: pos0 + pos1 = 7 for R <= 2, pos0 + pos1 + pos2 in {10, 11} for R >= 3 (identity positions leave
+// warp 0 with 8 + 16 + 24 words against 1 + 9 + 17 for warp 7).
+template <int R>
+__device__ __forceinline__ int k1_warp_pos(int r, int w) {
+  static_assert(K1_THREADS == 256, "the position tables are for 8 warps per CTA");
+  if (r == 0) return w;
+  if (R <= 2) return 7 - w;
+  if (r == 1) return (w < 4 ? 7 : 14) - 2 * w;  // 7 5 3 1 6 4 2 0
+  if (r == 2) return (w + 4) & 7;               // 4 5 6 7 0 1 2 3
+  return 7 - ((w + 4) & 7);
+}
+
 // One CTA = a block of TI = 256 R rows x a chunk of `tiles_per_cta` column tiles (TJ columns each),
 // starting at the tile that holds the diagonal of the row block; the column tiles stream through a
-// two-stage shared-memory ring filled by 1-D TMA bulk copies, so the copy of tile k+1 overlaps the
-// arithmetic of tile k.  Words that lie entirely below the diagonal inside a live tile are written
+// K1_STAGES-deep shared-memory ring filled by 1-D TMA bulk copies.  Warps are not coupled by a CTA barrier:
+// a warp waits for the "full" mbarrier of its next tile and arrives on the stage's "empty" mbarrier when it
+// is done with it; thread 0 refills a stage once all eight warps have left it (with chunks of at most
+// K1_STAGES tiles -- the cfg-A batches -- every tile is requested up front and nobody waits for anybody).
+// Words that lie entirely below the diagonal inside a live tile are written
 // as zeros; tiles entirely below it are not touched (callers that need them defined clear the mask
 // first -- psulvsb_consistency_mask does, the engine never reads them).
+template <int TJ>
+struct K1Ring {
+  static constexpr int STAGES = TJ <= 128 ? 8 : (TJ <= 256 ? 4 : 2);  // 32 KB of tiles per CTA
+};
+
 template <int R, int TJ>
 __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
     k1_mask_kernel(const K1Job* __restrict__ jobs, int tiles_per_cta) {
@@ -179,9 +214,13 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
   unsigned long long* __restrict__ border_count = job.border;
   constexpr int TI = K1_THREADS * R;
   constexpr int WORDS = TJ / 32;
-  __shared__ __align__(128) float4 cs[2][TJ];
-  __shared__ __align__(128) float4 ct[2][TJ];
-  __shared__ __align__(8) uint64_t bar[2];
+  constexpr int S = K1Ring<TJ>::STAGES;
+  constexpr int NWARPS = K1_THREADS / 32;
+  __shared__ __align__(128) float4 cs[S][TJ];
+  __shared__ __align__(128) float4 ct[S][TJ];
+  __shared__ __align__(8) uint64_t bar[S];        // "full": the tile's bytes have landed
+  __shared__ __align__(8) uint64_t bar_empty[S];  // "empty": all warps are done with the stage
+  __shared__ __align__(8) K1Slow slow;
 
   const int row0 = row_begin + blockIdx.y * TI;
   if (row0 >= row_end) return;  // grid is sized for the largest job
@@ -193,18 +232,25 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
   const int tid = threadIdx.x, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&bar[s], 1);
+      mbar_init(&bar_empty[s], NWARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    slow.c = c;
+    slow.src64 = job.src64;
+    slow.dst64 = job.dst64;
+    slow.n = n;
   }
   // slots past the end of the arrays keep a finite dummy point; their bits are masked off below
-  for (int k = tid; k < 2 * TJ; k += K1_THREADS) {
+  for (int k = tid; k < S * TJ; k += K1_THREADS) {
     (&cs[0][0])[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     (&ct[0][0])[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  auto issue = [&](int k) {  // thread 0: bulk copies of tile t_begin + k into stage k & 1
-    const int st = k & 1;
+  auto issue = [&](int k) {  // thread 0: bulk copies of tile t_begin + k into stage k % S
+    const int st = k % S;
     const int col0 = (t_begin + k) * TJ;
     const uint32_t bytes = (uint32_t)min(TJ, n - col0) * (uint32_t)sizeof(float4);
     // order the generic-proxy accesses of the stage's previous use before the async-proxy writes
@@ -213,14 +259,17 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
     tma_load_1d(cs[st], src + col0, bytes, &bar[st]);
     tma_load_1d(ct[st], dst + col0, bytes, &bar[st]);
   };
-  if (tid == 0) issue(0);
+  if (tid == 0)
+    for (int k = 0; k < S && k < nt; ++k) issue(k);
 
   // row points -> registers, pre-scaled by -2 for the norm form (overlaps the bulk copy)
   float4 ms[R], mt[R];
   int irow[R];
+  int grp_row_min[R];  // smallest row of this warp in row group r (warp-uniform, increasing in r)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    irow[r] = row0 + tid + r * K1_THREADS;
+    grp_row_min[r] = row0 + r * K1_THREADS + 32 * k1_warp_pos<R>(r, tid >> 5);
+    irow[r] = grp_row_min[r] + lane;
     const bool ok = irow[r] < row_end;
     const float4 a = ok ? src[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 b = ok ? dst[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -229,7 +278,7 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
     mt[r] = make_float4(-2.f * b.x, -2.f * b.y, -2.f * b.z, -2.f * c.two_beta2 * b.w);  // .w = c2
   }
   const float two_beta2 = -2.f * c.two_beta2, beta4 = c.beta4, t_fast = c.t_fast;  // (pair_fast takes -4 beta^2)
-  const int warp_row_min = row0 + (tid & ~31);  // smallest row this warp owns (r = 0)
+  const int warp_row_min = grp_row_min[0];  // smallest row this warp owns
 
   uint32_t cnt[R];
 #pragma unroll
@@ -237,9 +286,12 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
   unsigned int nborder = 0;
 
   for (int k = 0; k < nt; ++k) {
-    const int st = k & 1;
-    if (tid == 0 && k + 1 < nt) issue(k + 1);  // stage (k+1)&1 was released by the barrier ending iteration k-1
-    mbar_wait(&bar[st], (k >> 1) & 1);
+    const int st = k % S;
+    if (tid == 0 && k >= 1 && k + S - 1 < nt) {  // refill the stage of tile k-1 once every warp has left it
+      mbar_wait(&bar_empty[(k - 1) % S], ((k - 1) / S) & 1);
+      issue(k + S - 1);
+    }
+    mbar_wait(&bar[st], (k / S) & 1);
     const int col0 = (t_begin + k) * TJ;
     for (int wj = 0; wj < WORDS; ++wj) {
       const int cb = col0 + wj * 32;  // first column of this word
@@ -257,13 +309,11 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
         acc[r] = 0u;
         mv[r] = 3.0e38f;
       }
-      // row group r of this warp (rows warp_row_min + 256 r ..) still has live columns in this word iff
-      // cb + 31 > its smallest row; the groups die in the order R-1, ..., 0 along the diagonal tile
-      int n_live = R;
-      if (R > 1) {
-        n_live = (cb + 31 - warp_row_min + K1_THREADS - 1) / K1_THREADS;  // >= 1 here
-        n_live = n_live > R ? R : n_live;
-      }
+      // row group r of this warp still has live columns in this word iff cb + 31 > its smallest row; the
+      // groups die in the order R-1, ..., 0 along the diagonal tiles (grp_row_min increases with r)
+      int n_live = 1;
+#pragma unroll
+      for (int r = 1; r < R; ++r) n_live += (cb + 31 > grp_row_min[r]) ? 1 : 0;
       const float4* cw = &cs[st][wj * 32];
       const float4* tw = &ct[st][wj * 32];
       if (n_live == R)
@@ -290,7 +340,14 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
           const int owner = __ffs(flagged) - 1;
           flagged &= flagged - 1;
           const int oi = __shfl_sync(0xffffffffu, i, owner);
-          const uint32_t res = slow_word_coop(job, oi, cb, sl, tl, nborder);
+          // the owner's row point back from its pre-scaled registers (x -2 and x -0.5 are exact)
+          const float4 si = make_float4(-0.5f * __shfl_sync(0xffffffffu, ms[r].x, owner),
+                                        -0.5f * __shfl_sync(0xffffffffu, ms[r].y, owner),
+                                        -0.5f * __shfl_sync(0xffffffffu, ms[r].z, owner), 0.f);
+          const float4 ti = make_float4(-0.5f * __shfl_sync(0xffffffffu, mt[r].x, owner),
+                                        -0.5f * __shfl_sync(0xffffffffu, mt[r].y, owner),
+                                        -0.5f * __shfl_sync(0xffffffffu, mt[r].z, owner), 0.f);
+          const uint32_t res = slow_word_coop(slow, oi, cb, si, ti, sl, tl, nborder);
           if (lane == owner) word = res & live;
         }
         if (row_ok) {
@@ -299,7 +356,8 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
         }
       }
     }
-    __syncthreads();  // every warp is done with stage st
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_empty[st]);  // this warp is done with stage st
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
