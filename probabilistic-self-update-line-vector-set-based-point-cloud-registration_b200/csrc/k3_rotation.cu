@@ -711,19 +711,28 @@ __global__ void __launch_bounds__(T, CPS)
         }
         // the i-th deep sleeper inside the new range trades places with the i-th survivor behind it
         const int n_swap = base_h < base_m ? base_h : base_m;  // (equal by construction)
+        // (every load of a swap is issued before its first store: with load -> store per array the seven
+        // arrays cost seven global round trips per swap, 10 % of the kernel's warp time in the ncu source page)
         for (int i = tid; i < n_swap; i += T) {
           const int a = (int)holes[i], b = (int)movers[i];
+          const bool a_sm = a < (int)ncached, b_sm = b < (int)ncached;
+          const uint32_t qa = perm[k_lo + a], qb = perm[k_lo + b];
+          double va[7], vb[7];
 #pragma unroll
           for (int c = 0; c < 7; ++c) {
             // (shared-memory cache, or the L2-level scratch the passes read with ld.cg / write with st.cg)
+            const double* ga = (c < 6 ? lvg + (size_t)c * lv_cap : gw) + k_lo + a;
+            const double* gb = (c < 6 ? lvg + (size_t)c * lv_cap : gw) + k_lo + b;
+            va[c] = a_sm ? lv[(size_t)c * cap + a] : __ldcg(ga);
+            vb[c] = b_sm ? lv[(size_t)c * cap + b] : __ldcg(gb);
+          }
+#pragma unroll
+          for (int c = 0; c < 7; ++c) {
             double* ga = (c < 6 ? lvg + (size_t)c * lv_cap : gw) + k_lo + a;
             double* gb = (c < 6 ? lvg + (size_t)c * lv_cap : gw) + k_lo + b;
-            const double va = (a < (int)ncached) ? lv[(size_t)c * cap + a] : __ldcg(ga);
-            const double vb = (b < (int)ncached) ? lv[(size_t)c * cap + b] : __ldcg(gb);
-            if (a < (int)ncached) lv[(size_t)c * cap + a] = vb; else __stcg(ga, vb);
-            if (b < (int)ncached) lv[(size_t)c * cap + b] = va; else __stcg(gb, va);
+            if (a_sm) lv[(size_t)c * cap + a] = vb[c]; else __stcg(ga, vb[c]);
+            if (b_sm) lv[(size_t)c * cap + b] = va[c]; else __stcg(gb, va[c]);
           }
-          const uint32_t qa = perm[k_lo + a], qb = perm[k_lo + b];
           perm[k_lo + a] = qb;
           perm[k_lo + b] = qa;
         }
