@@ -46,9 +46,9 @@ K1_SLOTS_PER_PAIR = 16
 K1_TRAFFIC_BYTES_B64 = 79_636_736 + 128_738_304
 # the same at --batch 256 (profiles/r1_ncu_k1_mask_b256_final.txt: 336.4 MB read + 692.0 MB written; algorithmic
 # output 4 x 204.8 MB): the default batch
-# and at the default --batch 296 (profiles/r1_ncu_k1_mask_b296_final.txt: 473.5 MB read + 901.7 MB written; the
+# and at the default --batch 296 (profiles/r1_ncu_step_b296_final.txt: 472.1 MB read + 899.6 MB written; the
 # algorithmic output is 296 x 5000 x 160 words = 947 MB incl. row padding and the untouched lower triangle)
-K1_TRAFFIC_BYTES = {64: K1_TRAFFIC_BYTES_B64, 256: 336_378_368 + 691_986_688, 296: 473_451_264 + 901_693_952}
+K1_TRAFFIC_BYTES = {64: K1_TRAFFIC_BYTES_B64, 256: 336_378_368 + 691_986_688, 296: 472_137_000 + 899_623_000}
 # (other batch sizes: scaled from the 296 capture -- the kernel's traffic is per registration)
 
 
@@ -322,9 +322,9 @@ def main():
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": ((B * gnc_k_mean * 48) / (gnc_ms / ticks / 1e3) / 1e9 / hbm_peak)
                              if ticks and gnc_ms > 0 else None,
-                             "traffic": int((2_878_978_000 + 694_162_944) * B / 296) if B >= 148 else None,
+                             "traffic": int((2_886_296_000 + 692_751_000) * B / 296) if B >= 148 else None,
                              "note": "traffic = dram read + write of one launch at B = 296 "
-                                     "(profiles/r1_ncu_gnc_b296_final.txt): 12x the algorithmic bytes -- the line vectors "
+                                     "(profiles/r1_ncu_step_b296_final.txt): 12x the algorithmic bytes -- the line vectors "
                                      "beyond the shared-memory cache are re-read every GNC iteration until they are "
                                      "parked; FP64 pipe 18 % busy, long-scoreboard bound"},
                          "hbm_mask_write": {"achieved": mask_bytes / k1_s / 1e9 if k1_s > 0 else None,
