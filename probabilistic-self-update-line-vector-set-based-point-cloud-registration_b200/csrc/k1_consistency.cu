@@ -37,6 +37,9 @@ namespace psulvsb {
 namespace {
 
 constexpr int K1_THREADS = 256;
+#ifndef K1_R4_CTAS
+#define K1_R4_CTAS 2  // measured with the packed fast path: 3 CTAs per SM (80 registers, 36 B of spills) 2.19 ms vs 2.05 ms
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -151,21 +154,77 @@ __device__ __noinline__ uint32_t slow_word_coop(const K1Slow& sl, int i, int cb,
   return __ballot_sync(0xffffffffu, in);
 }
 
+// Packed FP32 (Blackwell FFMA2 / FADD2: two FP32 operations per lane and issue slot).  Rows travel in pairs --
+// (row 2p, row 2p+1) in the two halves of a 64-bit register -- and the column values enter as scalar broadcasts
+// (ptxas folds a {x, x} operand into the instruction's .F32 operand form: no duplicated tile, no MOV).  Each half is
+// an IEEE round-to-nearest fma / add: v is bit for bit what pair_fast computes.
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 bc2(const float x) { return make_float2(x, x); }
+
+// pair_fast for rows (r0, r1) against one column: 8 FFMA2 + 1 FADD2 + 1 FFMA2 (A - B as fma(B, -1, A): one rounding,
+// the same value as the FADD) = 10 packed instructions for two pairs
+__device__ __forceinline__ float2 pair_fast2(const float4 ms0, const float4 ms1, const float4 mt0, const float4 mt1,
+                                             const float4 sj, const float4 tj, const float neg_four_beta2) {
+  const float2 A = fma2(make_float2(ms0.x, ms1.x), bc2(sj.x),
+                        fma2(make_float2(ms0.y, ms1.y), bc2(sj.y), fma2(make_float2(ms0.z, ms1.z), bc2(sj.z), bc2(sj.w))));
+  const float2 B = fma2(make_float2(mt0.x, mt1.x), bc2(tj.x),
+                        fma2(make_float2(mt0.y, mt1.y), bc2(tj.y), fma2(make_float2(mt0.z, mt1.z), bc2(tj.z), bc2(tj.w))));
+  const float2 u = add2(fma2(B, bc2(-1.f), A), make_float2(ms0.w, ms1.w));
+  const float2 w = fma2(bc2(neg_four_beta2), B, make_float2(mt0.w, mt1.w));
+  return fma2(u, u, w);
+}
+
 // the 32 pairs (row r, columns of one mask word) for the first RL of a thread's R rows
 template <int RL, int R>
 __device__ __forceinline__ void eval_word(const float4* __restrict__ cs, const float4* __restrict__ ct,
                                           const float4 (&ms)[R], const float4 (&mt)[R], const float two_beta2,
                                           const float beta4, uint32_t (&acc)[R], float (&mv)[R]) {
   constexpr int kUnroll = 8;  // measured: 4 -> 0.593, 8 -> 0.602, 16 -> 0.438 (instruction cache) of the FP32-pipe peak on cfg-A batches
+  if constexpr (R % 2 == 0) {
+    // packed: row pairs (0, 1), (2, 3); a half-live pair evaluates its dead row too (its bits are masked off)
+    constexpr int PL = (RL + 1) / 2;
 #pragma unroll kUnroll
-  for (int jj = 31; jj >= 0; --jj) {
-    const float4 sj = cs[jj];
-    const float4 tj = ct[jj];
+    for (int jj = 31; jj >= 0; --jj) {
+      const float4 sj = cs[jj];
+      const float4 tj = ct[jj];
 #pragma unroll
-    for (int r = 0; r < RL; ++r) {
-      const float v = pair_fast(ms[r], mt[r], sj, tj, two_beta2, beta4);
-      acc[r] = __funnelshift_l(__float_as_uint(v), acc[r], 1);  // bit jj <- sign(v)
-      mv[r] = fminf(mv[r], fabsf(v));
+      for (int p = 0; p < PL; ++p) {
+        const float2 v = pair_fast2(ms[2 * p], ms[2 * p + 1], mt[2 * p], mt[2 * p + 1], sj, tj, two_beta2);
+        acc[2 * p] = __funnelshift_l(__float_as_uint(v.x), acc[2 * p], 1);  // bit jj <- sign(v)
+        acc[2 * p + 1] = __funnelshift_l(__float_as_uint(v.y), acc[2 * p + 1], 1);
+        mv[2 * p] = fminf(mv[2 * p], fabsf(v.x));
+        mv[2 * p + 1] = fminf(mv[2 * p + 1], fabsf(v.y));
+      }
+    }
+  } else {
+#pragma unroll kUnroll
+    for (int jj = 31; jj >= 0; --jj) {
+      const float4 sj = cs[jj];
+      const float4 tj = ct[jj];
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        const float v = pair_fast(ms[r], mt[r], sj, tj, two_beta2, beta4);
+        acc[r] = __funnelshift_l(__float_as_uint(v), acc[r], 1);  // bit jj <- sign(v)
+        mv[r] = fminf(mv[r], fabsf(v));
+      }
     }
   }
 }
@@ -200,7 +259,7 @@ struct K1Ring {
 };
 
 template <int R, int TJ>
-__global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? 2 : (R >= 2 ? 3 : 4)))
+__global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3 : 4)))
     k1_mask_kernel(const K1Job* __restrict__ jobs, int tiles_per_cta) {
   const K1Job& job = jobs[blockIdx.z];
   if (!job.active) return;
