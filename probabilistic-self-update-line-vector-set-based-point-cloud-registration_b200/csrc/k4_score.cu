@@ -56,6 +56,19 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 
+// packed FP32 helpers (Blackwell FFMA2; ptxas folds a {x, x} operand into the .F32 broadcast operand form)
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 bc2(const float x) { return make_float2(x, x); }
+
 struct ScoreArgs {
   double scale, tau;
   double csrc[3], cdst[3];  // centres the float4 tiles were packed with
@@ -140,14 +153,30 @@ __global__ void __launch_bounds__(SB_THREADS)
     for (int j = 0; j < np; ++j) {
       const float4 p = ps[st][j];
       const float4 q = qs[st][j];
+      // packed FP32 (FFMA2): hypotheses (k, k+1) in the halves of a 64-bit register pair, the point's coordinates as
+      // scalar-broadcast operands; tf - q as fma(q, -1, tf) (one rounding: the FADD's value).  15 packed
+      // instructions per two (hypothesis, point) units instead of 30, every half the IEEE result of the scalar
+      // form the fix-up below re-evaluates.
+      static_assert(SB_HPT % 2 == 0, "hypotheses are scored in pairs");
 #pragma unroll
-      for (int k = 0; k < SB_HPT; ++k) {
-        const float d0 = fmaf(Rf[k][0], p.x, fmaf(Rf[k][1], p.y, fmaf(Rf[k][2], p.z, tf[k][0] - q.x)));
-        const float d1 = fmaf(Rf[k][3], p.x, fmaf(Rf[k][4], p.y, fmaf(Rf[k][5], p.z, tf[k][1] - q.y)));
-        const float d2 = fmaf(Rf[k][6], p.x, fmaf(Rf[k][7], p.y, fmaf(Rf[k][8], p.z, tf[k][2] - q.z)));
-        const float u = fmaf(d2, d2, fmaf(d1, d1, fmaf(d0, d0, -tau2)));
-        cnt[k] += (int)(__float_as_uint(u) >> 31);
-        mn[k] = fminf(mn[k], fabsf(u));
+      for (int k = 0; k < SB_HPT; k += 2) {
+        const float2 e0 = fma2(bc2(q.x), bc2(-1.f), make_float2(tf[k][0], tf[k + 1][0]));
+        const float2 e1 = fma2(bc2(q.y), bc2(-1.f), make_float2(tf[k][1], tf[k + 1][1]));
+        const float2 e2 = fma2(bc2(q.z), bc2(-1.f), make_float2(tf[k][2], tf[k + 1][2]));
+        const float2 d0 = fma2(make_float2(Rf[k][0], Rf[k + 1][0]), bc2(p.x),
+                               fma2(make_float2(Rf[k][1], Rf[k + 1][1]), bc2(p.y),
+                                    fma2(make_float2(Rf[k][2], Rf[k + 1][2]), bc2(p.z), e0)));
+        const float2 d1 = fma2(make_float2(Rf[k][3], Rf[k + 1][3]), bc2(p.x),
+                               fma2(make_float2(Rf[k][4], Rf[k + 1][4]), bc2(p.y),
+                                    fma2(make_float2(Rf[k][5], Rf[k + 1][5]), bc2(p.z), e1)));
+        const float2 d2 = fma2(make_float2(Rf[k][6], Rf[k + 1][6]), bc2(p.x),
+                               fma2(make_float2(Rf[k][7], Rf[k + 1][7]), bc2(p.y),
+                                    fma2(make_float2(Rf[k][8], Rf[k + 1][8]), bc2(p.z), e2)));
+        const float2 u = fma2(d2, d2, fma2(d1, d1, fma2(d0, d0, bc2(-tau2))));
+        cnt[k] += (int)(__float_as_uint(u.x) >> 31);
+        cnt[k + 1] += (int)(__float_as_uint(u.y) >> 31);
+        mn[k] = fminf(mn[k], fabsf(u.x));
+        mn[k + 1] = fminf(mn[k + 1], fabsf(u.y));
       }
     }
     __syncthreads();  // everyone is done with stage st
