@@ -246,6 +246,7 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
       acc = (tid == max_index) ? fmax(acc, x) : acc + x;
     }
     sm->part[parity][tid] = acc;
+    if (NC == 1) sm->total[tid] = acc;  // single CTA: the partial sums are the totals (one barrier less per reduction)
   }
   if (NC > 1) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -259,9 +260,6 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
       }
       sm->total[tid] = acc;
     }
-  } else {
-    __syncthreads();
-    if (tid < GNC_NRED) sm->total[tid] = sm->part[parity][tid];
   }
   __syncthreads();
 }
