@@ -101,3 +101,34 @@ def test_argument_validation_without_device():
     n = C.c_longlong(0)
     assert L.psulvsb_ply_vertex_count(b"/nonexistent/file.ply", C.byref(n)) == capi.ERR_INVALID
     assert b"cannot open" in L.psulvsb_last_error()
+
+
+def test_fp32_pipe_kernels_are_packed_and_tma_staged():
+    """The SASS of the consistency-mask and scoring kernels carries what DESIGN.md section 6 says they are built on:
+    packed FP32 (FFMA2) in the pair / score loops and 1-D TMA bulk copies (UBLKCP) for the tile rings."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    per_fn, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_fn[name] = {"FFMA2": 0, "UBLKCP": 0, "FFMA": 0}
+        elif name:
+            for op in ("FFMA2", "UBLKCP"):
+                if re.search(r"\b%s\b" % op, line):
+                    per_fn[name][op] += 1
+            if re.search(r"\bFFMA\b", line):
+                per_fn[name]["FFMA"] += 1
+    k1 = {k: v for k, v in per_fn.items() if "k1_mask_kernelILi4ELi256" in k}
+    k4 = {k: v for k, v in per_fn.items() if "score_batch_kernel" in k}
+    assert len(k1) == 1 and len(k4) == 1, (list(k1), list(k4))
+    for ops in list(k1.values()) + list(k4.values()):
+        assert ops["UBLKCP"] >= 2, ops          # both tile arrays come by bulk copy
+        assert ops["FFMA2"] >= 100, ops         # the unrolled loops are packed ...
+        assert ops["FFMA2"] > 4 * ops["FFMA"], ops  # ... and what is left scalar is the rare slow / fix-up path
