@@ -762,12 +762,12 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   PSU_CUDA(cudaEventRecord(ev_k1, st));
 
   // ---- ticks
-  const int gnc_cluster = gnc_cluster_for(B);
+  // CTAs per registration follow the registrations still RUNNING (the previous tick's count): the CTAs of finished
+  // jobs leave at once, so the last stragglers of a batch get 2 / 4 / 8 SMs each instead of one (the tail ticks of a
+  // lock-step batch are what weak scaling loses: the slowest rank of 8 ran 25.5 ms against 20.8 ms on one GPU)
+  int n_running = B;
   int max_ccap = 0;
   for (int b = 0; b < B; ++b) max_ccap = lay[(size_t)b].Ccap > max_ccap ? lay[(size_t)b].Ccap : max_ccap;
-  int gnc_cap = (int)((0.03 * (double)max_nred) / (double)gnc_cluster) + 64;
-  gnc_cap = (gnc_cap + 31) & ~31;
-  if (gnc_cap > gnc_default_capacity()) gnc_cap = gnc_default_capacity();
   const unsigned long long draws_bound = sample_default_max_draws(max_cap, max_cap / 8 + 1);
   int ticks = 0;
   double gnc_ms = 0.0;
@@ -796,6 +796,10 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       launches += 6;
     }
     PSU_CUDA(cudaEventRecord(ev_g0, st));
+    const int gnc_cluster = gnc_cluster_for(n_running);
+    int gnc_cap = (int)((0.03 * (double)max_nred) / (double)gnc_cluster) + 64;
+    gnc_cap = (gnc_cap + 31) & ~31;
+    if (gnc_cap > gnc_default_capacity()) gnc_cap = gnc_default_capacity();
     if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster, max_ccap)) return rc;
     PSU_CUDA(cudaEventRecord(ev_g1, st));
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
@@ -809,6 +813,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       if (cudaEventElapsedTime(&g, ev_g0, ev_g1) == cudaSuccess) gnc_ms += g;  // (the tick's poll already synchronised)
     }
     if (h_done[0] >= B) break;
+    n_running = B - h_done[0];
     round_start_pending = h_done[1] > 0;
     clique_pending = h_done[2] > 0 && params->inlier_selection_mode != 3;
     if (ticks >= max_ticks) return fail(PSULVSB_ERR_INTERNAL, "engine did not converge within the tick limit");
