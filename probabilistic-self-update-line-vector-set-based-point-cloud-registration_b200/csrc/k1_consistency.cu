@@ -2,7 +2,8 @@
 //
 // Replaces the reference's O(C^2) line-vector set build and the ScaleInliersSelector pass
 // (registration.cc:693-732, :418-434, :756-766).  The reference materialises every line vector
-// (~130 B per pair, twice); here a pair costs ~20 FP32-pipe instructions and one output BIT.
+// (~130 B per pair, twice); here a pair costs 10 FP32 lane-operations (5 packed FFMA2 / FADD2 issue slots) + 2 ALU
+// instructions and one output BIT.
 //
 // Arithmetic.  The reference decides   | sqrt(A) - sqrt(B) | <= beta   in FP64 with
 // A = |s_j - s_i|^2, B = |t_j - t_i|^2.  With D = A - B, S = A + B this is, for a + b > beta,
@@ -14,8 +15,8 @@
 // re-evaluated pairs is counted.
 //
 // Fast path.  A and B are formed in the "norm" form  |s_i|^2 + |s_j|^2 - 2 s_i.s_j  (the squared
-// norms travel in the .w lane of the float4 tiles, -2 s_i is pre-scaled in registers): 14 FP32-pipe
-// instructions per pair.  That form loses relative accuracy for short line vectors, so its sign is
+// norms travel in the .w lane of the float4 tiles, -2 s_i and the per-row constants are pre-folded in registers;
+// see pair_fast / pair_fast2).  That form loses relative accuracy for short line vectors, so its sign is
 // trusted only when |v| exceeds ONE uniform threshold t_fast (derivation in DESIGN.md "K1 fast-path
 // threshold"; it also covers a + b <= beta, where the polynomial's sign is not the answer); a mask
 // word with any pair below it is redone with the accurate difference form above, whose own band
