@@ -151,6 +151,10 @@ int psulvsb_device_count(void);
  * be used from different threads (the reference's solver is neither re-entrant nor thread safe,
  * registration.cc:40-50). */
 int psulvsb_create(psulvsb_handle_t* out, int device);
+/* Debug / test switches (process-wide; the library reads NO environment variable).  They select among code paths
+ * that produce identical results: "gnc_deep_margin" (rad), "gnc_prefetch", "sample_list_cap_test", "k1_variant"
+ * (1..4 rows per thread), "upload_prof" (1: phase timings on stderr), "reset" (all back to defaults). */
+int psulvsb_debug_set(const char* name, double value);
 int psulvsb_destroy(psulvsb_handle_t h);
 
 /* ------------------------------------------------------------------------------------------ */
@@ -166,8 +170,12 @@ int psulvsb_solve_batch(psulvsb_handle_t h, const psulvsb_params_t* params, cons
 /* Resident variant: upload once, then solve the resident batch any number of times (inputs stay
  * in HBM; only the solutions come back).  Used for the device-resident throughput figure. */
 int psulvsb_batch_upload(psulvsb_handle_t h, const psulvsb_problem_t* problems, int B);
+/* n_solutions: capacity of `solutions`; must equal the resident batch size (psulvsb_batch_resident_size), which
+ * every upload / psulvsb_solve / psulvsb_solve_batch on the handle replaces -- a mismatch is PSULVSB_ERR_INVALID. */
 int psulvsb_batch_solve_resident(psulvsb_handle_t h, const psulvsb_params_t* params, const uint64_t* seeds,
-                                 psulvsb_solution_t* solutions);
+                                 psulvsb_solution_t* solutions, int n_solutions);
+/* Problems currently resident on the handle (0: nothing uploaded, or the last upload failed). */
+int psulvsb_batch_resident_size(psulvsb_handle_t h);
 /* Kernel launches issued by the handle since creation / device time (ms) of the last solve call,
  * measured with CUDA events on the handle's stream. */
 long long psulvsb_launch_count(psulvsb_handle_t h);

@@ -1,6 +1,7 @@
 /*
  * psulvsb_io.h -- C ABI of the host-side callers' helpers around the PSULVSB hot path
- * (libpsulvsb_b200.so, host code only: no CUDA device is needed for these).
+ * (libpsulvsb_b200.so).  The file readers are host code; the pre-filter and the reduced-set builder run on the
+ * device (csrc/k7_prefilter.cu) and return PSULVSB_ERR_NO_DEVICE without one -- there is no CPU fallback.
  *
  * They replace, dependency-free, what the reference's experiment drivers do on the host on either
  * side of RobustRegistrationSolver::solve():
@@ -33,6 +34,12 @@ int psulvsb_histogram_outlier_removal(const double* src_normals, const double* t
  * of original i or -1 (dense form of the reference's std::map<int,int>); *C = number of kept columns. */
 int psulvsb_mask_filter(const double* src, const double* tgt, const int* keep_mask, int n, double* src_reduce,
                         double* tgt_reduce, int* reduce_map, int* C);
+
+/* Both of the above in one device call (one staging copy, one launch): what the reference driver times before
+ * solve(), PSULVSB.cc:310-317.  keep_mask[n] in/out as for psulvsb_histogram_outlier_removal. */
+int psulvsb_prefilter_reduce(const double* src_normals, const double* tgt_normals, const double* src, const double* tgt,
+                             int n, int* keep_mask, double* src_reduce, double* tgt_reduce, int* reduce_map, int* C,
+                             int* remain_count);
 
 /* PLY: number of vertices, then their x, y, z as float (teaser::PointXYZ is 3 x float). */
 int psulvsb_ply_vertex_count(const char* path, long long* n);

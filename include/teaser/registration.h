@@ -299,6 +299,9 @@ public:
     p.rotation_max_iterations = static_cast<int>(params_.rotation_max_iterations);
     p.rotation_gnc_factor = params_.rotation_gnc_factor;
     p.rotation_cost_threshold = params_.rotation_cost_threshold;
+    // deprecated fields first, exactly as registration.cc:628-637 (the second one wins when both are cleared)
+    if (!params_.use_max_clique) params_.inlier_selection_mode = INLIER_SELECTION_MODE::NONE;
+    if (!params_.max_clique_exact_solution) params_.inlier_selection_mode = INLIER_SELECTION_MODE::PMC_HEU;
     p.inlier_selection_mode = static_cast<int>(params_.inlier_selection_mode);
     p.kcore_heuristic_threshold = params_.kcore_heuristic_threshold;
     p.seed = params_.seed;
@@ -312,6 +315,14 @@ public:
       keep = params_.keep_mask;
       for (const auto& kv : params_.reduce_map)
         if (kv.first >= 0 && kv.first < M) dense[static_cast<size_t>(kv.first)] = kv.second;
+      // the reference reads params_.reduce_map[j] through std::map::operator[] (registration.cc:1433): a kept
+      // correspondence without an entry yields column 0
+      for (int j = 0; j < M; ++j)
+        if (keep[static_cast<size_t>(j)] == 1 && dense[static_cast<size_t>(j)] < 0) dense[static_cast<size_t>(j)] = 0;
+    } else if (have_ori && M != C) {
+      // ori_src / ori_dst without a keep_mask of M entries: the reference would index keep_mask out of bounds
+      last_status_ = PSULVSB_ERR_INVALID;
+      return solution_;
     } else {
       for (int j = 0; j < M; ++j) dense[static_cast<size_t>(j)] = j;
     }

@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <functional>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -690,6 +691,43 @@ std::vector<int> max_clique(int n, const std::vector<std::pair<int, int>>& edges
   for (int v : cs.best) out.push_back(perm[(size_t)v]);
   if (out.empty() && n > 0) out.push_back(0);
   std::sort(out.begin(), out.end());
+  // WHICH maximum clique PMC returns is not pinned by anything in the reference (un-vendored, unpinned, threaded).
+  // Position taken, the same in the product (csrc/k5_clique.cu): of all cliques of the maximum size omega, the one
+  // whose ascending vertex list is lexicographically smallest.  Found by a depth-first search over the ORIGINAL
+  // numbering, candidates ascending, cut only where omega cannot be reached.
+  const int omega = (int)out.size();
+  if (omega >= 2) {
+    const int words = (n + 63) / 64;
+    std::vector<uint64_t> A((size_t)n * words, 0);
+    for (auto& e : edges) {
+      if (e.first == e.second) continue;
+      A[(size_t)e.first * words + (e.second >> 6)] |= 1ull << (e.second & 63);
+      A[(size_t)e.second * words + (e.first >> 6)] |= 1ull << (e.first & 63);
+    }
+    std::vector<int> cur;
+    std::function<bool(const std::vector<uint64_t>&)> dfs = [&](const std::vector<uint64_t>& cand) -> bool {
+      if ((int)cur.size() == omega) return true;
+      int cnt = 0;
+      for (int w = 0; w < words; ++w) cnt += __builtin_popcountll(cand[(size_t)w]);
+      if ((int)cur.size() + cnt < omega) return false;
+      std::vector<uint64_t> rest = cand, next((size_t)words);
+      for (int w = 0; w < words; ++w)
+        while (rest[(size_t)w]) {
+          const int v = w * 64 + __builtin_ctzll(rest[(size_t)w]);
+          rest[(size_t)w] &= rest[(size_t)w] - 1;
+          // later candidates adjacent to v (everything at or below v is gone from `rest`)
+          for (int x = 0; x < words; ++x) next[(size_t)x] = rest[(size_t)x] & A[(size_t)v * words + x];
+          cur.push_back(v);
+          if (dfs(next)) return true;
+          cur.pop_back();
+        }
+      return false;
+    };
+    std::vector<uint64_t> all((size_t)words, 0);
+    for (int v = 0; v < n; ++v)
+      if (deg[(size_t)v] >= omega - 1) all[(size_t)(v >> 6)] |= 1ull << (v & 63);
+    if (dfs(all)) out = cur;
+  }
   return out;
 }
 

@@ -20,7 +20,7 @@ DOMAIN_L_SAMPLED, DOMAIN_BASIC, DOMAIN_UNIFORM, DOMAIN_SCALE = 1, 2, 3, 4
 SYMBOLS = [
     "psulvsb_version", "psulvsb_last_error", "psulvsb_default_params", "psulvsb_device_count",
     "psulvsb_create", "psulvsb_destroy", "psulvsb_solve", "psulvsb_solve_batch", "psulvsb_batch_upload",
-    "psulvsb_batch_solve_resident", "psulvsb_launch_count", "psulvsb_last_device_ms", "psulvsb_last_stage_ms",
+    "psulvsb_batch_solve_resident", "psulvsb_batch_resident_size", "psulvsb_debug_set", "psulvsb_launch_count", "psulvsb_last_device_ms", "psulvsb_last_stage_ms",
     "psulvsb_last_ticks", "psulvsb_pack_points", "psulvsb_consistency_mask", "psulvsb_consistency_mask_rows",
     "psulvsb_mask_symmetrize", "psulvsb_compact_edges", "psulvsb_sample_workspace_bytes",
     "psulvsb_sample_default_max_draws", "psulvsb_sample", "psulvsb_philox_fill", "psulvsb_gnc_tls_rotation",
@@ -162,7 +162,11 @@ def _declare(L: C.CDLL) -> None:
     L.psulvsb_solve_batch.argtypes = [_vp, C.POINTER(Params), C.POINTER(Problem), C.c_int, C.POINTER(C.c_uint64),
                                       C.POINTER(Solution)]
     L.psulvsb_batch_upload.argtypes = [_vp, C.POINTER(Problem), C.c_int]
-    L.psulvsb_batch_solve_resident.argtypes = [_vp, C.POINTER(Params), C.POINTER(C.c_uint64), C.POINTER(Solution)]
+    L.psulvsb_batch_solve_resident.argtypes = [_vp, C.POINTER(Params), C.POINTER(C.c_uint64), C.POINTER(Solution),
+                                               C.c_int]
+    L.psulvsb_debug_set.argtypes = [C.c_char_p, C.c_double]
+    L.psulvsb_batch_resident_size.argtypes = [_vp]
+    L.psulvsb_batch_resident_size.restype = C.c_int
     L.psulvsb_launch_count.argtypes = [_vp]
     L.psulvsb_launch_count.restype = C.c_longlong
     L.psulvsb_last_device_ms.argtypes = [_vp]
@@ -212,6 +216,11 @@ def _declare(L: C.CDLL) -> None:
 def check(rc: int) -> None:
     if rc != OK:
         raise PsulvsbError(rc, lib().psulvsb_last_error().decode("utf-8", "replace"))
+
+
+def debug_set(name: str, value: float) -> None:
+    """psulvsb_debug_set: test switches between equivalent code paths ("reset" restores the defaults)."""
+    check(lib().psulvsb_debug_set(name.encode(), float(value)))
 
 
 def default_params(**kw) -> Params:
@@ -338,13 +347,21 @@ class Handle:
         arr = self._problem_array(self._problems)
         check(lib().psulvsb_batch_upload(self._h, arr, len(self._problems)))
 
+    @property
+    def resident_size(self) -> int:
+        return lib().psulvsb_batch_resident_size(self._h)
+
     def solve_resident(self, params: Params, seeds=None):
-        n = len(self._problems)
+        n = self.resident_size  # (solve / solve_batch on this handle replace the resident batch)
+        if n <= 0:
+            raise PsulvsbError(ERR_INVALID, "solve_resident: nothing is resident on this handle (upload first)")
         sols = (Solution * n)()
         sd = None
         if seeds is not None:
+            if len(seeds) != n:
+                raise PsulvsbError(ERR_INVALID, f"solve_resident: {len(seeds)} seeds for a resident batch of {n}")
             sd = (C.c_uint64 * n)(*[int(s) for s in seeds])
-        check(lib().psulvsb_batch_solve_resident(self._h, C.byref(params), sd, sols))
+        check(lib().psulvsb_batch_solve_resident(self._h, C.byref(params), sd, sols, n))
         return list(sols)
 
     @property

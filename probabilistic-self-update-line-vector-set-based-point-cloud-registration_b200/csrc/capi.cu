@@ -22,6 +22,23 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 
+int sm_count() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+DebugKnobs& debug_knobs() {
+  static DebugKnobs k;
+  return k;
+}
+
 namespace {
 
 int need_device() {
@@ -143,10 +160,31 @@ int psulvsb_batch_upload(psulvsb_handle_t h, const psulvsb_problem_t* problems, 
 }
 
 int psulvsb_batch_solve_resident(psulvsb_handle_t h, const psulvsb_params_t* params, const uint64_t* seeds,
-                                 psulvsb_solution_t* solutions) {
+                                 psulvsb_solution_t* solutions, int n_solutions) {
   if (!h || !params || !solutions) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_solve_resident: NULL argument");
+  const int B = engine_batch_size(h->engine);
+  if (B <= 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_solve_resident: nothing is resident (upload first)");
+  if (n_solutions != B)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_solve_resident: " + std::to_string(n_solutions) +
+                                         " solution slots for a resident batch of " + std::to_string(B));
   return engine_solve_resident(h->engine, params, seeds, solutions, nullptr);
 }
+
+int psulvsb_debug_set(const char* name, double value) {
+  if (!name) return fail(PSULVSB_ERR_INVALID, "psulvsb_debug_set: NULL name");
+  DebugKnobs& k = debug_knobs();
+  const std::string n(name);
+  if (n == "gnc_deep_margin") k.gnc_deep_margin = value;
+  else if (n == "gnc_prefetch") k.gnc_prefetch = (int)value;
+  else if (n == "sample_list_cap_test") k.sample_list_cap_test = (int)value;
+  else if (n == "k1_variant") k.k1_variant = (int)value;
+  else if (n == "upload_prof") k.upload_prof = (int)value;
+  else if (n == "reset") k = DebugKnobs();
+  else return fail(PSULVSB_ERR_INVALID, "psulvsb_debug_set: unknown switch " + n);
+  return PSULVSB_OK;
+}
+
+int psulvsb_batch_resident_size(psulvsb_handle_t h) { return h ? engine_batch_size(h->engine) : 0; }
 
 long long psulvsb_launch_count(psulvsb_handle_t h) { return h ? engine_launch_count(h->engine) : 0; }
 double psulvsb_last_device_ms(psulvsb_handle_t h) { return h ? engine_last_device_ms(h->engine) : 0.0; }
@@ -378,16 +416,21 @@ int psulvsb_gnc_tls_rotation_batch(void* stream, const double* d_src64, const do
     j.prof = d_prof ? d_prof + (size_t)b * 8 : nullptr;
     j.active = 1;
   }
-  GncJob* d_jobs = nullptr;
-  PSU_CUDA(cudaMallocAsync((void**)&d_jobs, sizeof(GncJob) * (size_t)n_jobs, st));
-  PSU_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(GncJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, st));
+  struct AsyncJobs {  // freed on every exit path (stream-ordered, after the launch that reads it)
+    GncJob* d = nullptr;
+    cudaStream_t st;
+    explicit AsyncJobs(cudaStream_t s) : st(s) {}
+    ~AsyncJobs() {
+      if (d) cudaFreeAsync(d, st);
+    }
+  } dj(st);
+  PSU_CUDA(cudaMallocAsync((void**)&dj.d, sizeof(GncJob) * (size_t)n_jobs, st));
+  PSU_CUDA(cudaMemcpyAsync(dj.d, jobs.data(), sizeof(GncJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, st));
   PSU_CUDA(cudaStreamSynchronize(st));  // jobs is pageable host memory
   if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = gnc_cluster_for(n_jobs);
   int cap = (int)((K + (unsigned long long)cluster - 1) / (unsigned long long)cluster) + 32;
   cap = (cap + 31) & ~31;
-  const int rc = launch_gnc_tls(st, d_jobs, n_jobs, cap, cluster, 0);
-  cudaFreeAsync(d_jobs, st);
-  return rc;
+  return launch_gnc_tls(st, dj.d, n_jobs, cap, cluster, 0);
 }
 
 int psulvsb_kabsch_batch(void* stream, const double* d_src64, const double* d_dst64, const void* d_edges_uint2,

@@ -33,6 +33,20 @@ int fail(int code, const std::string& msg);
     }                                                                                               \
   } while (0)
 
+// SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device): every grid is sized from it
+int sm_count();
+
+// Debug / test switches (psulvsb_debug_set in include/psulvsb.h).  They never change results, only which of several
+// equivalent code paths runs; production callers leave them alone.  No environment variable is read anywhere.
+struct DebugKnobs {
+  double gnc_deep_margin = 0.0;   // > 0: overrides the remaining-margin threshold (rad) for parking sleeping line vectors
+  int gnc_prefetch = -1;          // >= 0: look-ahead (double-steps) of the L2 prefetch in the streamed GNC pass
+  int sample_list_cap_test = 0;   // > 0: caps the sampler's bucket lists (exercises the overflow fallback)
+  int k1_variant = 0;             // 1..4: rows per thread of the consistency kernel
+  int upload_prof = 0;            // 1: print the upload's phase timings to stderr
+};
+DebugKnobs& debug_knobs();
+
 inline unsigned long long ceil_div_ull(unsigned long long a, unsigned long long b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------

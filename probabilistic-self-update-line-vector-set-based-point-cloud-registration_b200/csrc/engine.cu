@@ -244,7 +244,11 @@ inline void stage_points(double* dst, const double* src, size_t n_doubles, doubl
 int Engine::upload(const psulvsb_problem_t* problems, int nb) {
   if (!problems || nb <= 0) return fail(PSULVSB_ERR_INVALID, "upload: no problems");
   if (st) cudaStreamSynchronize(st);  // earlier copies out of the staging buffer (and solves on its contents) are done
-  static const bool prof = getenv("PSULVSB_UPLOAD_PROF") != nullptr;
+  // nothing is resident until this upload has fully succeeded (a failed re-upload must not leave the previous batch
+  // size paired with a half-overwritten layout / input arena)
+  B = 0;
+  reserve.clear();
+  const bool prof = debug_knobs().upload_prof != 0;
   const auto t_up0 = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up0).count(); };
   double t_layout = 0, t_staged = 0;
@@ -279,7 +283,7 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
   // staging copy + centres / coordinate bound of the FP32 tiles, split over a few host threads (33 MB for a
   // batch of 64 cfg-A pairs: a single-threaded memcpy would cost more than the H2D copy that follows)
   t_layout = since();
-  std::atomic<int> bad_problem(-1), copy_error(0);
+  std::atomic<int> bad_problem(-1), bad_map(-1), copy_error(0);
   // a staged group of problems goes to the device at once (its H2D copy overlaps the staging of the next group)
   auto push_group = [&](int g0, int g1) {
     const size_t d0 = lay[(size_t)g0].in_dbl, d1 = (g1 < nb) ? lay[(size_t)g1].in_dbl : od;
@@ -305,7 +309,12 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
       std::memcpy(hi + L.in_int + p.M, p.reduce_map, sizeof(int) * (size_t)p.M);
       {
         int zeros = 0;
-        for (int j = 0; j < p.M; ++j) zeros += (p.keep_mask[j] == 0) ? 1 : 0;
+        for (int j = 0; j < p.M; ++j) {
+          zeros += (p.keep_mask[j] == 0) ? 1 : 0;
+          // a kept correspondence's reduced column becomes a line-vector endpoint on the device (inlier_map,
+          // registration.cc:1432-1434): it must name a column of src / dst
+          if (p.keep_mask[j] == 1 && (p.reduce_map[j] < 0 || p.reduce_map[j] >= p.C)) bad_map.store(b);
+        }
         L.Ccap = p.C + zeros;  // every original correspondence can be appended at most once (registration.cc:828)
       }
       // (differences are translation invariant: each cloud is centred on its own bounding box)
@@ -378,6 +387,11 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
     cudaStreamSynchronize(st);
     return fail(PSULVSB_ERR_INVALID, "upload: problem " + std::to_string(bad_problem.load()) + " has non-finite coordinates");
   }
+  if (bad_map.load() >= 0) {
+    cudaStreamSynchronize(st);
+    return fail(PSULVSB_ERR_INVALID, "upload: problem " + std::to_string(bad_map.load()) +
+                                         " has keep_mask[j] == 1 with reduce_map[j] outside [0, C)");
+  }
   if (copy_error.load()) {
     cudaStreamSynchronize(st);
     return fail(PSULVSB_ERR_CUDA, "upload: host-to-device copy failed");
@@ -397,6 +411,14 @@ int Engine::solve(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb
   if (!params || !solutions) return fail(PSULVSB_ERR_INVALID, "solve: null params / solutions");
   if (params->host_round_limit < 0 || params->rotation_max_iterations < 0 || params->inloop_max_iterations < 0)
     return fail(PSULVSB_ERR_INVALID, "solve: negative iteration limits");
+  if (params->inlier_selection_mode < 0 || params->inlier_selection_mode > 3)
+    return fail(PSULVSB_ERR_INVALID, "solve: inlier_selection_mode must be 0 (PMC_EXACT) .. 3 (NONE)");
+  // KCORE_HEU (graph.cc:63-80) returns the maximum k-core when it is larger than threshold * |V| and otherwise the
+  // heuristic clique; only the second half exists here (threshold == 1 short-circuits to it in the reference too)
+  if (params->inlier_selection_mode == 2 && params->kcore_heuristic_threshold != 1.0)
+    return fail(PSULVSB_ERR_UNSUPPORTED,
+                "solve: INLIER_SELECTION_MODE::KCORE_HEU with kcore_heuristic_threshold != 1 is not implemented "
+                "(PMC_EXACT, PMC_HEU and NONE are)");
   for (int attempt = 0; attempt < 6; ++attempt) {
     if (int rc = solve_once(params, seeds, solutions, trace_first)) return rc;
     // self-update outgrew the edge head-room of some job: enlarge and redo (results are
@@ -739,6 +761,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   P.self_update = params->self_update;
   P.inlier_selection_mode = params->inlier_selection_mode;
   P.max_local_iters = 4096;
+  P.sampler_counters = (int)sample_list_counters();
   {
     // The sampler leaves its accept bitmask and value bitmap zeroed after every use.  They are cleared here only when
     // that cannot be relied on: a new arena layout (other pointers / sizes than the last COMPLETED solve) or a
@@ -792,8 +815,11 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     if (clique_pending) {  // some registration is in its clique round (rare, last escalation)
       int maxCcap = 0;
       for (int b = 0; b < B; ++b) maxCcap = lay[(size_t)b].Ccap > maxCcap ? lay[(size_t)b].Ccap : maxCcap;
-      if (int rc = launch_max_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap, true)) return rc;
-      launches += 6;
+      // PMC_EXACT: greedy lower bound + exact improvement search; PMC_HEU / KCORE_HEU: the heuristic clique only
+      // (graph.cc:86-121).  max_clique_time_limit has no counterpart: the search has a node budget instead.
+      if (int rc = launch_max_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap, params->inlier_selection_mode == 0))
+        return rc;
+      launches += 8;
     }
     PSU_CUDA(cudaEventRecord(ev_g0, st));
     const int gnc_cluster = gnc_cluster_for(n_running);

@@ -30,6 +30,7 @@ struct SubParams {
 
 struct EngineParams {
   SubParams caller, inloop;
+  int sampler_counters;      // sample_list_counters(): entries of JobCtl::bcount
   int zero_sampler_scratch;  // 1: engine_init_kernel clears the accept bitmask / value bitmap (see engine.cu)
   double pr_noise;          // 2 * score_noise_bound (registration.cc:36)
   double score_sigma;       // score_noise_bound: sigma of computeInlierProbability (registration.cc:1428)

@@ -1,5 +1,5 @@
 // host_io.cpp -- host-side helpers of the callers around the hot path (include/psulvsb_io.h):
-// normal-angle histogram pre-filter, reduced-set builder, PLY vertex reader, correspondence files.
+// PLY vertex reader, correspondence files.  (The pre-filter and reduced-set builder are device code: k7_prefilter.cu.)
 // Plain C++17, no CUDA, no third-party dependency (the reference uses PCL/Eigen/tinyply here).
 #include <algorithm>
 #include <climits>
@@ -19,114 +19,6 @@ namespace psulvsb {
 int fail(int code, const std::string& msg);
 }
 using psulvsb::fail;
-
-extern "C" {
-
-// examples/teaser_cpp_ply/PSULVSB.cc:87-172, statement for statement (sequential on purpose: the peak
-// is "the first bin to reach the running maximum", an order-dependent rule).  Positions taken where the
-// reference is undefined: sigma == 0 (all angles equal) -> one bin; an angle that lands exactly on the
-// upper edge of the last bin is put into the last bin (the reference indexes one past the end there).
-int psulvsb_histogram_outlier_removal(const double* src_normals, const double* tgt_normals, int n, int* keep_mask,
-                                      int* remain_count) {
-  if (!src_normals || !tgt_normals || !keep_mask || n < 0)
-    return fail(PSULVSB_ERR_INVALID, "psulvsb_histogram_outlier_removal: bad argument");
-  std::vector<double> all_angles((size_t)n, -1.0);
-  std::vector<double> remain_angles;
-  remain_angles.reserve((size_t)n);
-  double o_max = 0, o_min = INT_MAX, angle_sum = 0;
-  auto normalized = [](const double* v, double out[3]) {  // Eigen's normalized(): v / |v|, v itself when |v| = 0
-    const double z = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
-    if (z > 0) {
-      const double nrm = std::sqrt(z);
-      out[0] = v[0] / nrm;
-      out[1] = v[1] / nrm;
-      out[2] = v[2] / nrm;
-    } else {
-      out[0] = v[0];
-      out[1] = v[1];
-      out[2] = v[2];
-    }
-  };
-  for (int i = 0; i < n; ++i) {
-    double a[3], b[3];
-    normalized(src_normals + 3 * (size_t)i, a);
-    normalized(tgt_normals + 3 * (size_t)i, b);
-    double cos_theta = (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
-    cos_theta = std::max(-1.0, std::min(1.0, cos_theta));
-    const double angle_deg = std::acos(cos_theta) * 180.0 / M_PI;
-    if (std::isnan(angle_deg)) continue;
-    remain_angles.push_back(angle_deg);
-    all_angles[(size_t)i] = angle_deg;
-    o_min = std::min(angle_deg, o_min);
-    o_max = std::max(angle_deg, o_max);
-    angle_sum += angle_deg;
-  }
-  if (remain_count) *remain_count = 0;
-  if (remain_angles.empty()) return PSULVSB_OK;
-  const double cnt = (double)remain_angles.size();
-  const double angle_mean = angle_sum / cnt;
-  double sq = 0.0;
-  for (const double& deg : remain_angles) sq += std::pow(deg - angle_mean, 2);
-  const double sd = std::sqrt(sq / cnt);
-  const double bin_width = 3.49 * sd / std::pow(cnt, 1.0 / 3.0);
-  int hist_size = 1;
-  if (bin_width > 0 && std::isfinite(bin_width)) hist_size = std::max(1, (int)std::ceil((o_max - o_min) / bin_width));
-  std::vector<std::vector<int>> hist((size_t)hist_size);
-  int peak_id = 0;
-  size_t peak_height = 0;
-  for (int i = 0; i < n; ++i) {
-    if (all_angles[(size_t)i] == -1) continue;
-    int bin = 0;
-    if (bin_width > 0 && std::isfinite(bin_width)) bin = (int)((all_angles[(size_t)i] - o_min) / bin_width);
-    if (bin >= hist_size) bin = hist_size - 1;
-    if (bin < 0) bin = 0;
-    hist[(size_t)bin].push_back(i);
-    if (hist[(size_t)bin].size() > peak_height) {
-      peak_height = hist[(size_t)bin].size();
-      peak_id = bin;
-    }
-  }
-  double hsum = 0.0;
-  for (auto& h : hist) hsum += (double)h.size();
-  const double hmean = hsum / (double)hist_size;
-  double hvar = 0.0;
-  for (auto& h : hist) hvar += std::pow((double)(int)h.size() - hmean, 2);
-  const double threshold = hmean + 1 * std::sqrt(hvar / (double)hist_size);
-  int remain = 0;
-  for (int i = 0; i < hist_size; ++i) {
-    if (std::abs(i - peak_id) > 2)
-      for (int j : hist[(size_t)i]) keep_mask[j] = -1;
-    if ((double)hist[(size_t)i].size() > threshold)
-      for (int j : hist[(size_t)i]) {
-        keep_mask[j] = 1;
-        remain++;
-      }
-  }
-  if (remain_count) *remain_count = remain;
-  return PSULVSB_OK;
-}
-
-int psulvsb_mask_filter(const double* src, const double* tgt, const int* keep_mask, int n, double* src_reduce,
-                        double* tgt_reduce, int* reduce_map, int* C) {
-  if (!src || !tgt || !keep_mask || !src_reduce || !tgt_reduce || !reduce_map || !C || n < 0)
-    return fail(PSULVSB_ERR_INVALID, "psulvsb_mask_filter: bad argument");
-  int col = 0;
-  for (int i = 0; i < n; ++i) {
-    reduce_map[i] = -1;
-    if (keep_mask[i] == 1) {
-      reduce_map[i] = col;
-      for (int r = 0; r < 3; ++r) {
-        src_reduce[3 * (size_t)col + r] = src[3 * (size_t)i + r];
-        tgt_reduce[3 * (size_t)col + r] = tgt[3 * (size_t)i + r];
-      }
-      col++;
-    }
-  }
-  *C = col;
-  return PSULVSB_OK;
-}
-
-}  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
 // PLY
@@ -194,8 +86,9 @@ int parse_header(std::ifstream& f, PlyHeader& h, std::string& err) {
         std::string ct, it;
         iss >> ct >> it >> p.name;
         p.is_list = true;
-        char k;
-        if (!type_info(ct, p.list_count_size, k) || !type_info(it, p.list_item_size, k)) { err = "bad list type"; return 1; }
+        char kc, ki;
+        if (!type_info(ct, p.list_count_size, kc) || !type_info(it, p.list_item_size, ki)) { err = "bad list type"; return 1; }
+        if (kc == 'f') { err = "list count type must be an integer type, got " + ct; return 1; }
       } else {
         iss >> p.name;
         if (!type_info(t, p.size, p.kind)) { err = "unknown property type " + t; return 1; }
@@ -289,7 +182,8 @@ int ply_read(const char* path, float* xyz, long long capacity, long long* n_out)
           if (pr.is_list) {
             if (!f.read((char*)buf, pr.list_count_size)) return fail(PSULVSB_ERR_INVALID, "ply: truncated data");
             const unsigned long long c = list_count(buf, pr.list_count_size, swap);
-            f.seekg((std::streamoff)(c * (unsigned long long)pr.list_item_size), std::ios::cur);
+            if (!f.seekg((std::streamoff)(c * (unsigned long long)pr.list_item_size), std::ios::cur))
+              return fail(PSULVSB_ERR_INVALID, "ply: cannot skip a list property (truncated data)");
           } else {
             if (!f.read((char*)buf, pr.size)) return fail(PSULVSB_ERR_INVALID, "ply: truncated data");
             if (is_vertex) {

@@ -571,7 +571,7 @@ static int launch_k1_variant(cudaStream_t st, const K1Job* d_jobs, int n_jobs, i
   const int row_blocks = (max_rows + TI - 1) / TI;
   // column tiles per CTA: long-lived CTAs amortise their prologue, but keep the grid many waves deep
   const double live_tiles = 0.55 * (double)n_tiles * row_blocks * n_jobs;
-  int tpc = (int)(live_tiles / (148.0 * 3.0 * 12.0));  // ~12 waves of resident CTAs: short tail
+  int tpc = (int)(live_tiles / ((double)sm_count() * 3.0 * 12.0));  // ~12 waves of resident CTAs: short tail
   if (tpc < 1) tpc = 1;
   if (tpc > 16) tpc = 16;
   if (tpc > n_tiles) tpc = n_tiles;
@@ -585,27 +585,15 @@ int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, in
   if (n_jobs <= 0 || max_n < 1 || max_rows < 1) return PSULVSB_OK;
   // rows per thread by the amount of work: R = 4 / 2 want enough row blocks x tiles to fill the GPU
   const double pairs = 0.5 * (double)max_rows * max_n * n_jobs;
-  static const char* force = getenv("PSULVSB_K1_VARIANT");
   // measured on B200 (256-column tiles, dead row groups skipped): R = 4 wins once there is enough work
   // (N = 100k: 0.68-0.72 of the FP32-pipe peak vs 0.63; 256 x 5k-point problems: 0.59 vs 0.57; 64: 0.56 vs 0.55)
   int variant = pairs >= 5.0e8 ? 4 : (pairs >= 1.0e8 ? 2 : 1);
-  if (force && (force[0] == '1' || force[0] == '2' || force[0] == '3' || force[0] == '4')) variant = force[0] - '0';
-  static const char* tj_env = getenv("PSULVSB_K1_TJ");  // '1': 128-column tiles, '5': 512; default 256
-  if (tj_env && tj_env[0] == '5') {
-    if (variant == 4) return launch_k1_variant<4, 512>(st, d_jobs, n_jobs, max_n, max_rows);
-    if (variant == 2) return launch_k1_variant<2, 512>(st, d_jobs, n_jobs, max_n, max_rows);
-    return launch_k1_variant<1, 512>(st, d_jobs, n_jobs, max_n, max_rows);
-  }
-  const bool wide = tj_env ? (tj_env[0] != '1') : true;  // measured: 256-column tiles halve the barrier stalls
-  if (wide) {
-    if (variant == 3) return launch_k1_variant<3, 256>(st, d_jobs, n_jobs, max_n, max_rows);
-    if (variant == 4) return launch_k1_variant<4, 256>(st, d_jobs, n_jobs, max_n, max_rows);
-    if (variant == 2) return launch_k1_variant<2, 256>(st, d_jobs, n_jobs, max_n, max_rows);
-    return launch_k1_variant<1, 256>(st, d_jobs, n_jobs, max_n, max_rows);
-  }
-  if (variant == 4) return launch_k1_variant<4, 128>(st, d_jobs, n_jobs, max_n, max_rows);
-  if (variant == 2) return launch_k1_variant<2, 128>(st, d_jobs, n_jobs, max_n, max_rows);
-  return launch_k1_variant<1, 128>(st, d_jobs, n_jobs, max_n, max_rows);
+  if (debug_knobs().k1_variant >= 1 && debug_knobs().k1_variant <= 4) variant = debug_knobs().k1_variant;
+  // 256-column tiles (measured: half the barrier stalls of 128-column tiles; 512 is no better)
+  if (variant == 3) return launch_k1_variant<3, 256>(st, d_jobs, n_jobs, max_n, max_rows);
+  if (variant == 4) return launch_k1_variant<4, 256>(st, d_jobs, n_jobs, max_n, max_rows);
+  if (variant == 2) return launch_k1_variant<2, 256>(st, d_jobs, n_jobs, max_n, max_rows);
+  return launch_k1_variant<1, 256>(st, d_jobs, n_jobs, max_n, max_rows);
 }
 
 int launch_pack_points(cudaStream_t st, const double* pts, int n, const double center[3], float4* out) {

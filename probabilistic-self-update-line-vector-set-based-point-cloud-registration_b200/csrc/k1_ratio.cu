@@ -349,7 +349,7 @@ int launch_ratio_reduced_set(cudaStream_t st, const RatioJob* d_jobs, int n_jobs
     PSU_CHECK_LAUNCH("ratio_max_kernel");
     const unsigned long long L = (unsigned long long)max_n * (unsigned long long)(max_n - 1) / 2ull;
     unsigned long long gx = (L + RB_THREADS * 8 - 1) / (RB_THREADS * 8);
-    if (gx > 148 * 16) gx = 148 * 16;
+    if (gx > sm_count() * 16) gx = sm_count() * 16;
     if (gx < 1) gx = 1;
     ratio_last_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), RB_THREADS, 0, st>>>(d_jobs);
     PSU_CHECK_LAUNCH("ratio_last_kernel");

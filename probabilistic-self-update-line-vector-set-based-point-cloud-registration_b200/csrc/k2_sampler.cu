@@ -596,17 +596,16 @@ int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned
   }
   const unsigned long long nchunks = (max_draws_bound + SMP_CHUNK - 1) / SMP_CHUNK;
   unsigned long long gx = nchunks;
-  const unsigned long long cap = (unsigned long long)(148 * 16) / (unsigned long long)(n_jobs < 64 ? n_jobs : 64) + 1;
+  const unsigned long long cap = (unsigned long long)(sm_count() * 16) / (unsigned long long)(n_jobs < 64 ? n_jobs : 64) + 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  unsigned int list_cap_test = 0u;  // PSULVSB_SAMPLE_LIST_CAP_TEST: exercise the list-overflow fallback (tests only)
-  if (const char* e = getenv("PSULVSB_SAMPLE_LIST_CAP_TEST")) list_cap_test = (unsigned int)atoi(e);
+  const unsigned int list_cap_test = (unsigned int)debug_knobs().sample_list_cap_test;  // tests: list-overflow fallback
   sample_draws_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), 256, 0, st>>>(d_jobs, list_cap_test);
   PSU_CHECK_LAUNCH("sample_draws_kernel");
   // bucket CTAs: one per SM at a time; a CTA walks several buckets when the batch alone fills the GPU
   unsigned long long nb = (n_bound + SMP_BW - 1) / SMP_BW;
   if (nb < 1) nb = 1;
-  unsigned long long bx = (148ull * 3ull + (unsigned long long)n_jobs - 1) / (unsigned long long)n_jobs;
+  unsigned long long bx = ((unsigned long long)sm_count() * 3ull + (unsigned long long)n_jobs - 1) / (unsigned long long)n_jobs;
   if (bx > nb) bx = nb;
   if (bx < 1) bx = 1;
   sample_bucket_kernel<<<dim3((unsigned)bx, (unsigned)n_jobs), SMB_THREADS, smem, st>>>(d_jobs);
@@ -615,7 +614,7 @@ int launch_sample(cudaStream_t st, const SampleJob* d_jobs, int n_jobs, unsigned
   PSU_CHECK_LAUNCH("sample_emit_kernel");
   if (flag_pass) {
     unsigned long long fx = (n_bound + 32ull * 256 - 1) / (32ull * 256);  // CTAs of 256 lanes x one 32-value row each
-    const unsigned long long fcap = (148ull * 16 + (unsigned long long)n_jobs - 1) / (unsigned long long)n_jobs;
+    const unsigned long long fcap = ((unsigned long long)sm_count() * 16 + (unsigned long long)n_jobs - 1) / (unsigned long long)n_jobs;
     if (fx > fcap) fx = fcap;
     if (fx < 1) fx = 1;
     sample_flag_kernel<<<dim3((unsigned)fx, (unsigned)n_jobs), 256, 0, st>>>(d_jobs);

@@ -264,6 +264,108 @@ __device__ __forceinline__ void cluster_reduce(GncSmem* sm, double vals[GNC_NRED
   __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiny problems (K <= GNC_SERIAL_MAX line vectors): one thread replays GNCTLSRotationSolver::solveForRotation
+// (registration.cc:1563-1692) with the reference's sequential sums and operation order (this file is built with
+// -fmad=false; no fma() below), the two-sided Jacobi of svd3.cuh standing in for Eigen's.  A basic subset of ONE line
+// vector makes H = w x y^T rank 1, where R = V U^T is decided by how the algorithm completes the null space from
+// 1-ulp entries: only the same arithmetic reproduces the oracle's R there (and with it the rest of the run).
+// ------------------------------------------------------------------------------------------
+constexpr int GNC_SERIAL_MAX = 32;
+
+__device__ __noinline__ void gnc_tls_serial(const GncJob& job_g) {
+  const GncJob job = job_g;
+  const int K = (int)job.K;
+  double sv[GNC_SERIAL_MAX][3], tv[GNC_SERIAL_MAX][3], w[GNC_SERIAL_MAX], res[GNC_SERIAL_MAX];
+  for (int k = 0; k < K; ++k) {
+    load_lv(job.src, job.dst, job.edges[k], job.inv_scale, sv[k], tv[k]);
+    w[k] = 1.0;
+  }
+  double nb2 = job.noise_bound * job.noise_bound;
+  if (nb2 < 1e-16) nb2 = 1e-2;  // registration.cc:1592-1595
+  double mu = 1.0, prev_cost = INFINITY, cost = INFINITY;
+  double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  bool use_init = job.use_init != 0;
+  int it_done = 0;
+  for (int it = 0; it < job.max_iterations; ++it) {
+    it_done = it + 1;
+    if (use_init) {  // registration.cc:1617-1621
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r][c] = job.R_init[c * 3 + r];
+      use_init = false;
+    } else {  // svdRot, utils.h:121-136
+      double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int k = 0; k < K; ++k)
+        for (int r = 0; r < 3; ++r) {
+          const double xw = sv[k][r] * w[k];
+          for (int c = 0; c < 3; ++c) H[r][c] += xw * tv[k][c];
+        }
+      Svd3 d;
+      svd3_two_sided(H, d);
+      rotation_from_svd(d, R);
+    }
+    for (int k = 0; k < K; ++k) {
+      const double d0 = tv[k][0] - ((R[0][0] * sv[k][0] + R[0][1] * sv[k][1]) + R[0][2] * sv[k][2]);
+      const double d1 = tv[k][1] - ((R[1][0] * sv[k][0] + R[1][1] * sv[k][1]) + R[1][2] * sv[k][2]);
+      const double d2 = tv[k][2] - ((R[2][0] * sv[k][0] + R[2][1] * sv[k][1]) + R[2][2] * sv[k][2]);
+      res[k] = (d0 * d0 + d1 * d1) + d2 * d2;
+    }
+    if (it == 0) {  // registration.cc:1628-1639
+      double max_residual = K > 0 ? res[0] : 0.0;
+      for (int k = 1; k < K; ++k) max_residual = (max_residual < res[k]) ? res[k] : max_residual;
+      mu = 1 / (2 * max_residual / nb2 - 1);
+      if (mu <= 0) break;
+    }
+    const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
+    cost = 0;
+    for (int k = 0; k < K; ++k) {
+      cost += w[k] * res[k];
+      if (res[k] >= th1)
+        w[k] = 0;
+      else if (res[k] <= th2)
+        w[k] = 1;
+      else
+        w[k] = sqrt(nb2 * mu * (mu + 1) / res[k]) - mu;
+    }
+    const double cost_diff = fabs(cost - prev_cost);
+    mu = mu * job.gnc_factor;
+    prev_cost = cost;
+    if (cost_diff < job.cost_threshold) break;
+  }
+  int gf = 0;
+  for (int k = 0; k < K; ++k) gf += (w[k] >= 0.5) ? 1 : 0;
+  const bool all_in = gf <= 10;  // registration.cc:1685-1690
+  for (int k = 0; k < K; ++k) {
+    const bool in = all_in || w[k] >= 0.5;
+    if (job.inliers) job.inliers[k] = in ? 1 : 0;
+    if (in && job.point_flags) {
+      const uint2 e = job.edges[k];
+      job.point_flags[e.x] = 1;
+      job.point_flags[e.y] = 1;
+    }
+  }
+  if (job.R_out)
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) job.R_out[c * 3 + r] = R[r][c];
+  if (job.info) {
+    job.info[0] = it_done;
+    job.info[1] = all_in ? K : gf;
+    job.info[2] = 0;
+    job.info[3] = 0;
+  }
+  if (job.cost) job.cost[0] = cost;
+}
+
+// one CTA per job; jobs above GNC_SERIAL_MAX line vectors belong to gnc_tls_kernel
+__global__ void __launch_bounds__(128) gnc_tls_small_kernel(const GncJob* __restrict__ jobs) {
+  const GncJob& job = jobs[blockIdx.x];
+  if (!job.active || job.K > (unsigned long long)GNC_SERIAL_MAX) return;
+  if (job.point_flags)
+    for (int i = threadIdx.x; i < job.n_points; i += 128) job.point_flags[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) gnc_tls_serial(job);
+}
+
 template <int NC, int T, int CPS, bool PC>
 __global__ void __launch_bounds__(T, CPS)
     gnc_tls_kernel(const GncJob* __restrict__ jobs, int cap_per_cta, const double GNC_DEEP_MARGIN, const int pf_steps) {
@@ -276,6 +378,7 @@ __global__ void __launch_bounds__(T, CPS)
   const long long t_kernel0 = clock64();
   const int tid = threadIdx.x;
   const unsigned rank = (NC > 1) ? cg::this_cluster().block_rank() : 0u;
+  if (job.K <= (unsigned long long)GNC_SERIAL_MAX) return;  // gnc_tls_small_kernel's (uniform over the cluster)
   const unsigned long long K = job.K;
   // contiguous slice of the line vectors for this CTA
   const unsigned long long per = (K + NC - 1) / NC;
@@ -893,14 +996,10 @@ int launch_gnc_nc(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // (a performance knob only -- any value gives the same results; the tests shrink it to force wake-ups)
-  double deep_margin = GNC_DEEP_MARGIN_DEFAULT;
-  if (const char* e = getenv("PSULVSB_GNC_DEEP_MARGIN")) {
-    const double v = atof(e);
-    if (v > 0.0) deep_margin = v;
-  }
-  int pf_steps = 1;  // look-ahead of the L2 prefetch in the streamed pass, in double-steps (0 = off; measured: 1 is best)
-  if (const char* e = getenv("PSULVSB_GNC_PREFETCH")) pf_steps = atoi(e);
+  // (performance knobs only -- any value gives the same results; the tests shrink the margin to force wake-ups)
+  const double deep_margin = debug_knobs().gnc_deep_margin > 0.0 ? debug_knobs().gnc_deep_margin : GNC_DEEP_MARGIN_DEFAULT;
+  // look-ahead of the L2 prefetch in the streamed pass, in double-steps (0 = off; measured: 1 is best)
+  const int pf_steps = debug_knobs().gnc_prefetch >= 0 ? debug_knobs().gnc_prefetch : 1;
   PSU_CUDA(cudaLaunchKernelEx(&cfg, gnc_tls_kernel<NC, T, CPS, PC>, d_jobs, cap_per_cta, deep_margin, pf_steps));
   return PSULVSB_OK;
 }
@@ -922,8 +1021,7 @@ int gnc_default_capacity() { return gnc_capacity_for(1); }
 
 // CTAs per hypothesis for a batch of n_jobs: as many SMs per job as keeps the whole batch resident
 int gnc_cluster_for(int n_jobs) {
-  static const char* lean_env = getenv("PSULVSB_GNC_LEAN");
-  const int slots = 148 * ((lean_env && lean_env[0] == '1') ? 4 : GNC_CTAS_PER_SM);
+  const int slots = sm_count() * GNC_CTAS_PER_SM;
   if (n_jobs * 8 <= slots) return 8;
   if (n_jobs * 4 <= slots) return 4;
   if (n_jobs * 2 <= slots) return 2;
@@ -932,32 +1030,22 @@ int gnc_cluster_for(int n_jobs) {
 
 int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster, int max_points) {
   if (n_jobs <= 0) return PSULVSB_OK;
-  static const char* pc_env = getenv("PSULVSB_GNC_POINT_CACHE");
-  // opt-in only: measured on B200 it does not pay (B = 256: 29.9 vs 28.1 ms per step, B = 512: 55.4 vs 54.7)
-  const bool point_cache = max_points > 0 && pc_env && pc_env[0] == '1';
+  (void)max_points;
+  gnc_tls_small_kernel<<<n_jobs, 128, 0, st>>>(d_jobs);  // tiny subsets: the reference's arithmetic replayed by one thread
+  PSU_CHECK_LAUNCH("gnc_tls_small_kernel");
   if (cap_per_cta < 32) cap_per_cta = 32;
-  static const char* lean_env = getenv("PSULVSB_GNC_LEAN");
-  const bool lean = lean_env && lean_env[0] == '1';
   switch (cluster) {
     // (measured: 512 threads x 2 CTAs per SM = 64 registers spills 1.3 KB per thread and loses 25 %)
     case 8:
       // few registrations (8 CTAs each still leave SMs idle): 512 threads, one CTA per SM -- half the line
       // vectors per thread in the latency-bound pass
-      if (!lean && n_jobs * 8 <= 148) return launch_gnc_nc<8, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
-      return lean ? launch_gnc_nc<8, 256, 4, false>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<8, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
-    case 4: return lean ? launch_gnc_nc<4, 256, 4, false>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<4, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
-    case 2: return lean ? launch_gnc_nc<2, 256, 4, false>(st, d_jobs, n_jobs, cap_per_cta) : launch_gnc_nc<2, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
-    case 1:
-      if (lean) return launch_gnc_nc<1, 512, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
-      // one CTA per hypothesis (large batches); PSULVSB_GNC_POINT_CACHE=1 caches the points instead of line vectors
-      if (point_cache) return launch_gnc_nc<1, 512, 1, true>(st, d_jobs, n_jobs, max_points);
-      {
-        static const char* v_env = getenv("PSULVSB_GNC_NC1");
-        if (v_env && v_env[0] == '2') return launch_gnc_nc<1, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
-        if (v_env && v_env[0] == '3') return launch_gnc_nc<1, 768, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
-        if (v_env && v_env[0] == '4') return launch_gnc_nc<1, 640, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
-      }
-      return launch_gnc_nc<1, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+      if (n_jobs * 8 <= sm_count()) return launch_gnc_nc<8, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+      return launch_gnc_nc<8, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
+    case 4: return launch_gnc_nc<4, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
+    case 2: return launch_gnc_nc<2, 256, 2, false>(st, d_jobs, n_jobs, cap_per_cta);
+    // one CTA per hypothesis (large batches).  Measured and dropped: caching the points instead of the line vectors
+    // (B = 256: 29.9 vs 28.1 ms per step), 2 x 256-thread CTAs per SM (-6 %), 640 / 768-thread CTAs (-1..2 %)
+    case 1: return launch_gnc_nc<1, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
     default: return fail(PSULVSB_ERR_INVALID, "launch_gnc_tls: cluster must be 1, 2, 4 or 8");
   }
 }

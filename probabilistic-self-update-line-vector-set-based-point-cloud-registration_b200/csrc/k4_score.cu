@@ -337,7 +337,7 @@ int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, co
   const unsigned long long per_cta = (unsigned long long)SB_THREADS * SB_HPT;
   const unsigned long long gx = (n_hyp + per_cta - 1) / per_cta;
   // slice the correspondences too until the grid is ~10 waves deep (2 CTAs per SM), >= 8 tiles per slice
-  unsigned long long chunks = (148ull * 2ull * 10ull + gx - 1) / gx;
+  unsigned long long chunks = ((unsigned long long)sm_count() * 2ull * 10ull + gx - 1) / gx;
   const unsigned long long max_chunks = ((unsigned long long)n + 8 * SB_TP - 1) / (8 * SB_TP);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -351,7 +351,7 @@ int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, co
   PSU_CHECK_LAUNCH("score_batch_kernel");
   if (best) {
     unsigned long long ga = (n_hyp + 255) / 256;
-    if (ga > 148 * 8) ga = 148 * 8;
+    if (ga > sm_count() * 8) ga = sm_count() * 8;
     argmax_counts_kernel<<<(unsigned)ga, 256, 0, st>>>(counts, n_hyp, hyp_begin, best);
     PSU_CHECK_LAUNCH("argmax_counts_kernel");
   }

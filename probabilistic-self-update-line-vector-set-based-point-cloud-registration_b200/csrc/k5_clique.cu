@@ -4,8 +4,9 @@
 // translation solver (registration.cc:1238-1244).
 //
 // The reference calls PMC (teaser/src/graph.cc:12-125; an un-vendored, unpinned dependency) for an
-// exact maximum clique; which maximum clique it returns is not unique, so parity for this branch is
-// defined on the clique SIZE.  Two steps on a bit-matrix adjacency:
+// exact maximum clique; which maximum clique it returns is not pinned by anything in the reference.  Position
+// taken (the same in the CPU oracle): of all cliques of the maximum size, the one whose ascending vertex list is
+// lexicographically smallest -- so size AND members are comparable.  Three steps on a bit-matrix adjacency:
 //  1. a deterministic greedy maximal clique (repeatedly take the candidate with the most neighbours
 //     among the remaining candidates, ties: lowest index, and intersect the candidate set with its
 //     adjacency row): the lower bound lb.  On registration graphs with consensus (one large planted
@@ -16,7 +17,11 @@
 //     <= best).  Roots only use lb and their own improvements, so the result does not depend on
 //     scheduling: the largest size wins, ties go to the lowest root, and a second launch replays that
 //     root to write the members.  Neighbourhoods above 512 vertices that the bound does not cut, or a
-//     root that exhausts its node budget, leave the greedy answer in place and clear *proven.
+//     root that exhausts its node budget, leave the greedy answer in place and clear *proven;
+//  3. the canonical members: with the size omega known, every vertex of degree >= omega - 1 is tried as the
+//     SMALLEST member -- a depth-first search over its later neighbours, candidates ascending, cut only where
+//     omega cannot be reached, stops at its first clique of size omega, which is the lexicographically smallest
+//     one with that root; the lowest successful root wins (atomicMin) and is replayed to write the flags.
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -116,23 +121,36 @@ __device__ __forceinline__ unsigned long long* cx_key(const CliqueJob& job) {
   return reinterpret_cast<unsigned long long*>(job.adj + (((size_t)job.n_vertices * job.stride + 3) & ~(size_t)3));
 }
 
-// flags bit 1: vertex has degree >= lb (can belong to a clique larger than the greedy one)
-__global__ void __launch_bounds__(256) clique_core_kernel(const CliqueJob* __restrict__ jobs) {
+// the maximum size known after the improvement search: the greedy bound or what a root found beyond it
+__device__ __forceinline__ int cx_omega(const CliqueJob& job) {
+  const int found = (int)(cx_key(job)[0] >> 32);
+  const int lb = *job.size;
+  return found > lb ? found : lb;
+}
+
+// phase 0 -- flags bit 1 (value 2): degree >= lb (can belong to a clique larger than the greedy one); work area reset.
+// phase 1 -- flags bit 2 (value 4): degree >= omega - 1 (can belong to a clique of the maximum size).
+__global__ void __launch_bounds__(256) clique_core_kernel(const CliqueJob* __restrict__ jobs, int phase) {
   const CliqueJob& job = jobs[blockIdx.y];
   if (!job.active) return;
   const int lane = threadIdx.x & 31;
   const int lb = *job.size;
+  const int thr = phase == 0 ? lb : cx_omega(job) - 1;
+  const int bit = phase == 0 ? 2 : 4;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long* key = cx_key(job);
-    key[0] = 0ull;
-    key[1] = 0ull;
-    *job.proven = 1;
+    if (phase == 0) {
+      key[0] = 0ull;
+      key[1] = 0ull;
+      *job.proven = 1;
+    }
+    key[2] = ~0ull;  // lowest root with a clique of the maximum size
   }
   for (int v = blockIdx.x * 8 + (threadIdx.x >> 5); v < job.n_vertices; v += gridDim.x * 8) {
     int deg = 0;
     for (int w = lane; w < job.stride; w += 32) deg += __popc(job.adj[(size_t)v * job.stride + w]);
     deg = __reduce_add_sync(0xffffffffu, deg);
-    if (lane == 0) job.flags[v] = (uint8_t)((job.flags[v] & 1) | ((deg >= lb && lb > 0) ? 2 : 0));
+    if (lane == 0) job.flags[v] = (uint8_t)((job.flags[v] & ~bit) | ((deg >= thr && lb > 0) ? bit : 0));
   }
 }
 
@@ -145,7 +163,8 @@ struct CxSmem {
 
 // Branch and bound below root v.  Returns the best clique size found (> floor_size) or 0; target != 0: stop at the
 // first clique of exactly that size and leave its local members in sm.chosen[0 .. target - 2].
-__device__ int cx_search_root(const CliqueJob& job, const CxSmem& sm, int v, int floor_size, int target, int* status) {
+__device__ int cx_search_root(const CliqueJob& job, const CxSmem& sm, int v, int floor_size, int target, int* status,
+                              int core_bit) {
   const int lane = threadIdx.x;
   const int W = job.stride;
   const uint32_t* __restrict__ adj = job.adj;
@@ -159,7 +178,7 @@ __device__ int cx_search_root(const CliqueJob& job, const CxSmem& sm, int v, int
     uint32_t keep = 0u;
     for (uint32_t b = bits; b; b &= b - 1u) {
       const int u = w * 32 + (__ffs(b) - 1);
-      if (job.flags[u] & 2) keep |= 1u << (u & 31);
+      if (job.flags[u] & core_bit) keep |= 1u << (u & 31);
     }
     const int c = __popc(keep);
     int pre = c;
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(32) clique_exact_kernel(const CliqueJob* __res
   for (int v = blockIdx.x; v < job.n_vertices; v += gridDim.x) {
     if (!(job.flags[v] & 2)) continue;
     int status = 0;
-    const int s = cx_search_root(job, sm, v, lb, 0, &status);
+    const int s = cx_search_root(job, sm, v, lb, 0, &status, 2);
     if (threadIdx.x == 0) {
       if (status) atomicExch(reinterpret_cast<unsigned int*>(key + 1), 1u);
       if (s > lb) atomicMax(key, ((unsigned long long)s << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)v));
@@ -281,24 +300,50 @@ __global__ void __launch_bounds__(32) clique_exact_kernel(const CliqueJob* __res
   }
 }
 
-// replay the winning root and write the members (or just strip the core marks when the greedy clique stands)
+// step 3: the lowest root that is the smallest member of a clique of the maximum size
+__global__ void __launch_bounds__(32) clique_canon_kernel(const CliqueJob* __restrict__ jobs) {
+  const CliqueJob& job = jobs[blockIdx.y];
+  if (!job.active) return;
+  extern __shared__ uint32_t cx_raw[];
+  const CxSmem sm = cx_carve(cx_raw);
+  if (*job.size < 1) return;
+  const int omega = cx_omega(job);
+  unsigned long long* key = cx_key(job);
+  for (int v = blockIdx.x; v < job.n_vertices; v += gridDim.x) {
+    if (!(job.flags[v] & 4)) continue;
+    // (a root above the current minimum cannot win; skipping it does not change the minimum)
+    if ((unsigned long long)v > *reinterpret_cast<volatile unsigned long long*>(key + 2)) continue;
+    int status = 0;
+    const int s = cx_search_root(job, sm, v, omega - 1, omega, &status, 4);
+    if (threadIdx.x == 0) {
+      if (status) atomicExch(reinterpret_cast<unsigned int*>(key + 1), 1u);
+      if (s == omega) atomicMin(key + 2, (unsigned long long)v);
+    }
+    __syncwarp();
+  }
+}
+
+// replay the winning root and write the members
 __global__ void __launch_bounds__(32) clique_record_kernel(const CliqueJob* __restrict__ jobs) {
   const CliqueJob& job = jobs[blockIdx.x];
   if (!job.active) return;
   extern __shared__ uint32_t cx_raw[];
   const CxSmem sm = cx_carve(cx_raw);
   const int lane = threadIdx.x;
+  if (*job.size < 1) return;
   unsigned long long* key = cx_key(job);
-  const unsigned long long k = key[0];
   if (lane == 0 && (unsigned int)key[1] != 0u) *job.proven = 0;
-  if (k == 0ull) {
+  const int target = cx_omega(job);
+  const unsigned long long r = key[2];
+  if (r == ~0ull) {
+    // no root reported a clique of the known size (only possible when a search gave up): the greedy clique stands
     for (int v = lane; v < job.n_vertices; v += 32) job.flags[v] &= 1;
+    if (lane == 0) *job.proven = 0;
     return;
   }
-  const int target = (int)(k >> 32);
-  const int root = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+  const int root = (int)r;
   int status = 0;
-  const int s = cx_search_root(job, sm, root, target - 1, target, &status);
+  const int s = cx_search_root(job, sm, root, target - 1, target, &status, 4);
   __syncwarp();
   for (int v = lane; v < job.n_vertices; v += 32) job.flags[v] = 0;
   __syncwarp();
@@ -328,12 +373,12 @@ int launch_max_clique(cudaStream_t st, const CliqueJob* d_jobs, int n_jobs, int 
   }
   const size_t words = (size_t)max_vertices * max_stride;
   unsigned long long gz = (words + 256 * 8 - 1) / (256 * 8);
-  if (gz > 148 * 8) gz = 148 * 8;
+  if (gz > sm_count() * 8) gz = sm_count() * 8;
   if (gz < 1) gz = 1;
   clique_zero_kernel<<<dim3((unsigned)gz, (unsigned)n_jobs), 256, 0, st>>>(d_jobs);
   PSU_CHECK_LAUNCH("clique_zero_kernel");
   unsigned long long ge = (max_edges + 255) / 256;
-  if (ge > 148 * 8) ge = 148 * 8;
+  if (ge > sm_count() * 8) ge = sm_count() * 8;
   if (ge < 1) ge = 1;
   clique_edges_kernel<<<dim3((unsigned)ge, (unsigned)n_jobs), 256, 0, st>>>(d_jobs);
   PSU_CHECK_LAUNCH("clique_edges_kernel");
@@ -344,15 +389,20 @@ int launch_max_clique(cudaStream_t st, const CliqueJob* d_jobs, int n_jobs, int 
   if (!attr2_set) {
     PSU_CUDA(cudaFuncSetAttribute(clique_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CX_SMEM));
     PSU_CUDA(cudaFuncSetAttribute(clique_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CX_SMEM));
+    PSU_CUDA(cudaFuncSetAttribute(clique_canon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CX_SMEM));
     attr2_set = true;
   }
   int gc = (max_vertices + 7) / 8;
-  if (gc > 148 * 8) gc = 148 * 8;
-  clique_core_kernel<<<dim3((unsigned)gc, (unsigned)n_jobs), 256, 0, st>>>(d_jobs);
+  if (gc > sm_count() * 8) gc = sm_count() * 8;
+  clique_core_kernel<<<dim3((unsigned)gc, (unsigned)n_jobs), 256, 0, st>>>(d_jobs, 0);
   PSU_CHECK_LAUNCH("clique_core_kernel");
-  int gx = max_vertices < 148 * 3 ? max_vertices : 148 * 3;
+  int gx = max_vertices < sm_count() * 3 ? max_vertices : sm_count() * 3;
   clique_exact_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), 32, CX_SMEM, st>>>(d_jobs);
   PSU_CHECK_LAUNCH("clique_exact_kernel");
+  clique_core_kernel<<<dim3((unsigned)gc, (unsigned)n_jobs), 256, 0, st>>>(d_jobs, 1);
+  PSU_CHECK_LAUNCH("clique_core_kernel");
+  clique_canon_kernel<<<dim3((unsigned)gx, (unsigned)n_jobs), 32, CX_SMEM, st>>>(d_jobs);
+  PSU_CHECK_LAUNCH("clique_canon_kernel");
   clique_record_kernel<<<n_jobs, 32, CX_SMEM, st>>>(d_jobs);
   PSU_CHECK_LAUNCH("clique_record_kernel");
   return PSULVSB_OK;

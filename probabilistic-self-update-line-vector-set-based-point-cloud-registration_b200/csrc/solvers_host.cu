@@ -124,7 +124,7 @@ __global__ void gnc_points_kernel(const double* __restrict__ tims, unsigned long
 
 unsigned grid_for(unsigned long long n) {
   unsigned long long g = (n + 255) / 256;
-  if (g > 148ull * 16) g = 148ull * 16;
+  if (g > (unsigned long long)sm_count() * 16) g = (unsigned long long)sm_count() * 16;
   return (unsigned)(g ? g : 1);
 }
 

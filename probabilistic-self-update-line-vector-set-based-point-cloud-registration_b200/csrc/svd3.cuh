@@ -17,6 +17,147 @@ __device__ __forceinline__ double det3(const double a[3][3]) {
          a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Two-sided Jacobi SVD of a 3x3 matrix in the operation order of Eigen::JacobiSVD<Matrix3d> as the CPU oracle
+// restates it (oracle/psulvsb_oracle.cpp svd3; utils.h:127, registration.cc:550): sweeps over (p, q) =
+// (1,0), (2,0), (2,1); each 2x2 block is first made symmetric by a left rotation, then diagonalised by a
+// symmetric Jacobi rotation; threshold max(DBL_MIN, 2 eps max|diag|); singular values made non-negative by
+// flipping U's columns, then sorted descending.  This file is compiled with -fmad=false, so every line below
+// rounds exactly like the x86-64 build of the reference: for a rank-deficient H (a basic subset of ONE line
+// vector gives H = w x y^T) the null-space completion -- which decides R = V U^T there and is determined by
+// 1-ulp entries -- comes out identical to the oracle's, not merely "also valid".
+// ------------------------------------------------------------------------------------------------------------
+struct Svd3 {
+  double U[3][3], S[3], V[3][3];
+};
+
+__device__ inline void svd3_two_sided(const double Ain[3][3], Svd3& o) {
+  const double eps = 2.220446049250313e-16, tiny = 2.2250738585072014e-308;
+  const double precision = 2.0 * eps;
+  double scale = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const double a = fabs(Ain[i][j]);
+      scale = (scale < a) ? a : scale;
+    }
+  if (!(scale > 0.0) || !isfinite(scale)) scale = 1.0;
+  double W[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      W[i][j] = Ain[i][j] / scale;
+      o.U[i][j] = (i == j) ? 1.0 : 0.0;
+      o.V[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+  auto mx = [](double a, double b) { return (a < b) ? b : a; };
+  double max_diag = mx(fabs(W[0][0]), mx(fabs(W[1][1]), fabs(W[2][2])));
+  // W <- rows (p, q) combined:  row_p' = c row_p + s row_q,  row_q' = -s row_p + c row_q
+  auto rows = [](double M[3][3], int p, int q, double c, double s) {
+    for (int k = 0; k < 3; ++k) {
+      const double xp = M[p][k], xq = M[q][k];
+      M[p][k] = c * xp + s * xq;
+      M[q][k] = -s * xp + c * xq;
+    }
+  };
+  // M <- columns (p, q) combined:  col_p' = c col_p - s col_q,  col_q' = s col_p + c col_q
+  auto cols = [](double M[3][3], int p, int q, double c, double s) {
+    for (int k = 0; k < 3; ++k) {
+      const double xp = M[k][p], xq = M[k][q];
+      M[k][p] = c * xp - s * xq;
+      M[k][q] = s * xp + c * xq;
+    }
+  };
+  bool finished = false;
+  for (int guard = 0; !finished && guard < 200; ++guard) {
+    finished = true;
+    for (int p = 1; p < 3; ++p)
+      for (int q = 0; q < p; ++q) {
+        const double threshold = mx(tiny, precision * max_diag);
+        if (fabs(W[p][q]) > threshold || fabs(W[q][p]) > threshold) {
+          finished = false;
+          const double a = W[p][p], b = W[p][q], c = W[q][p], d = W[q][q];
+          // left rotation that makes the block symmetric
+          const double t = a + d, dd = c - b;
+          double r1c, r1s;
+          if (fabs(dd) < tiny) {
+            r1c = 1.0;
+            r1s = 0.0;
+          } else {
+            const double u = t / dd;
+            const double tmp = sqrt(1.0 + u * u);
+            r1s = 1.0 / tmp;
+            r1c = u / tmp;
+          }
+          const double a1 = r1c * a + r1s * c, b1 = r1c * b + r1s * d, d1 = -r1s * b + r1c * d;
+          // symmetric 2x2 Jacobi rotation of [a1 b1; b1 d1]
+          double jc, js;
+          const double deno = 2.0 * fabs(b1);
+          if (deno < tiny) {
+            jc = 1.0;
+            js = 0.0;
+          } else {
+            const double tau = (a1 - d1) / deno;
+            const double w = sqrt(tau * tau + 1.0);
+            const double tt = (tau > 0) ? 1.0 / (tau + w) : 1.0 / (tau - w);
+            const double sign_t = tt > 0 ? 1.0 : -1.0;
+            const double n = 1.0 / sqrt(tt * tt + 1.0);
+            js = -sign_t * (b1 / fabs(b1)) * fabs(tt) * n;
+            jc = n;
+          }
+          const double lc = r1c * jc + r1s * js, ls = -r1c * js + r1s * jc;
+          rows(W, p, q, lc, ls);
+          cols(o.U, p, q, lc, -ls);
+          cols(W, p, q, jc, js);
+          cols(o.V, p, q, jc, js);
+          max_diag = mx(max_diag, mx(fabs(W[p][p]), fabs(W[q][q])));
+        }
+      }
+  }
+  for (int i = 0; i < 3; ++i) {
+    const double a = W[i][i];
+    o.S[i] = fabs(a) * scale;
+    if (a < 0)
+      for (int k = 0; k < 3; ++k) o.U[k][i] = -o.U[k][i];
+  }
+  for (int i = 0; i < 3; ++i) {  // selection sort, descending; columns of U and V follow
+    int best = i;
+    for (int k = i + 1; k < 3; ++k)
+      if (o.S[k] > o.S[best]) best = k;
+    if (best != i) {
+      double t = o.S[i];
+      o.S[i] = o.S[best];
+      o.S[best] = t;
+      for (int k = 0; k < 3; ++k) {
+        t = o.U[k][i];
+        o.U[k][i] = o.U[k][best];
+        o.U[k][best] = t;
+        t = o.V[k][i];
+        o.V[k][i] = o.V[k][best];
+        o.V[k][best] = t;
+      }
+    }
+  }
+}
+
+// svdRot's tail (utils.h:129-135): flip V.col(2) when det(U) det(V) < 0, R = V U^T with the oracle's association
+__device__ inline void rotation_from_svd(Svd3& d, double R[3][3]) {
+  if (det3(d.U) * det3(d.V) < 0)
+    for (int k = 0; k < 3; ++k) d.V[k][2] = -d.V[k][2];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i][j] = (d.V[i][0] * d.U[j][0] + d.V[i][1] * d.U[j][1]) + d.V[i][2] * d.U[j][2];
+}
+
+// (out of line: rare, and its arrays must not weigh on the register allocation of the callers' loops)
+static __device__ __noinline__ void kabsch_rank_deficient(const double* Hin, double* R) {
+  double H[3][3], Rm[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) H[i][j] = Hin[i * 3 + j];
+  Svd3 d;
+  svd3_two_sided(H, d);
+  rotation_from_svd(d, Rm);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = Rm[i][j];
+}
+
 // H: row-major 3x3 (H = sum w x y^T, rows index x).  Returns R = V U^T (row-major) where
 // H = U S V^T.  det_mode 0: flip when det(U) det(V) < 0 (svdRot); 1: flip when det(V U^T) < 0
 // (weightedSVD) -- the same condition, kept separate to mirror the two reference sites.
@@ -129,6 +270,11 @@ __device__ inline void kabsch_rotation(const double Hin[3][3], double R[3][3], d
   // sigma_x > 1e-14 sigma_0  <=>  a2[x] v2[i0] > 1e-28 a2[i0] v2[x]
   const bool ok1 = a2[i1] * v2[i0] > 1e-28 * (a2[i0] * v2[i1]);
   const bool ok2 = a2[i2] * v2[i0] > 1e-28 * (a2[i0] * v2[i2]);
+  if (!ok1 || !ok2) {
+    // rank-deficient H: R = V U^T is not unique; take the completion of the reference's own algorithm
+    kabsch_rank_deficient(&Hin[0][0], &R[0][0]);
+    return;
+  }
   {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -137,27 +283,10 @@ __device__ inline void kabsch_rotation(const double Hin[3][3], double R[3][3], d
       Vs[k][1] = V[k][i1] * iv[i1];
       Vs[k][2] = V[k][i2] * iv[i2];
     }
-    if (ok1) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) U[k][1] = A[k][i1] * ia[i1];
-    } else {
-      // rank 1: any unit vector orthogonal to u0 (the reference's completion is arbitrary too)
-      double ax = fabs(U[0][0]), ay = fabs(U[1][0]), az = fabs(U[2][0]);
-      double e[3] = {0, 0, 0};
-      if (ax <= ay && ax <= az) e[0] = 1; else if (ay <= az) e[1] = 1; else e[2] = 1;
-      const double d = e[0] * U[0][0] + e[1] * U[1][0] + e[2] * U[2][0];
-      double w[3] = {e[0] - d * U[0][0], e[1] - d * U[1][0], e[2] - d * U[2][0]};
-      const double nw = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) U[k][1] = w[k] / nw;
-    }
-    if (ok2) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) U[k][2] = A[k][i2] * ia[i2];
-    } else {
-      U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
-      U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
-      U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+    for (int k = 0; k < 3; ++k) {
+      U[k][1] = A[k][i1] * ia[i1];
+      U[k][2] = A[k][i2] * ia[i2];
     }
   }
   if (det3(U) * det3(Vs) < 0.0) {

@@ -8,7 +8,8 @@ import numpy as np
 
 from . import capi
 
-IO_SYMBOLS = ["psulvsb_histogram_outlier_removal", "psulvsb_mask_filter", "psulvsb_ply_vertex_count",
+IO_SYMBOLS = ["psulvsb_histogram_outlier_removal", "psulvsb_mask_filter", "psulvsb_prefilter_reduce",
+              "psulvsb_ply_vertex_count",
               "psulvsb_ply_read_xyz", "psulvsb_corr_count", "psulvsb_corr_read", "psulvsb_gtmat_read",
               "psulvsb_gtlog_read"]
 
@@ -25,6 +26,7 @@ def _lib():
     if not _declared:
         L.psulvsb_histogram_outlier_removal.argtypes = [_dp, _dp, C.c_int, _ip, _ip]
         L.psulvsb_mask_filter.argtypes = [_dp, _dp, _ip, C.c_int, _dp, _dp, _ip, _ip]
+        L.psulvsb_prefilter_reduce.argtypes = [_dp, _dp, _dp, _dp, C.c_int, _ip, _dp, _dp, _ip, _ip, _ip]
         L.psulvsb_ply_vertex_count.argtypes = [C.c_char_p, _llp]
         L.psulvsb_ply_read_xyz.argtypes = [C.c_char_p, _fp, C.c_longlong, _llp]
         L.psulvsb_corr_count.argtypes = [C.c_char_p, _llp]
@@ -65,6 +67,23 @@ def mask_filter(src, tgt, keep_mask):
                                           sr.ctypes.data_as(_dp), tr.ctypes.data_as(_dp), rm.ctypes.data_as(_ip),
                                           C.byref(c)))
     return np.asfortranarray(sr[:, :c.value]), np.asfortranarray(tr[:, :c.value]), rm
+
+
+def prefilter_reduce(src_normals, tgt_normals, src, tgt):
+    """The driver's whole timed pre-filter (PSULVSB.cc:310-317) in one device call:
+    -> (keep_mask[n], src_reduce 3xC, tgt_reduce 3xC, dense reduce_map[n], remain_count)."""
+    a, b, p, q = _cm(src_normals), _cm(tgt_normals), _cm(src), _cm(tgt)
+    n = a.shape[1]
+    keep = np.zeros(n, dtype=np.int32)
+    sr = np.zeros((3, max(n, 1)), order="F")
+    tr = np.zeros((3, max(n, 1)), order="F")
+    rm = np.zeros(n, dtype=np.int32)
+    c, rem = C.c_int(0), C.c_int(0)
+    capi.check(_lib().psulvsb_prefilter_reduce(a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), p.ctypes.data_as(_dp),
+                                               q.ctypes.data_as(_dp), n, keep.ctypes.data_as(_ip),
+                                               sr.ctypes.data_as(_dp), tr.ctypes.data_as(_dp), rm.ctypes.data_as(_ip),
+                                               C.byref(c), C.byref(rem)))
+    return keep, np.asfortranarray(sr[:, :c.value]), np.asfortranarray(tr[:, :c.value]), rm, rem.value
 
 
 def read_ply_xyz(path: str) -> np.ndarray:

@@ -90,10 +90,16 @@ class RobustRegistrationSolver:
         p = self._params
         if p.rotation_estimation_algorithm != ROTATION_ESTIMATION_ALGORITHM.GNC_TLS:
             raise capi.PsulvsbError(capi.ERR_UNSUPPORTED, "only GNC_TLS is on the PSULVSB path (registration.cc:1111)")
+        # deprecated fields first, exactly as registration.cc:628-637 (the second one wins when both are cleared)
+        mode = p.inlier_selection_mode
+        if not p.use_max_clique:
+            mode = INLIER_SELECTION_MODE.NONE
+        if not p.max_clique_exact_solution:
+            mode = INLIER_SELECTION_MODE.PMC_HEU
         return capi.default_params(
             noise_bound=p.noise_bound, cbar2=p.cbar2, estimate_scaling=int(bool(p.estimate_scaling)),
             rotation_max_iterations=p.rotation_max_iterations, rotation_gnc_factor=p.rotation_gnc_factor,
-            rotation_cost_threshold=p.rotation_cost_threshold, inlier_selection_mode=int(p.inlier_selection_mode),
+            rotation_cost_threshold=p.rotation_cost_threshold, inlier_selection_mode=int(mode),
             kcore_heuristic_threshold=p.kcore_heuristic_threshold, seed=p.seed,
             wallclock_cap_s=0.0 if p.replay else 60.0)
 

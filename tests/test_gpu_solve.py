@@ -261,13 +261,20 @@ def test_unknown_scale_histogram_growth_matches_oracle(env):
 
 def test_unknown_scale_benchmark_1_rank_deficient(env, golden):
     """benchmark_1 has 10 points: |L_sampled| = 4 and the basic subset is ONE line vector, so H = sv tv^T has
-    rank 1 and R = V U^T is not unique (any SVD completes the null space differently -- Eigen's, the oracle's
-    and the device's all do).  No step-by-step parity is defined there; the fixture's ground truth is."""
-    capi = env["capi"]
+    rank 1 and R = V U^T is decided by the SVD's null-space completion.  Tiny subsets replay the reference's
+    arithmetic on the device (k3_rotation.cu gnc_tls_serial + the two-sided Jacobi of svd3.cuh), so the run is
+    identical to the oracle's step by step -- and it meets the fixture's ground-truth scale."""
+    capi, O = env["capi"], env["O"]
     b = golden["bench"]
     nb = float(b["b1_noise_bound"][0])
     kw = dict(noise_bound=nb, cbar2=1.0, estimate_scaling=1, rotation_cost_threshold=0.005, wallclock_cap_s=0.0,
               inloop_noise_bound=nb, score_noise_bound=nb)
+    for seed in (1, 2, 3, 4):
+        so, to = O.solve(O.default_params(seed=seed, **kw), b["b1_src"], b["b1_dst"])
+        sg, tg = env["h"].solve(capi.default_params(seed=seed, **kw), capi.HostProblem(b["b1_src"], b["b1_dst"]),
+                                trace_cap=4096)
+        assert_same_run(env, so, to, sg, tg)
+        assert any(rec.basic_choose == 1 for rec in tg["local"])      # the rank-1 case did occur
     sg, _ = env["h"].solve(capi.default_params(seed=1, **kw), capi.HostProblem(b["b1_src"], b["b1_dst"]))
     assert sg.status == 0 and sg.valid
     assert abs(sg.scale - float(b["b1_s"][0])) < 0.02 * float(b["b1_s"][0])
@@ -334,10 +341,32 @@ def test_invalid_problems_are_refused(env):
         h.solve(p, capi.HostProblem(bad, np.ones((3, 10))))
     assert ei.value.code == capi.ERR_INVALID
     with pytest.raises(capi.PsulvsbError):                           # nothing uploaded
-        capi.Handle(0).solve_resident.__func__  # attribute exists
-        hh = capi.Handle(0)
-        hh._problems = []
+        capi.Handle(0).solve_resident(p)
+    # a failed re-upload leaves NOTHING resident (not the previous batch size over a half-overwritten arena)
+    hh = capi.Handle(0)
+    good = env["synth"].make_pair(200, 0.5, 2)
+    hh.upload([capi.HostProblem(good["src"], good["dst"])] * 3)
+    assert hh.resident_size == 3
+    with pytest.raises(capi.PsulvsbError):
+        hh.upload([capi.HostProblem(good["src"], good["dst"]), capi.HostProblem(bad, np.ones((3, 10)))])
+    assert hh.resident_size == 0
+    with pytest.raises(capi.PsulvsbError):
         hh.solve_resident(p)
+    # solve() on the handle replaces the resident batch; solve_resident follows the library's count
+    hh.upload([capi.HostProblem(good["src"], good["dst"])] * 3)
+    hh.solve(p, capi.HostProblem(good["src"], good["dst"]))
+    assert hh.resident_size == 1 and len(hh.solve_resident(p)) == 1
+    # keep_mask == 1 with a reduce_map entry that is not a column of src / dst would index out of bounds on the device
+    km = np.ones(200, dtype=np.int32)
+    rm = np.arange(200, dtype=np.int32)
+    rm[17] = -1
+    with pytest.raises(capi.PsulvsbError) as ei:
+        h.solve(p, capi.HostProblem(good["src"], good["dst"], good["src"], good["dst"], km, rm))
+    assert ei.value.code == capi.ERR_INVALID
+    rm[17] = 200
+    with pytest.raises(capi.PsulvsbError) as ei:
+        h.solve(p, capi.HostProblem(good["src"], good["dst"], good["src"], good["dst"], km, rm))
+    assert ei.value.code == capi.ERR_INVALID
     # the handle is still usable afterwards
     pair = env["synth"].make_pair(300, 0.5, 1)
     sol, _ = h.solve(p, capi.HostProblem(pair["src"], pair["dst"]))

@@ -47,16 +47,18 @@ def test_sampler_replays_rejection_sampling(P, O, n, count):
         assert consumed == want_consumed          # same stream position afterwards
 
 
-def test_sampler_list_overflow_falls_back_to_the_walk(P, O, monkeypatch):
+def test_sampler_list_overflow_falls_back_to_the_walk(P, O):
     """The per-bucket draw lists have room for the mean + 10 sigma of the uniform draws; should one ever overflow, the
     bucket pass walks the whole window instead.  Forced here by filling the lists only to 100 entries."""
-    monkeypatch.setenv("PSULVSB_SAMPLE_LIST_CAP_TEST", "100")
+    P["capi"].debug_set("sample_list_cap_test", 100)
     st = P["stages"]
-    for n, count in [(627562, 62756), (150000, 75000)]:
-        got, consumed = st.sample(7, 1, 3, n, count)
-        want, want_consumed = O.sample_without_replacement(7, 1, 3, n, count)
-        assert np.array_equal(got, want) and consumed == want_consumed
-    monkeypatch.delenv("PSULVSB_SAMPLE_LIST_CAP_TEST")
+    try:
+        for n, count in [(627562, 62756), (150000, 75000)]:
+            got, consumed = st.sample(7, 1, 3, n, count)
+            want, want_consumed = O.sample_without_replacement(7, 1, 3, n, count)
+            assert np.array_equal(got, want) and consumed == want_consumed
+    finally:
+        P["capi"].debug_set("reset", 0)
     got, consumed = st.sample(7, 1, 3, 627562, 62756)          # and the lists work again afterwards (counters were reset)
     want, want_consumed = O.sample_without_replacement(7, 1, 3, 627562, 62756)
     assert np.array_equal(got, want) and consumed == want_consumed
@@ -169,6 +171,45 @@ def test_gnc_tls_rotation_vs_oracle(P, O, n, seed, warm):
     assert abs(cost_g - cost_w) <= 1e-9 * max(1.0, abs(cost_w))
 
 
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 12, 32])
+def test_gnc_tiny_subsets_replay_the_reference_arithmetic_bit_for_bit(P, O, K):
+    """A basic subset of ONE line vector gives H = w x y^T of rank 1: R = V U^T is then decided by how the SVD completes
+    the null space from 1-ulp entries, so only the reference's own arithmetic reproduces it.  Subsets of up to 32 line
+    vectors run through a single thread that replays the oracle's loop (sequential sums, two-sided Jacobi, no FMA):
+    rotation, cost, iteration count and inlier mask must be IDENTICAL, cold and warm started, also when the weights
+    become fractional (consistent pairs with a length difference near beta) and when all line vectors are parallel."""
+    st = P["stages"]
+    rng = np.random.default_rng(100 + K)
+    for trial in range(12):
+        n = 2 * K
+        src = rng.uniform(-1.5, 1.5, (3, n))
+        ang = rng.uniform(0.1, 3.0)
+        ax = rng.standard_normal(3)
+        ax /= np.linalg.norm(ax)
+        Kx = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        Rt = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+        dst = Rt @ src + rng.uniform(-0.04, 0.04, (3, n))
+        if trial % 3 == 1:                       # stretch some targets: length differences near beta = 0.1
+            dst[:, 1::2] += 0.085 * (dst[:, 1::2] - dst[:, 0::2]) / np.linalg.norm(dst[:, 1::2] - dst[:, 0::2], axis=0)
+        if trial % 4 == 3:                       # every line vector parallel: rank 1 whatever K is
+            d = src[:, 1] - src[:, 0]
+            src[:, 1::2] = src[:, 0::2] + d[:, None] * rng.uniform(0.5, 2.0, K)
+            dst = Rt @ src
+        e = np.stack([np.arange(0, n, 2), np.arange(1, n, 2)], axis=1).astype(np.int32)
+        sv = src[:, e[:, 1]] - src[:, e[:, 0]]
+        tv = dst[:, e[:, 1]] - dst[:, e[:, 0]]
+        R_init = None
+        if trial % 2:
+            R_init = Rt @ (np.eye(3) + np.sin(0.05) * Kx + (1 - np.cos(0.05)) * Kx @ Kx)
+        Rw, inl_w, its_w, cost_w = O.gnc_tls(sv, tv, 0.1, 100, 1.4, 0.005, R_init)
+        Rg, inl_g, its_g, cost_g, n_inl = st.gnc_tls_rotation(st.to_device_points(src), st.to_device_points(dst),
+                                                             torch.from_numpy(e).cuda(), 0.1, 100, 1.4, 0.005, R_init)
+        assert its_g == its_w
+        assert np.array_equal(Rg, Rw), (K, trial, np.abs(Rg - Rw).max())       # bit for bit
+        assert np.array_equal(inl_g, inl_w) and n_inl == int(inl_w.sum())
+        assert cost_g == cost_w or (np.isinf(cost_g) and np.isinf(cost_w))
+
+
 def test_gnc_tls_golden_rotation_only(P, O, golden):
     """rotation-solver-test.cc:221-250: rotation_only_src.csv rotated by expected_R, tol 1e-5 rad."""
     st = P["stages"]
@@ -219,11 +260,12 @@ def test_gnc_batch_parks_sleeping_line_vectors_exactly(P, O, cluster, parking):
 
 
 @pytest.mark.parametrize("margin", ["1e-9", "1e-4"])
-def test_gnc_parking_wakes_line_vectors_up_again(P, O, margin, monkeypatch):
+def test_gnc_parking_wakes_line_vectors_up_again(P, O, margin, request):
     """The parking threshold is a performance knob: with a tiny one, line vectors are parked with almost no margin,
     the rotation drift reaches their wake-up values within an iteration or two and the active range is reopened
     again and again.  The result must not change."""
-    monkeypatch.setenv("PSULVSB_GNC_DEEP_MARGIN", margin)
+    P["capi"].debug_set("gnc_deep_margin", float(margin))
+    request.addfinalizer(lambda: P["capi"].debug_set("reset", 0))
     st, synth = P["stages"], P["synth"]
     pair = synth.make_pair(5000, 0.95, 11, outliers="fpfh")
     pi, pj = O.reduced_set(pair["src"], pair["dst"], 0.1)
@@ -403,6 +445,7 @@ def test_greedy_clique_on_planted_graphs(P, O):
         if len(edges):
             got_x, size_x, proven = st.max_clique(edges, n)   # the exact search confirms it
             assert proven and size_x == size and np.array_equal(got_x, got)
+            assert np.array_equal(got_x, O.max_clique(n, edges))   # same members as the oracle (canonical clique)
         full = A | A.T
         for a in got:                                    # a clique ...
             for b in got:
@@ -442,6 +485,8 @@ def test_exact_clique_on_random_graphs(P, O, n, p_edge, seed):
     got, size, proven = st.max_clique(edges, n)
     assert size == len(got) and _is_clique(edges, n, got)
     assert proven and size == len(exact)
+    # members too: both sides return the lexicographically smallest clique of the maximum size
+    assert np.array_equal(np.sort(got), np.asarray(exact))
     g_got, g_size = st.greedy_clique(edges, n)
     assert g_size == len(g_got) <= size and _is_clique(edges, n, g_got)
     got2, size2, _ = st.max_clique(edges, n)            # deterministic: same members on a second run

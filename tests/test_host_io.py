@@ -1,5 +1,5 @@
-"""Host-side helpers around the hot path (include/psulvsb_io.h): pre-filter vs its numpy restatement,
-PLY and correspondence-file readers on files written by the test.  CPU only."""
+"""Helpers around the hot path (include/psulvsb_io.h): the device pre-filter vs its numpy restatement (-m gpu),
+PLY and correspondence-file readers on files written by the test (CPU)."""
 import struct
 
 import numpy as np
@@ -25,7 +25,8 @@ def _normals(n, seed, agree=0.6):
     return a, b
 
 
-@pytest.mark.parametrize("n,seed", [(50, 0), (500, 1), (5000, 2), (1889, 3)])
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed", [(50, 0), (500, 1), (5000, 2), (1889, 3), (20000, 4)])
 def test_histogram_outlier_removal_matches_restatement(n, seed):
     a, b = _normals(n, seed)
     if seed == 1:
@@ -38,6 +39,7 @@ def test_histogram_outlier_removal_matches_restatement(n, seed):
     assert rem_g == int((keep_g == 1).sum()) and rem_g > 0
 
 
+@pytest.mark.gpu
 def test_histogram_degenerate_inputs():
     a = np.tile(np.array([[0.0], [0.0], [1.0]]), (1, 20))
     keep, rem = io.histogram_outlier_removal(a, a.copy())        # all angles equal: one bin, nothing above mean+sigma
@@ -47,6 +49,26 @@ def test_histogram_degenerate_inputs():
     assert keep.size == 0 and rem == 0
 
 
+@pytest.mark.gpu
+def test_prefilter_reduce_is_histogram_then_mask_filter():
+    a, b = _normals(3000, 9)
+    rng = np.random.default_rng(10)
+    src, tgt = rng.standard_normal((3, 3000)), rng.standard_normal((3, 3000))
+    keep, sr, tr, rm, rem = io.prefilter_reduce(a, b, src, tgt)
+    keep_o, rem_o = OP.histogram_outlier_removal(a, b)
+    sro, tro, rmo = OP.mask_filter(src, tgt, keep_o)
+    assert np.array_equal(keep, keep_o) and rem == rem_o == sr.shape[1]
+    assert np.array_equal(sr, sro) and np.array_equal(tr, tro) and np.array_equal(rm, rmo)
+
+
+def test_prefilter_has_no_cpu_fallback():
+    if capi.lib().psulvsb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(Exception):
+        io.histogram_outlier_removal(np.ones((3, 8)), np.ones((3, 8)))
+
+
+@pytest.mark.gpu
 def test_mask_filter_matches_restatement():
     rng = np.random.default_rng(5)
     src, tgt = rng.standard_normal((3, 300)), rng.standard_normal((3, 300))

@@ -38,15 +38,16 @@ def first_difference(tg, to):
     return None
 
 
-def main():
-    n_prob = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+def sweep(n_prob, sizes=(150, 300, 600, 1000, 2000, 3000), verbose=True):
+    """-> (groups, refused, differing): groups[group][kind] = [identical, total]."""
     rng = np.random.default_rng(2026)
     h = capi.Handle(0)
     groups = {"consensus": {}, "no consensus": {}}
     refused = 0
+    differing = []
     max_r, max_t = 0.0, 0.0
     for k in range(n_prob):
-        n = int(rng.choice([150, 300, 600, 1000, 2000, 3000]))
+        n = int(rng.choice(list(sizes)))
         ratio = float(rng.choice([0.5, 0.8, 0.9, 0.95]))
         kind = ["full", "prefilter", "unknown_scale"][k % 3]
         outl = "gross" if (kind == "unknown_scale" or k % 2) else "fpfh"
@@ -64,7 +65,8 @@ def main():
             sg, tg = h.solve(capi.default_params(**kw), prob, trace_cap=4096)
         except capi.PsulvsbError as e:
             refused += 1
-            print(f"  refused: problem {k} kind={kind} n={n}: {e}")
+            if verbose:
+                print(f"  refused: problem {k} kind={kind} n={n}: {e}")
             continue
         grp = "consensus" if so.final_inlier_count >= 10 else "no consensus"
         diff = first_difference(tg, to)
@@ -82,15 +84,25 @@ def main():
         if same:
             max_r, max_t = max(max_r, dr), max(max_t, dt)
         else:
-            print(f"  differs [{grp}]: problem {k} kind={kind} n={n} outliers={ratio} ({outl}): iters gpu/oracle "
-                  f"{sg.local_iters}/{so.local_iters}, inliers {sg.final_inlier_count}/{so.final_inlier_count}, "
-                  f"dR={dr:.2e} dt={dt:.2e}; first difference (iter, field, gpu, oracle, basic_choose, b_rate): {diff}")
+            msg = (f"  differs [{grp}]: problem {k} kind={kind} n={n} outliers={ratio} ({outl}): iters gpu/oracle "
+                   f"{sg.local_iters}/{so.local_iters}, inliers {sg.final_inlier_count}/{so.final_inlier_count}, "
+                   f"dR={dr:.2e} dt={dt:.2e}; first difference (iter, field, gpu, oracle, basic_choose, b_rate): {diff}")
+            differing.append((grp, k, msg))
+            if verbose:
+                print(msg)
+    if verbose:
+        print(f"largest deviation of the final transform over the identical runs: R {max_r:.3e} rad, t {max_t:.3e}")
+    return groups, refused, differing
+
+
+def main():
+    n_prob = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    groups, refused, _ = sweep(n_prob)
     for grp, kinds in groups.items():
         a = sum(v[0] for v in kinds.values())
         b = sum(v[1] for v in kinds.values())
         print(f"{grp}: identical step by step {a}/{b}   " + "  ".join(f"{k} {v[0]}/{v[1]}" for k, v in kinds.items()))
     print(f"refused: {refused}")
-    print(f"largest deviation of the final transform over the identical runs: R {max_r:.3e} rad, t {max_t:.3e}")
 
 
 if __name__ == "__main__":
