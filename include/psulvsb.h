@@ -147,10 +147,17 @@ const char* psulvsb_last_error(void);
 void psulvsb_default_params(psulvsb_params_t* p);
 /* Number of CUDA devices the library can use (0 when none; never fails). */
 int psulvsb_device_count(void);
-/* One handle = one device, one stream, private device arenas; handles are independent and may
- * be used from different threads (the reference's solver is neither re-entrant nor thread safe,
- * registration.cc:40-50). */
+/* One handle = one device and a small pool of lock-step engines (each its own stream and private device arenas);
+ * handles are independent and may be used from different threads (the reference's solver is neither re-entrant nor
+ * thread safe, registration.cc:40-50). */
 int psulvsb_create(psulvsb_handle_t* out, int device);
+/* How a batch is advanced.  chunk: registrations per lock-step chunk (0 = one per SM of the device); lanes: chunks in
+ * flight at once, each on its own engine, stream and host thread (0 = 4).  A batch of at most `chunk` problems runs as
+ * one chunk.  With host buffers (psulvsb_solve_batch) chunks are handed to the lanes dynamically, so chunk k + 1 is
+ * staged and copied while chunk k is solved; a resident batch is split evenly over at most `lanes` engines.  Results
+ * never depend on these settings (every registration has its own state and sample stream).  Changing them drops the
+ * resident batch. */
+int psulvsb_set_batching(psulvsb_handle_t h, int chunk, int lanes);
 /* Debug / test switches (process-wide; the library reads NO environment variable).  They select among code paths
  * that produce identical results: "gnc_deep_margin" (rad), "gnc_prefetch", "sample_list_cap_test", "k1_variant"
  * (1..4 rows per thread), "upload_prof" (1: phase timings on stderr), "reset" (all back to defaults). */
@@ -176,17 +183,21 @@ int psulvsb_batch_solve_resident(psulvsb_handle_t h, const psulvsb_params_t* par
                                  psulvsb_solution_t* solutions, int n_solutions);
 /* Problems currently resident on the handle (0: nothing uploaded, or the last upload failed). */
 int psulvsb_batch_resident_size(psulvsb_handle_t h);
-/* Kernel launches issued by the handle since creation / device time (ms) of the last solve call,
- * measured with CUDA events on the handle's stream. */
+/* Kernel launches issued by the handle since creation / device time (ms) of the last solve call: CUDA events,
+ * from the start of the call to the end of its last chunk (the chunks run on the engines' own streams). */
 long long psulvsb_launch_count(psulvsb_handle_t h);
 double psulvsb_last_device_ms(psulvsb_handle_t h);
-/* Device time (ms), CUDA events on the handle's stream, of part `which` of the last solve call:
- * 0 stage 1 in full (float4 packing, mask, row scan, n_red read-back, edge compaction, state init),
- * 1 the tick loop (sampling, GNC-TLS, translation, scoring, control), 2 the consistency-mask kernel
- * alone (one launch over the whole batch), 3 the GNC-TLS launches of all ticks, 4 refinement + solution copy. */
+/* Device time (ms), CUDA events on the engines' streams, of part `which` of the last solve call:
+ * 0 stage 1 in full (float4 packing, mask, row scan, n_red read-back, edge compaction, state init), mean over chunks,
+ * 1 the tick loop (sampling, GNC-TLS, translation, scoring, control), mean over chunks,
+ * 2 the consistency-mask kernel alone: time during which the launch of SOME chunk was running (union of the
+ *   launches' intervals; one launch per chunk),
+ * 3 the GNC-TLS launches of all ticks, union over chunks likewise, 4 refinement + solution copy, mean over chunks. */
 double psulvsb_last_stage_ms(psulvsb_handle_t h, int which);
-/* Engine ticks (lock-step local iterations over the whole batch) of the last solve call. */
+/* Engine ticks (lock-step local iterations of a chunk) of the last solve call: the largest over its chunks ... */
 int psulvsb_last_ticks(psulvsb_handle_t h);
+/* ... and per chunk: writes min(cap, n_chunks) entries, returns n_chunks. */
+int psulvsb_last_chunk_ticks(psulvsb_handle_t h, int* out, int cap);
 
 /* ------------------------------------------------------------------------------------------ */
 /* stage entry points: DEVICE pointers, asynchronous on `stream` (a cudaStream_t, may be NULL) */
@@ -335,6 +346,43 @@ int psulvsb_score_batch(void* stream, const void* d_src_f4, const void* d_dst_f4
                         unsigned long long hyp_begin, double scale, double tau, double coord_bound,
                         const double center_src[3], const double center_dst[3], uint32_t* d_counts,
                         unsigned long long* d_best, unsigned long long* d_border_count);
+/* ------------------------------------------------------------------------------------------ */
+/* multi-GPU: one process per GPU, one NCCL communicator per handle.  The reference  */
+/* is single-threaded CPU code and has no counterpart; the path shards where its work splits:       */
+/* independent registrations (no exchange: give every rank its own slice of psulvsb_solve_batch),   */
+/* hypothesis batches (psulvsb_score_batch_sharded) and, for one large registration, the rows of    */
+/* the consistency stage (psulvsb_solve_sharded; loop registration.cc:682-767).                     */
+/* ------------------------------------------------------------------------------------------ */
+#define PSULVSB_UNIQUE_ID_BYTES 128
+/* Rank 0 makes the communicator id (ncclGetUniqueId) and hands its PSULVSB_UNIQUE_ID_BYTES bytes to the other ranks by
+ * any means it has (MPI, a socket, a file, torch.distributed); then every rank calls psulvsb_comm_create with its rank.
+ * NCCL is bound at run time (libnccl.so.2); without it these entry points fail with PSULVSB_ERR_UNSUPPORTED. */
+int psulvsb_comm_unique_id(void* out_id);
+int psulvsb_comm_create(psulvsb_handle_t h, int rank, int world, const void* id);
+int psulvsb_comm_destroy(psulvsb_handle_t h);
+int psulvsb_comm_rank(psulvsb_handle_t h);
+int psulvsb_comm_world(psulvsb_handle_t h);
+/* In-stream collectives on DEVICE buffers (no-ops on a handle without a communicator): element-wise sum of uint32
+ * (per-row popcounts of row blocks built with psulvsb_consistency_mask_rows: rows a rank does not own stay 0, so the
+ * sum is the all-gather) and max of uint64 (packed best-hypothesis keys). */
+int psulvsb_comm_allreduce_sum_u32(psulvsb_handle_t h, void* stream, uint32_t* d_inout, unsigned long long n);
+int psulvsb_comm_allreduce_max_u64(psulvsb_handle_t h, void* stream, unsigned long long* d_inout, unsigned long long n);
+/* psulvsb_score_batch over this rank's slice of the hypotheses (hyp_begin = the slice's first global id) followed, on
+ * the same stream, by ONE 8-byte ncclAllReduce(max) of *d_best: afterwards every rank holds the global best key. */
+int psulvsb_score_batch_sharded(psulvsb_handle_t h, void* stream, const void* d_src_f4, const void* d_dst_f4,
+                                const double* d_src64, const double* d_dst64, int n, const double* d_hyp,
+                                unsigned long long n_hyp, unsigned long long hyp_begin, double scale, double tau,
+                                double coord_bound, const double center_src[3], const double center_dst[3],
+                                uint32_t* d_counts, unsigned long long* d_best, unsigned long long* d_border_count);
+/* psulvsb_solve of ONE (large) registration by all ranks of the handle's communicator: every rank passes the SAME
+ * problem and params and receives the same solution.  Rank r builds a triangular-balanced block of the consistency
+ * mask's rows and compacts its edges; the ranks exchange their edge counts (8 bytes each) and then their blocks of the
+ * edge list (in-place all-gather-v over NVLink), so that every rank holds the reference's L_reduced_set in the
+ * reference's row-major order; the sequential RANSAC that follows is replicated (it is deterministic: same sample
+ * stream, same result).  Known scale only.  Without a communicator (or world = 1) this is psulvsb_solve. */
+int psulvsb_solve_sharded(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                          psulvsb_solution_t* solution, psulvsb_trace_t* trace /* may be NULL */);
+
 /* Single-hypothesis FP64 scoring with per-point outputs (inlier flags, residuals). */
 int psulvsb_score_one(void* stream, const double* d_src64, const double* d_dst64, int n, double scale,
                       const double* d_R, const double* d_t, double tau, uint8_t* d_inliers, double* d_residuals,

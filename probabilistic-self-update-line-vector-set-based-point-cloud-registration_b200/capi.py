@@ -21,14 +21,18 @@ SYMBOLS = [
     "psulvsb_version", "psulvsb_last_error", "psulvsb_default_params", "psulvsb_device_count",
     "psulvsb_create", "psulvsb_destroy", "psulvsb_solve", "psulvsb_solve_batch", "psulvsb_batch_upload",
     "psulvsb_batch_solve_resident", "psulvsb_batch_resident_size", "psulvsb_debug_set", "psulvsb_launch_count", "psulvsb_last_device_ms", "psulvsb_last_stage_ms",
-    "psulvsb_last_ticks", "psulvsb_pack_points", "psulvsb_consistency_mask", "psulvsb_consistency_mask_rows",
+    "psulvsb_last_ticks", "psulvsb_last_chunk_ticks", "psulvsb_set_batching", "psulvsb_pack_points", "psulvsb_consistency_mask", "psulvsb_consistency_mask_rows",
     "psulvsb_mask_symmetrize", "psulvsb_compact_edges", "psulvsb_sample_workspace_bytes",
     "psulvsb_sample_default_max_draws", "psulvsb_sample", "psulvsb_philox_fill", "psulvsb_gnc_tls_rotation",
     "psulvsb_kabsch_batch", "psulvsb_tls_translation", "psulvsb_score_batch", "psulvsb_score_one",
     "psulvsb_max_clique", "psulvsb_max_clique_scratch_words", "psulvsb_gnc_tls_rotation_batch",
     "psulvsb_compute_tims_host", "psulvsb_scale_inliers_host", "psulvsb_tls_scale_host",
     "psulvsb_gnc_tls_rotation_host", "psulvsb_tls_translation_host", "psulvsb_estimate_normals", "psulvsb_estimate_normals_host",
+    "psulvsb_comm_unique_id", "psulvsb_comm_create", "psulvsb_comm_destroy", "psulvsb_comm_rank", "psulvsb_comm_world",
+    "psulvsb_comm_allreduce_sum_u32", "psulvsb_comm_allreduce_max_u64", "psulvsb_score_batch_sharded",
+    "psulvsb_solve_sharded",
 ]
+UNIQUE_ID_BYTES = 128
 
 
 class PsulvsbError(RuntimeError):
@@ -175,6 +179,9 @@ def _declare(L: C.CDLL) -> None:
     L.psulvsb_last_stage_ms.restype = C.c_double
     L.psulvsb_last_ticks.argtypes = [_vp]
     L.psulvsb_last_ticks.restype = C.c_int
+    L.psulvsb_last_chunk_ticks.argtypes = [_vp, C.POINTER(C.c_int), C.c_int]
+    L.psulvsb_last_chunk_ticks.restype = C.c_int
+    L.psulvsb_set_batching.argtypes = [_vp, C.c_int, C.c_int]
     L.psulvsb_pack_points.argtypes = [_vp, _vp, C.c_int, C.POINTER(C.c_double), _vp]
     L.psulvsb_consistency_mask.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_double, _vp, C.c_int,
                                            _vp, _vp]
@@ -208,6 +215,15 @@ def _declare(L: C.CDLL) -> None:
                                                 _vp, _vp, _vp]
     L.psulvsb_tls_translation_host.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp]
     L.psulvsb_max_clique_scratch_words.restype = _ull
+    L.psulvsb_comm_unique_id.argtypes = [_vp]
+    L.psulvsb_comm_create.argtypes = [_vp, C.c_int, C.c_int, _vp]
+    L.psulvsb_comm_destroy.argtypes = [_vp]
+    L.psulvsb_comm_rank.argtypes = [_vp]
+    L.psulvsb_comm_world.argtypes = [_vp]
+    L.psulvsb_comm_allreduce_sum_u32.argtypes = [_vp, _vp, _vp, _ull]
+    L.psulvsb_comm_allreduce_max_u64.argtypes = [_vp, _vp, _vp, _ull]
+    L.psulvsb_score_batch_sharded.argtypes = [_vp] + list(L.psulvsb_score_batch.argtypes)
+    L.psulvsb_solve_sharded.argtypes = [_vp, C.POINTER(Params), C.POINTER(Problem), C.POINTER(Solution), C.POINTER(Trace)]
     L.psulvsb_score_one.argtypes = [_vp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, C.c_double, _vp, _vp, _vp]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here = the library does not export what the header declares
@@ -221,6 +237,13 @@ def check(rc: int) -> None:
 def debug_set(name: str, value: float) -> None:
     """psulvsb_debug_set: test switches between equivalent code paths ("reset" restores the defaults)."""
     check(lib().psulvsb_debug_set(name.encode(), float(value)))
+
+
+def comm_unique_id() -> bytes:
+    """psulvsb_comm_unique_id: rank 0 makes it, the caller carries the bytes to the other ranks."""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    check(lib().psulvsb_comm_unique_id(buf))
+    return buf.raw
 
 
 def default_params(**kw) -> Params:
@@ -364,6 +387,31 @@ class Handle:
         check(lib().psulvsb_batch_solve_resident(self._h, C.byref(params), sd, sols, n))
         return list(sols)
 
+    def comm_create(self, rank: int, world: int, unique_id: bytes) -> None:
+        if len(unique_id) != UNIQUE_ID_BYTES:
+            raise ValueError("unique_id must have UNIQUE_ID_BYTES bytes")
+        check(lib().psulvsb_comm_create(self._h, rank, world, C.c_char_p(unique_id)))
+
+    def comm_destroy(self) -> None:
+        check(lib().psulvsb_comm_destroy(self._h))
+
+    @property
+    def comm_world(self) -> int:
+        return lib().psulvsb_comm_world(self._h)
+
+    def comm_allreduce_sum_u32(self, d_ptr: int, n: int, stream: int = 0) -> None:
+        check(lib().psulvsb_comm_allreduce_sum_u32(self._h, stream, d_ptr, n))
+
+    def comm_allreduce_max_u64(self, d_ptr: int, n: int, stream: int = 0) -> None:
+        check(lib().psulvsb_comm_allreduce_max_u64(self._h, stream, d_ptr, n))
+
+    def solve_sharded(self, params: Params, problem: HostProblem) -> Solution:
+        """psulvsb_solve_sharded: every rank passes the same problem; the consistency rows are split over the ranks."""
+        sol = Solution()
+        ps = problem.c_struct()
+        check(lib().psulvsb_solve_sharded(self._h, C.byref(params), C.byref(ps), C.byref(sol), None))
+        return sol
+
     @property
     def launch_count(self) -> int:
         return lib().psulvsb_launch_count(self._h)
@@ -378,3 +426,13 @@ class Handle:
     @property
     def last_ticks(self) -> int:
         return lib().psulvsb_last_ticks(self._h)
+
+    @property
+    def last_chunk_ticks(self):
+        buf = (C.c_int * 256)()
+        n = lib().psulvsb_last_chunk_ticks(self._h, buf, 256)
+        return [buf[i] for i in range(min(n, 256))]
+
+    def set_batching(self, chunk: int = 0, lanes: int = 0) -> None:
+        """psulvsb_set_batching: registrations per lock-step chunk / chunks in flight (0 = defaults)."""
+        check(lib().psulvsb_set_batching(self._h, chunk, lanes))

@@ -72,7 +72,9 @@ struct DeviceJob {
 using namespace psulvsb;
 
 struct psulvsb_handle_s {
-  Engine* engine;
+  EnginePool* pool;
+  Comm* comm;
+  int device;
 };
 
 extern "C" {
@@ -123,7 +125,9 @@ int psulvsb_create(psulvsb_handle_t* out, int device) {
   if (int rc = need_device()) return rc;
   psulvsb_handle_s* h = new (std::nothrow) psulvsb_handle_s();
   if (!h) return fail(PSULVSB_ERR_INTERNAL, "out of host memory");
-  const int rc = engine_create(&h->engine, device);
+  h->comm = nullptr;
+  h->device = device;
+  const int rc = pool_create(&h->pool, device);
   if (rc) {
     delete h;
     return rc;
@@ -134,7 +138,8 @@ int psulvsb_create(psulvsb_handle_t* out, int device) {
 
 int psulvsb_destroy(psulvsb_handle_t h) {
   if (!h) return PSULVSB_OK;
-  engine_destroy(h->engine);
+  comm_destroy(h->comm);
+  pool_destroy(h->pool);
   delete h;
   return PSULVSB_OK;
 }
@@ -142,32 +147,30 @@ int psulvsb_destroy(psulvsb_handle_t h) {
 int psulvsb_solve(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
                   psulvsb_solution_t* solution, psulvsb_trace_t* trace) {
   if (!h || !params || !problem || !solution) return fail(PSULVSB_ERR_INVALID, "psulvsb_solve: NULL argument");
-  if (int rc = engine_upload(h->engine, problem, 1)) return rc;
-  return engine_solve_resident(h->engine, params, nullptr, solution, trace);
+  return pool_solve_one(h->pool, params, problem, solution, trace);
 }
 
 int psulvsb_solve_batch(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,
                         const uint64_t* seeds, psulvsb_solution_t* solutions) {
   if (!h || !params || !problems || !solutions || B <= 0)
     return fail(PSULVSB_ERR_INVALID, "psulvsb_solve_batch: NULL argument or B <= 0");
-  if (int rc = engine_upload(h->engine, problems, B)) return rc;
-  return engine_solve_resident(h->engine, params, seeds, solutions, nullptr);
+  return pool_solve_batch(h->pool, params, problems, B, seeds, solutions);
 }
 
 int psulvsb_batch_upload(psulvsb_handle_t h, const psulvsb_problem_t* problems, int B) {
   if (!h || !problems || B <= 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_upload: NULL argument or B <= 0");
-  return engine_upload(h->engine, problems, B);
+  return pool_upload(h->pool, problems, B);
 }
 
 int psulvsb_batch_solve_resident(psulvsb_handle_t h, const psulvsb_params_t* params, const uint64_t* seeds,
                                  psulvsb_solution_t* solutions, int n_solutions) {
   if (!h || !params || !solutions) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_solve_resident: NULL argument");
-  const int B = engine_batch_size(h->engine);
+  const int B = pool_batch_size(h->pool);
   if (B <= 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_solve_resident: nothing is resident (upload first)");
   if (n_solutions != B)
     return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_solve_resident: " + std::to_string(n_solutions) +
                                          " solution slots for a resident batch of " + std::to_string(B));
-  return engine_solve_resident(h->engine, params, seeds, solutions, nullptr);
+  return pool_solve_resident(h->pool, params, seeds, solutions, nullptr);
 }
 
 int psulvsb_debug_set(const char* name, double value) {
@@ -176,6 +179,7 @@ int psulvsb_debug_set(const char* name, double value) {
   const std::string n(name);
   if (n == "gnc_deep_margin") k.gnc_deep_margin = value;
   else if (n == "gnc_prefetch") k.gnc_prefetch = (int)value;
+  else if (n == "gnc_cluster") k.gnc_cluster = (int)value;
   else if (n == "sample_list_cap_test") k.sample_list_cap_test = (int)value;
   else if (n == "k1_variant") k.k1_variant = (int)value;
   else if (n == "upload_prof") k.upload_prof = (int)value;
@@ -184,12 +188,21 @@ int psulvsb_debug_set(const char* name, double value) {
   return PSULVSB_OK;
 }
 
-int psulvsb_batch_resident_size(psulvsb_handle_t h) { return h ? engine_batch_size(h->engine) : 0; }
+int psulvsb_batch_resident_size(psulvsb_handle_t h) { return h ? pool_batch_size(h->pool) : 0; }
 
-long long psulvsb_launch_count(psulvsb_handle_t h) { return h ? engine_launch_count(h->engine) : 0; }
-double psulvsb_last_device_ms(psulvsb_handle_t h) { return h ? engine_last_device_ms(h->engine) : 0.0; }
-double psulvsb_last_stage_ms(psulvsb_handle_t h, int which) { return h ? engine_last_stage_ms(h->engine, which) : 0.0; }
-int psulvsb_last_ticks(psulvsb_handle_t h) { return h ? engine_last_ticks(h->engine) : 0; }
+int psulvsb_set_batching(psulvsb_handle_t h, int chunk, int lanes) {
+  if (!h) return fail(PSULVSB_ERR_INVALID, "psulvsb_set_batching: NULL handle");
+  return pool_set_batching(h->pool, chunk, lanes);
+}
+
+long long psulvsb_launch_count(psulvsb_handle_t h) { return h ? pool_launch_count(h->pool) : 0; }
+double psulvsb_last_device_ms(psulvsb_handle_t h) { return h ? pool_last_device_ms(h->pool) : 0.0; }
+double psulvsb_last_stage_ms(psulvsb_handle_t h, int which) { return h ? pool_last_stage_ms(h->pool, which) : 0.0; }
+int psulvsb_last_ticks(psulvsb_handle_t h) { return h ? pool_last_ticks(h->pool) : 0; }
+int psulvsb_last_chunk_ticks(psulvsb_handle_t h, int* out, int cap) {
+  if (!h || (cap > 0 && !out)) return 0;
+  return pool_last_chunk_ticks(h->pool, out, cap);
+}
 
 /* ---------------------------------------------------------------------------------------------- */
 /* stage entry points                                                                              */
@@ -522,6 +535,63 @@ int psulvsb_score_batch(void* stream, const void* d_src_f4, const void* d_dst_f4
   return launch_score_batch((cudaStream_t)stream, (const float4*)d_src_f4, (const float4*)d_dst_f4, d_src64, d_dst64, n,
                             d_hyp, n_hyp, hyp_begin, scale, tau, coord_bound, center_src, center_dst, d_counts, d_best,
                             d_border_count);
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* multi-GPU: one process per GPU, one NCCL communicator per handle                                */
+/* ---------------------------------------------------------------------------------------------- */
+
+int psulvsb_comm_unique_id(void* out_id) {
+  if (!out_id) return fail(PSULVSB_ERR_INVALID, "psulvsb_comm_unique_id: NULL");
+  return comm_unique_id(out_id);
+}
+
+int psulvsb_comm_create(psulvsb_handle_t h, int rank, int world, const void* id) {
+  if (!h || !id) return fail(PSULVSB_ERR_INVALID, "psulvsb_comm_create: NULL argument");
+  if (h->comm) {
+    comm_destroy(h->comm);
+    h->comm = nullptr;
+  }
+  return comm_create(&h->comm, h->device, rank, world, id);
+}
+
+int psulvsb_comm_destroy(psulvsb_handle_t h) {
+  if (!h) return PSULVSB_OK;
+  comm_destroy(h->comm);
+  h->comm = nullptr;
+  return PSULVSB_OK;
+}
+
+int psulvsb_comm_rank(psulvsb_handle_t h) { return h ? comm_rank(h->comm) : 0; }
+int psulvsb_comm_world(psulvsb_handle_t h) { return h ? comm_world(h->comm) : 1; }
+
+int psulvsb_comm_allreduce_sum_u32(psulvsb_handle_t h, void* stream, uint32_t* d_inout, unsigned long long n) {
+  if (!h || !d_inout) return fail(PSULVSB_ERR_INVALID, "psulvsb_comm_allreduce_sum_u32: NULL argument");
+  return comm_allreduce_sum_u32(h->comm, (cudaStream_t)stream, d_inout, (size_t)n);
+}
+
+int psulvsb_comm_allreduce_max_u64(psulvsb_handle_t h, void* stream, unsigned long long* d_inout, unsigned long long n) {
+  if (!h || !d_inout) return fail(PSULVSB_ERR_INVALID, "psulvsb_comm_allreduce_max_u64: NULL argument");
+  return comm_allreduce_max_u64(h->comm, (cudaStream_t)stream, d_inout, (size_t)n);
+}
+
+int psulvsb_score_batch_sharded(psulvsb_handle_t h, void* stream, const void* d_src_f4, const void* d_dst_f4,
+                                const double* d_src64, const double* d_dst64, int n, const double* d_hyp,
+                                unsigned long long n_hyp, unsigned long long hyp_begin, double scale, double tau,
+                                double coord_bound, const double center_src[3], const double center_dst[3],
+                                uint32_t* d_counts, unsigned long long* d_best, unsigned long long* d_border_count) {
+  if (!h || !d_best) return fail(PSULVSB_ERR_INVALID, "psulvsb_score_batch_sharded: NULL handle / d_best");
+  if (int rc = psulvsb_score_batch(stream, d_src_f4, d_dst_f4, d_src64, d_dst64, n, d_hyp, n_hyp, hyp_begin, scale, tau,
+                                   coord_bound, center_src, center_dst, d_counts, d_best, d_border_count))
+    return rc;
+  // the global best = max of the packed keys (count << 32 | ~id): 8 bytes over NVLink, in-stream
+  return comm_allreduce_max_u64(h->comm, (cudaStream_t)stream, d_best, 1);
+}
+
+int psulvsb_solve_sharded(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                          psulvsb_solution_t* solution, psulvsb_trace_t* trace) {
+  if (!h || !params || !problem || !solution) return fail(PSULVSB_ERR_INVALID, "psulvsb_solve_sharded: NULL argument");
+  return pool_solve_sharded(h->pool, h->comm, params, problem, solution, trace);
 }
 
 int psulvsb_score_one(void* stream, const double* d_src64, const double* d_dst64, int n, double scale,

@@ -40,6 +40,7 @@ int sm_count();
 // equivalent code paths runs; production callers leave them alone.  No environment variable is read anywhere.
 struct DebugKnobs {
   double gnc_deep_margin = 0.0;   // > 0: overrides the remaining-margin threshold (rad) for parking sleeping line vectors
+  int gnc_cluster = 0;            // 1, 2, 4, 8: CTAs per registration of the GNC-TLS kernel (512 threads, one CTA per SM)
   int gnc_prefetch = -1;          // >= 0: look-ahead (double-steps) of the L2 prefetch in the streamed GNC pass
   int sample_list_cap_test = 0;   // > 0: caps the sampler's bucket lists (exercises the overflow fallback)
   int k1_variant = 0;             // 1..4: rows per thread of the consistency kernel

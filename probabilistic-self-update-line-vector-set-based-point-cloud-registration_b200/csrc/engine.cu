@@ -9,6 +9,7 @@
 // The only host synchronisations are the n_red read-back and one 4-byte "jobs done" poll per tick.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #if defined(__SSE2__)
@@ -17,7 +18,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -139,6 +143,17 @@ class Engine {
   double last_ms = 0.0;
   double stage_ms[5] = {0, 0, 0, 0, 0};
   int last_ticks = 0;
+  // set by the pool: an event recorded when the pool call began.  The solve then leaves the offsets (ms) of its own
+  // begin / end, of the consistency-mask launch and of every GNC-TLS launch relative to it, so that the pool can report
+  // device time and per-kernel busy time over several engines running concurrently on their own streams.
+  cudaEvent_t origin = nullptr;
+  float off_begin = 0.f, off_end = 0.f, off_m0 = 0.f, off_m1 = 0.f;
+  std::vector<std::pair<float, float>> gnc_iv, k1_iv;
+  int max_chunk = 0;            // largest lock-step sub-batch of a resident batch (0: the whole batch at once)
+  int sub_b0 = 0, sub_nb = 0;   // the sub-batch solve_once advances
+  std::vector<int> part_ticks;  // ticks of every sub-batch of the last solve
+  Comm* comm = nullptr;  // set for one solve by pool_solve_sharded: the consistency rows of the single problem are sharded
+  int stage_threads_cap = 12;  // host threads of the staging copy (the pool divides the cores among its engines)
 
   ~Engine() {
     if (st) cudaStreamSynchronize(st);
@@ -361,7 +376,7 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
   };
   {
     int nthreads = (int)std::thread::hardware_concurrency();
-    if (nthreads > 12) nthreads = 12;
+    if (nthreads > stage_threads_cap) nthreads = stage_threads_cap;
     if (nthreads > nb) nthreads = nb;
     if (nthreads < 1 || bytes_d < (4u << 20)) nthreads = 1;
     if (nthreads == 1) {
@@ -419,23 +434,55 @@ int Engine::solve(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb
     return fail(PSULVSB_ERR_UNSUPPORTED,
                 "solve: INLIER_SELECTION_MODE::KCORE_HEU with kcore_heuristic_threshold != 1 is not implemented "
                 "(PMC_EXACT, PMC_HEU and NONE are)");
-  for (int attempt = 0; attempt < 6; ++attempt) {
-    if (int rc = solve_once(params, seeds, solutions, trace_first)) return rc;
-    // self-update outgrew the edge head-room of some job: enlarge and redo (results are
-    // deterministic, so the retry reproduces the same run with room to finish)
-    bool again = false;
-    for (int b = 0; b < B; ++b)
-      if (solutions[b].status == PSULVSB_ERR_CAPACITY) {
-        const ProbLayout& L = lay[(size_t)b];
-        const unsigned long long full = (unsigned long long)(L.Ccap - L.C0) * (unsigned long long)L.Ccap;
-        if (reserve[(size_t)b] < full) {
-          unsigned long long r = reserve[(size_t)b] * 8ull;
-          reserve[(size_t)b] = r > full ? full : r;
-          again = true;
+  // The resident batch advances in lock-step sub-batches of at most max_chunk registrations (the working arenas are
+  // sized per sub-batch, the inputs stay resident); statistics accumulate over them.
+  const int step = (max_chunk > 0 && max_chunk < B) ? max_chunk : B;
+  const int parts = (B + step - 1) / step;
+  double acc_ms = 0.0, acc_stage[5] = {0, 0, 0, 0, 0};
+  int acc_ticks = 0;
+  float first_begin = 0.f;
+  std::vector<std::pair<float, float>> all_gnc, all_k1;
+  part_ticks.clear();
+  for (int part = 0; part < parts; ++part) {
+    sub_b0 = (int)((long long)B * part / parts);
+    sub_nb = (int)((long long)B * (part + 1) / parts) - sub_b0;
+    const uint64_t* sd = seeds ? seeds + sub_b0 : nullptr;
+    psulvsb_params_t pp = *params;
+    pp.seed = params->seed + (uint64_t)sub_b0;  // default seeds follow the index in the resident batch
+    psulvsb_solution_t* out = solutions + sub_b0;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+      if (int rc = solve_once(&pp, sd, out, part == 0 ? trace_first : nullptr)) return rc;
+      // self-update outgrew the edge head-room of some job: enlarge and redo (results are
+      // deterministic, so the retry reproduces the same run with room to finish)
+      bool again = false;
+      for (int b = 0; b < sub_nb; ++b)
+        if (out[b].status == PSULVSB_ERR_CAPACITY) {
+          const ProbLayout& L = lay[(size_t)(sub_b0 + b)];
+          const unsigned long long full = (unsigned long long)(L.Ccap - L.C0) * (unsigned long long)L.Ccap;
+          if (reserve[(size_t)(sub_b0 + b)] < full) {
+            unsigned long long r = reserve[(size_t)(sub_b0 + b)] * 8ull;
+            reserve[(size_t)(sub_b0 + b)] = r > full ? full : r;
+            again = true;
+          }
         }
-      }
-    if (!again) break;
+      if (!again) break;
+    }
+    acc_ms += last_ms;
+    for (int i = 0; i < 5; ++i) acc_stage[i] += stage_ms[i];
+    acc_ticks = last_ticks > acc_ticks ? last_ticks : acc_ticks;
+    part_ticks.push_back(last_ticks);
+    all_gnc.insert(all_gnc.end(), gnc_iv.begin(), gnc_iv.end());
+    if (origin && off_m1 > off_m0) all_k1.emplace_back(off_m0, off_m1);
+    if (part == 0) first_begin = off_begin;
   }
+  sub_b0 = 0;
+  sub_nb = B;
+  last_ms = acc_ms;
+  for (int i = 0; i < 5; ++i) stage_ms[i] = acc_stage[i];
+  last_ticks = acc_ticks;
+  gnc_iv.swap(all_gnc);
+  k1_iv.swap(all_k1);
+  off_begin = first_begin;
   return PSULVSB_OK;
 }
 
@@ -443,6 +490,9 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
                        psulvsb_trace_t* trace_first) {
   PSU_CUDA(cudaSetDevice(device));
   const auto t_begin = std::chrono::steady_clock::now();
+  // this call advances the resident problems [sub_b0, sub_b0 + sub_nb) as one lock-step batch (seeds / solutions are
+  // already offset by the caller); `B` below is the size of that sub-batch
+  const int b0 = sub_b0, B = sub_nb;
   const int local_cap = 512;
   const int host_cap = params->host_round_limit > 0 ? params->host_round_limit : 1;
 
@@ -452,6 +502,15 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   std::vector<CompactJob> cj((size_t)B);
   std::vector<PackJob> pj((size_t)2 * B);
   const bool ratio = params->estimate_scaling != 0;  // unknown scale: ratio histogram instead of the bit mask
+  const bool sharded = comm != nullptr && comm_world(comm) > 1;
+  int row_b = 0, row_e = 0;
+  if (sharded) {
+    if (B != 1 || ratio)
+      return fail(PSULVSB_ERR_UNSUPPORTED, "sharded solve: one known-scale registration at a time (independent "
+                                           "registrations shard across ranks with no exchange: psulvsb_solve_batch)");
+    if (comm_world(comm) > 64) return fail(PSULVSB_ERR_UNSUPPORTED, "sharded solve: at most 64 ranks");
+    triangular_row_range(lay[(size_t)b0].C0, comm_rank(comm), comm_world(comm), &row_b, &row_e);
+  }
   std::vector<RatioJob> rj(ratio ? (size_t)B : 0);
   struct Misc {
     RatioJob* rj;
@@ -466,6 +525,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     GncJob* gj;
     unsigned long long* n_edges;
     unsigned long long* border;
+    unsigned long long* counts_all;  // sharded solve: every rank's edge count
     int* n_done;
     psulvsb_solution_t* sols;
   } m;
@@ -482,6 +542,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       m.gj = bm.take<GncJob>((size_t)B);
       m.n_edges = bm.take<unsigned long long>((size_t)B);
       m.border = bm.take<unsigned long long>((size_t)B);
+      m.counts_all = bm.take<unsigned long long>(64);
       m.n_done = bm.take<int>(4);
       m.sols = bm.take<psulvsb_solution_t>((size_t)B);
       m.rj = bm.take<RatioJob>((size_t)B);
@@ -502,7 +563,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       bw.off = 0;
       bk.off = 0;
       for (int b = 0; b < B; ++b) {
-        const ProbLayout& L = lay[(size_t)b];
+        const ProbLayout& L = lay[(size_t)(b0 + b)];
         JobCtl& J = jobs[(size_t)b];
         std::memset(&J, 0, sizeof(J));
         J.C0 = L.C0;
@@ -550,8 +611,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         K.src64 = J.src0;
         K.dst64 = J.dst0;
         K.n = L.C0;
-        K.row_begin = 0;
-        K.row_end = L.C0;
+        K.row_begin = sharded ? row_b : 0;  // sharded: this rank's block of mask rows (other rows keep count 0)
+        K.row_end = sharded ? row_e : L.C0;
         K.c = make_k1_consts(2.0 * params->noise_bound * std::sqrt(params->cbar2), L.coord_bound);
         K.mask = ratio ? nullptr : bk.take<uint32_t>((size_t)L.C0 * L.stride);
         K.stride = L.stride;
@@ -674,17 +735,34 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       ++launches;
     }
     PSU_CUDA(cudaEventRecord(ev_m0, st));
-    if (int rc = launch_consistency_mask(st, m.k1, B, maxC, maxC)) return rc;
+    if (!sharded || row_e > row_b)
+      if (int rc = launch_consistency_mask(st, m.k1, B, maxC, sharded ? row_e - row_b : maxC)) return rc;
     PSU_CUDA(cudaEventRecord(ev_m1, st));
     ++launches;
     if (int rc = launch_compact_edges(st, m.cj, B, maxC, true, false)) return rc;
     ++launches;
   }
-  if (int rc = h_small.ensure((sizeof(unsigned long long) + sizeof(int)) * (size_t)B + 64)) return rc;
+  if (int rc = h_small.ensure((sizeof(unsigned long long) + sizeof(int)) * (size_t)B + 64 + 66 * sizeof(unsigned long long)))
+    return rc;
   unsigned long long* h_nedges = reinterpret_cast<unsigned long long*>(h_small.p);
   volatile int* h_done = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(h_small.p) + sizeof(unsigned long long) * (size_t)B);
-  PSU_CUDA(cudaMemcpyAsync(h_nedges, m.n_edges, sizeof(unsigned long long) * (size_t)B, cudaMemcpyDeviceToHost, st));
-  PSU_CUDA(cudaStreamSynchronize(st));
+  unsigned long long* h_counts = reinterpret_cast<unsigned long long*>(
+      reinterpret_cast<char*>(h_small.p) + align_up((sizeof(unsigned long long) + sizeof(int)) * (size_t)B + 16, 16));
+  std::vector<unsigned long long> shard_off;  // sharded: rank r's edges are [shard_off[r], shard_off[r + 1]) of the list
+  if (sharded) {
+    // every rank's edge count (8 bytes each) -> the offsets of the rank blocks in the global, row-major edge list
+    if (int rc = comm_allgather_u64(comm, st, m.n_edges, m.counts_all)) return rc;
+    PSU_CUDA(cudaMemcpyAsync(h_counts, m.counts_all, sizeof(unsigned long long) * (size_t)comm_world(comm),
+                             cudaMemcpyDeviceToHost, st));
+    PSU_CUDA(cudaStreamSynchronize(st));
+    shard_off.assign((size_t)comm_world(comm) + 1, 0ull);
+    for (int r = 0; r < comm_world(comm); ++r) shard_off[(size_t)r + 1] = shard_off[(size_t)r] + h_counts[r];
+    h_nedges[0] = shard_off.back();
+    PSU_CUDA(cudaMemcpyAsync(m.n_edges, h_nedges, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));  // n_red
+  } else {
+    PSU_CUDA(cudaMemcpyAsync(h_nedges, m.n_edges, sizeof(unsigned long long) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    PSU_CUDA(cudaStreamSynchronize(st));
+  }
 
   // ---- edge arena, sized from the measured reduced-set sizes
   unsigned long long max_cap = 0, max_nred = 0;
@@ -694,7 +772,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       be.off = 0;
       for (int b = 0; b < B; ++b) {
         JobCtl& J = jobs[(size_t)b];
-        unsigned long long cap = h_nedges[b] + reserve[(size_t)b];
+        unsigned long long cap = h_nedges[b] + reserve[(size_t)(b0 + b)];
         if (cap < 64) cap = 64;
         J.edge_cap = cap;
         J.edges = be.take<uint2>((size_t)cap);
@@ -723,8 +801,9 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
           rj[(size_t)b].edges = J.edges;
           rj[(size_t)b].cap = cap;
         }
-        cj[(size_t)b].edges = J.edges;
-        cj[(size_t)b].cap = cap;
+        // (sharded: this rank's rows land at their place in the global list)
+        cj[(size_t)b].edges = J.edges + (sharded && be.base ? shard_off[(size_t)comm_rank(comm)] : 0ull);
+        cj[(size_t)b].cap = cap - (sharded ? shard_off[(size_t)comm_rank(comm)] : 0ull);
         max_cap = cap > max_cap ? cap : max_cap;
         max_nred = h_nedges[b] > max_nred ? h_nedges[b] : max_nred;
       }
@@ -742,6 +821,11 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   } else {
     PSU_CUDA(cudaMemcpyAsync(m.cj, cj.data(), sizeof(CompactJob) * (size_t)B, cudaMemcpyHostToDevice, st));
     if (int rc = launch_compact_edges(st, m.cj, B, maxC, false, true)) return rc;
+    if (sharded) {  // every rank receives every other rank's block of the edge list (8 bytes per edge, over NVLink)
+      std::vector<unsigned long long> off32(shard_off);
+      for (auto& o : off32) o *= 2ull;
+      if (int rc = comm_allgatherv_inplace_u32(comm, st, reinterpret_cast<uint32_t*>(jobs[0].edges), off32.data())) return rc;
+    }
   }
   ++launches;
 
@@ -790,10 +874,11 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   // lock-step batch are what weak scaling loses: the slowest rank of 8 ran 25.5 ms against 20.8 ms on one GPU)
   int n_running = B;
   int max_ccap = 0;
-  for (int b = 0; b < B; ++b) max_ccap = lay[(size_t)b].Ccap > max_ccap ? lay[(size_t)b].Ccap : max_ccap;
+  for (int b = 0; b < B; ++b) max_ccap = lay[(size_t)(b0 + b)].Ccap > max_ccap ? lay[(size_t)(b0 + b)].Ccap : max_ccap;
   const unsigned long long draws_bound = sample_default_max_draws(max_cap, max_cap / 8 + 1);
   int ticks = 0;
   double gnc_ms = 0.0;
+  gnc_iv.clear();
   const int max_ticks = P.max_local_iters + P.host_round_limit + 8;
   bool round_start_pending = true;  // every job begins with a round start
   bool clique_pending = false;
@@ -814,7 +899,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     }
     if (clique_pending) {  // some registration is in its clique round (rare, last escalation)
       int maxCcap = 0;
-      for (int b = 0; b < B; ++b) maxCcap = lay[(size_t)b].Ccap > maxCcap ? lay[(size_t)b].Ccap : maxCcap;
+      for (int b = 0; b < B; ++b) maxCcap = lay[(size_t)(b0 + b)].Ccap > maxCcap ? lay[(size_t)(b0 + b)].Ccap : maxCcap;
       // PMC_EXACT: greedy lower bound + exact improvement search; PMC_HEU / KCORE_HEU: the heuristic clique only
       // (graph.cc:86-121).  max_clique_time_limit has no counterpart: the search has a node budget instead.
       if (int rc = launch_max_clique(st, m.cq, B, maxCcap, (maxCcap + 31) / 32, max_cap, params->inlier_selection_mode == 0))
@@ -837,6 +922,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     {
       float g = 0.f;
       if (cudaEventElapsedTime(&g, ev_g0, ev_g1) == cudaSuccess) gnc_ms += g;  // (the tick's poll already synchronised)
+      float a = 0.f;
+      if (origin && cudaEventElapsedTime(&a, origin, ev_g0) == cudaSuccess) gnc_iv.emplace_back(a, a + g);
     }
     if (h_done[0] >= B) break;
     n_running = B - h_done[0];
@@ -865,6 +952,12 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   cudaEventElapsedTime(&ms, ev_m0, ev_m1);
   stage_ms[2] = ms;  // the consistency-mask kernel alone (one launch over the whole batch)
   stage_ms[3] = gnc_ms;  // the GNC-TLS launches of all ticks
+  if (origin) {
+    cudaEventElapsedTime(&off_begin, origin, ev_begin);
+    cudaEventElapsedTime(&off_end, origin, ev_end);
+    cudaEventElapsedTime(&off_m0, origin, ev_m0);
+    cudaEventElapsedTime(&off_m1, origin, ev_m1);
+  }
 
   if (trace_first) {
     JobCtl j0;
@@ -895,28 +988,313 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   return PSULVSB_OK;
 }
 
+// ---- engine pool -----------------------------------------------------------------------------
+// A handle owns a small pool of engines on one device, each with its own stream and arenas.  A batch larger than one
+// lock-step chunk is cut into chunks that advance CONCURRENTLY, one per engine, each driven by its own host thread:
+//   * a chunk's latency-bound phases (GNC-TLS, control kernels, the per-tick poll) overlap another chunk's
+//     bandwidth-bound ones (sampler passes, compaction), and the straggler ticks at the end of one chunk -- a handful of
+//     registrations on a few SMs -- overlap the bulk of the next instead of idling the device;
+//   * with host buffers (psulvsb_solve_batch) the chunks are handed out dynamically, so the staging + H2D copy of chunk
+//     k + 1 runs while chunk k is being solved.
+// Results do not depend on the partition: every registration's state and sample stream are its own.
+namespace {
+// length of the union of intervals (ms)
+double union_ms(std::vector<std::pair<float, float>>& iv) {
+  if (iv.empty()) return 0.0;
+  std::sort(iv.begin(), iv.end());
+  double total = 0.0;
+  float lo = iv[0].first, hi = iv[0].second;
+  for (size_t i = 1; i < iv.size(); ++i) {
+    if (iv[i].first > hi) {
+      total += hi - lo;
+      lo = iv[i].first;
+      hi = iv[i].second;
+    } else if (iv[i].second > hi) {
+      hi = iv[i].second;
+    }
+  }
+  return total + (hi - lo);
+}
+}  // namespace
+
+class EnginePool {
+ public:
+  int device = 0;
+  int chunk = 0;  // registrations per lock-step chunk (0: one per SM)
+  int lanes = 0;  // engines that may run concurrently (0: default)
+  std::vector<Engine*> eng;
+  cudaEvent_t origin = nullptr;
+  std::vector<int> res_begin;  // resident partition: engine e holds problems [res_begin[e], res_begin[e + 1])
+  int resident_B = 0;
+  double last_ms = 0.0;
+  double stage_ms[5] = {0, 0, 0, 0, 0};
+  int last_ticks = 0;
+  std::vector<int> chunk_ticks;  // ticks of every chunk of the last call
+  long long retired_launches = 0;
+
+  ~EnginePool() {
+    for (Engine* e : eng) delete e;
+    if (origin) cudaEventDestroy(origin);
+  }
+  int init(int dev) {
+    device = dev;
+    Engine* e = new Engine();
+    if (int rc = e->init(dev)) {
+      delete e;
+      return rc;
+    }
+    eng.push_back(e);
+    PSU_CUDA(cudaEventCreate(&origin));
+    return ensure_engines(1);
+  }
+  int chunk_size() const { return chunk > 0 ? chunk : 2 * sm_count(); }
+  int lane_count() const { return lanes > 0 ? lanes : 2; }
+  int ensure_engines(int n) {
+    while ((int)eng.size() < n) {
+      Engine* e = new Engine();
+      if (int rc = e->init(device)) {
+        delete e;
+        return rc;
+      }
+      eng.push_back(e);
+    }
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    int per = hw / (n > 0 ? n : 1);
+    per = per < 2 ? 2 : (per > 12 ? 12 : per);
+    for (Engine* e : eng) {
+      e->stage_threads_cap = (n > 1) ? per : 12;
+      e->max_chunk = chunk_size();
+    }
+    return PSULVSB_OK;
+  }
+  long long launch_count() const {
+    long long n = retired_launches;
+    for (const Engine* e : eng) n += e->launches;
+    return n;
+  }
+
+  // statistics of a call from the engines that took part; `records` holds one entry per chunk
+  struct ChunkRecord {
+    float off_begin, off_end;
+    double stage[5];
+    int ticks;
+    std::vector<int> part_ticks;
+    std::vector<std::pair<float, float>> gnc, k1;
+  };
+  static ChunkRecord record_of(const Engine* e) {
+    ChunkRecord r;
+    r.off_begin = e->off_begin;
+    r.off_end = e->off_end;
+    r.k1 = e->k1_iv;
+    for (int i = 0; i < 5; ++i) r.stage[i] = e->stage_ms[i];
+    r.ticks = e->last_ticks;
+    r.part_ticks = e->part_ticks;
+    r.gnc = e->gnc_iv;
+    return r;
+  }
+  void fold(std::vector<ChunkRecord>& recs) {
+    last_ms = 0.0;
+    last_ticks = 0;
+    chunk_ticks.clear();
+    for (int i = 0; i < 5; ++i) stage_ms[i] = 0.0;
+    std::vector<std::pair<float, float>> k1, gnc;
+    for (const ChunkRecord& r : recs) {
+      last_ms = r.off_end > last_ms ? r.off_end : last_ms;
+      last_ticks = r.ticks > last_ticks ? r.ticks : last_ticks;
+      chunk_ticks.insert(chunk_ticks.end(), r.part_ticks.begin(), r.part_ticks.end());
+      stage_ms[0] += r.stage[0] / (double)recs.size();
+      stage_ms[1] += r.stage[1] / (double)recs.size();
+      stage_ms[4] += r.stage[4] / (double)recs.size();
+      k1.insert(k1.end(), r.k1.begin(), r.k1.end());
+      gnc.insert(gnc.end(), r.gnc.begin(), r.gnc.end());
+    }
+    stage_ms[2] = union_ms(k1);   // time during which a consistency-mask launch of some chunk was running
+    stage_ms[3] = union_ms(gnc);  // ... a GNC-TLS launch of some chunk
+  }
+
+  int solve_one(const psulvsb_params_t* params, const psulvsb_problem_t* problem, psulvsb_solution_t* solution,
+                psulvsb_trace_t* trace) {
+    resident_B = 0;
+    Engine* e = eng[0];
+    e->stage_threads_cap = 12;
+    PSU_CUDA(cudaSetDevice(device));
+    PSU_CUDA(cudaEventRecord(origin, e->st));
+    e->origin = origin;
+    if (int rc = e->upload(problem, 1)) return rc;
+    if (int rc = e->solve(params, nullptr, solution, trace)) return rc;
+    std::vector<ChunkRecord> recs(1, record_of(e));
+    fold(recs);
+    res_begin.assign({0, 1});
+    resident_B = 1;
+    return PSULVSB_OK;
+  }
+
+  int solve_sharded(Comm* comm, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                    psulvsb_solution_t* solution, psulvsb_trace_t* trace) {
+    Engine* e = eng[0];
+    e->comm = comm;
+    const int rc = solve_one(params, problem, solution, trace);
+    e->comm = nullptr;
+    return rc;
+  }
+
+  // evenly sized chunks of at most chunk_size() registrations
+  static void partition(int B, int parts, std::vector<int>& begin) {
+    begin.resize((size_t)parts + 1);
+    for (int c = 0; c <= parts; ++c) begin[(size_t)c] = (int)((long long)B * c / parts);
+  }
+
+  int run_parallel(int n_workers, const std::function<int(int)>& work) {
+    std::vector<int> rcs((size_t)n_workers, PSULVSB_OK);
+    std::vector<std::string> msgs((size_t)n_workers);
+    auto body = [&](int w) {
+      const int rc = work(w);
+      rcs[(size_t)w] = rc;
+      if (rc) msgs[(size_t)w] = psulvsb_last_error();  // (the message is thread-local: carry it to the caller)
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < n_workers; ++w) th.emplace_back(body, w);
+    body(0);
+    for (auto& t : th) t.join();
+    for (int w = 0; w < n_workers; ++w)
+      if (rcs[(size_t)w]) return fail(rcs[(size_t)w], msgs[(size_t)w]);
+    return PSULVSB_OK;
+  }
+
+  int solve_batch(const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B, const uint64_t* seeds,
+                  psulvsb_solution_t* solutions) {
+    if (!params) return fail(PSULVSB_ERR_INVALID, "solve_batch: null params");
+    resident_B = 0;
+    PSU_CUDA(cudaSetDevice(device));
+    const int ch = chunk_size();
+    const int n_chunks = (B + ch - 1) / ch;
+    const int n_workers = n_chunks < lane_count() ? n_chunks : lane_count();
+    if (int rc = ensure_engines(n_workers)) return rc;
+    std::vector<int> begin;
+    partition(B, n_chunks, begin);
+    std::vector<uint64_t> own_seeds;
+    if (!seeds && n_chunks > 1) {  // the default seed of a problem follows its index in the CALLER's batch
+      own_seeds.resize((size_t)B);
+      for (int b = 0; b < B; ++b) own_seeds[(size_t)b] = params->seed + (uint64_t)b;
+      seeds = own_seeds.data();
+    }
+    PSU_CUDA(cudaEventRecord(origin, eng[0]->st));
+    std::vector<ChunkRecord> recs((size_t)n_chunks);
+    std::atomic<int> next(0);
+    const int rc = run_parallel(n_workers, [&](int w) -> int {
+      Engine* e = eng[(size_t)w];
+      e->origin = origin;
+      for (int c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) {
+        const int b0 = begin[(size_t)c], nb = begin[(size_t)c + 1] - b0;
+        if (int r = e->upload(problems + b0, nb)) return r;
+        if (int r = e->solve(params, seeds ? seeds + b0 : nullptr, solutions + b0, nullptr)) return r;
+        recs[(size_t)c] = record_of(e);
+      }
+      return PSULVSB_OK;
+    });
+    if (rc) return rc;
+    fold(recs);
+    if (n_chunks == 1) {  // the batch is still resident on the first engine
+      res_begin.assign({0, B});
+      resident_B = B;
+    }
+    return PSULVSB_OK;
+  }
+
+  int upload(const psulvsb_problem_t* problems, int B) {
+    resident_B = 0;
+    PSU_CUDA(cudaSetDevice(device));
+    const int ch = chunk_size();
+    int parts = (B + ch - 1) / ch;
+    if (parts > lane_count()) parts = lane_count();  // resident chunks all run at once: one engine each
+    if (int rc = ensure_engines(parts)) return rc;
+    partition(B, parts, res_begin);
+    for (int e = 0; e < parts; ++e)
+      if (int rc = eng[(size_t)e]->upload(problems + res_begin[(size_t)e], res_begin[(size_t)e + 1] - res_begin[(size_t)e]))
+        return rc;
+    resident_B = B;
+    return PSULVSB_OK;
+  }
+
+  int solve_resident(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb_solution_t* solutions,
+                     psulvsb_trace_t* trace_first) {
+    if (resident_B <= 0) return fail(PSULVSB_ERR_INVALID, "solve: nothing uploaded");
+    if (!params) return fail(PSULVSB_ERR_INVALID, "solve: null params");
+    PSU_CUDA(cudaSetDevice(device));
+    const int parts = (int)res_begin.size() - 1;
+    std::vector<uint64_t> own_seeds;
+    if (!seeds && parts > 1) {
+      own_seeds.resize((size_t)resident_B);
+      for (int b = 0; b < resident_B; ++b) own_seeds[(size_t)b] = params->seed + (uint64_t)b;
+      seeds = own_seeds.data();
+    }
+    for (int e = 0; e < parts; ++e) PSU_CUDA(cudaStreamSynchronize(eng[(size_t)e]->st));  // pending input copies
+    PSU_CUDA(cudaEventRecord(origin, eng[0]->st));
+    std::vector<ChunkRecord> recs((size_t)parts);
+    const int rc = run_parallel(parts, [&](int w) -> int {
+      Engine* e = eng[(size_t)w];
+      e->origin = origin;
+      const int b0 = res_begin[(size_t)w];
+      if (int r = e->solve(params, seeds ? seeds + b0 : nullptr, solutions + b0, w == 0 ? trace_first : nullptr)) return r;
+      recs[(size_t)w] = record_of(e);
+      return PSULVSB_OK;
+    });
+    if (rc) {
+      // a failed solve leaves the engines' resident inputs intact; nothing to undo
+      return rc;
+    }
+    fold(recs);
+    return PSULVSB_OK;
+  }
+};
+
 // ---- C-linkage-free façade used by capi.cu ---------------------------------------------------
-int engine_create(Engine** out, int device) {
-  Engine* e = new Engine();
-  const int rc = e->init(device);
+int pool_create(EnginePool** out, int device) {
+  EnginePool* p = new EnginePool();
+  const int rc = p->init(device);
   if (rc) {
-    delete e;
+    delete p;
     *out = nullptr;
     return rc;
   }
-  *out = e;
+  *out = p;
   return PSULVSB_OK;
 }
-void engine_destroy(Engine* e) { delete e; }
-int engine_upload(Engine* e, const psulvsb_problem_t* problems, int B) { return e->upload(problems, B); }
-int engine_solve_resident(Engine* e, const psulvsb_params_t* params, const uint64_t* seeds,
-                          psulvsb_solution_t* solutions, psulvsb_trace_t* trace_first) {
-  return e->solve(params, seeds, solutions, trace_first);
+void pool_destroy(EnginePool* p) { delete p; }
+int pool_set_batching(EnginePool* p, int chunk, int lanes) {
+  if (chunk < 0 || lanes < 0 || lanes > 16) return fail(PSULVSB_ERR_INVALID, "set_batching: chunk >= 0, 0 <= lanes <= 16");
+  p->chunk = chunk;
+  p->lanes = lanes;
+  p->resident_B = 0;  // the resident partition followed the old setting
+  return p->ensure_engines((int)p->eng.size());
 }
-int engine_batch_size(const Engine* e) { return e->B; }
-long long engine_launch_count(const Engine* e) { return e->launches; }
-double engine_last_device_ms(const Engine* e) { return e->last_ms; }
-double engine_last_stage_ms(const Engine* e, int which) { return (which >= 0 && which < 5) ? e->stage_ms[which] : 0.0; }
-int engine_last_ticks(const Engine* e) { return e->last_ticks; }
+int pool_solve_one(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                   psulvsb_solution_t* solution, psulvsb_trace_t* trace) {
+  return p->solve_one(params, problem, solution, trace);
+}
+int pool_solve_batch(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,
+                     const uint64_t* seeds, psulvsb_solution_t* solutions) {
+  return p->solve_batch(params, problems, B, seeds, solutions);
+}
+int pool_solve_sharded(EnginePool* p, Comm* comm, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                       psulvsb_solution_t* solution, psulvsb_trace_t* trace) {
+  return p->solve_sharded(comm, params, problem, solution, trace);
+}
+int pool_upload(EnginePool* p, const psulvsb_problem_t* problems, int B) { return p->upload(problems, B); }
+int pool_solve_resident(EnginePool* p, const psulvsb_params_t* params, const uint64_t* seeds,
+                        psulvsb_solution_t* solutions, psulvsb_trace_t* trace_first) {
+  return p->solve_resident(params, seeds, solutions, trace_first);
+}
+int pool_batch_size(const EnginePool* p) { return p->resident_B; }
+long long pool_launch_count(const EnginePool* p) { return p->launch_count(); }
+double pool_last_device_ms(const EnginePool* p) { return p->last_ms; }
+double pool_last_stage_ms(const EnginePool* p, int which) { return (which >= 0 && which < 5) ? p->stage_ms[which] : 0.0; }
+int pool_last_ticks(const EnginePool* p) { return p->last_ticks; }
+int pool_last_chunk_ticks(const EnginePool* p, int* out, int cap) {
+  const int n = (int)p->chunk_ticks.size();
+  for (int i = 0; i < n && i < cap; ++i) out[i] = p->chunk_ticks[(size_t)i];
+  return n;
+}
 
 }  // namespace psulvsb

@@ -219,17 +219,40 @@ int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, co
                        double tau, double coord_bound, const double* csrc, const double* cdst, uint32_t* counts,
                        unsigned long long* best, unsigned long long* border);
 
-// ---- batch engine (engine.cu) -------------------------------------------------------------------
-class Engine;
-int engine_create(Engine** out, int device);
-void engine_destroy(Engine* e);
-int engine_upload(Engine* e, const psulvsb_problem_t* problems, int B);
-int engine_solve_resident(Engine* e, const psulvsb_params_t* params, const uint64_t* seeds,
-                          psulvsb_solution_t* solutions, psulvsb_trace_t* trace_first);
-int engine_batch_size(const Engine* e);
-int engine_last_ticks(const Engine* e);
-long long engine_launch_count(const Engine* e);
-double engine_last_device_ms(const Engine* e);
-double engine_last_stage_ms(const Engine* e, int which);
+// ---- multi-GPU plumbing (comm.cu) -------------------------------------------------------------------
+struct Comm;
+int comm_unique_id(void* out128);
+int comm_create(Comm** out, int device, int rank, int world, const void* id128);
+void comm_destroy(Comm* c);
+int comm_rank(const Comm* c);
+int comm_world(const Comm* c);
+int comm_allreduce_sum_u32(Comm* c, cudaStream_t st, uint32_t* d_inout, size_t n);
+int comm_allreduce_max_u64(Comm* c, cudaStream_t st, unsigned long long* d_inout, size_t n);
+int comm_allgather_u64(Comm* c, cudaStream_t st, const unsigned long long* d_send, unsigned long long* d_recv);
+int comm_allgatherv_inplace_u32(Comm* c, cudaStream_t st, uint32_t* base, const unsigned long long* offsets);
+void triangular_row_range(int n, int rank, int world, int* begin, int* end);
+
+// ---- batch engine pool (engine.cu) --------------------------------------------------------------
+class EnginePool;
+int pool_create(EnginePool** out, int device);
+void pool_destroy(EnginePool* p);
+int pool_set_batching(EnginePool* p, int chunk, int lanes);
+int pool_solve_one(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                   psulvsb_solution_t* solution, psulvsb_trace_t* trace);
+int pool_solve_batch(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,
+                     const uint64_t* seeds, psulvsb_solution_t* solutions);
+int pool_upload(EnginePool* p, const psulvsb_problem_t* problems, int B);
+// ONE registration whose consistency rows are sharded over the ranks of `comm` (every rank passes the same problem and
+// gets the same solution)
+int pool_solve_sharded(EnginePool* p, Comm* comm, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
+                       psulvsb_solution_t* solution, psulvsb_trace_t* trace);
+int pool_solve_resident(EnginePool* p, const psulvsb_params_t* params, const uint64_t* seeds,
+                        psulvsb_solution_t* solutions, psulvsb_trace_t* trace_first);
+int pool_batch_size(const EnginePool* p);
+int pool_last_ticks(const EnginePool* p);
+int pool_last_chunk_ticks(const EnginePool* p, int* out, int cap);
+long long pool_launch_count(const EnginePool* p);
+double pool_last_device_ms(const EnginePool* p);
+double pool_last_stage_ms(const EnginePool* p, int which);
 
 }  // namespace psulvsb

@@ -508,6 +508,7 @@ __global__ void compact_edges_kernel(const CompactJob* __restrict__ jobs) {
   const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
+  if (job.row_counts && job.row_counts[row] == 0u) return;  // nothing to emit (or a row another rank owns: its words are not this rank's)
   const int W = (n + 31) >> 5;
   unsigned long long base = job.offsets[row];
   for (int w0 = row >> 5; w0 < W; w0 += 32) {

@@ -1021,6 +1021,8 @@ int gnc_default_capacity() { return gnc_capacity_for(1); }
 
 // CTAs per hypothesis for a batch of n_jobs: as many SMs per job as keeps the whole batch resident
 int gnc_cluster_for(int n_jobs) {
+  const int forced = debug_knobs().gnc_cluster;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
   const int slots = sm_count() * GNC_CTAS_PER_SM;
   if (n_jobs * 8 <= slots) return 8;
   if (n_jobs * 4 <= slots) return 4;
@@ -1034,6 +1036,14 @@ int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_pe
   gnc_tls_small_kernel<<<n_jobs, 128, 0, st>>>(d_jobs);  // tiny subsets: the reference's arithmetic replayed by one thread
   PSU_CHECK_LAUNCH("gnc_tls_small_kernel");
   if (cap_per_cta < 32) cap_per_cta = 32;
+  if (debug_knobs().gnc_cluster > 0) {
+    switch (cluster) {
+      case 8: return launch_gnc_nc<8, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+      case 4: return launch_gnc_nc<4, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+      case 2: return launch_gnc_nc<2, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+      default: return launch_gnc_nc<1, 512, 1, false>(st, d_jobs, n_jobs, cap_per_cta);
+    }
+  }
   switch (cluster) {
     // (measured: 512 threads x 2 CTAs per SM = 64 registers spills 1.3 KB per thread and loses 25 %)
     case 8:

@@ -96,6 +96,20 @@ def test_solve_matches_oracle_with_self_update(env, n, ratio, seed):
     assert sg.final_C >= pre["src_reduce"].shape[1]
 
 
+@pytest.mark.parametrize("n,ratio,side,seed", [(20_000, 0.95, 3.0, 21), (100_000, 0.99, 30.0, 11)])
+def test_large_n_matches_oracle_end_to_end(env, n, ratio, side, seed):
+    """BASELINE configs[2] as a REGISTRATION: N = 100 000 correspondences, 99 % outliers (5.0e9 line vectors, which
+    the reference's int pair indices, registration.cc:682-686, cannot hold; the oracle streams them with 64-bit
+    indices, ~35 s of CPU), and N = 20 000.  Same step-by-step bar as the small cases: reduced set, sample sizes,
+    GNC-TLS iterations, inlier sets, control flow bit-exact; R, t within 1e-5."""
+    pair = env["synth"].make_pair(n, ratio, 4242, side=side)
+    so, to, sg, tg = both(env, pair, seed=seed)
+    assert sg.n_line_vectors == n * (n - 1) // 2
+    assert_same_run(env, so, to, sg, tg)
+    assert sg.final_inlier_count >= int(0.9 * n * (1 - ratio))
+    assert env["synth"].rotation_error(sg.R, pair["R"]) < 0.01
+
+
 def test_solve_cfg_a_5k_95pct(env):
     """BASELINE config[1]: N = 5000 correspondences, 95 % outliers."""
     pair = env["synth"].make_pair(5000, 0.95, 101)
@@ -142,6 +156,48 @@ def test_batch_equals_individual_solves(env):
         assert np.array_equal(np.array(b.rotation[:]), np.array(one.rotation[:]))     # deterministic: bit-equal
         assert np.array_equal(np.array(b.translation[:]), np.array(one.translation[:]))
         assert b.final_inlier_count == one.final_inlier_count and b.local_iters == one.local_iters
+
+
+def test_chunked_pool_gives_the_same_results(env):
+    """psulvsb_set_batching: chunks advancing concurrently on the handle's engine pool (host buffers: dynamic hand-out;
+    resident: even split) return exactly what one lock-step batch returns, default seeds included."""
+    capi, synth = env["capi"], env["synth"]
+    pairs = [synth.make_pair(n, 0.9, 150 + i) for i, n in enumerate([300, 800, 1200, 500, 64, 700, 333, 900, 410, 256, 777])]
+    probs = [capi.HostProblem(p["src"], p["dst"]) for p in pairs]
+    params = capi.default_params(seed=21, **PKW)
+    h = capi.Handle(0)
+    h.set_batching(64, 1)
+    ref = h.solve_batch(params, probs)
+    assert h.last_chunk_ticks == [h.last_ticks]
+
+    def same(a, b):
+        for x, y in zip(a, b):
+            assert x.status == 0 and y.status == 0
+            assert np.array_equal(np.array(x.rotation[:]), np.array(y.rotation[:]))
+            assert np.array_equal(np.array(x.translation[:]), np.array(y.translation[:]))
+            assert (x.final_inlier_count, x.local_iters, x.n_reduced) == (y.final_inlier_count, y.local_iters, y.n_reduced)
+
+    for chunk, lanes in ((3, 2), (4, 3), (2, 4)):
+        h.set_batching(chunk, lanes)
+        same(ref, h.solve_batch(params, probs))
+        assert len(h.last_chunk_ticks) == (len(probs) + chunk - 1) // chunk
+        assert h.resident_size == 0  # a chunked host-buffer batch leaves nothing resident
+        h.upload(probs)
+        assert h.resident_size == len(probs)
+        same(ref, h.solve_resident(params))
+        assert len(h.last_chunk_ticks) >= min(lanes, (len(probs) + chunk - 1) // chunk)  # engines x their sub-batches
+        assert h.last_device_ms > 0 and h.last_stage_ms(2) > 0 and h.last_stage_ms(3) > 0
+    seeds = list(range(100, 100 + len(probs)))
+    h.set_batching(64, 1)
+    ref = h.solve_batch(params, probs, seeds)
+    h.set_batching(3, 2)
+    same(ref, h.solve_batch(params, probs, seeds))
+    # an invalid problem in a later chunk fails the call with its message on the calling thread
+    bad = capi.HostProblem(pairs[0]["src"].copy(), pairs[0]["dst"].copy())
+    bad.src[0, 0] = np.nan
+    with pytest.raises(capi.PsulvsbError, match="non-finite"):
+        h.solve_batch(params, probs[:7] + [bad])
+    h.close()
 
 
 def test_resident_solve_is_repeatable(env):
