@@ -28,6 +28,8 @@
 // sign bit, so no ballot and no divergence on the fast path.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -328,8 +330,19 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
   int grp_row_min[R];  // smallest row of this warp in row group r (warp-uniform, increasing in r)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    grp_row_min[r] = row0 + r * K1_THREADS + 32 * k1_warp_pos<R>(r, tid >> 5);
-    irow[r] = grp_row_min[r] + lane;
+    if (R == 4) {
+      // Two strips of 64 consecutive rows per warp, strip w and strip 15 - w of the block's 16: a lane's packed row
+      // pairs (2 l, 2 l + 1) are neighbours, so both halves of an FFMA2 die together along the diagonal (with row
+      // groups 256 apart, a half-live pair evaluated its dead row: half of the work in the diagonal tiles of an
+      // N = 5000 problem, where they are a third of all tiles, was below the diagonal), and every warp owns the same
+      // number of live words over the 4 diagonal tiles of its block (32 - 2 w + 2 + 2 w).
+      const int strip = (r < 2) ? (tid >> 5) : 15 - (tid >> 5);
+      grp_row_min[r] = row0 + 64 * strip;
+      irow[r] = grp_row_min[r] + 2 * lane + (r & 1);
+    } else {
+      grp_row_min[r] = row0 + r * K1_THREADS + 32 * k1_warp_pos<R>(r, tid >> 5);
+      irow[r] = grp_row_min[r] + lane;
+    }
     const bool ok = irow[r] < row_end;
     const float4 a = ok ? src[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 b = ok ? dst[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -378,43 +391,55 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
       const float4* tw = &ct[st][wj * 32];
       if (n_live == R)
         eval_word<R, R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
+      else if (R == 4)  // (strips of adjacent rows: a pair is live or dead as a whole)
+        eval_word<(R == 4 ? 2 : 1), R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
       else if (R > 1 && n_live == 1)
         eval_word<1, R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
       else if (R > 2 && n_live == 2)
         eval_word<(R > 2 ? 2 : 1), R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
       else
         eval_word<(R > 3 ? 3 : 1), R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
-      const uint32_t valid = (cb + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - cb)) - 1u);
-      const float4 sl = cs[st][wj * 32 + lane];  // this lane's column of the word (slow path only)
-      const float4 tl = ct[st][wj * 32 + lane];
+      // the word's epilogue.  FULL: every column of the word is right of every row of the CTA and inside the arrays (all
+      // tiles but the block's diagonal ones and the last): no triangle / tail masks
+      auto finish = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const uint32_t valid = (FULL || cb + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - cb)) - 1u);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i = irow[r];
-        const bool row_ok = i < row_end;
-        const uint32_t upper = (i < cb) ? 0xFFFFFFFFu : ((i >= cb + 31) ? 0u : (0xFFFFFFFFu << (i - cb + 1)));
-        const uint32_t live = row_ok ? (valid & upper) : 0u;
-        uint32_t word = acc[r] & live;
-        // rare: some pair of this word is one the fast path cannot vouch for -> warp-cooperative redo
-        unsigned int flagged = __ballot_sync(0xffffffffu, live != 0u && !(mv[r] > t_fast));
-        while (flagged) {
-          const int owner = __ffs(flagged) - 1;
-          flagged &= flagged - 1;
-          const int oi = __shfl_sync(0xffffffffu, i, owner);
-          // the owner's row point back from its pre-scaled registers (x -2 and x -0.5 are exact)
-          const float4 si = make_float4(-0.5f * __shfl_sync(0xffffffffu, ms[r].x, owner),
-                                        -0.5f * __shfl_sync(0xffffffffu, ms[r].y, owner),
-                                        -0.5f * __shfl_sync(0xffffffffu, ms[r].z, owner), 0.f);
-          const float4 ti = make_float4(-0.5f * __shfl_sync(0xffffffffu, mt[r].x, owner),
-                                        -0.5f * __shfl_sync(0xffffffffu, mt[r].y, owner),
-                                        -0.5f * __shfl_sync(0xffffffffu, mt[r].z, owner), 0.f);
-          const uint32_t res = slow_word_coop(slow, oi, cb, si, ti, sl, tl, nborder);
-          if (lane == owner) word = res & live;
+        for (int r = 0; r < R; ++r) {
+          const int i = irow[r];
+          const bool row_ok = i < row_end;
+          const uint32_t upper =
+              (FULL || i < cb) ? 0xFFFFFFFFu : ((i >= cb + 31) ? 0u : (0xFFFFFFFFu << (i - cb + 1)));
+          const uint32_t live = row_ok ? (valid & upper) : 0u;
+          uint32_t word = acc[r] & live;
+          // rare: some pair of this word is one the fast path cannot vouch for -> warp-cooperative redo
+          unsigned int flagged = __ballot_sync(0xffffffffu, live != 0u && !(mv[r] > t_fast));
+          while (flagged) {
+            const int owner = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            const int oi = __shfl_sync(0xffffffffu, i, owner);
+            // the owner's row point back from its pre-scaled registers (x -2 and x -0.5 are exact)
+            const float4 si = make_float4(-0.5f * __shfl_sync(0xffffffffu, ms[r].x, owner),
+                                          -0.5f * __shfl_sync(0xffffffffu, ms[r].y, owner),
+                                          -0.5f * __shfl_sync(0xffffffffu, ms[r].z, owner), 0.f);
+            const float4 ti = make_float4(-0.5f * __shfl_sync(0xffffffffu, mt[r].x, owner),
+                                          -0.5f * __shfl_sync(0xffffffffu, mt[r].y, owner),
+                                          -0.5f * __shfl_sync(0xffffffffu, mt[r].z, owner), 0.f);
+            // this lane's column of the word (read only here: the slow path is rare)
+            const uint32_t res =
+                slow_word_coop(slow, oi, cb, si, ti, cs[st][wj * 32 + lane], ct[st][wj * 32 + lane], nborder);
+            if (lane == owner) word = res & live;
+          }
+          if (row_ok) {
+            mask[(size_t)i * stride + (cb >> 5)] = word;
+            cnt[r] += __popc(word);
+          }
         }
-        if (row_ok) {
-          mask[(size_t)i * stride + (cb >> 5)] = word;
-          cnt[r] += __popc(word);
-        }
-      }
+      };
+      if (cb >= row0 + TI && cb + 32 <= n)
+        finish(std::true_type());
+      else
+        finish(std::false_type());
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_empty[st]);  // this warp is done with stage st
@@ -575,6 +600,8 @@ static int launch_k1_variant(cudaStream_t st, const K1Job* d_jobs, int n_jobs, i
   int tpc = (int)(live_tiles / ((double)sm_count() * 3.0 * 12.0));  // ~12 waves of resident CTAs: short tail
   if (tpc < 1) tpc = 1;
   if (tpc > 16) tpc = 16;
+  // whole diagonal blocks per chunk (TI / TJ tiles): the row permutation balances the warps over a block's diagonal tiles
+  if (R == 4 && tpc >= 3) tpc = (tpc + 3) / 4 * 4;
   if (tpc > n_tiles) tpc = n_tiles;
   dim3 grid((n_tiles + tpc - 1) / tpc, row_blocks, n_jobs);
   k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs, tpc);
