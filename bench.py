@@ -849,8 +849,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="cfgA", choices=["cfgA", "cfgB", "cfgC", "cfgD", "bunny"])
-    ap.add_argument("--batch", type=int, default=296,
-                    help="cfgA: fragment pairs per GPU per step (default: two per SM of a 148-SM B200)")
+    ap.add_argument("--batch", type=int, default=592,
+                    help="cfgA: fragment pairs per GPU per step (default: four per SM of a 148-SM B200; the library "
+                         "advances them as two lock-step chunks of 296 on two engines)")
     ap.add_argument("--chunk", type=int, default=0, help="registrations per lock-step chunk (0: library default)")
     ap.add_argument("--lanes", type=int, default=0, help="chunks in flight at once (0: library default)")
     ap.add_argument("--debug", default="", help="name=value[,name=value] for psulvsb_debug_set")

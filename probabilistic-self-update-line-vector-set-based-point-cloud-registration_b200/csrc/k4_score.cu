@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(SB_THREADS)
                        const double* __restrict__ src64, const double* __restrict__ dst64, int n,
                        const double* __restrict__ hyp, unsigned long long n_hyp, unsigned long long hyp_begin,
                        ScoreArgs a, int chunk_points, uint32_t* __restrict__ counts,
-                       unsigned long long* __restrict__ border_count) {
+                       unsigned long long* __restrict__ border_count, unsigned int* __restrict__ tickets,
+                       unsigned long long* __restrict__ best) {
   __shared__ __align__(128) float4 ps[2][SB_TP];
   __shared__ __align__(128) float4 qs[2][SB_TP];
   __shared__ __align__(8) uint64_t bar[2];
@@ -177,31 +178,43 @@ __global__ void __launch_bounds__(SB_THREADS)
   }
   const unsigned int nb = (unsigned int)warp_sum_int((int)nborder);
   if (lane == 0 && nb && border_count) atomicAdd(border_count, (unsigned long long)nb);
-}
 
-// warp -> block -> grid argmax of (count, hypothesis) packed in 64 bits: the first best hypothesis wins
-__global__ void __launch_bounds__(256)
-    argmax_counts_kernel(const uint32_t* __restrict__ counts, unsigned long long n_hyp, unsigned long long hyp_begin,
-                         unsigned long long* __restrict__ best) {
-  __shared__ unsigned long long warp_best[8];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // ---- argmax, fused: the CTA that completes a hypothesis group (the last of its gridDim.y correspondence slices to
+  // add its counts) reduces the group's keys (count << 32 | ~id: the first best hypothesis wins, as the strict '>' of
+  // registration.cc:1337) warp -> block and issues ONE atomicMax.  With a single slice the counts never leave the
+  // registers before the reduction.
+  if (best == nullptr) return;
+  __shared__ int is_last;
+  __shared__ unsigned long long warp_best[SB_THREADS / 32];
+  if (gridDim.y > 1) {
+    __threadfence();  // this CTA's atomicAdds are visible before its ticket
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1u) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+  }
   unsigned long long mybest = 0ull;
-  for (unsigned long long h = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; h < n_hyp;
-       h += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long key =
-        ((unsigned long long)counts[h] << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(hyp_begin + h));
-    mybest = key > mybest ? key : mybest;
+#pragma unroll
+  for (int k = 0; k < SB_HPT; ++k) {
+    const unsigned long long h = h0 + k;
+    if (h < n_hyp) {
+      const uint32_t c = (gridDim.y > 1) ? __ldcg(&counts[h]) : (uint32_t)cnt[k];
+      const unsigned long long key = ((unsigned long long)c << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(hyp_begin + h));
+      mybest = key > mybest ? key : mybest;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const unsigned long long x = __shfl_xor_sync(0xffffffffu, mybest, o);
     mybest = x > mybest ? x : mybest;
   }
-  if (lane == 0) warp_best[wid] = mybest;
+  if (lane == 0) warp_best[tid >> 5] = mybest;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     unsigned long long b = warp_best[0];
-    for (int w = 1; w < 8; ++w) b = warp_best[w] > b ? warp_best[w] : b;
+#pragma unroll
+    for (int w = 1; w < SB_THREADS / 32; ++w) b = warp_best[w] > b ? warp_best[w] : b;
     if (b) atomicMax(best, b);
   }
 }
@@ -303,15 +316,16 @@ int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, co
   chunk_points = (chunk_points + SB_TP - 1) / SB_TP * SB_TP;  // tile-aligned: every bulk copy stays 16-byte aligned
   const unsigned gy = (unsigned)((n + chunk_points - 1) / chunk_points);
   PSU_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * n_hyp, st));
-  score_batch_kernel<<<dim3((unsigned)gx, gy), SB_THREADS, 0, st>>>(src, dst, src64, dst64, n, hyp, n_hyp, hyp_begin, a,
-                                                                     chunk_points, counts, border);
-  PSU_CHECK_LAUNCH("score_batch_kernel");
-  if (best) {
-    unsigned long long ga = (n_hyp + 255) / 256;
-    if (ga > sm_count() * 8) ga = sm_count() * 8;
-    argmax_counts_kernel<<<(unsigned)ga, 256, 0, st>>>(counts, n_hyp, hyp_begin, best);
-    PSU_CHECK_LAUNCH("argmax_counts_kernel");
+  unsigned int* tickets = nullptr;  // one "slices done" counter per hypothesis group (stream-ordered scratch)
+  if (best && gy > 1) {
+    PSU_CUDA(cudaMallocAsync((void**)&tickets, sizeof(unsigned int) * gx, st));
+    PSU_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned int) * gx, st));
   }
+  score_batch_kernel<<<dim3((unsigned)gx, gy), SB_THREADS, 0, st>>>(src, dst, src64, dst64, n, hyp, n_hyp, hyp_begin, a,
+                                                                     chunk_points, counts, border, tickets, best);
+  const cudaError_t le = cudaGetLastError();
+  if (tickets) cudaFreeAsync(tickets, st);
+  if (le != cudaSuccess) return fail(PSULVSB_ERR_CUDA, std::string("score_batch_kernel launch: ") + cudaGetErrorString(le));
   return PSULVSB_OK;
 }
 
