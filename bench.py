@@ -595,48 +595,38 @@ def timed_stream(c, fn, steps, warmup):
     return max_over_ranks(c, float(np.mean(ms)))[0]
 
 
-def stage_k1(c, n=100_000, steps=3, warmup=3):
-    """The consistency kernel at cfg-B's size: rows sharded over the ranks (triangular balancing), nothing exchanged
-    but the per-row popcounts (summed over the library's communicator)."""
-    torch, capi = c.torch, c.capi
-    from psulvsb_b200 import sharding, stages
-
-    L = capi.lib()
+def stage_k1(c, n=100_000, steps=3, warmup=2):
+    """The consistency kernel at cfg-B's size, inside the library's own sharded registration (psulvsb_solve_sharded:
+    rows split over the ranks with triangular balancing, edge counts and edge lists exchanged over NCCL).  Timed by the
+    engine's CUDA events around the kernel launch alone (psulvsb_last_stage_ms(2)); max over ranks."""
+    capi = c.capi
     pair = c.synth.make_pair(n, 0.99, 4242, side=30.0)
-    beta = 0.1
-    (cs, cd), bound = stages.centre_and_bound(pair["src"], pair["dst"])
-    d_src, d_dst = stages.to_device_points(pair["src"]), stages.to_device_points(pair["dst"])
-    f_src, f_dst = stages.pack_points(d_src, cs), stages.pack_points(d_dst, cd)
-    stride = ((n + 31) // 32 + 7) // 8 * 8
-    ranges = [sharding.triangular_row_range(n, r, c.world) for r in range(c.world)]
-    rb, re = ranges[c.rank]
-    mask = torch.empty((re - rb, stride), dtype=torch.int32, device="cuda")  # this rank's rows only
-    counts = torch.zeros(n, dtype=torch.int32, device="cuda")
-    border = torch.zeros(1, dtype=torch.int64, device="cuda")
-    mask_base = mask.data_ptr() - rb * stride * 4  # row i lives at base + i * stride words
-
-    def run():
-        capi.check(L.psulvsb_consistency_mask_rows(torch.cuda.current_stream().cuda_stream, f_src.data_ptr(),
-                                                   f_dst.data_ptr(), d_src.data_ptr(), d_dst.data_ptr(), n, rb, re,
-                                                   beta, bound, mask_base, stride, counts.data_ptr(), border.data_ptr()))
-
-    ms = timed_stream(c, run, steps, warmup)
+    prob = capi.HostProblem(pair["src"], pair["dst"])
+    params = capi.default_params(seed=11, **PARAM_KW)
+    solve = (lambda: c.h.solve_sharded(params, prob)) if c.world > 1 else (lambda: c.h.solve(params, prob)[0])
+    for _ in range(warmup):
+        sol = solve()
+    barrier(c)
+    k1 = dev = 0.0
+    for _ in range(steps):
+        sol = solve()
+        k1 += c.h.last_stage_ms(2)
+        dev += c.h.last_device_ms
+    barrier(c)
     f = sm_clock_now(c) or 1965.0
-    counts.zero_()
-    run()
-    if c.world > 1:  # owned rows only are non-zero: the sum is the all-gather
-        c.h.comm_allreduce_sum_u32(counts.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    n_red = int(counts.to(torch.int64).sum().item())
+    k1_max, dev_max = max_over_ranks(c, k1 / steps, dev / steps)
     pairs_total = n * (n - 1) // 2
     peak = c.world * c.sms * 128 * f * 1e6 / 1e9
-    ach = pairs_total * 16 / (ms / 1e3) / 1e9
-    return {"case": "consistency kernel, N = 100000 correspondences, 99% outliers", "n": n, "n_gpus": c.world,
-            "pairs": pairs_total, "n_reduced": n_red, "ms": ms, "pairs_per_s": pairs_total / (ms / 1e3),
+    ach = pairs_total * 16 / (k1_max / 1e3) / 1e9
+    return {"case": "consistency kernel of ONE registration, N = 100000 correspondences, 99% outliers (cfg-B)", "n": n,
+            "n_gpus": c.world, "pairs": pairs_total, "n_reduced": int(sol.n_reduced), "ms": k1_max,
+            "pairs_per_s": pairs_total / (k1_max / 1e3), "registration_ms": dev_max,
+            "final_inliers": int(sol.final_inlier_count),
             "roofline": {"bound": "fp32-pipe", "achieved": ach, "peak": peak, "frac": ach / peak,
                          "unit": "Gslot/s (16 FP32-pipe issue slots per unordered pair)",
                          "peak_source": f"{c.world} x {c.sms} SMs x 128 lanes x {f:.0f} MHz (nvidia-smi after the run)"},
-            "sharding": "triangular row blocks; per-row popcounts summed over the library's NCCL communicator"}
+            "sharding": "triangular row blocks inside psulvsb_solve_sharded; edge counts all-gathered, edge lists "
+                        "all-gathered in place (grouped ncclBroadcast), RANSAC replicated"}
 
 
 def stage_k4(c, n=50_000, H=1 << 20, steps=3, warmup=3):
@@ -769,7 +759,7 @@ def run_bunny(args, c):
     capi = c.capi
     from psulvsb_b200 import io as pio
 
-    trials = 64
+    trials = 592  # one batch of lock-step chunks, like cfgA
     cases = [bunny_case(500 + c.rank * 1000 + i) for i in range(trials)]
     seeds = [500 + c.rank * 1000 + i for i in range(trials)]
     normals = [(pio.estimate_normals(p["src"]), pio.estimate_normals(p["dst"])) for p in cases]  # untimed (PSULVSB.cc:307)

@@ -361,6 +361,9 @@ int psulvsb_comm_unique_id(void* out_id);
 int psulvsb_comm_create(psulvsb_handle_t h, int rank, int world, const void* id);
 int psulvsb_comm_destroy(psulvsb_handle_t h);
 int psulvsb_comm_rank(psulvsb_handle_t h);
+/* The row block [begin, end) of the consistency stage that psulvsb_solve_sharded gives rank `rank` of `world`: every
+ * rank owns about the same number of line vectors (row i has n - 1 - i of them).  Host arithmetic, no device. */
+int psulvsb_shard_row_range(int n, int rank, int world, int* begin, int* end);
 int psulvsb_comm_world(psulvsb_handle_t h);
 /* In-stream collectives on DEVICE buffers (no-ops on a handle without a communicator): element-wise sum of uint32
  * (per-row popcounts of row blocks built with psulvsb_consistency_mask_rows: rows a rank does not own stay 0, so the

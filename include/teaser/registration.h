@@ -22,6 +22,7 @@
 
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <utility>
 #include <vector>
 
@@ -87,6 +88,8 @@ public:
     detail::fill_mask(inliers, m);
   }
   int lastStatus() const { return status_; }
+  double noiseBound() const { return noise_bound_; }
+  double cbar2() const { return cbar2_; }
 
 private:
   double noise_bound_;
@@ -117,6 +120,8 @@ public:
     detail::fill_mask(inliers, m);
   }
   int lastStatus() const { return status_; }
+  double noiseBound() const { return noise_bound_; }
+  double cbar2() const { return cbar2_; }
 
 private:
   double noise_bound_;
@@ -149,6 +154,8 @@ public:
     detail::fill_mask(inliers, m);
   }
   int lastStatus() const { return status_; }
+  double noiseBound() const { return noise_bound_; }
+  double cbar2() const { return cbar2_; }
 
 private:
   double noise_bound_;
@@ -259,6 +266,17 @@ public:
   }
   Params getParams() { return params_; }
   RegistrationSolution getSolution() { return solution_; }
+
+  /// registration.h:559-580.  The reference's solve() calls whatever estimator objects it holds; here the path runs
+  /// as CUDA kernels, so an estimator is accepted when it is one of this header's own classes (the kernels behind
+  /// them ARE the path) -- its parameters then replace the corresponding Params fields, as installing it in the
+  /// reference would -- and any other AbstractScaleSolver / GNCRotationSolver / AbstractTranslationSolver subclass
+  /// makes the next solve() fail with PSULVSB_ERR_UNSUPPORTED (valid = false) instead of being silently ignored.
+  void setScaleEstimator(std::unique_ptr<AbstractScaleSolver> estimator) { scale_solver_ = std::move(estimator); }
+  void setRotationEstimator(std::unique_ptr<GNCRotationSolver> estimator) { rotation_solver_ = std::move(estimator); }
+  void setTranslationEstimator(std::unique_ptr<AbstractTranslationSolver> estimator) {
+    translation_solver_ = std::move(estimator);
+  }
   // status / message of the last solve (PSULVSB_OK = 0); diagnostics of the run
   int lastStatus() const { return last_status_; }
   const psulvsb_solution_t& diagnostics() const { return raw_; }
@@ -306,6 +324,35 @@ public:
     p.kcore_heuristic_threshold = params_.kcore_heuristic_threshold;
     p.seed = params_.seed;
     if (params_.replay) p.wallclock_cap_s = 0.0;
+    if (scale_solver_) {
+      if (auto* sel = dynamic_cast<ScaleInliersSelector*>(scale_solver_.get())) {
+        p.estimate_scaling = 0;
+        p.noise_bound = sel->noiseBound();
+        p.cbar2 = sel->cbar2();
+      } else if (auto* tls = dynamic_cast<TLSScaleSolver*>(scale_solver_.get())) {
+        p.estimate_scaling = 1;
+        p.noise_bound = tls->noiseBound();
+        p.cbar2 = tls->cbar2();
+      } else {
+        last_status_ = PSULVSB_ERR_UNSUPPORTED;
+        return solution_;
+      }
+    }
+    if (rotation_solver_) {
+      if (auto* gnc = dynamic_cast<GNCTLSRotationSolver*>(rotation_solver_.get())) {
+        const GNCRotationSolver::Params rp = gnc->getParams();
+        p.rotation_max_iterations = static_cast<int>(rp.max_iterations);
+        p.rotation_cost_threshold = rp.cost_threshold;
+        p.rotation_gnc_factor = rp.gnc_factor;
+      } else {
+        last_status_ = PSULVSB_ERR_UNSUPPORTED;
+        return solution_;
+      }
+    }
+    if (translation_solver_ && !dynamic_cast<TLSTranslationSolver*>(translation_solver_.get())) {
+      last_status_ = PSULVSB_ERR_UNSUPPORTED;
+      return solution_;
+    }
     const int C = static_cast<int>(src.cols());
     // ori_src / ori_dst absent (upstream-style callers): the reduced set is the whole set
     const bool have_ori = params_.ori_src.cols() > 0;
@@ -426,6 +473,9 @@ private:
   Params params_;
   RegistrationSolution solution_;
   psulvsb_handle_t handle_ = nullptr;
+  std::unique_ptr<AbstractScaleSolver> scale_solver_;
+  std::unique_ptr<GNCRotationSolver> rotation_solver_;
+  std::unique_ptr<AbstractTranslationSolver> translation_solver_;
   psulvsb_solution_t raw_ = {};
   int last_status_ = PSULVSB_OK;
   std::vector<int> final_inliers_;

@@ -30,7 +30,7 @@ SYMBOLS = [
     "psulvsb_gnc_tls_rotation_host", "psulvsb_tls_translation_host", "psulvsb_estimate_normals", "psulvsb_estimate_normals_host",
     "psulvsb_comm_unique_id", "psulvsb_comm_create", "psulvsb_comm_destroy", "psulvsb_comm_rank", "psulvsb_comm_world",
     "psulvsb_comm_allreduce_sum_u32", "psulvsb_comm_allreduce_max_u64", "psulvsb_score_batch_sharded",
-    "psulvsb_solve_sharded",
+    "psulvsb_solve_sharded", "psulvsb_shard_row_range",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -224,6 +224,7 @@ def _declare(L: C.CDLL) -> None:
     L.psulvsb_comm_allreduce_max_u64.argtypes = [_vp, _vp, _vp, _ull]
     L.psulvsb_score_batch_sharded.argtypes = [_vp] + list(L.psulvsb_score_batch.argtypes)
     L.psulvsb_solve_sharded.argtypes = [_vp, C.POINTER(Params), C.POINTER(Problem), C.POINTER(Solution), C.POINTER(Trace)]
+    L.psulvsb_shard_row_range.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.psulvsb_score_one.argtypes = [_vp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, C.c_double, _vp, _vp, _vp]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here = the library does not export what the header declares
@@ -244,6 +245,13 @@ def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(UNIQUE_ID_BYTES)
     check(lib().psulvsb_comm_unique_id(buf))
     return buf.raw
+
+
+def shard_row_range(n: int, rank: int, world: int):
+    """psulvsb_shard_row_range: the consistency rows psulvsb_solve_sharded gives `rank` (host arithmetic)."""
+    b, e = C.c_int(0), C.c_int(0)
+    check(lib().psulvsb_shard_row_range(n, rank, world, C.byref(b), C.byref(e)))
+    return b.value, e.value
 
 
 def default_params(**kw) -> Params:

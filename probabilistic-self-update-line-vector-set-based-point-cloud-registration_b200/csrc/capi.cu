@@ -562,6 +562,13 @@ int psulvsb_comm_destroy(psulvsb_handle_t h) {
   return PSULVSB_OK;
 }
 
+int psulvsb_shard_row_range(int n, int rank, int world, int* begin, int* end) {
+  if (!begin || !end || n < 0 || world < 1 || rank < 0 || rank >= world)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_shard_row_range: bad argument");
+  triangular_row_range(n, rank, world, begin, end);
+  return PSULVSB_OK;
+}
+
 int psulvsb_comm_rank(psulvsb_handle_t h) { return h ? comm_rank(h->comm) : 0; }
 int psulvsb_comm_world(psulvsb_handle_t h) { return h ? comm_world(h->comm) : 1; }
 

@@ -67,6 +67,18 @@ def test_subsolver_classes_pass_the_reference_unit_test_sequences(tmp_path):
     assert r.returncode == 0 and "FAIL" not in r.stdout and r.stdout.count(" ok") >= 10, r.stdout + r.stderr
 
 
+def test_estimator_setters_and_ply_writer(tmp_path):
+    """setScale/Rotation/TranslationEstimator (registration.h:559-580) and PLYWriter (ply_io.h:35-50)."""
+    exe = str(tmp_path / "facade_extras")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "tests", "shim"),
+                           os.path.join(ROOT, "tests", "cpp", "facade_extras_snippet.cc"), "-o", exe, "-L", libdir,
+                           "-l:libpsulvsb_b200.so", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe, str(tmp_path / "roundtrip.ply")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.count(" ok") == 3, r.stdout + r.stderr
+
+
 def build_example(tmp_path):
     exe = str(tmp_path / "psulvsb_ply")
     libdir = os.path.dirname(capi.LIB_PATH)

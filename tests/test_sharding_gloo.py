@@ -79,6 +79,70 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _edge_worker(rank, world, port, q):
+    """What psulvsb_solve_sharded exchanges, replayed on the CPU over gloo: every rank compacts the edges of ITS rows
+    (the library's own row partition), the ranks all-gather their counts and then their blocks of the edge list."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from psulvsb_b200 import capi, synth
+
+        n = 700
+        pair = synth.make_pair(n, 0.8, 31)
+        pi, pj = O.reduced_set(pair["src"], pair["dst"], 0.1)   # the reference's L_reduced_set, row-major
+        rb, re = capi.shard_row_range(n, rank, world)
+        mine = (pi >= rb) & (pi < re)
+        block = torch.from_numpy(np.stack([pi[mine], pj[mine]], axis=1).astype(np.int64))
+        cnt = torch.tensor([block.shape[0]], dtype=torch.int64)
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, cnt)
+        counts = [int(c.item()) for c in counts]
+        width = max(counts)
+        padded = torch.zeros((width, 2), dtype=torch.int64)
+        padded[: block.shape[0]] = block
+        parts = [torch.zeros_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded)
+        full = torch.cat([p[:c] for p, c in zip(parts, counts)]).numpy()
+        ok = bool(np.array_equal(full[:, 0], pi) and np.array_equal(full[:, 1], pj))
+        pairs_owned = sum(n - 1 - i for i in range(rb, re))
+        q.put((rank, ok, (rb, re), pairs_owned, counts))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_row_sharded_edge_lists_concatenate_to_the_reference_order():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_edge_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res)                       # rank-order concatenation == the global row-major list
+    assert res[0][2][0] == 0 and res[0][2][1] == res[1][2][0] and res[1][2][1] == 700
+    assert abs(res[0][3] - res[1][3]) < 0.01 * (res[0][3] + res[1][3])  # balanced line-vector counts
+    assert res[0][4] == res[1][4]
+
+
+def test_library_row_partition_matches_the_python_one():
+    from psulvsb_b200 import capi
+
+    for n in (7, 700, 5000, 100_000):
+        for world in (1, 2, 3, 8):
+            parts = [capi.shard_row_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            for r in range(world):
+                b, e = sharding.triangular_row_range(n, r, world)
+                assert abs(parts[r][0] - b) <= 1 and abs(parts[r][1] - e) <= 1  # (round-half differences only)
+
+
 def test_world2_gloo_best_and_row_counts():
     world = 2
     port = _free_port()
