@@ -158,6 +158,10 @@ int psulvsb_create(psulvsb_handle_t* out, int device);
  * never depend on these settings (every registration has its own state and sample stream).  Changing them drops the
  * resident batch. */
 int psulvsb_set_batching(psulvsb_handle_t h, int chunk, int lanes);
+/* Host threads the handle may use for staging uploads (psulvsb_solve_batch / psulvsb_batch_upload copy the caller's
+ * arrays into pinned memory while earlier groups are already on their way to the device).  0 = the CPUs available to
+ * the process (its affinity mask).  On a multi-GPU node give every rank its share (cores / ranks). */
+int psulvsb_set_host_threads(psulvsb_handle_t h, int n);
 /* Debug / test switches (process-wide; the library reads NO environment variable).  They select among code paths
  * that produce identical results: "gnc_deep_margin" (rad), "gnc_prefetch", "sample_list_cap_test", "k1_variant"
  * (1..4 rows per thread), "upload_prof" (1: phase timings on stderr), "reset" (all back to defaults). */

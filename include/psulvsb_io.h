@@ -41,6 +41,13 @@ int psulvsb_prefilter_reduce(const double* src_normals, const double* tgt_normal
                              int n, int* keep_mask, double* src_reduce, double* tgt_reduce, int* reduce_map, int* C,
                              int* remain_count);
 
+/* The same for B correspondence sets in ONE device launch (one CTA per set): arrays of B pointers, n[B] sizes in,
+ * C[B] and (optional) remain_count[B] out.  What a batched driver runs before psulvsb_solve_batch. */
+int psulvsb_prefilter_reduce_batch(int B, const double* const* src_normals, const double* const* tgt_normals,
+                                   const double* const* src, const double* const* tgt, const int* n,
+                                   int* const* keep_mask, double* const* src_reduce, double* const* tgt_reduce,
+                                   int* const* reduce_map, int* C, int* remain_count);
+
 /* PLY: number of vertices, then their x, y, z as float (teaser::PointXYZ is 3 x float). */
 int psulvsb_ply_vertex_count(const char* path, long long* n);
 int psulvsb_ply_read_xyz(const char* path, float* xyz, long long capacity, long long* n);

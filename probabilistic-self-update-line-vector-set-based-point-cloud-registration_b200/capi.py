@@ -21,7 +21,7 @@ SYMBOLS = [
     "psulvsb_version", "psulvsb_last_error", "psulvsb_default_params", "psulvsb_device_count",
     "psulvsb_create", "psulvsb_destroy", "psulvsb_solve", "psulvsb_solve_batch", "psulvsb_batch_upload",
     "psulvsb_batch_solve_resident", "psulvsb_batch_resident_size", "psulvsb_debug_set", "psulvsb_launch_count", "psulvsb_last_device_ms", "psulvsb_last_stage_ms",
-    "psulvsb_last_ticks", "psulvsb_last_chunk_ticks", "psulvsb_set_batching", "psulvsb_pack_points", "psulvsb_consistency_mask", "psulvsb_consistency_mask_rows",
+    "psulvsb_last_ticks", "psulvsb_last_chunk_ticks", "psulvsb_set_batching", "psulvsb_set_host_threads", "psulvsb_pack_points", "psulvsb_consistency_mask", "psulvsb_consistency_mask_rows",
     "psulvsb_mask_symmetrize", "psulvsb_compact_edges", "psulvsb_sample_workspace_bytes",
     "psulvsb_sample_default_max_draws", "psulvsb_sample", "psulvsb_philox_fill", "psulvsb_gnc_tls_rotation",
     "psulvsb_kabsch_batch", "psulvsb_tls_translation", "psulvsb_score_batch", "psulvsb_score_one",
@@ -182,6 +182,7 @@ def _declare(L: C.CDLL) -> None:
     L.psulvsb_last_chunk_ticks.argtypes = [_vp, C.POINTER(C.c_int), C.c_int]
     L.psulvsb_last_chunk_ticks.restype = C.c_int
     L.psulvsb_set_batching.argtypes = [_vp, C.c_int, C.c_int]
+    L.psulvsb_set_host_threads.argtypes = [_vp, C.c_int]
     L.psulvsb_pack_points.argtypes = [_vp, _vp, C.c_int, C.POINTER(C.c_double), _vp]
     L.psulvsb_consistency_mask.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_double, _vp, C.c_int,
                                            _vp, _vp]
@@ -394,6 +395,10 @@ class Handle:
             sd = (C.c_uint64 * n)(*[int(s) for s in seeds])
         check(lib().psulvsb_batch_solve_resident(self._h, C.byref(params), sd, sols, n))
         return list(sols)
+
+    def set_host_threads(self, n: int = 0) -> None:
+        """psulvsb_set_host_threads: staging threads of uploads (0 = the CPUs available to the process)."""
+        check(lib().psulvsb_set_host_threads(self._h, n))
 
     def comm_create(self, rank: int, world: int, unique_id: bytes) -> None:
         if len(unique_id) != UNIQUE_ID_BYTES:

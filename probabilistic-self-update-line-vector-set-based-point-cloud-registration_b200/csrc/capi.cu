@@ -195,6 +195,11 @@ int psulvsb_set_batching(psulvsb_handle_t h, int chunk, int lanes) {
   return pool_set_batching(h->pool, chunk, lanes);
 }
 
+int psulvsb_set_host_threads(psulvsb_handle_t h, int n) {
+  if (!h) return fail(PSULVSB_ERR_INVALID, "psulvsb_set_host_threads: NULL handle");
+  return pool_set_host_threads(h->pool, n);
+}
+
 long long psulvsb_launch_count(psulvsb_handle_t h) { return h ? pool_launch_count(h->pool) : 0; }
 double psulvsb_last_device_ms(psulvsb_handle_t h) { return h ? pool_last_device_ms(h->pool) : 0.0; }
 double psulvsb_last_stage_ms(psulvsb_handle_t h, int which) { return h ? pool_last_stage_ms(h->pool, which) : 0.0; }

@@ -8,6 +8,7 @@
 //            -> refinement -> solutions to host.
 // The only host synchronisations are the n_red read-back and one 4-byte "jobs done" poll per tick.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -1017,11 +1018,25 @@ double union_ms(std::vector<std::pair<float, float>>& iv) {
 }
 }  // namespace
 
+namespace {
+int available_cpus() {
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+    const int n = CPU_COUNT(&set);
+    if (n > 0) return n;
+  }
+  const int hw = (int)std::thread::hardware_concurrency();
+  return hw > 0 ? hw : 1;
+}
+}  // namespace
+
 class EnginePool {
  public:
   int device = 0;
   int chunk = 0;  // registrations per lock-step chunk (0: one per SM)
   int lanes = 0;  // engines that may run concurrently (0: default)
+  int host_threads = 0;  // host threads for staging (0: the CPUs available to the process)
   std::vector<Engine*> eng;
   cudaEvent_t origin = nullptr;
   std::vector<int> res_begin;  // resident partition: engine e holds problems [res_begin[e], res_begin[e + 1])
@@ -1058,12 +1073,14 @@ class EnginePool {
       }
       eng.push_back(e);
     }
-    int hw = (int)std::thread::hardware_concurrency();
-    if (hw < 1) hw = 1;
+    // host threads of the staging copies: the CPUs this PROCESS may run on (its affinity mask / cgroup share, not the
+    // machine's core count), or the caller's figure (psulvsb_set_host_threads: e.g. cores / ranks on a multi-GPU node,
+    // where eight ranks staging with a dozen threads each oversubscribe a 32-CPU container), shared by the engines
+    int hw = host_threads > 0 ? host_threads : available_cpus();
     int per = hw / (n > 0 ? n : 1);
-    per = per < 2 ? 2 : (per > 12 ? 12 : per);
+    per = per < 1 ? 1 : (per > 12 ? 12 : per);
     for (Engine* e : eng) {
-      e->stage_threads_cap = (n > 1) ? per : 12;
+      e->stage_threads_cap = per;
       e->max_chunk = chunk_size();
     }
     return PSULVSB_OK;
@@ -1117,7 +1134,6 @@ class EnginePool {
                 psulvsb_trace_t* trace) {
     resident_B = 0;
     Engine* e = eng[0];
-    e->stage_threads_cap = 12;
     PSU_CUDA(cudaSetDevice(device));
     PSU_CUDA(cudaEventRecord(origin, e->st));
     e->origin = origin;
@@ -1267,6 +1283,11 @@ int pool_set_batching(EnginePool* p, int chunk, int lanes) {
   p->chunk = chunk;
   p->lanes = lanes;
   p->resident_B = 0;  // the resident partition followed the old setting
+  return p->ensure_engines((int)p->eng.size());
+}
+int pool_set_host_threads(EnginePool* p, int n) {
+  if (n < 0) return fail(PSULVSB_ERR_INVALID, "set_host_threads: n >= 0");
+  p->host_threads = n;
   return p->ensure_engines((int)p->eng.size());
 }
 int pool_solve_one(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problem,

@@ -237,6 +237,7 @@ class EnginePool;
 int pool_create(EnginePool** out, int device);
 void pool_destroy(EnginePool* p);
 int pool_set_batching(EnginePool* p, int chunk, int lanes);
+int pool_set_host_threads(EnginePool* p, int n);
 int pool_solve_one(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
                    psulvsb_solution_t* solution, psulvsb_trace_t* trace);
 int pool_solve_batch(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,

@@ -347,37 +347,47 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
       auto finish = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         const uint32_t valid = (FULL || cb + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - cb)) - 1u);
+        uint32_t live[R], word[R];
+        bool doubt = false;  // some pair of this lane's R words is one the fast path cannot vouch for
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int i = irow[r];
-          const bool row_ok = i < row_end;
           const uint32_t upper =
               (FULL || i < cb) ? 0xFFFFFFFFu : ((i >= cb + 31) ? 0u : (0xFFFFFFFFu << (i - cb + 1)));
-          const uint32_t live = row_ok ? (valid & upper) : 0u;
-          uint32_t word = acc[r] & live;
-          // rare: some pair of this word is one the fast path cannot vouch for -> warp-cooperative redo
-          unsigned int flagged = __ballot_sync(0xffffffffu, live != 0u && !(mv[r] > t_fast));
-          while (flagged) {
-            const int owner = __ffs(flagged) - 1;
-            flagged &= flagged - 1;
-            const int oi = __shfl_sync(0xffffffffu, i, owner);
-            // the owner's row point back from its pre-scaled registers (x -2 and x -0.5 are exact)
-            const float4 si = make_float4(-0.5f * __shfl_sync(0xffffffffu, ms[r].x, owner),
-                                          -0.5f * __shfl_sync(0xffffffffu, ms[r].y, owner),
-                                          -0.5f * __shfl_sync(0xffffffffu, ms[r].z, owner), 0.f);
-            const float4 ti = make_float4(-0.5f * __shfl_sync(0xffffffffu, mt[r].x, owner),
-                                          -0.5f * __shfl_sync(0xffffffffu, mt[r].y, owner),
-                                          -0.5f * __shfl_sync(0xffffffffu, mt[r].z, owner), 0.f);
-            // this lane's column of the word (read only here: the slow path is rare)
-            const uint32_t res =
-                slow_word_coop(slow, oi, cb, si, ti, cs[st][wj * 32 + lane], ct[st][wj * 32 + lane], nborder);
-            if (lane == owner) word = res & live;
-          }
-          if (row_ok) {
-            mask[(size_t)i * stride + (cb >> 5)] = word;
-            cnt[r] += __popc(word);
+          live[r] = (i < row_end) ? (valid & upper) : 0u;
+          word[r] = acc[r] & live[r];
+          doubt = doubt || (live[r] != 0u && !(mv[r] > t_fast));
+        }
+        // rare (1.7 % of the words, but 4 in 10 warp steps see one): ONE vote decides whether the warp leaves the
+        // fast lane at all; only then the per-row votes and the warp-cooperative redo
+        if (__ballot_sync(0xffffffffu, doubt) != 0u) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            unsigned int flagged = __ballot_sync(0xffffffffu, live[r] != 0u && !(mv[r] > t_fast));
+            while (flagged) {
+              const int owner = __ffs(flagged) - 1;
+              flagged &= flagged - 1;
+              const int oi = __shfl_sync(0xffffffffu, irow[r], owner);
+              // the owner's row point back from its pre-scaled registers (x -2 and x -0.5 are exact)
+              const float4 si = make_float4(-0.5f * __shfl_sync(0xffffffffu, ms[r].x, owner),
+                                            -0.5f * __shfl_sync(0xffffffffu, ms[r].y, owner),
+                                            -0.5f * __shfl_sync(0xffffffffu, ms[r].z, owner), 0.f);
+              const float4 ti = make_float4(-0.5f * __shfl_sync(0xffffffffu, mt[r].x, owner),
+                                            -0.5f * __shfl_sync(0xffffffffu, mt[r].y, owner),
+                                            -0.5f * __shfl_sync(0xffffffffu, mt[r].z, owner), 0.f);
+              // this lane's column of the word (read only here: the slow path is rare)
+              const uint32_t res =
+                  slow_word_coop(slow, oi, cb, si, ti, cs[st][wj * 32 + lane], ct[st][wj * 32 + lane], nborder);
+              if (lane == owner) word[r] = res & live[r];
+            }
           }
         }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (irow[r] < row_end) {
+            mask[(size_t)irow[r] * stride + (cb >> 5)] = word[r];
+            cnt[r] += __popc(word[r]);
+          }
       };
       if (cb >= row0 + TI && cb + 32 <= n)
         finish(std::true_type());

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -252,76 +253,134 @@ struct DevMem {
 
 inline size_t up(size_t x) { return (x + 255) & ~size_t(255); }
 
-// one correspondence set on host buffers: stage, launch, copy back.  Any of the optional groups may be absent.
-int run_host(const double* src_normals, const double* tgt_normals, const double* src, const double* tgt, int n,
-             bool histogram, int* keep_mask, double* src_reduce, double* tgt_reduce, int* reduce_map, int* remain,
-             int* C) {
+// B correspondence sets on host buffers: one arena, one launch (a CTA per set), results copied back.  Any of the
+// optional groups may be absent (the same for every set).
+int run_host_batch(int B, const double* const* src_normals, const double* const* tgt_normals, const double* const* src,
+                   const double* const* tgt, const int* n_arr, bool histogram, int* const* keep_mask,
+                   double* const* src_reduce, double* const* tgt_reduce, int* const* reduce_map, int* remain, int* C) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     cudaGetLastError();
     return fail(PSULVSB_ERR_NO_DEVICE, "pre-filter: no CUDA device available (there is no CPU fallback)");
   }
-  if (remain) *remain = 0;
-  if (C) *C = 0;
-  if (n == 0) return PSULVSB_OK;
-  const size_t nn = (size_t)n;
+  for (int b = 0; b < B; ++b) {
+    if (remain) remain[b] = 0;
+    if (C) C[b] = 0;
+  }
   const bool gather = src_reduce != nullptr;
-  // arena: [normals 6n] [points 6n] [angle n] [reduced 6n] | [keep n] [bin n] [height n+16] [last n+16] [map n] [out 2]
+  // arena per set: [normals 6n] [points 6n] [angle n] [reduced 6n] | [keep n] [bin n] [height n+16] [last n+16] [map n] [out 2]
+  struct Off {
+    size_t sn, tn, s, t, ang, sr, tr, keep, bin, h, l, map, out;
+  };
+  std::vector<Off> offs((size_t)B);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
     off += up(bytes);
     return o;
   };
-  const size_t o_sn = take(histogram ? 24 * nn : 0), o_tn = take(histogram ? 24 * nn : 0);
-  const size_t o_s = take(gather ? 24 * nn : 0), o_t = take(gather ? 24 * nn : 0);
-  const size_t o_ang = take(8 * nn), o_sr = take(gather ? 24 * nn : 0), o_tr = take(gather ? 24 * nn : 0);
-  const size_t o_keep = take(4 * nn), o_bin = take(4 * nn), o_h = take(4 * (nn + 16)), o_l = take(4 * (nn + 16));
-  const size_t o_map = take(4 * nn), o_out = take(8), o_job = take(sizeof(PrefilterJob));
-  DevMem mem;
-  if (int rc = mem.alloc(off)) return rc;
-  char* base = static_cast<char*>(mem.p);
-  cudaStream_t st = nullptr;  // (the legacy stream: these calls are synchronous by contract)
-  if (histogram) {
-    PSU_CUDA(cudaMemcpyAsync(base + o_sn, src_normals, 24 * nn, cudaMemcpyHostToDevice, st));
-    PSU_CUDA(cudaMemcpyAsync(base + o_tn, tgt_normals, 24 * nn, cudaMemcpyHostToDevice, st));
+  bool any = false;
+  for (int b = 0; b < B; ++b) {
+    const size_t nn = (size_t)n_arr[b];
+    any = any || nn > 0;
+    Off& o = offs[(size_t)b];
+    o.sn = take(histogram ? 24 * nn : 0);
+    o.tn = take(histogram ? 24 * nn : 0);
+    o.s = take(gather ? 24 * nn : 0);
+    o.t = take(gather ? 24 * nn : 0);
+    o.ang = take(8 * nn);
+    o.sr = take(gather ? 24 * nn : 0);
+    o.tr = take(gather ? 24 * nn : 0);
+    o.keep = take(4 * nn);
+    o.bin = take(4 * nn);
+    o.h = take(4 * (nn + 16));
+    o.l = take(4 * (nn + 16));
+    o.map = take(4 * nn);
+    o.out = take(8);
   }
-  if (gather) {
-    PSU_CUDA(cudaMemcpyAsync(base + o_s, src, 24 * nn, cudaMemcpyHostToDevice, st));
-    PSU_CUDA(cudaMemcpyAsync(base + o_t, tgt, 24 * nn, cudaMemcpyHostToDevice, st));
+  if (!any) return PSULVSB_OK;
+  const size_t o_jobs = take(sizeof(PrefilterJob) * (size_t)B);
+  // grow-only arena shared by the calls of this process (cudaMalloc + cudaFree of a few hundred MB per call cost more
+  // than the launch they serve); the calls are synchronous by contract, the mutex serialises concurrent callers
+  static std::mutex arena_mutex;
+  static DevMem arena;
+  static size_t arena_cap = 0;
+  std::lock_guard<std::mutex> lock(arena_mutex);
+  if (off > arena_cap) {
+    if (arena.p) cudaFree(arena.p);
+    arena.p = nullptr;
+    arena_cap = 0;
+    if (int rc = arena.alloc(off + off / 4)) return rc;
+    arena_cap = off + off / 4;
   }
-  PSU_CUDA(cudaMemcpyAsync(base + o_keep, keep_mask, 4 * nn, cudaMemcpyHostToDevice, st));
-  PrefilterJob J;
-  J.src_normals = reinterpret_cast<const double*>(base + o_sn);
-  J.tgt_normals = reinterpret_cast<const double*>(base + o_tn);
-  J.src = reinterpret_cast<const double*>(base + o_s);
-  J.tgt = reinterpret_cast<const double*>(base + o_t);
-  J.n = n;
-  J.run_histogram = histogram ? 1 : 0;
-  J.keep_mask = reinterpret_cast<int*>(base + o_keep);
-  J.angle = reinterpret_cast<double*>(base + o_ang);
-  J.bin = reinterpret_cast<int*>(base + o_bin);
-  J.height = reinterpret_cast<unsigned int*>(base + o_h);
-  J.last = reinterpret_cast<int*>(base + o_l);
-  J.src_reduce = gather ? reinterpret_cast<double*>(base + o_sr) : nullptr;
-  J.tgt_reduce = gather ? reinterpret_cast<double*>(base + o_tr) : nullptr;
-  J.reduce_map = reduce_map ? reinterpret_cast<int*>(base + o_map) : nullptr;
-  J.out = reinterpret_cast<int*>(base + o_out);
-  PSU_CUDA(cudaMemcpyAsync(base + o_job, &J, sizeof(J), cudaMemcpyHostToDevice, st));
-  prefilter_kernel<<<1, BLK, 0, st>>>(reinterpret_cast<const PrefilterJob*>(base + o_job));
+  char* base = static_cast<char*>(arena.p);
+  cudaStream_t st = nullptr;  // (the legacy stream)
+  std::vector<PrefilterJob> jobs((size_t)B);
+  for (int b = 0; b < B; ++b) {
+    const size_t nn = (size_t)n_arr[b];
+    const Off& o = offs[(size_t)b];
+    if (nn > 0) {
+      if (histogram) {
+        PSU_CUDA(cudaMemcpyAsync(base + o.sn, src_normals[b], 24 * nn, cudaMemcpyHostToDevice, st));
+        PSU_CUDA(cudaMemcpyAsync(base + o.tn, tgt_normals[b], 24 * nn, cudaMemcpyHostToDevice, st));
+      }
+      if (gather) {
+        PSU_CUDA(cudaMemcpyAsync(base + o.s, src[b], 24 * nn, cudaMemcpyHostToDevice, st));
+        PSU_CUDA(cudaMemcpyAsync(base + o.t, tgt[b], 24 * nn, cudaMemcpyHostToDevice, st));
+      }
+      PSU_CUDA(cudaMemcpyAsync(base + o.keep, keep_mask[b], 4 * nn, cudaMemcpyHostToDevice, st));
+    }
+    PrefilterJob& J = jobs[(size_t)b];
+    J.src_normals = reinterpret_cast<const double*>(base + o.sn);
+    J.tgt_normals = reinterpret_cast<const double*>(base + o.tn);
+    J.src = reinterpret_cast<const double*>(base + o.s);
+    J.tgt = reinterpret_cast<const double*>(base + o.t);
+    J.n = n_arr[b];
+    J.run_histogram = histogram ? 1 : 0;
+    J.keep_mask = reinterpret_cast<int*>(base + o.keep);
+    J.angle = reinterpret_cast<double*>(base + o.ang);
+    J.bin = reinterpret_cast<int*>(base + o.bin);
+    J.height = reinterpret_cast<unsigned int*>(base + o.h);
+    J.last = reinterpret_cast<int*>(base + o.l);
+    J.src_reduce = gather ? reinterpret_cast<double*>(base + o.sr) : nullptr;
+    J.tgt_reduce = gather ? reinterpret_cast<double*>(base + o.tr) : nullptr;
+    J.reduce_map = reduce_map ? reinterpret_cast<int*>(base + o.map) : nullptr;
+    J.out = reinterpret_cast<int*>(base + o.out);
+  }
+  PSU_CUDA(cudaMemcpyAsync(base + o_jobs, jobs.data(), sizeof(PrefilterJob) * (size_t)B, cudaMemcpyHostToDevice, st));
+  prefilter_kernel<<<B, BLK, 0, st>>>(reinterpret_cast<const PrefilterJob*>(base + o_jobs));
   PSU_CHECK_LAUNCH("prefilter_kernel");
-  int out[2] = {0, 0};
-  PSU_CUDA(cudaMemcpyAsync(out, base + o_out, 8, cudaMemcpyDeviceToHost, st));
-  if (histogram) PSU_CUDA(cudaMemcpyAsync(keep_mask, base + o_keep, 4 * nn, cudaMemcpyDeviceToHost, st));
-  if (reduce_map) PSU_CUDA(cudaMemcpyAsync(reduce_map, base + o_map, 4 * nn, cudaMemcpyDeviceToHost, st));
-  PSU_CUDA(cudaStreamSynchronize(st));
-  if (gather && out[1] > 0) {
-    PSU_CUDA(cudaMemcpy(src_reduce, base + o_sr, 24 * (size_t)out[1], cudaMemcpyDeviceToHost));
-    PSU_CUDA(cudaMemcpy(tgt_reduce, base + o_tr, 24 * (size_t)out[1], cudaMemcpyDeviceToHost));
+  std::vector<int> out((size_t)2 * B, 0);
+  for (int b = 0; b < B; ++b) {
+    const size_t nn = (size_t)n_arr[b];
+    const Off& o = offs[(size_t)b];
+    PSU_CUDA(cudaMemcpyAsync(&out[(size_t)2 * b], base + o.out, 8, cudaMemcpyDeviceToHost, st));
+    if (nn == 0) continue;
+    if (histogram) PSU_CUDA(cudaMemcpyAsync(keep_mask[b], base + o.keep, 4 * nn, cudaMemcpyDeviceToHost, st));
+    if (reduce_map) PSU_CUDA(cudaMemcpyAsync(reduce_map[b], base + o.map, 4 * nn, cudaMemcpyDeviceToHost, st));
   }
-  if (remain) *remain = out[0];
-  if (C) *C = out[1];
+  PSU_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b) {
+    const Off& o = offs[(size_t)b];
+    const int kept = n_arr[b] > 0 ? out[(size_t)2 * b + 1] : 0;
+    if (gather && kept > 0) {
+      PSU_CUDA(cudaMemcpyAsync(src_reduce[b], base + o.sr, 24 * (size_t)kept, cudaMemcpyDeviceToHost, st));
+      PSU_CUDA(cudaMemcpyAsync(tgt_reduce[b], base + o.tr, 24 * (size_t)kept, cudaMemcpyDeviceToHost, st));
+    }
+    if (remain) remain[b] = n_arr[b] > 0 ? out[(size_t)2 * b] : 0;
+    if (C) C[b] = kept;
+  }
+  PSU_CUDA(cudaStreamSynchronize(st));
   return PSULVSB_OK;
+}
+
+// one correspondence set
+int run_host(const double* src_normals, const double* tgt_normals, const double* src, const double* tgt, int n,
+             bool histogram, int* keep_mask, double* src_reduce, double* tgt_reduce, int* reduce_map, int* remain,
+             int* C) {
+  return run_host_batch(1, &src_normals, &tgt_normals, &src, &tgt, &n, histogram, &keep_mask,
+                        src_reduce ? &src_reduce : nullptr, tgt_reduce ? &tgt_reduce : nullptr,
+                        reduce_map ? &reduce_map : nullptr, remain, C);
 }
 
 }  // namespace
@@ -364,6 +423,21 @@ int psulvsb_prefilter_reduce(const double* src_normals, const double* tgt_normal
     return fail(PSULVSB_ERR_INVALID, "psulvsb_prefilter_reduce: bad argument");
   return psulvsb::run_host(src_normals, tgt_normals, src, tgt, n, true, keep_mask, src_reduce, tgt_reduce, reduce_map,
                            remain_count, C);
+}
+
+int psulvsb_prefilter_reduce_batch(int B, const double* const* src_normals, const double* const* tgt_normals,
+                                   const double* const* src, const double* const* tgt, const int* n,
+                                   int* const* keep_mask, double* const* src_reduce, double* const* tgt_reduce,
+                                   int* const* reduce_map, int* C, int* remain_count) {
+  if (B <= 0 || !src_normals || !tgt_normals || !src || !tgt || !n || !keep_mask || !src_reduce || !tgt_reduce ||
+      !reduce_map || !C)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_prefilter_reduce_batch: bad argument");
+  for (int b = 0; b < B; ++b)
+    if (n[b] < 0 || (n[b] > 0 && (!src_normals[b] || !tgt_normals[b] || !src[b] || !tgt[b] || !keep_mask[b] ||
+                                  !src_reduce[b] || !tgt_reduce[b] || !reduce_map[b])))
+      return fail(PSULVSB_ERR_INVALID, "psulvsb_prefilter_reduce_batch: set " + std::to_string(b) + " has a null array");
+  return psulvsb::run_host_batch(B, src_normals, tgt_normals, src, tgt, n, true, keep_mask, src_reduce, tgt_reduce,
+                                 reduce_map, remain_count, C);
 }
 
 }  // extern "C"

@@ -9,7 +9,7 @@ import numpy as np
 from . import capi
 
 IO_SYMBOLS = ["psulvsb_histogram_outlier_removal", "psulvsb_mask_filter", "psulvsb_prefilter_reduce",
-              "psulvsb_ply_vertex_count",
+              "psulvsb_prefilter_reduce_batch", "psulvsb_ply_vertex_count",
               "psulvsb_ply_read_xyz", "psulvsb_corr_count", "psulvsb_corr_read", "psulvsb_gtmat_read",
               "psulvsb_gtlog_read"]
 
@@ -27,6 +27,8 @@ def _lib():
         L.psulvsb_histogram_outlier_removal.argtypes = [_dp, _dp, C.c_int, _ip, _ip]
         L.psulvsb_mask_filter.argtypes = [_dp, _dp, _ip, C.c_int, _dp, _dp, _ip, _ip]
         L.psulvsb_prefilter_reduce.argtypes = [_dp, _dp, _dp, _dp, C.c_int, _ip, _dp, _dp, _ip, _ip, _ip]
+        pp = C.POINTER(C.c_void_p)
+        L.psulvsb_prefilter_reduce_batch.argtypes = [C.c_int, pp, pp, pp, pp, _ip, pp, pp, pp, pp, _ip, _ip]
         L.psulvsb_ply_vertex_count.argtypes = [C.c_char_p, _llp]
         L.psulvsb_ply_read_xyz.argtypes = [C.c_char_p, _fp, C.c_longlong, _llp]
         L.psulvsb_corr_count.argtypes = [C.c_char_p, _llp]
@@ -84,6 +86,32 @@ def prefilter_reduce(src_normals, tgt_normals, src, tgt):
                                                sr.ctypes.data_as(_dp), tr.ctypes.data_as(_dp), rm.ctypes.data_as(_ip),
                                                C.byref(c), C.byref(rem)))
     return keep, np.asfortranarray(sr[:, :c.value]), np.asfortranarray(tr[:, :c.value]), rm, rem.value
+
+
+def prefilter_reduce_batch(src_normals, tgt_normals, srcs, tgts):
+    """psulvsb_prefilter_reduce_batch: the pre-filter of B correspondence sets in ONE device launch (a CTA per set).
+    Lists of 3xN arrays in; list of (keep_mask, src_reduce, tgt_reduce, reduce_map, remain_count) out."""
+    B = len(srcs)
+    a = [_cm(x) for x in src_normals]
+    b = [_cm(x) for x in tgt_normals]
+    p = [_cm(x) for x in srcs]
+    q = [_cm(x) for x in tgts]
+    n = np.array([x.shape[1] for x in p], dtype=np.int32)
+    keep = [np.zeros(k, dtype=np.int32) for k in n]
+    sr = [np.zeros((3, max(int(k), 1)), order="F") for k in n]
+    tr = [np.zeros((3, max(int(k), 1)), order="F") for k in n]
+    rm = [np.zeros(k, dtype=np.int32) for k in n]
+    cc = np.zeros(B, dtype=np.int32)
+    rem = np.zeros(B, dtype=np.int32)
+
+    def ptrs(arrs):
+        return (C.c_void_p * B)(*[x.ctypes.data for x in arrs])
+
+    capi.check(_lib().psulvsb_prefilter_reduce_batch(B, ptrs(a), ptrs(b), ptrs(p), ptrs(q), n.ctypes.data_as(_ip),
+                                                     ptrs(keep), ptrs(sr), ptrs(tr), ptrs(rm), cc.ctypes.data_as(_ip),
+                                                     rem.ctypes.data_as(_ip)))
+    return [(keep[i], np.asfortranarray(sr[i][:, :cc[i]]), np.asfortranarray(tr[i][:, :cc[i]]), rm[i], int(rem[i]))
+            for i in range(B)]
 
 
 def read_ply_xyz(path: str) -> np.ndarray:

@@ -61,6 +61,23 @@ def test_prefilter_reduce_is_histogram_then_mask_filter():
     assert np.array_equal(sr, sro) and np.array_equal(tr, tro) and np.array_equal(rm, rmo)
 
 
+@pytest.mark.gpu
+def test_prefilter_reduce_batch_equals_single_calls():
+    sets = []
+    for k, n in enumerate([3000, 17, 1200, 0, 800]):
+        a, b = _normals(max(n, 1), 20 + k)
+        rng = np.random.default_rng(40 + k)
+        sets.append((a[:, :n], b[:, :n], rng.standard_normal((3, n)), rng.standard_normal((3, n))))
+    got = io.prefilter_reduce_batch([s[0] for s in sets], [s[1] for s in sets], [s[2] for s in sets], [s[3] for s in sets])
+    for (a, b, src, tgt), (keep, sr, tr, rm, rem) in zip(sets, got):
+        if src.shape[1] == 0:
+            assert keep.size == 0 and sr.shape[1] == 0 and rem == 0
+            continue
+        k1, s1, t1, r1, rem1 = io.prefilter_reduce(a, b, src, tgt)
+        assert np.array_equal(keep, k1) and rem == rem1
+        assert np.array_equal(sr, s1) and np.array_equal(tr, t1) and np.array_equal(rm, r1)
+
+
 def test_prefilter_has_no_cpu_fallback():
     if capi.lib().psulvsb_device_count() > 0:
         pytest.skip("a CUDA device is present")
