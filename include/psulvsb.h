@@ -178,6 +178,17 @@ int psulvsb_solve(psulvsb_handle_t h, const psulvsb_params_t* params, const psul
  * seeds: optional per-problem Philox keys (default params->seed + index). */
 int psulvsb_solve_batch(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problems,
                         int B, const uint64_t* seeds, psulvsb_solution_t* solutions);
+/* A STREAM of batches, pipelined.  psulvsb_batch_submit queues the batch and returns at once with a ticket;
+ * psulvsb_batch_wait(ticket) returns when its solutions are written (tickets may be waited for in any order, each
+ * once).  Everything the call was given -- the problem records, the point arrays they reference, seeds, solutions --
+ * must stay valid and untouched until the wait has returned; params is copied.  The handle's lanes pull lock-step
+ * chunks from ONE queue across calls, so the staging and the H2D copy of batch n + 1 run while batch n is still being
+ * solved: with two batches in flight the uploads cost nothing (psulvsb_solve_batch, which must drain the device before
+ * it returns, pays for them).  Results are those of psulvsb_solve_batch.  Every other call on the handle first waits
+ * for the queue to empty.  (The reference solves one pair at a time on one thread: PSULVSB.cc:326-331.) */
+int psulvsb_batch_submit(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problems,
+                         int B, const uint64_t* seeds, psulvsb_solution_t* solutions, uint64_t* ticket);
+int psulvsb_batch_wait(psulvsb_handle_t h, uint64_t ticket);
 /* Resident variant: upload once, then solve the resident batch any number of times (inputs stay
  * in HBM; only the solutions come back).  Used for the device-resident throughput figure. */
 int psulvsb_batch_upload(psulvsb_handle_t h, const psulvsb_problem_t* problems, int B);

@@ -20,7 +20,7 @@ DOMAIN_L_SAMPLED, DOMAIN_BASIC, DOMAIN_UNIFORM, DOMAIN_SCALE = 1, 2, 3, 4
 SYMBOLS = [
     "psulvsb_version", "psulvsb_last_error", "psulvsb_default_params", "psulvsb_device_count",
     "psulvsb_create", "psulvsb_destroy", "psulvsb_solve", "psulvsb_solve_batch", "psulvsb_batch_upload",
-    "psulvsb_batch_solve_resident", "psulvsb_batch_resident_size", "psulvsb_debug_set", "psulvsb_launch_count", "psulvsb_last_device_ms", "psulvsb_last_stage_ms",
+    "psulvsb_batch_solve_resident", "psulvsb_batch_submit", "psulvsb_batch_wait", "psulvsb_batch_resident_size", "psulvsb_debug_set", "psulvsb_launch_count", "psulvsb_last_device_ms", "psulvsb_last_stage_ms",
     "psulvsb_last_ticks", "psulvsb_last_chunk_ticks", "psulvsb_set_batching", "psulvsb_set_host_threads", "psulvsb_pack_points", "psulvsb_consistency_mask", "psulvsb_consistency_mask_rows",
     "psulvsb_mask_symmetrize", "psulvsb_compact_edges", "psulvsb_sample_workspace_bytes",
     "psulvsb_sample_default_max_draws", "psulvsb_sample", "psulvsb_philox_fill", "psulvsb_gnc_tls_rotation",
@@ -165,6 +165,9 @@ def _declare(L: C.CDLL) -> None:
     L.psulvsb_solve.argtypes = [_vp, C.POINTER(Params), C.POINTER(Problem), C.POINTER(Solution), C.POINTER(Trace)]
     L.psulvsb_solve_batch.argtypes = [_vp, C.POINTER(Params), C.POINTER(Problem), C.c_int, C.POINTER(C.c_uint64),
                                       C.POINTER(Solution)]
+    L.psulvsb_batch_submit.argtypes = [_vp, C.POINTER(Params), C.POINTER(Problem), C.c_int, C.POINTER(C.c_uint64),
+                                       C.POINTER(Solution), C.POINTER(C.c_uint64)]
+    L.psulvsb_batch_wait.argtypes = [_vp, C.c_uint64]
     L.psulvsb_batch_upload.argtypes = [_vp, C.POINTER(Problem), C.c_int]
     L.psulvsb_batch_solve_resident.argtypes = [_vp, C.POINTER(Params), C.POINTER(C.c_uint64), C.POINTER(Solution),
                                                C.c_int]
@@ -373,6 +376,22 @@ class Handle:
             sd = (C.c_uint64 * len(problems))(*[int(s) for s in seeds])
         check(lib().psulvsb_solve_batch(self._h, C.byref(params), arr, len(problems), sd, sols))
         return list(sols)
+
+    def submit(self, params: Params, problems, seeds=None):
+        """psulvsb_batch_submit: queue a batch, return a ticket for wait().  The ticket keeps the host arrays alive."""
+        arr = self._problem_array(problems)
+        sols = (Solution * len(problems))()
+        sd = None
+        if seeds is not None:
+            sd = (C.c_uint64 * len(problems))(*[int(s) for s in seeds])
+        tk = C.c_uint64(0)
+        check(lib().psulvsb_batch_submit(self._h, C.byref(params), arr, len(problems), sd, sols, C.byref(tk)))
+        return (tk.value, sols, arr, sd, list(problems))
+
+    def wait(self, ticket):
+        """psulvsb_batch_wait: the solutions of a submitted batch."""
+        check(lib().psulvsb_batch_wait(self._h, C.c_uint64(ticket[0])))
+        return list(ticket[1])
 
     def upload(self, problems) -> None:
         self._problems = list(problems)  # keep the host arrays alive

@@ -157,6 +157,18 @@ int psulvsb_solve_batch(psulvsb_handle_t h, const psulvsb_params_t* params, cons
   return pool_solve_batch(h->pool, params, problems, B, seeds, solutions);
 }
 
+int psulvsb_batch_submit(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,
+                         const uint64_t* seeds, psulvsb_solution_t* solutions, uint64_t* ticket) {
+  if (!h || !params || !problems || !solutions || !ticket || B <= 0)
+    return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_submit: NULL argument or B <= 0");
+  return pool_submit(h->pool, params, problems, B, seeds, solutions, ticket);
+}
+
+int psulvsb_batch_wait(psulvsb_handle_t h, uint64_t ticket) {
+  if (!h) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_wait: NULL handle");
+  return pool_wait(h->pool, ticket);
+}
+
 int psulvsb_batch_upload(psulvsb_handle_t h, const psulvsb_problem_t* problems, int B) {
   if (!h || !problems || B <= 0) return fail(PSULVSB_ERR_INVALID, "psulvsb_batch_upload: NULL argument or B <= 0");
   return pool_upload(h->pool, problems, B);
@@ -180,6 +192,7 @@ int psulvsb_debug_set(const char* name, double value) {
   if (n == "gnc_deep_margin") k.gnc_deep_margin = value;
   else if (n == "gnc_prefetch") k.gnc_prefetch = (int)value;
   else if (n == "gnc_cluster") k.gnc_cluster = (int)value;
+  else if (n == "gnc_park_pct") k.gnc_park_pct = (int)value;
   else if (n == "sample_list_cap_test") k.sample_list_cap_test = (int)value;
   else if (n == "k1_variant") k.k1_variant = (int)value;
   else if (n == "upload_prof") k.upload_prof = (int)value;

@@ -19,7 +19,12 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <utility>
@@ -1048,8 +1053,10 @@ class EnginePool {
   long long retired_launches = 0;
 
   ~EnginePool() {
+    stop_workers();
     for (Engine* e : eng) delete e;
     if (origin) cudaEventDestroy(origin);
+    if (mark_st) cudaStreamDestroy(mark_st);
   }
   int init(int dev) {
     device = dev;
@@ -1130,8 +1137,150 @@ class EnginePool {
     stage_ms[3] = union_ms(gnc);  // ... a GNC-TLS launch of some chunk
   }
 
+  // ---- pipelined batches (psulvsb_batch_submit / psulvsb_batch_wait) -------------------------------
+  // One persistent host thread per lane, each bound to its own engine, pulls lock-step chunks from a queue that runs
+  // ACROSS calls: while one lane solves the last chunk of batch n, the other already stages and copies the first chunk
+  // of batch n + 1, so a stream of batches keeps the device busy and the uploads disappear behind the solves.
+  struct Call {
+    uint64_t id = 0;
+    psulvsb_params_t params;
+    const psulvsb_problem_t* problems = nullptr;
+    int B = 0;
+    std::vector<uint64_t> seeds;
+    psulvsb_solution_t* solutions = nullptr;
+    std::vector<int> begin;
+    int n_chunks = 0, next_chunk = 0, done_chunks = 0;
+    int rc = PSULVSB_OK;
+    std::string msg;
+    std::vector<ChunkRecord> recs;
+    cudaEvent_t origin = nullptr;
+  };
+  std::mutex q_mu;
+  std::condition_variable q_work, q_done;
+  std::deque<std::shared_ptr<Call>> q_pending;          // calls with chunks still to hand out, in submission order
+  std::map<uint64_t, std::shared_ptr<Call>> q_calls;    // submitted and not yet waited for
+  std::vector<std::thread> workers;
+  bool q_stop = false;
+  uint64_t next_ticket = 1;
+  int in_flight = 0;  // calls submitted and not yet complete
+  cudaStream_t mark_st = nullptr;
+
+  void worker_main(int w) {
+    cudaSetDevice(device);
+    Engine* e = eng[(size_t)w];
+    for (;;) {
+      std::shared_ptr<Call> call;
+      int c = -1;
+      {
+        std::unique_lock<std::mutex> lk(q_mu);
+        q_work.wait(lk, [&] { return q_stop || !q_pending.empty(); });
+        if (q_stop) return;
+        call = q_pending.front();
+        c = call->next_chunk++;
+        if (call->next_chunk >= call->n_chunks) q_pending.pop_front();
+      }
+      int rc = PSULVSB_OK;
+      std::string msg;
+      bool skip;
+      {
+        std::lock_guard<std::mutex> lk(q_mu);
+        skip = call->rc != PSULVSB_OK;  // an earlier chunk of the call failed: its result is void anyway
+      }
+      if (!skip) {
+        const int b0 = call->begin[(size_t)c], nb = call->begin[(size_t)c + 1] - b0;
+        e->origin = call->origin;
+        rc = e->upload(call->problems + b0, nb);
+        if (!rc) rc = e->solve(&call->params, call->seeds.data() + b0, call->solutions + b0, nullptr);
+        if (rc) msg = psulvsb_last_error();
+        else call->recs[(size_t)c] = record_of(e);
+      }
+      {
+        std::lock_guard<std::mutex> lk(q_mu);
+        if (rc && call->rc == PSULVSB_OK) {
+          call->rc = rc;
+          call->msg = msg;
+        }
+        if (++call->done_chunks == call->n_chunks) {
+          --in_flight;
+          q_done.notify_all();
+        }
+      }
+    }
+  }
+  int start_workers() {
+    const int n = lane_count();
+    if ((int)workers.size() == n) return PSULVSB_OK;
+    stop_workers();
+    if (int rc = ensure_engines(n)) return rc;
+    if (!mark_st) PSU_CUDA(cudaStreamCreateWithFlags(&mark_st, cudaStreamNonBlocking));
+    q_stop = false;
+    for (int w = 0; w < n; ++w) workers.emplace_back([this, w] { worker_main(w); });
+    return PSULVSB_OK;
+  }
+  void stop_workers() {
+    {
+      std::lock_guard<std::mutex> lk(q_mu);
+      q_stop = true;
+    }
+    q_work.notify_all();
+    for (auto& t : workers) t.join();
+    workers.clear();
+  }
+  // every other entry point runs on the caller's thread with the engines to itself
+  void drain() {
+    std::unique_lock<std::mutex> lk(q_mu);
+    q_done.wait(lk, [&] { return in_flight == 0; });
+  }
+  int submit(const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B, const uint64_t* seeds,
+             psulvsb_solution_t* solutions, uint64_t* ticket) {
+    if (!params || !problems || !solutions || !ticket || B <= 0)
+      return fail(PSULVSB_ERR_INVALID, "batch_submit: NULL argument or B <= 0");
+    PSU_CUDA(cudaSetDevice(device));
+    if (int rc = start_workers()) return rc;
+    auto call = std::make_shared<Call>();
+    call->params = *params;
+    call->problems = problems;
+    call->B = B;
+    call->solutions = solutions;
+    call->seeds.resize((size_t)B);
+    for (int b = 0; b < B; ++b) call->seeds[(size_t)b] = seeds ? seeds[b] : params->seed + (uint64_t)b;
+    const int ch = chunk_size();
+    call->n_chunks = (B + ch - 1) / ch;
+    partition(B, call->n_chunks, call->begin);
+    call->recs.resize((size_t)call->n_chunks);
+    PSU_CUDA(cudaEventCreate(&call->origin));
+    PSU_CUDA(cudaEventRecord(call->origin, mark_st));
+    {
+      std::lock_guard<std::mutex> lk(q_mu);
+      resident_B = 0;
+      call->id = next_ticket++;
+      q_calls[call->id] = call;
+      q_pending.push_back(call);
+      ++in_flight;
+    }
+    q_work.notify_all();
+    *ticket = call->id;
+    return PSULVSB_OK;
+  }
+  int wait(uint64_t ticket) {
+    std::shared_ptr<Call> call;
+    {
+      std::unique_lock<std::mutex> lk(q_mu);
+      auto it = q_calls.find(ticket);
+      if (it == q_calls.end()) return fail(PSULVSB_ERR_INVALID, "batch_wait: unknown ticket");
+      call = it->second;
+      q_done.wait(lk, [&] { return call->done_chunks == call->n_chunks; });
+      q_calls.erase(it);
+    }
+    cudaEventDestroy(call->origin);
+    if (call->rc) return fail(call->rc, call->msg);
+    fold(call->recs);
+    return PSULVSB_OK;
+  }
+
   int solve_one(const psulvsb_params_t* params, const psulvsb_problem_t* problem, psulvsb_solution_t* solution,
                 psulvsb_trace_t* trace) {
+    drain();
     resident_B = 0;
     Engine* e = eng[0];
     PSU_CUDA(cudaSetDevice(device));
@@ -1181,6 +1330,7 @@ class EnginePool {
   int solve_batch(const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B, const uint64_t* seeds,
                   psulvsb_solution_t* solutions) {
     if (!params) return fail(PSULVSB_ERR_INVALID, "solve_batch: null params");
+    drain();
     resident_B = 0;
     PSU_CUDA(cudaSetDevice(device));
     const int ch = chunk_size();
@@ -1219,6 +1369,7 @@ class EnginePool {
   }
 
   int upload(const psulvsb_problem_t* problems, int B) {
+    drain();
     resident_B = 0;
     PSU_CUDA(cudaSetDevice(device));
     const int ch = chunk_size();
@@ -1235,6 +1386,7 @@ class EnginePool {
 
   int solve_resident(const psulvsb_params_t* params, const uint64_t* seeds, psulvsb_solution_t* solutions,
                      psulvsb_trace_t* trace_first) {
+    drain();
     if (resident_B <= 0) return fail(PSULVSB_ERR_INVALID, "solve: nothing uploaded");
     if (!params) return fail(PSULVSB_ERR_INVALID, "solve: null params");
     PSU_CUDA(cudaSetDevice(device));
@@ -1280,6 +1432,8 @@ int pool_create(EnginePool** out, int device) {
 void pool_destroy(EnginePool* p) { delete p; }
 int pool_set_batching(EnginePool* p, int chunk, int lanes) {
   if (chunk < 0 || lanes < 0 || lanes > 16) return fail(PSULVSB_ERR_INVALID, "set_batching: chunk >= 0, 0 <= lanes <= 16");
+  p->drain();
+  p->stop_workers();  // (the worker threads follow the lane count; they restart with the next submit)
   p->chunk = chunk;
   p->lanes = lanes;
   p->resident_B = 0;  // the resident partition followed the old setting
@@ -1298,6 +1452,11 @@ int pool_solve_batch(EnginePool* p, const psulvsb_params_t* params, const psulvs
                      const uint64_t* seeds, psulvsb_solution_t* solutions) {
   return p->solve_batch(params, problems, B, seeds, solutions);
 }
+int pool_submit(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,
+                const uint64_t* seeds, psulvsb_solution_t* solutions, uint64_t* ticket) {
+  return p->submit(params, problems, B, seeds, solutions, ticket);
+}
+int pool_wait(EnginePool* p, uint64_t ticket) { return p->wait(ticket); }
 int pool_solve_sharded(EnginePool* p, Comm* comm, const psulvsb_params_t* params, const psulvsb_problem_t* problem,
                        psulvsb_solution_t* solution, psulvsb_trace_t* trace) {
   return p->solve_sharded(comm, params, problem, solution, trace);

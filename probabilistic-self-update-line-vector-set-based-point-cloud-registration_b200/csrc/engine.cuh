@@ -137,8 +137,12 @@ struct GncJob {
   int* info;             // [4]: iterations, inlier count
   double* cost;
   long long* prof;       // optional [8] diagnostics: pass / loop / SVD cycles, cached count, prologue / epilogue cycles
+  // grid mode (more than 8 CTAs per registration): [2][ctas][16] doubles and one counter, see k3_rotation.cu
+  double* grid_red;
+  unsigned int* grid_bar;
   int active;
 };
+constexpr int GNC_GRID_RED_DOUBLES = 2 * 16;  // per CTA of a registration in grid mode
 
 // ---- clique escalation (k5_clique.cu) -----------------------------------------------------------
 struct CliqueJob {
@@ -242,6 +246,9 @@ int pool_solve_one(EnginePool* p, const psulvsb_params_t* params, const psulvsb_
                    psulvsb_solution_t* solution, psulvsb_trace_t* trace);
 int pool_solve_batch(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,
                      const uint64_t* seeds, psulvsb_solution_t* solutions);
+int pool_submit(EnginePool* p, const psulvsb_params_t* params, const psulvsb_problem_t* problems, int B,
+                const uint64_t* seeds, psulvsb_solution_t* solutions, uint64_t* ticket);
+int pool_wait(EnginePool* p, uint64_t ticket);
 int pool_upload(EnginePool* p, const psulvsb_problem_t* problems, int B);
 // ONE registration whose consistency rows are sharded over the ranks of `comm` (every rank passes the same problem and
 // gets the same solution)

@@ -17,6 +17,10 @@ def main():
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 22000
     use_lv = (sys.argv[3] != "0") if len(sys.argv) > 3 else True
     use_perm = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
+    force = (sys.argv[5] != "0") if len(sys.argv) > 5 else False  # 512-thread CTAs, one per SM, at every cluster size
+    for kv in sys.argv[6:]:  # debug switches, e.g. gnc_prefetch=2 gnc_park_pct=40
+        k, v = kv.split("=")
+        capi.debug_set(k, float(v))
     pair = synth.make_pair(5000, 0.95, 3, outliers="fpfh")
     r = stages.consistency_mask(pair["src"], pair["dst"], 0.1)  # the reduced set from the product's own stage 1
     e_all, _ = stages.compact_edges(r["mask"], r["row_counts"], r["n"], r["stride"])
@@ -40,8 +44,10 @@ def main():
     print(f"B={B} K={K} reduced set {len(pi)} lv scratch {'on' if use_lv else 'off'} parking {'on' if perm is not None else 'off'}")
     Rs = {}
     for cluster in (0, 1, 2, 4, 8):
-        if cluster * B > 148 * 2 and cluster > 1:
+        if cluster * B > 148 * 2 and cluster > 1 and not force:
             continue
+        if force:
+            capi.debug_set("gnc_cluster", cluster)
 
         def run():
             capi.check(L.psulvsb_gnc_tls_rotation_batch(torch.cuda.current_stream().cuda_stream, d_src.data_ptr(),
@@ -68,7 +74,7 @@ def main():
               f"{(p[:, 1] - p[:, 0] - p[:, 2]).mean() / its:6.0f};  cached {int(p[0, 3])} per CTA; whole kernel: prologue "
               f"{p[:, 4].mean():8.0f} + loop {p[:, 1].mean():8.0f} + epilogue {p[:, 5].mean():8.0f} cycles; parking: "
               f"{(p[:, 7] % 100).mean():.1f} compactions (first after iteration {((p[:, 7] // 100) % 100).mean() - 1:.1f}, "
-              f"{(p[:, 7] // 10000).mean():.0f} cycles), mean active positions per pass {p[:, 6].mean() / its:.0f}")
+              f"{(p[:, 7] // 10000).mean():.3f} repeated without sleeping), mean active positions per pass {p[:, 6].mean() / its:.0f}")
     # every configuration must end at the same rotations, iteration counts and inlier counts
     ref = Rs[1]
     for c, (r, ii) in Rs.items():

@@ -200,6 +200,55 @@ def test_chunked_pool_gives_the_same_results(env):
     h.close()
 
 
+def test_pipelined_batches_match_solve_batch(env):
+    """psulvsb_batch_submit / psulvsb_batch_wait: several batches in flight on one handle (the lanes pull chunks from one
+    queue across calls, so a later batch's upload overlaps an earlier batch's solve) return what psulvsb_solve_batch
+    returns for each of them; tickets may be waited for out of order; a failing batch fails its own wait only; the
+    other entry points first let the queue drain."""
+    capi, synth = env["capi"], env["synth"]
+    batches = []
+    for k in range(4):
+        pairs = [synth.make_pair(n, 0.9, 400 + 10 * k + i) for i, n in enumerate([300, 640, 150, 900, 420, 64, 510][: 4 + k])]
+        batches.append([capi.HostProblem(p["src"], p["dst"]) for p in pairs])
+    params = capi.default_params(seed=33, **PKW)
+    h = capi.Handle(0)
+    h.set_batching(64, 1)
+    refs = [h.solve_batch(params, b) for b in batches]
+
+    def same(a, b):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert x.status == 0 and y.status == 0
+            assert np.array_equal(np.array(x.rotation[:]), np.array(y.rotation[:]))
+            assert np.array_equal(np.array(x.translation[:]), np.array(y.translation[:]))
+            assert (x.final_inlier_count, x.local_iters, x.n_reduced) == (y.final_inlier_count, y.local_iters, y.n_reduced)
+
+    for chunk, lanes in ((64, 2), (3, 2), (2, 3)):
+        h.set_batching(chunk, lanes)
+        tickets = [h.submit(params, b) for b in batches]
+        for k in (2, 0, 3, 1):
+            same(refs[k], h.wait(tickets[k]))
+        assert h.last_device_ms > 0
+        with pytest.raises(capi.PsulvsbError, match="unknown ticket"):
+            h.wait(tickets[0])
+    # seeds, a failing batch between two good ones, and a synchronous call that has to wait for the queue
+    seeds = list(range(7, 7 + len(batches[1])))
+    h.set_batching(64, 1)
+    ref_seeded = h.solve_batch(params, batches[1], seeds)
+    h.set_batching(3, 2)
+    bad = capi.HostProblem(batches[0][0].src.copy(), batches[0][0].dst.copy())
+    bad.src[0, 0] = np.nan
+    t_a = h.submit(params, batches[1], seeds)
+    t_bad = h.submit(params, batches[2][:3] + [bad])
+    t_b = h.submit(params, batches[3])
+    same(refs[0], h.solve_batch(params, batches[0]))  # drains the queue first
+    with pytest.raises(capi.PsulvsbError, match="non-finite"):
+        h.wait(t_bad)
+    same(ref_seeded, h.wait(t_a))
+    same(refs[3], h.wait(t_b))
+    h.close()
+
+
 def test_resident_solve_is_repeatable(env):
     capi, synth = env["capi"], env["synth"]
     probs = [capi.HostProblem(*(lambda p: (p["src"], p["dst"]))(synth.make_pair(700, 0.9, 70 + i))) for i in range(3)]
