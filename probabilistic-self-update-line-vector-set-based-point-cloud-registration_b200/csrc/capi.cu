@@ -449,16 +449,29 @@ int psulvsb_gnc_tls_rotation_batch(void* stream, const double* d_src64, const do
   }
   struct AsyncJobs {  // freed on every exit path (stream-ordered, after the launch that reads it)
     GncJob* d = nullptr;
+    double* red = nullptr;  // grid mode: the CTAs' partial results and arrival counters
+    unsigned int* bar = nullptr;
     cudaStream_t st;
     explicit AsyncJobs(cudaStream_t s) : st(s) {}
     ~AsyncJobs() {
       if (d) cudaFreeAsync(d, st);
+      if (red) cudaFreeAsync(red, st);
+      if (bar) cudaFreeAsync(bar, st);
     }
   } dj(st);
+  const bool grid_mode = cluster > 8;  // `cluster` CTAs per registration, launched cooperatively
+  if (grid_mode) {
+    PSU_CUDA(cudaMallocAsync((void**)&dj.red, sizeof(double) * (size_t)n_jobs * cluster * GNC_GRID_RED_DOUBLES, st));
+    PSU_CUDA(cudaMallocAsync((void**)&dj.bar, sizeof(unsigned int) * (size_t)n_jobs, st));
+    for (int b = 0; b < n_jobs; ++b) {
+      jobs[(size_t)b].grid_red = dj.red + (size_t)b * cluster * GNC_GRID_RED_DOUBLES;
+      jobs[(size_t)b].grid_bar = dj.bar + b;
+    }
+  }
   PSU_CUDA(cudaMallocAsync((void**)&dj.d, sizeof(GncJob) * (size_t)n_jobs, st));
   PSU_CUDA(cudaMemcpyAsync(dj.d, jobs.data(), sizeof(GncJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, st));
   PSU_CUDA(cudaStreamSynchronize(st));  // jobs is pageable host memory
-  if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = gnc_cluster_for(n_jobs);
+  if (!grid_mode && cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = gnc_cluster_for(n_jobs);
   int cap = (int)((K + (unsigned long long)cluster - 1) / (unsigned long long)cluster) + 32;
   cap = (cap + 31) & ~31;
   return launch_gnc_tls(st, dj.d, n_jobs, cap, cluster, 0);

@@ -771,6 +771,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   }
 
   // ---- edge arena, sized from the measured reduced-set sizes
+  const int grid_ctas_max = sm_count() / (B > 0 ? B : 1);  // CTAs per registration the GNC kernel's grid mode may use
   unsigned long long max_cap = 0, max_nred = 0;
   {
     Bump be;
@@ -802,6 +803,10 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.lv_cap = cap / 6 + 64;
         J.lv = be.take<double>((size_t)6 * J.lv_cap);
         J.gnc_perm = be.take<uint32_t>((size_t)2 * J.lv_cap);
+        if (grid_ctas_max >= 16) {  // few registrations: the GNC kernel may spread each over many SMs (grid mode)
+          J.gnc_grid_red = be.take<double>((size_t)grid_ctas_max * GNC_GRID_RED_DOUBLES);
+          J.gnc_grid_bar = be.take<unsigned int>(4);
+        }
         J.pruned_edges = ratio ? be.take<uint2>((size_t)cap) : nullptr;
         if (ratio) {
           rj[(size_t)b].edges = J.edges;
@@ -913,7 +918,14 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       launches += 8;
     }
     PSU_CUDA(cudaEventRecord(ev_g0, st));
-    const int gnc_cluster = gnc_cluster_for(n_running);
+    int gnc_cluster = gnc_cluster_for(n_running);
+    // few registrations with very many line vectors (cfg-B: one with ~ 10^6): grid mode, as many CTAs per registration as
+    // give each a few thousand line vectors and as the SMs allow
+    if (gnc_cluster == 8 && grid_ctas_max >= 16) {
+      const long long k_est = (long long)(0.03 * (double)max_nred);
+      const long long g = std::min<long long>(grid_ctas_max, k_est / 4096);
+      if (g >= 16) gnc_cluster = (int)g;
+    }
     int gnc_cap = (int)((0.03 * (double)max_nred) / (double)gnc_cluster) + 64;
     gnc_cap = (gnc_cap + 31) & ~31;
     if (gnc_cap > gnc_default_capacity()) gnc_cap = gnc_default_capacity();

@@ -94,6 +94,8 @@ __device__ void prepare_local(JobCtl& J, SampleJob& sb, GncJob& g, CliqueJob& q,
   g.lv = J.lv;
   g.lv_cap = J.lv_cap;
   g.perm = J.gnc_perm;
+  g.grid_red = J.gnc_grid_red;
+  g.grid_bar = J.gnc_grid_bar;
   g.pts8 = J.pts8;
   g.lv_ready = (J.estimate_scaling || sb.identity) ? 0 : 1;  // (unknown scale: pruned subset, rescaled -- formed in the kernel)
   g.R_out = J.R_gnc;

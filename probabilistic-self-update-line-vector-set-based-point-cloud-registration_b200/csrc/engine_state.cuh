@@ -87,6 +87,8 @@ struct JobCtl {
   unsigned long long lv_cap;
   double* pts8;        // [Ccap][8] working points as 64-byte records (sx sy sz tx ty tz 0 0) for the GNC prologue
   uint32_t* gnc_perm;  // [2][lv_cap] index scratch of the GNC kernel's line-vector parking
+  double* gnc_grid_red;        // grid mode of the GNC kernel (few registrations): partial results of its CTAs, or NULL
+  unsigned int* gnc_grid_bar;  // ... and their arrival counter
   uint32_t* adj;        // clique escalation: Ccap x adj_stride bit matrix
   int adj_stride;
   uint8_t* clique_flags;  // [Ccap]

@@ -230,13 +230,14 @@ def test_gnc_tls_golden_rotation_only(P, O, golden):
     assert P["synth"].rotation_error(Rg, Rexp) < 1e-5
 
 
-@pytest.mark.parametrize("cluster,parking", [(1, True), (4, True), (8, True), (4, False)])
+@pytest.mark.parametrize("cluster,parking", [(1, True), (4, True), (8, True), (4, False), (24, True), (37, False)])
 def test_gnc_batch_parks_sleeping_line_vectors_exactly(P, O, cluster, parking):
     """The shape of one engine tick of cfg-A (K = 22 000 line vectors, 95 % FPFH-style outliers per job).  From the
     tenth iteration on most line vectors sit at weight 0 with a margin the remaining rotation drift cannot consume;
-    the kernel parks them behind the active range (k3_rotation.cu).  Nothing is approximated: rotation, iteration
-    count and the inlier mask -- reported by ORIGINAL index although the positions were permuted -- must match
-    the oracle's plain loop."""
+    the kernel parks them (k3_rotation.cu).  Nothing is approximated: rotation, iteration count and the inlier mask --
+    reported by ORIGINAL index although the positions were permuted -- must match the oracle's plain loop.  Cluster
+    sizes above 8 select the kernel's grid mode (that many CTAs per registration, cooperative launch, partial results
+    combined through global memory)."""
     st, synth = P["stages"], P["synth"]
     pair = synth.make_pair(5000, 0.95, 3, outliers="fpfh")
     pi, pj = O.reduced_set(pair["src"], pair["dst"], 0.1)
@@ -275,7 +276,7 @@ def test_gnc_parking_wakes_line_vectors_up_again(P, O, margin, request):
     for b in range(B):
         sel = rng.permutation(len(pi))[:K]
         edges[b, :, 0], edges[b, :, 1] = pi[sel], pj[sel]
-    for cluster in (1, 4):
+    for cluster in (1, 4, 20):
         Rg, inl, its, n_inl = st.gnc_tls_rotation_batch(st.to_device_points(pair["src"]), st.to_device_points(pair["dst"]),
                                                         torch.from_numpy(edges).cuda(), 0.1, 100, 1.4, 0.005,
                                                         cluster=cluster)
