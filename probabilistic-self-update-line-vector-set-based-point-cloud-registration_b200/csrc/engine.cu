@@ -929,7 +929,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     int gnc_cap = (int)((0.03 * (double)max_nred) / (double)gnc_cluster) + 64;
     gnc_cap = (gnc_cap + 31) & ~31;
     if (gnc_cap > gnc_default_capacity()) gnc_cap = gnc_default_capacity();
-    if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster, max_ccap)) return rc;
+    if (int rc = launch_gnc_tls(st, m.gj, B, gnc_cap, gnc_cluster, n_running)) return rc;
     PSU_CUDA(cudaEventRecord(ev_g1, st));
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");
@@ -1081,7 +1081,7 @@ class EnginePool {
     PSU_CUDA(cudaEventCreate(&origin));
     return ensure_engines(1);
   }
-  int chunk_size() const { return chunk > 0 ? chunk : 2 * sm_count(); }
+  int chunk_size() const { return chunk > 0 ? chunk : 4 * sm_count(); }
   int lane_count() const { return lanes > 0 ? lanes : 2; }
   int ensure_engines(int n) {
     while ((int)eng.size() < n) {

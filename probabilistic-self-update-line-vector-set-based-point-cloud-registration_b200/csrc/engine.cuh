@@ -209,7 +209,7 @@ int launch_philox_fill(cudaStream_t st, uint64_t seed, uint32_t domain, uint32_t
 int gnc_default_capacity();
 int gnc_cluster_for(int n_jobs);
 // max_points > 0 allows the point-cache mode of the single-CTA variant (upper bound of GncJob::n_points)
-int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster, int max_points = 0);
+int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster, int n_active = 0);
 int launch_kabsch_batch(cudaStream_t st, const double* src, const double* dst, const uint2* edges,
                         const uint32_t* sets, int k, unsigned long long n_hyp, double* R, double* t);
 

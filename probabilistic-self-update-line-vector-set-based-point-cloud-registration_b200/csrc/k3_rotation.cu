@@ -378,13 +378,21 @@ __device__ __forceinline__ void block_reduce16(GncSmem* sm, double (&v)[GNC_NRED
         } while (seen < target);
       }
       __syncwarp();
-      if (lane < 16) {
-        double acc = 0.0;
-        for (unsigned r = 0; r < G; ++r) {
-          const double y = __ldcg(buf + (size_t)r * GNC_NRED + lane);
-          acc = (r == 0) ? y : ((lane == RED_MAX) ? fmax(acc, y) : acc + y);
+      {
+        // lane = result + 16 x half: each half adds its share of the ranks in order, eight loads in flight at a time
+        // (the additions wait for the loads: one load at a time would cost an L2 round trip per CTA of the registration)
+        const unsigned half_n = (G + 1) / 2, r_lo = half * half_n, r_hi = (r_lo + half_n < G) ? r_lo + half_n : G;
+        double acc = is_max ? -INFINITY : 0.0;
+        for (unsigned r = r_lo; r < r_hi; r += 8) {
+          double y[8];
+#pragma unroll
+          for (unsigned j = 0; j < 8; ++j) y[j] = (r + j < r_hi) ? __ldcg(buf + (size_t)(r + j) * GNC_NRED + idx) : (is_max ? -INFINITY : 0.0);
+#pragma unroll
+          for (unsigned j = 0; j < 8; ++j) acc = is_max ? fmax(acc, y[j]) : acc + y[j];
         }
-        sm->total[lane] = acc;
+        const double other = __shfl_xor_sync(0xffffffffu, acc, 16);
+        const double a_lo = half ? other : acc, a_hi = half ? acc : other;
+        if (lane < 16) sm->total[idx] = is_max ? fmax(a_lo, a_hi) : a_lo + a_hi;
       }
     }
   }
@@ -1072,9 +1080,9 @@ int gnc_cluster_for(int n_jobs) {
   return 1;
 }
 
-int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster, int max_points) {
+int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_per_cta, int cluster, int n_active) {
   if (n_jobs <= 0) return PSULVSB_OK;
-  (void)max_points;
+  if (n_active <= 0 || n_active > n_jobs) n_active = n_jobs;  // jobs that are not marked inactive (their CTAs exit at once)
   gnc_tls_small_kernel<<<n_jobs, 128, 0, st>>>(d_jobs);  // tiny subsets: the reference's arithmetic replayed by one thread
   PSU_CHECK_LAUNCH("gnc_tls_small_kernel");
   if (cap_per_cta < 32) cap_per_cta = 32;
@@ -1100,10 +1108,19 @@ int launch_gnc_tls(cudaStream_t st, const GncJob* d_jobs, int n_jobs, int cap_pe
       return launch_gnc_nc<8, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
     case 4: return launch_gnc_nc<4, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
     case 2: return launch_gnc_nc<2, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
-    // one CTA per hypothesis (large batches).  Measured and dropped: caching the points instead of the line vectors
-    // (shared-memory gathers of 96 bytes per line vector cost more than the coalesced stream), 2 x 256-thread CTAs per
-    // SM (-6 %), 640 / 768-thread CTAs (-1..2 %)
-    case 1: return launch_gnc_nc<1, 512, 1>(st, d_jobs, n_jobs, cap_per_cta);
+    case 1: {
+      // one CTA per hypothesis (large batches): 512 threads per SM in all, cut into as many CTAs as it takes to have the
+      // whole launch resident at once (up to four 128-thread CTAs per SM) -- one registration's serial phases (reductions,
+      // rotation update, barriers) then overlap the others' passes instead of idling the SM, and there is no second
+      // wave whose stragglers run alone.  Measured on 592 cfg-A pairs per step: 38.8 ms against 41.8 ms with
+      // 512-thread CTAs in two waves.  (Caching the points instead of the line vectors was measured and dropped:
+      // shared-memory gathers of 96 bytes per line vector cost more than the coalesced stream.)
+      int cps = debug_knobs().gnc_cps;
+      if (cps <= 0) cps = n_active > 2 * sm_count() ? 4 : (n_active > sm_count() ? 2 : 1);
+      if (cps >= 4) return launch_gnc_nc<1, 128, 4>(st, d_jobs, n_jobs, cap_per_cta);
+      if (cps >= 2) return launch_gnc_nc<1, 256, 2>(st, d_jobs, n_jobs, cap_per_cta);
+      return launch_gnc_nc<1, 512, 1>(st, d_jobs, n_jobs, cap_per_cta);
+    }
     default: return fail(PSULVSB_ERR_INVALID, "launch_gnc_tls: cluster must be 1, 2, 4, 8 or (grid mode) more");
   }
 }
