@@ -182,9 +182,9 @@ int psulvsb_solve_batch(psulvsb_handle_t h, const psulvsb_params_t* params, cons
  * psulvsb_batch_wait(ticket) returns when its solutions are written (tickets may be waited for in any order, each
  * once).  Everything the call was given -- the problem records, the point arrays they reference, seeds, solutions --
  * must stay valid and untouched until the wait has returned; params is copied.  The handle's lanes pull lock-step
- * chunks from ONE queue across calls, so the staging and the H2D copy of batch n + 1 run while batch n is still being
- * solved: with two batches in flight the uploads cost nothing (psulvsb_solve_batch, which must drain the device before
- * it returns, pays for them).  Results are those of psulvsb_solve_batch.  Every other call on the handle first waits
+ * chunks from ONE queue across calls; at most `lanes` chunks are being solved at a time and one more worker stages and
+ * copies the next chunk meanwhile, so with lanes + 1 batches (or chunks) in flight the uploads run under the solves and
+ * cost nothing (psulvsb_solve_batch, which must drain the device before it returns, pays for them).  Results are those of psulvsb_solve_batch.  Every other call on the handle first waits
  * for the queue to empty.  (The reference solves one pair at a time on one thread: PSULVSB.cc:326-331.) */
 int psulvsb_batch_submit(psulvsb_handle_t h, const psulvsb_params_t* params, const psulvsb_problem_t* problems,
                          int B, const uint64_t* seeds, psulvsb_solution_t* solutions, uint64_t* ticket);

@@ -1095,8 +1095,9 @@ class EnginePool {
     // host threads of the staging copies: the CPUs this PROCESS may run on (its affinity mask / cgroup share, not the
     // machine's core count), or the caller's figure (psulvsb_set_host_threads: e.g. cores / ranks on a multi-GPU node,
     // where eight ranks staging with a dozen threads each oversubscribe a 32-CPU container), shared by the engines
+    // (uploads take turns -- upload_mu -- so the uploading engine may have them all but one per solving lane)
     int hw = host_threads > 0 ? host_threads : available_cpus();
-    int per = hw / (n > 0 ? n : 1);
+    int per = hw - (n > 1 ? n - 1 : 0);
     per = per < 1 ? 1 : (per > 12 ? 12 : per);
     for (Engine* e : eng) {
       e->stage_threads_cap = per;
@@ -1167,8 +1168,10 @@ class EnginePool {
     std::vector<ChunkRecord> recs;
     cudaEvent_t origin = nullptr;
   };
+  std::mutex upload_mu;
   std::mutex q_mu;
-  std::condition_variable q_work, q_done;
+  std::condition_variable q_work, q_done, q_solve;
+  int solving = 0;  // chunks being solved right now
   std::deque<std::shared_ptr<Call>> q_pending;          // calls with chunks still to hand out, in submission order
   std::map<uint64_t, std::shared_ptr<Call>> q_calls;    // submitted and not yet waited for
   std::vector<std::thread> workers;
@@ -1201,8 +1204,40 @@ class EnginePool {
       if (!skip) {
         const int b0 = call->begin[(size_t)c], nb = call->begin[(size_t)c + 1] - b0;
         e->origin = call->origin;
-        rc = e->upload(call->problems + b0, nb);
-        if (!rc) rc = e->solve(&call->params, call->seeds.data() + b0, call->solutions + b0, nullptr);
+        const bool prof = debug_knobs().upload_prof != 0;
+        auto now_ms = [] {
+          return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        };
+        double t0, t1;
+        {
+          // one upload at a time: it has all the staging threads and the whole PCIe link
+          std::lock_guard<std::mutex> up(upload_mu);
+          t0 = prof ? now_ms() : 0.0;
+          rc = e->upload(call->problems + b0, nb);
+          if (!rc && cudaStreamSynchronize(e->st) != cudaSuccess)  // (the copies too: the link is the next upload's now)
+            rc = fail(PSULVSB_ERR_CUDA, "upload: copy failed");
+          t1 = prof ? now_ms() : 0.0;
+        }
+        if (!rc) {
+          // at most lane_count() chunks are being solved at a time; the extra worker has the next chunk uploaded by
+          // the time one of them finishes (chunks that run together finish together, whatever their head start, so
+          // without it every lane would upload while the device idles)
+          {
+            std::unique_lock<std::mutex> lk(q_mu);
+            q_solve.wait(lk, [&] { return solving < lane_count(); });
+            ++solving;
+          }
+          rc = e->solve(&call->params, call->seeds.data() + b0, call->solutions + b0, nullptr);
+          {
+            std::lock_guard<std::mutex> lk(q_mu);
+            --solving;
+          }
+          q_solve.notify_one();
+        }
+        if (prof)
+          std::fprintf(stderr, "lane %d: batch %llu chunk %d: upload %.2f .. %.2f, solve .. %.2f ms\n", w,
+                       (unsigned long long)call->id, c, std::fmod(t0, 100000.0), std::fmod(t1, 100000.0),
+                       std::fmod(now_ms(), 100000.0));
         if (rc) msg = psulvsb_last_error();
         else call->recs[(size_t)c] = record_of(e);
       }
@@ -1220,7 +1255,7 @@ class EnginePool {
     }
   }
   int start_workers() {
-    const int n = lane_count();
+    const int n = lane_count() + 1;  // one more than may solve at a time: it uploads meanwhile
     if ((int)workers.size() == n) return PSULVSB_OK;
     stop_workers();
     if (int rc = ensure_engines(n)) return rc;
@@ -1347,6 +1382,13 @@ class EnginePool {
     PSU_CUDA(cudaSetDevice(device));
     const int ch = chunk_size();
     const int n_chunks = (B + ch - 1) / ch;
+    if (n_chunks > lane_count()) {
+      // more chunks than lanes: through the queue of the pipelined calls, whose extra worker uploads the next chunk
+      // while the lanes solve (only the first chunk's upload is exposed)
+      uint64_t ticket = 0;
+      if (int rc = submit(params, problems, B, seeds, solutions, &ticket)) return rc;
+      return wait(ticket);
+    }
     const int n_workers = n_chunks < lane_count() ? n_chunks : lane_count();
     if (int rc = ensure_engines(n_workers)) return rc;
     std::vector<int> begin;
@@ -1365,7 +1407,10 @@ class EnginePool {
       e->origin = origin;
       for (int c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) {
         const int b0 = begin[(size_t)c], nb = begin[(size_t)c + 1] - b0;
-        if (int r = e->upload(problems + b0, nb)) return r;
+        {
+          std::lock_guard<std::mutex> up(upload_mu);  // (see worker_main)
+          if (int r = e->upload(problems + b0, nb)) return r;
+        }
         if (int r = e->solve(params, seeds ? seeds + b0 : nullptr, solutions + b0, nullptr)) return r;
         recs[(size_t)c] = record_of(e);
       }

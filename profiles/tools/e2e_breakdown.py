@@ -4,7 +4,7 @@ import psulvsb_b200
 from psulvsb_b200 import capi, synth
 import bench
 B=int(sys.argv[1]) if len(sys.argv) > 1 else 64
-pairs = bench.make_problems(0, B)
+pairs = bench.make_pairs(0, B)
 probs = [capi.HostProblem(p["src"], p["dst"]) for p in pairs]
 seeds = list(range(B))
 params = capi.default_params(**bench.PARAM_KW)
