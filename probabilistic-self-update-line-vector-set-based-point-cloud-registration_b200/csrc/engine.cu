@@ -284,7 +284,7 @@ int Engine::upload(const psulvsb_problem_t* problems, int nb) {
     L.C0 = p.C;
     L.M = p.M;
     L.Ccap = p.C;  // + the keep_mask zeros, counted by the staging threads below
-    L.stride = (int)align_up((size_t)(p.C + 31) / 32, 4);
+    L.stride = (int)align_up((size_t)(p.C + 31) / 32, 8);  // whole 32-byte sectors per row and column tile (K1 stores them as such)
     od = align_up(od, 16);
     L.in_dbl = od;
     L.alias_ori = (p.ori_src == p.src && p.ori_dst == p.dst && p.M == p.C);

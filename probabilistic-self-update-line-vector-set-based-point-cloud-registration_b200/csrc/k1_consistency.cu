@@ -226,6 +226,14 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
   __shared__ __align__(8) uint64_t bar[S];        // "full": the tile's bytes have landed
   __shared__ __align__(8) uint64_t bar_empty[S];  // "empty": all warps are done with the stage
   __shared__ __align__(8) K1Slow slow;
+  // a lane's words of the current tile, [WORDS][R][32] per warp: a row's WORDS words leave as ONE 32-byte sector
+  // (two 16-byte stores) when the tile is done -- word-by-word stores touch a row's sector eight times, four bytes
+  // at a time, and L2 fills the partial sectors from DRAM (ncu: 0.49 GB read per cfg-A batch by a kernel that reads
+  // nothing but 160 KB of points per registration)
+  extern __shared__ __align__(16) uint32_t k1_stage[];
+  uint32_t* __restrict__ sw = k1_stage + (threadIdx.x >> 5) * (WORDS * R * 32) + (threadIdx.x & 31);
+  static_assert(WORDS == 8, "a tile is one 32-byte sector per row");
+  const bool row_sectors = (stride & 7) == 0;  // rows start on sector boundaries and hold whole tiles
 
   const int row0 = row_begin + blockIdx.y * TI;
   if (row0 >= row_end) return;  // grid is sized for the largest job
@@ -311,11 +319,22 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
     const int col0 = (t_begin + k) * TJ;
     for (int wj = 0; wj < WORDS; ++wj) {
       const int cb = col0 + wj * 32;  // first column of this word
-      if (cb >= n) break;
+      if (cb >= n) {  // past the last column: the rest of the row's sector is padding
+        if (row_sectors) {
+          for (int w2 = wj; w2 < WORDS; ++w2)
+#pragma unroll
+            for (int r = 0; r < R; ++r) sw[(w2 * R + r) * 32] = 0u;
+        }
+        break;
+      }
       if (cb + 31 <= warp_row_min) {  // the word is below the diagonal for every row of this warp
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (irow[r] < row_end) mask[(size_t)irow[r] * stride + (cb >> 5)] = 0u;
+        for (int r = 0; r < R; ++r) {
+          if (row_sectors)
+            sw[(wj * R + r) * 32] = 0u;
+          else if (irow[r] < row_end)
+            mask[(size_t)irow[r] * stride + (cb >> 5)] = 0u;
+        }
         continue;
       }
       uint32_t acc[R];
@@ -383,16 +402,36 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
           }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r) {
+          if (row_sectors) sw[(wj * R + r) * 32] = word[r];  // (rows past row_end hold zeros: live == 0)
           if (irow[r] < row_end) {
-            mask[(size_t)irow[r] * stride + (cb >> 5)] = word[r];
+            if (!row_sectors) mask[(size_t)irow[r] * stride + (cb >> 5)] = word[r];
             cnt[r] += __popc(word[r]);
           }
+        }
       };
       if (cb >= row0 + TI && cb + 32 <= n)
         finish(std::true_type());
       else
         finish(std::false_type());
+    }
+    if (row_sectors) {  // the tile's sector of every row (a lane reads back only what it staged itself)
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (irow[r] < row_end) {
+          uint4 lo, hi;
+          lo.x = sw[(0 * R + r) * 32];
+          lo.y = sw[(1 * R + r) * 32];
+          lo.z = sw[(2 * R + r) * 32];
+          lo.w = sw[(3 * R + r) * 32];
+          hi.x = sw[(4 * R + r) * 32];
+          hi.y = sw[(5 * R + r) * 32];
+          hi.z = sw[(6 * R + r) * 32];
+          hi.w = sw[(7 * R + r) * 32];
+          uint4* __restrict__ out = reinterpret_cast<uint4*>(mask + (size_t)irow[r] * stride + (col0 >> 5));
+          out[0] = lo;
+          out[1] = hi;
+        }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_empty[st]);  // this warp is done with stage st
@@ -557,7 +596,14 @@ static int launch_k1_variant(cudaStream_t st, const K1Job* d_jobs, int n_jobs, i
   if (R == 4 && tpc >= 3) tpc = (tpc + 3) / 4 * 4;
   if (tpc > n_tiles) tpc = n_tiles;
   dim3 grid((n_tiles + tpc - 1) / tpc, row_blocks, n_jobs);
-  k1_mask_kernel<R, TJ><<<grid, K1_THREADS, 0, st>>>(d_jobs, tpc);
+  // staging of the mask words: one 32-byte sector per row and tile (static + dynamic shared memory exceed 48 KB for R = 4)
+  constexpr int stage_bytes = (K1_THREADS / 32) * (TJ / 32) * R * 32 * (int)sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PSU_CUDA(cudaFuncSetAttribute(k1_mask_kernel<R, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
+    attr_set = true;
+  }
+  k1_mask_kernel<R, TJ><<<grid, K1_THREADS, stage_bytes, st>>>(d_jobs, tpc);
   PSU_CHECK_LAUNCH("k1_mask_kernel");
   return PSULVSB_OK;
 }
