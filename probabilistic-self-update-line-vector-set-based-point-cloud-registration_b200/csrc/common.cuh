@@ -51,6 +51,12 @@ struct DebugKnobs {
 DebugKnobs& debug_knobs();
 
 inline unsigned long long ceil_div_ull(unsigned long long a, unsigned long long b) { return (a + b - 1) / b; }
+// doubles of sorting scratch block_translation (solve_dev.cuh) needs for n_points points (+ the pseudo-measurement)
+inline size_t translation_sort_doubles(int n_points) {
+  size_t m = 1;
+  while (m < (size_t)n_points + 1) m <<= 1;
+  return m;
+}
 
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11): the replayable sample stream.

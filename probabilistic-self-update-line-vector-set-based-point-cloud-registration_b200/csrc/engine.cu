@@ -586,6 +586,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.pts8 = bw.take<double>((size_t)8 * L.Ccap);
         J.residual_history = bw.take<double>((size_t)L.M);
         J.xs = bw.take<double>((size_t)3 * (L.Ccap + 1));
+        J.xs_sorted = bw.take<double>(translation_sort_doubles(L.Ccap));
         J.keep_mask = bw.take<int>((size_t)L.M);
         J.reduce_map = bw.take<int>((size_t)L.M);
         J.inlier_counter = bw.take<int>((size_t)L.M);
@@ -942,6 +943,11 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
       if (cudaEventElapsedTime(&g, ev_g0, ev_g1) == cudaSuccess) gnc_ms += g;  // (the tick's poll already synchronised)
       float a = 0.f;
       if (origin && cudaEventElapsedTime(&a, origin, ev_g0) == cudaSuccess) gnc_iv.emplace_back(a, a + g);
+    }
+    if (debug_knobs().upload_prof) {
+      const double now = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count() / 1e3;
+      std::fprintf(stderr, "tick %d: ends %.3f ms after the solve began; done %d of %d, waiting for a round start %d, clique %d\n",
+                   ticks, now, h_done[0], B, h_done[1], h_done[2]);
     }
     if (h_done[0] >= B) break;
     n_running = B - h_done[0];

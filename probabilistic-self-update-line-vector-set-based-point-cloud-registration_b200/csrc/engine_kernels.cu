@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(BLK)
     double lb[3] = {J.last_best.t[0], J.last_best.t[1], J.last_best.t[2]};
     const double sigma = J.cur.noise_bound * sqrt(J.cur.cbar2);
     block_translation(&scratch, J.src, J.dst, J.idx, n_rot_pts, sol_s.s, sol_s.R, sigma, J.first_time ? nullptr : lb,
-                      J.xs, t);
+                      J.xs, t, J.xs_sorted);
     __syncthreads();
     if (tid == 0) {
       J.translation_noise = sigma;

@@ -65,6 +65,7 @@ struct JobCtl {
   int* inlier_map;           // [Ccap]
   int* idx;                  // [Ccap] translation scratch
   double* xs;                // [3 * (Ccap + 1)]
+  double* xs_sorted;         // [translation_sort_doubles(Ccap)] sorting scratch of the max-stabbing translation
   uint8_t* sampled_flags;    // [Ccap]
   uint8_t* rot_flags;        // [Ccap]
   uint2* edges;              // reduced set (L_reduced_set) as endpoint pairs

@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(BLK)
     tls_translation_kernel(const double* __restrict__ src, const double* __restrict__ dst,
                            const uint8_t* __restrict__ flags, int n, double scale, const double* __restrict__ Rcm,
                            double sigma, const double* __restrict__ last_best, int* __restrict__ idx,
-                           double* __restrict__ xs, double* __restrict__ t_out, int* __restrict__ n_points) {
+                           double* __restrict__ xs, double* __restrict__ sorted, double* __restrict__ t_out,
+                           int* __restrict__ n_points) {
   __shared__ BlockScratch scratch;
   __shared__ int base_s;
   const int tid = threadIdx.x;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(BLK)
     lb[1] = last_best[1];
     lb[2] = last_best[2];
   }
-  block_translation(&scratch, src, dst, idx, P, scale, R, sigma, last_best ? lb : nullptr, xs, t);
+  block_translation(&scratch, src, dst, idx, P, scale, R, sigma, last_best ? lb : nullptr, xs, t, sorted);
   if (tid == 0) {
     t_out[0] = t[0];
     t_out[1] = t[1];
@@ -344,8 +345,9 @@ int launch_tls_translation(cudaStream_t st, const double* src, const double* dst
   int* idx = nullptr;
   double* xs = nullptr;
   PSU_CUDA(cudaMallocAsync((void**)&idx, sizeof(int) * (size_t)n, st));
-  PSU_CUDA(cudaMallocAsync((void**)&xs, sizeof(double) * 3 * ((size_t)n + 1), st));
-  tls_translation_kernel<<<1, BLK, 0, st>>>(src, dst, flags, n, scale, R, noise, last_best, idx, xs, t_out, n_points);
+  PSU_CUDA(cudaMallocAsync((void**)&xs, sizeof(double) * (3 * ((size_t)n + 1) + translation_sort_doubles(n)), st));
+  tls_translation_kernel<<<1, BLK, 0, st>>>(src, dst, flags, n, scale, R, noise, last_best, idx, xs,
+                                            xs + 3 * ((size_t)n + 1), t_out, n_points);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(idx, st);
   cudaFreeAsync(xs, st);

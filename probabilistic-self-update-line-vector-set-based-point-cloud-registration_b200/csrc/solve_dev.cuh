@@ -213,10 +213,18 @@ __device__ inline void block_tls_scale(BlockScratch* scratch, const double* __re
 }
 
 
+// Largest point sets (a rotation solve that found no consensus flags every endpoint; cfg-B) make the all-pairs count
+// quadratic on ONE CTA: 5000 points took 3.6 ms, on which the whole lock-step batch waited.  Above BT_SORT_MIN
+// measurements the axis is sorted instead (bitonic network in `sorted`, length a power of two >= N, padded with +inf):
+// x -> fl(x - sigma) and x -> fl(x + sigma) are monotone, so the members of a candidate are a contiguous run of the
+// sorted order, found by two binary searches with the SAME rounded predicates -- the same depths, the same winner
+// (largest depth, ties -> smallest closing endpoint) in O(N log^2 N).
+constexpr int BT_SORT_MIN = 1024;
+
 __device__ inline void block_translation(BlockScratch* s, const double* __restrict__ src,
                                          const double* __restrict__ dst, const int* __restrict__ idx, int P,
                                          double scale, const double R[9], double sigma, const double* last_best,
-                                         double* __restrict__ xs, double t_out[3]) {
+                                         double* __restrict__ xs, double t_out[3], double* __restrict__ sorted = nullptr) {
   __shared__ StabBest warp_best[BLK / 32];
   __shared__ StabBest blk_best;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -240,6 +248,60 @@ __device__ inline void block_translation(BlockScratch* s, const double* __restri
     best.depth = 0;
     best.hi = 0.0;
     best.k = -1;
+    if (sorted != nullptr && N > BT_SORT_MIN) {
+      int M = 1;
+      while (M < N) M <<= 1;
+      for (int i = tid; i < M; i += BLK) sorted[i] = (i < N) ? x[i] : INFINITY;
+      __syncthreads();
+      for (int kk = 2; kk <= M; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < M; i += BLK) {
+            const int l = i ^ j;
+            if (l > i) {
+              const double a = sorted[i], b = sorted[l];
+              const bool up = (i & kk) == 0;
+              if ((a > b) == up) {
+                sorted[i] = b;
+                sorted[l] = a;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      // candidate = sorted position k (ascending closing endpoints: the first best is the one with the smallest)
+      for (int k = tid; k < N; k += BLK) {
+        const double hik = dadd(sorted[k], sigma);
+        int lo = 0, hi = k;  // first position whose closing endpoint reaches hik (position k does)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (dadd(sorted[mid], sigma) >= hik) hi = mid; else lo = mid + 1;
+        }
+        const int first = lo;
+        lo = k;
+        hi = N - 1;  // last position whose opening endpoint is not beyond hik (position k is not)
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (dsub(sorted[mid], sigma) <= hik) lo = mid; else hi = mid - 1;
+        }
+        const int cnt = lo - first + 1;
+        if (cnt > best.depth) {  // (k ascends per thread: an equal depth later has a larger endpoint)
+          best.depth = cnt;
+          best.hi = hik;
+          best.k = k;
+        }
+      }
+      // warp-level combine, then the block-level code below
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        StabBest c;
+        c.depth = __shfl_xor_sync(0xffffffffu, best.depth, o);
+        c.hi = __shfl_xor_sync(0xffffffffu, best.hi, o);
+        c.k = __shfl_xor_sync(0xffffffffu, best.k, o);
+        if (c.k >= 0 && (best.k < 0 || c.depth > best.depth ||
+                         (c.depth == best.depth && (c.hi < best.hi || (c.hi == best.hi && c.k < best.k)))))
+          best = c;
+      }
+    } else
     for (int k = wid; k < N; k += BLK / 32) {
       const double hik = dadd(x[k], sigma);
       int cnt = 0;

@@ -332,13 +332,21 @@ def test_kabsch_rank2_is_unique_and_matches_oracle(P, O):
     assert worst < 1e-9, worst
 
 
-@pytest.mark.parametrize("n,with_last", [(34, False), (300, False), (300, True), (2500, True)])
-def test_tls_translation_vs_oracle(P, O, n, with_last):
+@pytest.mark.parametrize("n,with_last,grid", [(34, False, 0), (300, False, 0), (300, True, 0), (2500, True, 0),
+                                              (6000, False, 0), (6000, True, 0), (3000, True, 0.01), (1300, False, 0.02)])
+def test_tls_translation_vs_oracle(P, O, n, with_last, grid):
+    """Max-stabbing translation against the oracle's sorted sweep.  Up to 1024 measurements the device counts all pairs,
+    above it sorts the axis and finds every candidate's members by binary search with the same rounded predicates
+    (solve_dev.cuh); `grid` > 0 snaps the measurements to a lattice, so that many candidates tie in depth and many
+    endpoints coincide."""
     st = P["stages"]
     rng = np.random.default_rng(n)
     src = rng.uniform(-1, 1, (3, n))
     t_true = np.array([0.3, -0.7, 1.1])
     dst = src + t_true[:, None] + rng.uniform(-0.04, 0.04, (3, n))
+    if grid > 0:
+        src = np.round(src / grid) * grid
+        dst = np.round(dst / grid) * grid
     bad = rng.permutation(n)[: n // 2]
     dst[:, bad] += rng.uniform(-3, 3, (3, len(bad)))
     flags = np.ones(n, dtype=np.uint8)
