@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--hyp", type=int, default=1 << 20)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--debug", action="append", default=[], metavar="NAME=VALUE",
+                    help="psulvsb_debug_set switch (equivalent code paths, e.g. k4_variant=1); repeatable")
     args = ap.parse_args()
 
     import torch
@@ -47,6 +49,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = capi.lib()
+    for kv in args.debug:
+        name, _, value = kv.partition("=")
+        capi.debug_set(name, float(value))
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     peaks = {}
     try:

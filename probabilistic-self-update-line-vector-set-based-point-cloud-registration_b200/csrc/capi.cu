@@ -250,10 +250,21 @@ int psulvsb_consistency_mask_rows(void* stream, const void* d_src_f4, const void
     return fail(PSULVSB_ERR_INVALID, "psulvsb_consistency_mask: float4 arrays must be 16-byte aligned");
   if (row_begin == row_end) return PSULVSB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // the kernel streams pair-interleaved records (common.cuh il_store): built here from the caller's per-point ones
+  float4* il = nullptr;
+  const size_t nrec = il_records((size_t)n);
+  PSU_CUDA(cudaMallocAsync((void**)&il, sizeof(float4) * 2 * nrec, st));
+  struct IlFree {
+    float4* p;
+    cudaStream_t s;
+    ~IlFree() { cudaFreeAsync(p, s); }
+  } il_free{il, st};
+  if (int rc = launch_interleave_points(st, (const float4*)d_src_f4, n, il)) return rc;
+  if (int rc = launch_interleave_points(st, (const float4*)d_dst_f4, n, il + nrec)) return rc;
   K1Job j;
   std::memset(&j, 0, sizeof(j));
-  j.src = (const float4*)d_src_f4;
-  j.dst = (const float4*)d_dst_f4;
+  j.src = il;
+  j.dst = il + nrec;
   j.src64 = d_src64;
   j.dst64 = d_dst64;
   j.n = n;

@@ -134,6 +134,23 @@ __device__ __forceinline__ float4 pack_point(double x, double y, double z) {
   return make_float4(xf, yf, zf, (float)n2);
 }
 
+// Pair-interleaved tile layout of packed points (K1's column tiles): points 2q and 2q + 1 share two float4 records,
+//   il[2q] = (x_2q, x_2q+1, y_2q, y_2q+1),  il[2q + 1] = (z_2q, z_2q+1, n_2q, n_2q+1)      (n = |p|^2),
+// so that one LDS.128 hands a thread the SAME coordinate of two neighbouring columns in an aligned register pair -- the
+// 64-bit operand of an FFMA2.  An array of n points has (n + 1) & ~1 records (an odd n ends with a zero point).
+__host__ __device__ inline size_t il_records(size_t n) { return (n + 1) & ~(size_t)1; }
+__device__ __forceinline__ void il_store(float4* __restrict__ il, int i, const float4 p) {
+  float* f = reinterpret_cast<float*>(il + (i & ~1)) + (i & 1);
+  f[0] = p.x;
+  f[2] = p.y;
+  f[4] = p.z;
+  f[6] = p.w;
+}
+__device__ __forceinline__ float4 il_load(const float4* __restrict__ il, int i) {
+  const float* f = reinterpret_cast<const float*>(il + (i & ~1)) + (i & 1);
+  return make_float4(f[0], f[2], f[4], f[6]);
+}
+
 // ------------------------------------------------------------------------------------------
 // mbarrier / 1-D TMA bulk copy / packed FP32 helpers shared by the tile-streaming kernels (K1, K3, K4)
 // ------------------------------------------------------------------------------------------

@@ -114,7 +114,9 @@ __global__ void engine_pack_kernel(const PackJob* __restrict__ jobs) {
   const PackJob& j = jobs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < j.n) {
-    j.out[i] = pack_point(j.pts[3 * i] - j.c[0], j.pts[3 * i + 1] - j.c[1], j.pts[3 * i + 2] - j.c[2]);
+    // pair-interleaved records: K1 reads its column tiles (and its row points) from them
+    il_store(j.out, i, pack_point(j.pts[3 * i] - j.c[0], j.pts[3 * i + 1] - j.c[1], j.pts[3 * i + 2] - j.c[2]));
+    if (i == j.n - 1 && (j.n & 1)) il_store(j.out, j.n, make_float4(0.f, 0.f, 0.f, 0.f));  // the odd array's last slot
     if (j.zero) j.zero[i] = 0u;
   }
 }
@@ -609,8 +611,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.seed = seeds ? seeds[b] : params->seed + (uint64_t)b;
         const float a = 1 + (((float)L.C0) / (long)L.M);  // registration.cc:669 (float on purpose)
         J.tau = 2 * params->score_noise_bound * a;
-        float4* sf = bw.take<float4>((size_t)L.C0);
-        float4* df = bw.take<float4>((size_t)L.C0);
+        float4* sf = bw.take<float4>(il_records((size_t)L.C0));
+        float4* df = bw.take<float4>(il_records((size_t)L.C0));
         K1Job& K = k1[(size_t)b];
         std::memset(&K, 0, sizeof(K));
         K.src = sf;

@@ -29,7 +29,7 @@ struct K1Consts {
 K1Consts make_k1_consts(double beta, double coord_bound);
 
 struct K1Job {
-  const float4* src;  // packed (centred) points
+  const float4* src;  // packed (centred) points, PAIR-INTERLEAVED (common.cuh il_store): il_records(n) float4 records
   const float4* dst;
   const double* src64;  // column-major 3 x n, original coordinates
   const double* dst64;
@@ -171,6 +171,8 @@ int launch_knn_normals(cudaStream_t st, const double* pts, int n, int k, const d
 
 // ---- stage launchers (k1_consistency.cu, k2_sampler.cu, k3_rotation.cu, k4_score.cu) -----------
 int launch_pack_points(cudaStream_t st, const double* pts, int n, const double center[3], float4* out);
+// per-point float4 records -> K1's pair-interleaved records (out: il_records(n) float4)
+int launch_interleave_points(cudaStream_t st, const float4* in, int n, float4* out);
 // max_n / max_rows: grid extents over all jobs
 int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows);
 int launch_symmetrize(cudaStream_t st, uint32_t* mask, int n, int stride);

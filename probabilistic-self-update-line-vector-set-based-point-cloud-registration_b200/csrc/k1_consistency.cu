@@ -40,6 +40,9 @@ namespace psulvsb {
 namespace {
 
 constexpr int K1_THREADS = 256;
+#ifndef K1_COLPAIR_UNROLL
+#define K1_COLPAIR_UNROLL 4  // column pairs per unrolled step of the word loop (8 columns, as before)
+#endif
 #ifndef K1_R4_CTAS
 #define K1_R4_CTAS 2  // measured with the packed fast path: 3 CTAs per SM (80 registers, 36 B of spills) 2.19 ms vs 2.05 ms
 #endif
@@ -121,56 +124,50 @@ __device__ __noinline__ uint32_t slow_word_coop(const K1Slow& sl, int i, int cb,
   return __ballot_sync(0xffffffffu, in);
 }
 
-// Packed FP32 (Blackwell FFMA2 / FADD2: two FP32 operations per lane and issue slot).  Rows travel in pairs --
-// (row 2p, row 2p+1) in the two halves of a 64-bit register -- and the column values enter as scalar broadcasts
-// (ptxas folds a {x, x} operand into the instruction's .F32 operand form: no duplicated tile, no MOV).  Each half is
-// an IEEE round-to-nearest fma / add: v is bit for bit what pair_fast computes.
-// pair_fast for rows (r0, r1) against one column: 8 FFMA2 + 1 FADD2 + 1 FFMA2 (A - B as fma(B, -1, A): one rounding,
-// the same value as the FADD) = 10 packed instructions for two pairs
-__device__ __forceinline__ float2 pair_fast2(const float4 ms0, const float4 ms1, const float4 mt0, const float4 mt1,
-                                             const float4 sj, const float4 tj, const float neg_four_beta2) {
-  const float2 A = fma2(make_float2(ms0.x, ms1.x), bc2(sj.x),
-                        fma2(make_float2(ms0.y, ms1.y), bc2(sj.y), fma2(make_float2(ms0.z, ms1.z), bc2(sj.z), bc2(sj.w))));
-  const float2 B = fma2(make_float2(mt0.x, mt1.x), bc2(tj.x),
-                        fma2(make_float2(mt0.y, mt1.y), bc2(tj.y), fma2(make_float2(mt0.z, mt1.z), bc2(tj.z), bc2(tj.w))));
-  const float2 u = add2(fma2(B, bc2(-1.f), A), make_float2(ms0.w, ms1.w));
-  const float2 w = fma2(bc2(neg_four_beta2), B, make_float2(mt0.w, mt1.w));
+// Packed FP32 (Blackwell FFMA2, PTX fma.rn.f32x2: two FP32 operations per lane and issue slot).  COLUMNS travel in
+// pairs: the tiles are pair-interleaved (common.cuh il_store), one LDS.128 delivers the same coordinate of columns
+// (2q, 2q + 1) in an aligned register pair, and a thread's row values enter as scalar broadcasts (ptxas folds a {x, x}
+// operand into the instruction's .F32 operand form: no MOV).  Each half is an IEEE round-to-nearest fma: v is bit
+// for bit what pair_fast computes.  Why columns and not rows in the halves (r2, profiles/tools/fp32_pipe_probe.cu):
+//   * an FFMA2 whose 64-bit operand is the one consecutive instructions share (here: a column pair's coordinate,
+//     used by each of the thread's R rows in turn) sustains 0.99 of the FP32 peak; sharing the 32-bit scalar instead
+//     (rows packed, what the kernel did before) 0.92, because the register file then delivers 128 instead of 96 bits
+//     per lane and instruction;
+//   * ALU-pipe instructions are not free beside the FP32 pipe -- each costs ~ 1.6 - 2.3 issue cycles that FFMA2s
+//     cannot use -- and with both columns of a result pair in one row the band tracking is ONE three-input FMNMX3 per
+//     two pairs instead of two FMNMX;
+//   * no half-live register pairs along the diagonal: a dead row costs nothing.
+// pair_fast for one row against a column pair: 8 FFMA2 + 2 FFMA2 ((A - B) as fma(B, -1, A) and (.) + c1 as
+// fma(., 1, c1): one rounding each, the FADD's value) = 10 packed instructions for two pairs
+__device__ __forceinline__ float2 pair_fast2(const float4 ms, const float4 mt, const float4 sa, const float4 sb,
+                                             const float4 ta, const float4 tb, const float neg_four_beta2) {
+  const float2 A = fma2(bc2(ms.x), make_float2(sa.x, sa.y),
+                        fma2(bc2(ms.y), make_float2(sa.z, sa.w), fma2(bc2(ms.z), make_float2(sb.x, sb.y), make_float2(sb.z, sb.w))));
+  const float2 B = fma2(bc2(mt.x), make_float2(ta.x, ta.y),
+                        fma2(bc2(mt.y), make_float2(ta.z, ta.w), fma2(bc2(mt.z), make_float2(tb.x, tb.y), make_float2(tb.z, tb.w))));
+  const float2 u = fma2(fma2(B, bc2(-1.f), A), bc2(1.f), bc2(ms.w));
+  const float2 w = fma2(bc2(neg_four_beta2), B, bc2(mt.w));
   return fma2(u, u, w);
 }
 
-// the 32 pairs (row r, columns of one mask word) for the first RL of a thread's R rows
+// the 32 pairs (row r, columns of one mask word) for the first RL of a thread's R rows; cs / ct: the word's 32
+// pair-interleaved records
 template <int RL, int R>
 __device__ __forceinline__ void eval_word(const float4* __restrict__ cs, const float4* __restrict__ ct,
                                           const float4 (&ms)[R], const float4 (&mt)[R], const float two_beta2,
                                           const float beta4, uint32_t (&acc)[R], float (&mv)[R]) {
-  constexpr int kUnroll = 8;  // measured: 4 -> 0.593, 8 -> 0.602, 16 -> 0.438 (instruction cache) of the FP32-pipe peak on cfg-A batches
-  if constexpr (R % 2 == 0) {
-    // packed: row pairs (0, 1), (2, 3); a half-live pair evaluates its dead row too (its bits are masked off)
-    constexpr int PL = (RL + 1) / 2;
+  (void)beta4;
+  constexpr int kUnroll = K1_COLPAIR_UNROLL;
 #pragma unroll kUnroll
-    for (int jj = 31; jj >= 0; --jj) {
-      const float4 sj = cs[jj];
-      const float4 tj = ct[jj];
+  for (int q = 15; q >= 0; --q) {
+    const float4 sa = cs[2 * q], sb = cs[2 * q + 1];
+    const float4 ta = ct[2 * q], tb = ct[2 * q + 1];
 #pragma unroll
-      for (int p = 0; p < PL; ++p) {
-        const float2 v = pair_fast2(ms[2 * p], ms[2 * p + 1], mt[2 * p], mt[2 * p + 1], sj, tj, two_beta2);
-        acc[2 * p] = __funnelshift_l(__float_as_uint(v.x), acc[2 * p], 1);  // bit jj <- sign(v)
-        acc[2 * p + 1] = __funnelshift_l(__float_as_uint(v.y), acc[2 * p + 1], 1);
-        mv[2 * p] = fminf(mv[2 * p], fabsf(v.x));
-        mv[2 * p + 1] = fminf(mv[2 * p + 1], fabsf(v.y));
-      }
-    }
-  } else {
-#pragma unroll kUnroll
-    for (int jj = 31; jj >= 0; --jj) {
-      const float4 sj = cs[jj];
-      const float4 tj = ct[jj];
-#pragma unroll
-      for (int r = 0; r < RL; ++r) {
-        const float v = pair_fast(ms[r], mt[r], sj, tj, two_beta2, beta4);
-        acc[r] = __funnelshift_l(__float_as_uint(v), acc[r], 1);  // bit jj <- sign(v)
-        mv[r] = fminf(mv[r], fabsf(v));
-      }
+    for (int r = 0; r < RL; ++r) {
+      const float2 v = pair_fast2(ms[r], mt[r], sa, sb, ta, tb, two_beta2);
+      acc[r] = __funnelshift_l(__float_as_uint(v.y), acc[r], 1);  // bit 2q + 1 <- sign(v), then bit 2q
+      acc[r] = __funnelshift_l(__float_as_uint(v.x), acc[r], 1);
+      mv[r] = fminf(mv[r], fminf(fabsf(v.x), fabsf(v.y)));
     }
   }
 }
@@ -265,7 +262,7 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
   auto issue = [&](int k) {  // thread 0: bulk copies of tile t_begin + k into stage k % S
     const int st = k % S;
     const int col0 = (t_begin + k) * TJ;
-    const uint32_t bytes = (uint32_t)min(TJ, n - col0) * (uint32_t)sizeof(float4);
+    const uint32_t bytes = (uint32_t)min(TJ, (int)il_records((size_t)n) - col0) * (uint32_t)sizeof(float4);  // whole column pairs
     // order the generic-proxy accesses of the stage's previous use before the async-proxy writes
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&bar[st], 2 * bytes);
@@ -295,8 +292,8 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
       irow[r] = grp_row_min[r] + lane;
     }
     const bool ok = irow[r] < row_end;
-    const float4 a = ok ? src[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 b = ok ? dst[irow[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a = ok ? il_load(src, irow[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b = ok ? il_load(dst, irow[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float beta2 = 0.5f * c.two_beta2;
     ms[r] = make_float4(-2.f * a.x, -2.f * a.y, -2.f * a.z, (a.w - b.w) - beta2);        // .w = c1
     mt[r] = make_float4(-2.f * b.x, -2.f * b.y, -2.f * b.z, -2.f * c.two_beta2 * b.w);  // .w = c2
@@ -396,7 +393,7 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
                                             -0.5f * __shfl_sync(0xffffffffu, mt[r].z, owner), 0.f);
               // this lane's column of the word (read only here: the slow path is rare)
               const uint32_t res =
-                  slow_word_coop(slow, oi, cb, si, ti, cs[st][wj * 32 + lane], ct[st][wj * 32 + lane], nborder);
+                  slow_word_coop(slow, oi, cb, si, ti, il_load(&cs[st][wj * 32], lane), il_load(&ct[st][wj * 32], lane), nborder);
               if (lane == owner) word[r] = res & live[r];
             }
           }
@@ -450,6 +447,13 @@ __global__ void pack_points_kernel(const double* __restrict__ pts, int n, double
                                    float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = pack_point(pts[3 * i] - cx, pts[3 * i + 1] - cy, pts[3 * i + 2] - cz);
+}
+
+// per-point float4 records (psulvsb_pack_points) -> the pair-interleaved records K1 reads (common.cuh il_store)
+__global__ void interleave_points_kernel(const float4* __restrict__ in, int n, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) il_store(out, i, in[i]);
+  if (i == n && (n & 1)) il_store(out, n, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
 // mirror the upper triangle into the lower one: one warp per 32x32 bit block (bi >= bj)
@@ -628,6 +632,13 @@ int launch_pack_points(cudaStream_t st, const double* pts, int n, const double c
   const double cx = center ? center[0] : 0.0, cy = center ? center[1] : 0.0, cz = center ? center[2] : 0.0;
   pack_points_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, cx, cy, cz, out);
   PSU_CHECK_LAUNCH("pack_points_kernel");
+  return PSULVSB_OK;
+}
+
+int launch_interleave_points(cudaStream_t st, const float4* in, int n, float4* out) {
+  if (n <= 0) return PSULVSB_OK;
+  interleave_points_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(in, n, out);
+  PSU_CHECK_LAUNCH("interleave_points_kernel");
   return PSULVSB_OK;
 }
 

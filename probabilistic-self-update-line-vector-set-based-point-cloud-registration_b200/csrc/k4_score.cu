@@ -4,10 +4,16 @@
 // Reference: the three scoring loops of solve(), registration.cc:1303-1311, :1329-1336 (sampled
 // points) and :1417-1444 (all M points): count_j [ | q_j - s (R p_j + t) | <= tau ].
 //
-// score_batch_kernel: a thread owns HPT hypotheses (s*R, s*t' in registers), the CTA streams ALL n
+// score_batch_kernel: a thread owns HPT hypotheses (s*R, s*t' in registers), the CTA streams its slice of the
 // correspondences through shared memory in double-buffered tiles staged by 1-D TMA bulk copies, so a
 // thread finishes with the complete inlier count of its hypotheses: no cross-thread reduction of
 // counts, only a warp-shuffle / block / grid argmax of (count, hypothesis) packed in 64 bits.
+// Packed FP32 (FFMA2): two POINTS travel in the halves of a 64-bit register pair -- the tiles are pair-interleaved
+// (common.cuh il_store), so one LDS.128 delivers the same coordinate of points (2q, 2q + 1) as an aligned pair --
+// and the hypothesis values enter as scalar broadcasts.  A point pair's coordinate is then the 64-bit operand of the
+// 12 consecutive FFMA2 of a thread's 4 hypotheses x 3 rows, which keeps it in the operand-reuse cache: measured
+// (profiles/tools/fp32_pipe_probe.cu) 0.99 of the FP32 peak against 0.92 when the shared operand is the 32-bit scalar
+// (hypotheses packed, r1), and the band tracking is one three-input FMNMX3 per two units instead of two FMNMX.
 // FP32 evaluation on centred coordinates; u = |d|^2 - tau^2 is accumulated with its sign, and a
 // hypothesis with any point inside the FP32 error band of the threshold is re-scored exactly: the
 // borderline points are re-evaluated in FP64 with the reference's formula (counted).
@@ -33,7 +39,7 @@ struct ScoreArgs {
 };
 
 __global__ void __launch_bounds__(SB_THREADS)
-    score_batch_kernel(const float4* __restrict__ srcf, const float4* __restrict__ dstf,
+    score_batch_kernel(const float4* __restrict__ srcf, const float4* __restrict__ dstf,  // pair-interleaved records
                        const double* __restrict__ src64, const double* __restrict__ dst64, int n,
                        const double* __restrict__ hyp, unsigned long long n_hyp, unsigned long long hyp_begin,
                        ScoreArgs a, int chunk_points, uint32_t* __restrict__ counts,
@@ -93,7 +99,8 @@ __global__ void __launch_bounds__(SB_THREADS)
   auto issue = [&](int tile) {
     const int st = tile & 1;
     const int p0 = p_lo + tile * SB_TP;
-    const uint32_t bytes = (uint32_t)min(SB_TP, p_hi - p0) * (uint32_t)sizeof(float4);
+    // whole point pairs (an odd n ends with a zero record that is never scored)
+    const uint32_t bytes = (uint32_t)min(SB_TP, (int)il_records((size_t)p_hi) - p0) * (uint32_t)sizeof(float4);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&bar[st], 2 * bytes);
     tma_load_1d(ps[st], srcf + p0, bytes, &bar[st]);
@@ -107,34 +114,40 @@ __global__ void __launch_bounds__(SB_THREADS)
     const int st = tile & 1;
     mbar_wait(&bar[st], (tile >> 1) & 1);
     const int np = min(SB_TP, np_chunk - tile * SB_TP);
-#pragma unroll 4
-    for (int j = 0; j < np; ++j) {
-      const float4 p = ps[st][j];
-      const float4 q = qs[st][j];
-      // packed FP32 (FFMA2): hypotheses (k, k+1) in the halves of a 64-bit register pair, the point's coordinates as
-      // scalar-broadcast operands; tf - q as fma(q, -1, tf) (one rounding: the FADD's value).  15 packed
-      // instructions per two (hypothesis, point) units instead of 30, every half the IEEE result of the scalar
-      // form the fix-up below re-evaluates.
-      static_assert(SB_HPT % 2 == 0, "hypotheses are scored in pairs");
+    const int npairs = np >> 1;
+#pragma unroll 2
+    for (int q = 0; q < npairs; ++q) {
+      const float4 pa = ps[st][2 * q], pb = ps[st][2 * q + 1];  // (x0 x1 y0 y1) (z0 z1 . .)
+      const float4 qa = qs[st][2 * q], qb = qs[st][2 * q + 1];
+      const float2 PX = make_float2(pa.x, pa.y), PY = make_float2(pa.z, pa.w), PZ = make_float2(pb.x, pb.y);
+      const float2 QX = make_float2(qa.x, qa.y), QY = make_float2(qa.z, qa.w), QZ = make_float2(qb.x, qb.y);
+      // every half is the IEEE result of the scalar chain the fix-up below re-evaluates: tf - q as fma(q, -1, tf) (one
+      // rounding: the FADD's value), then z, y, x
 #pragma unroll
-      for (int k = 0; k < SB_HPT; k += 2) {
-        const float2 e0 = fma2(bc2(q.x), bc2(-1.f), make_float2(tf[k][0], tf[k + 1][0]));
-        const float2 e1 = fma2(bc2(q.y), bc2(-1.f), make_float2(tf[k][1], tf[k + 1][1]));
-        const float2 e2 = fma2(bc2(q.z), bc2(-1.f), make_float2(tf[k][2], tf[k + 1][2]));
-        const float2 d0 = fma2(make_float2(Rf[k][0], Rf[k + 1][0]), bc2(p.x),
-                               fma2(make_float2(Rf[k][1], Rf[k + 1][1]), bc2(p.y),
-                                    fma2(make_float2(Rf[k][2], Rf[k + 1][2]), bc2(p.z), e0)));
-        const float2 d1 = fma2(make_float2(Rf[k][3], Rf[k + 1][3]), bc2(p.x),
-                               fma2(make_float2(Rf[k][4], Rf[k + 1][4]), bc2(p.y),
-                                    fma2(make_float2(Rf[k][5], Rf[k + 1][5]), bc2(p.z), e1)));
-        const float2 d2 = fma2(make_float2(Rf[k][6], Rf[k + 1][6]), bc2(p.x),
-                               fma2(make_float2(Rf[k][7], Rf[k + 1][7]), bc2(p.y),
-                                    fma2(make_float2(Rf[k][8], Rf[k + 1][8]), bc2(p.z), e2)));
+      for (int k = 0; k < SB_HPT; ++k) {
+        const float2 e0 = fma2(QX, bc2(-1.f), bc2(tf[k][0]));
+        const float2 e1 = fma2(QY, bc2(-1.f), bc2(tf[k][1]));
+        const float2 e2 = fma2(QZ, bc2(-1.f), bc2(tf[k][2]));
+        const float2 d0 = fma2(bc2(Rf[k][0]), PX, fma2(bc2(Rf[k][1]), PY, fma2(bc2(Rf[k][2]), PZ, e0)));
+        const float2 d1 = fma2(bc2(Rf[k][3]), PX, fma2(bc2(Rf[k][4]), PY, fma2(bc2(Rf[k][5]), PZ, e1)));
+        const float2 d2 = fma2(bc2(Rf[k][6]), PX, fma2(bc2(Rf[k][7]), PY, fma2(bc2(Rf[k][8]), PZ, e2)));
         const float2 u = fma2(d2, d2, fma2(d1, d1, fma2(d0, d0, bc2(-tau2))));
         cnt[k] += (int)(__float_as_uint(u.x) >> 31);
-        cnt[k + 1] += (int)(__float_as_uint(u.y) >> 31);
-        mn[k] = fminf(mn[k], fabsf(u.x));
-        mn[k + 1] = fminf(mn[k + 1], fabsf(u.y));
+        cnt[k] += (int)(__float_as_uint(u.y) >> 31);
+        mn[k] = fminf(mn[k], fminf(fabsf(u.x), fabsf(u.y)));
+      }
+    }
+    if (np & 1) {  // the last point of an odd n
+      const float4 p = il_load(ps[st], np - 1);
+      const float4 q = il_load(qs[st], np - 1);
+#pragma unroll
+      for (int k = 0; k < SB_HPT; ++k) {
+        const float d0 = fmaf(Rf[k][0], p.x, fmaf(Rf[k][1], p.y, fmaf(Rf[k][2], p.z, fmaf(q.x, -1.f, tf[k][0]))));
+        const float d1 = fmaf(Rf[k][3], p.x, fmaf(Rf[k][4], p.y, fmaf(Rf[k][5], p.z, fmaf(q.y, -1.f, tf[k][1]))));
+        const float d2 = fmaf(Rf[k][6], p.x, fmaf(Rf[k][7], p.y, fmaf(Rf[k][8], p.z, fmaf(q.z, -1.f, tf[k][2]))));
+        const float u = fmaf(d2, d2, fmaf(d1, d1, fmaf(d0, d0, -tau2)));
+        cnt[k] += (int)(__float_as_uint(u) >> 31);
+        mn[k] = fminf(mn[k], fabsf(u));
       }
     }
     __syncthreads();  // everyone is done with stage st
@@ -154,8 +167,8 @@ __global__ void __launch_bounds__(SB_THREADS)
         t[r] = H[9 + r];
       }
       for (int j = p_lo; j < p_hi; ++j) {
-        const float4 p = srcf[j];
-        const float4 q = dstf[j];
+        const float4 p = il_load(srcf, j);
+        const float4 q = il_load(dstf, j);
         const float d0 = fmaf(Rf[k][0], p.x, fmaf(Rf[k][1], p.y, fmaf(Rf[k][2], p.z, tf[k][0] - q.x)));
         const float d1 = fmaf(Rf[k][3], p.x, fmaf(Rf[k][4], p.y, fmaf(Rf[k][5], p.z, tf[k][1] - q.y)));
         const float d2 = fmaf(Rf[k][6], p.x, fmaf(Rf[k][7], p.y, fmaf(Rf[k][8], p.z, tf[k][2] - q.z)));
@@ -307,25 +320,52 @@ int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, co
   a.coord_bound = (float)(coord_bound * 1.0000002);
   const unsigned long long per_cta = (unsigned long long)SB_THREADS * SB_HPT;
   const unsigned long long gx = (n_hyp + per_cta - 1) / per_cta;
-  // slice the correspondences too until the grid is ~10 waves deep (2 CTAs per SM), >= 8 tiles per slice
-  unsigned long long chunks = ((unsigned long long)sm_count() * 2ull * 10ull + gx - 1) / gx;
-  const unsigned long long max_chunks = ((unsigned long long)n + 8 * SB_TP - 1) / (8 * SB_TP);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  if (chunks > 65535) chunks = 65535;
-  int chunk_points = (int)(((unsigned long long)n + chunks - 1) / chunks);
-  chunk_points = (chunk_points + SB_TP - 1) / SB_TP * SB_TP;  // tile-aligned: every bulk copy stays 16-byte aligned
+  // slice the correspondences too (grid.y) until the grid is >= 10 waves deep (2 CTAs per SM), >= 2 tiles per slice; among
+  // the admissible slice lengths take the one that fills its last wave best (2^20 hypotheses x 50 000 points in three
+  // slices of 8 tiles are 10.4 waves: the eleventh runs a third full, 6 % of the sweep)
+  const unsigned long long slots = (unsigned long long)sm_count() * 2ull;
+  const int n_tiles = (n + SB_TP - 1) / SB_TP;
+  int best_tiles = n_tiles;
+  double best_eff = -1.0;
+  const int t_min = n_tiles < 4 ? n_tiles : 4;  // a slice amortises its CTA's prologue (48 doubles per thread) over >= 4 tiles
+  for (int t = n_tiles; t >= t_min; --t) {       // tiles per slice, long slices first (ties keep the longer)
+    const unsigned long long gy_t = (unsigned long long)((n_tiles + t - 1) / t);
+    if (gy_t > 65535ull) break;
+    const unsigned long long ctas = gx * gy_t;
+    const unsigned long long waves = (ctas + slots - 1) / slots;
+    double eff = (double)ctas / (double)(waves * slots);
+    if (waves < 10) eff *= 0.5 + 0.05 * (double)waves;  // few waves: the last CTAs' length weighs more than the fill
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best_tiles = t;
+    }
+  }
+  const int chunk_points = best_tiles * SB_TP;  // tile-aligned: every bulk copy stays 16-byte aligned
   const unsigned gy = (unsigned)((n + chunk_points - 1) / chunk_points);
+  // the kernel streams pair-interleaved records (common.cuh il_store), built here from the caller's per-point ones
+  struct AsyncScratch {  // stream-ordered scratch, returned on every path out of this function
+    void* p = nullptr;
+    cudaStream_t s;
+    explicit AsyncScratch(cudaStream_t st_) : s(st_) {}
+    ~AsyncScratch() {
+      if (p) cudaFreeAsync(p, s);
+    }
+  } il_mem(st), ticket_mem(st);
+  const size_t nrec = il_records((size_t)n);
+  PSU_CUDA(cudaMallocAsync(&il_mem.p, sizeof(float4) * 2 * nrec, st));
+  float4* il = static_cast<float4*>(il_mem.p);
+  if (int rc = launch_interleave_points(st, src, n, il)) return rc;
+  if (int rc = launch_interleave_points(st, dst, n, il + nrec)) return rc;
   PSU_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * n_hyp, st));
   unsigned int* tickets = nullptr;  // one "slices done" counter per hypothesis group (stream-ordered scratch)
   if (best && gy > 1) {
-    PSU_CUDA(cudaMallocAsync((void**)&tickets, sizeof(unsigned int) * gx, st));
+    PSU_CUDA(cudaMallocAsync(&ticket_mem.p, sizeof(unsigned int) * gx, st));
+    tickets = static_cast<unsigned int*>(ticket_mem.p);
     PSU_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned int) * gx, st));
   }
-  score_batch_kernel<<<dim3((unsigned)gx, gy), SB_THREADS, 0, st>>>(src, dst, src64, dst64, n, hyp, n_hyp, hyp_begin, a,
+  score_batch_kernel<<<dim3((unsigned)gx, gy), SB_THREADS, 0, st>>>(il, il + nrec, src64, dst64, n, hyp, n_hyp, hyp_begin, a,
                                                                      chunk_points, counts, border, tickets, best);
   const cudaError_t le = cudaGetLastError();
-  if (tickets) cudaFreeAsync(tickets, st);
   if (le != cudaSuccess) return fail(PSULVSB_ERR_CUDA, std::string("score_batch_kernel launch: ") + cudaGetErrorString(le));
   return PSULVSB_OK;
 }
