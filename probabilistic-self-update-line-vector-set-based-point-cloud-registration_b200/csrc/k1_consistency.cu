@@ -172,6 +172,35 @@ __device__ __forceinline__ void eval_word(const float4* __restrict__ cs, const f
   }
 }
 
+// A word that is only PARTLY live for some row of the warp -- the row's diagonal runs through it, or the arrays end
+// inside it: the dead columns' values must not enter the row's running minimum (the self pair j = i alone has
+// v = beta^4 <= t_fast: every row's diagonal word went down the slow path, N warp-cooperative redos per registration,
+// a fifth of the kernel's instructions on N = 5000 problems).  live[r]: the row's live columns of this word.  Rare (two
+// or three words per row): compact loop, not unrolled.
+template <int R>
+__device__ __forceinline__ void eval_word_masked(const float4* __restrict__ cs, const float4* __restrict__ ct,
+                                              const float4 (&ms)[R], const float4 (&mt)[R], const float two_beta2,
+                                              const uint32_t (&live)[R], uint32_t (&acc)[R], float (&mv)[R]) {
+  uint32_t lv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) lv[r] = live[r];
+#pragma unroll 1
+  for (int q = 15; q >= 0; --q) {
+    const float4 sa = cs[2 * q], sb = cs[2 * q + 1];
+    const float4 ta = ct[2 * q], tb = ct[2 * q + 1];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float2 v = pair_fast2(ms[r], mt[r], sa, sb, ta, tb, two_beta2);
+      acc[r] = __funnelshift_l(__float_as_uint(v.y), acc[r], 1);
+      acc[r] = __funnelshift_l(__float_as_uint(v.x), acc[r], 1);
+      const float ay = (lv[r] & 0x80000000u) ? fabsf(v.y) : 3.0e38f;  // column 2q + 1
+      const float ax = (lv[r] & 0x40000000u) ? fabsf(v.x) : 3.0e38f;  // column 2q
+      mv[r] = fminf(mv[r], fminf(ax, ay));
+      lv[r] <<= 2;
+    }
+  }
+}
+
 // Position (in units of 32 rows) of warp w's rows inside row group r of the CTA's row block.  Along the
 // diagonal a warp's work in the tile where group r is partially live is 8 - pos words per tile, so the
 // positions are permuted per group to give every warp (nearly) the same total over the diagonal tiles of a
@@ -218,6 +247,7 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
   constexpr int WORDS = TJ / 32;
   constexpr int S = K1Ring<TJ>::STAGES;
   constexpr int NWARPS = K1_THREADS / 32;
+  constexpr int kGroupSpan = (R == 4) ? 64 : 32;  // rows [grp_row_min[r], + kGroupSpan) hold the warp's rows of group r
   __shared__ __align__(128) float4 cs[S][TJ];
   __shared__ __align__(128) float4 ct[S][TJ];
   __shared__ __align__(8) uint64_t bar[S];        // "full": the tile's bytes have landed
@@ -348,7 +378,22 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
       for (int r = 1; r < R; ++r) n_live += (cb + 31 > grp_row_min[r]) ? 1 : 0;
       const float4* cw = &cs[st][wj * 32];
       const float4* tw = &ct[st][wj * 32];
-      if (n_live == R)
+      // partly live for some row of this warp (warp-uniform): the diagonal of one of its row groups runs through the
+      // word, or the arrays end inside it
+      bool partial = cb + 32 > n;
+#pragma unroll
+      for (int r = 0; r < R; ++r) partial = partial || (cb <= grp_row_min[r] + kGroupSpan - 1 && cb + 30 >= grp_row_min[r]);
+      if (partial) {
+        uint32_t lm[R];
+        const uint32_t valid = (cb + 32 <= n) ? 0xFFFFFFFFu : ((1u << (n - cb)) - 1u);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = irow[r];
+          const uint32_t upper = (i < cb) ? 0xFFFFFFFFu : ((i >= cb + 31) ? 0u : (0xFFFFFFFFu << (i - cb + 1)));
+          lm[r] = (i < row_end) ? (valid & upper) : 0u;
+        }
+        eval_word_masked<R>(cw, tw, ms, mt, two_beta2, lm, acc, mv);
+      } else if (n_live == R)
         eval_word<R, R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
       else if (R == 4)  // (strips of adjacent rows: a pair is live or dead as a whole)
         eval_word<(R == 4 ? 2 : 1), R>(cw, tw, ms, mt, two_beta2, beta4, acc, mv);
