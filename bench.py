@@ -66,6 +66,24 @@ try:
         NCU_TRAFFIC.update(json.load(_f))
 except Exception:
     pass
+# What the FP32 pipe sustains on this part, measured by profiles/tools/fp32_pipe_probe.cu (committed output:
+# profiles/r2_fp32_pipe_probe.jsonl): the nominal 128 lanes x clock of the roofline is reached by neither FFMA nor FFMA2
+# streams, and every ALU-pipe instruction beside them costs 1.6-2.3 issue cycles.  Reported next to the roofline, not
+# used as its peak.
+PIPE_PROBE = None
+try:
+    _rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r2_fp32_pipe_probe.jsonl")) if l.startswith("{")]
+
+    def _best(sub, key):
+        v = [r[key] for r in _rows if sub in r.get("case", "") and key in r]
+        return max(v) if v else None
+    PIPE_PROBE = {"ffma_stream_frac_of_128_lanes": _best("scalar FFMA", "frac_of_128"),
+                  "ffma2_stream_64bit_operand_shared": _best("matrix operand shared (6 x 4)", "frac_of_128"),
+                  "ffma2_stream_32bit_operand_shared": _best("scalar operand shared (6 x 4)", "frac_of_128"),
+                  "k1_word_loop_alone_frac_of_16_slot_roofline": _best("(the kernel's loop)", "frac_of_16_slot_roofline"),
+                  "source": "profiles/r2_fp32_pipe_probe.jsonl (profiles/tools/fp32_pipe_probe.cu on one B200)"}
+except Exception:
+    pass
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -439,6 +457,7 @@ def k1_roofline(c, clocks, B, k1_ms_per_step, dev_ms_per_step):
             "kernel_ms": k1_ms_per_step,
             "share_of_step": k1_ms_per_step / dev_ms_per_step if dev_ms_per_step > 0 else None,
             "peak_source": f"{c.sms} SMs x 128 lanes x {f_mhz:.0f} MHz (SM clock sampled during the run)",
+            "pipe_probe": PIPE_PROBE,
             "hbm_mask_write": {"achieved": mask_bytes / k1_s / 1e9 if k1_s > 0 else None, "peak": hbm_peak,
                                "unit": "GB/s", "frac": (mask_bytes / k1_s / 1e9 / hbm_peak) if k1_s > 0 else None,
                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in c.peaks
@@ -652,7 +671,7 @@ def stage_k1(c, n=100_000, steps=3, warmup=2):
                         "all-gathered in place (grouped ncclBroadcast), RANSAC replicated"}
 
 
-def stage_k4(c, n=50_000, H=1 << 20, steps=3, warmup=3):
+def stage_k4(c, n=50_000, H=1 << 20, steps=5, warmup=3):
     """cfg-D: hypotheses sharded over the ranks; psulvsb_score_batch_sharded ends with the 8-byte ncclAllReduce(max)."""
     torch, capi = c.torch, c.capi
     from psulvsb_b200 import sharding, stages
@@ -690,8 +709,19 @@ def stage_k4(c, n=50_000, H=1 << 20, steps=3, warmup=3):
                                                  hyp_local.data_ptr(), he - hb, hb, 1.0, tau, bound, csa, cda,
                                                  counts.data_ptr(), best.data_ptr(), border.data_ptr()))
 
+    # inside the default line this stage follows seconds of host-only work (CPU baseline, parity check): the SM clock
+    # has dropped to idle by then and three 26 ms warm-up launches do not bring it back (measured: 29.9 ms against
+    # 26.5 ms with the clocks up) -- warm up for half a second, then time with the clock sampled DURING the steps
+    import time as _time
+    t_w = _time.perf_counter()
+    while _time.perf_counter() - t_w < 0.5:
+        run()
+        torch.cuda.synchronize()
+    stage_sampler = ClockSampler(c.local_rank)
+    stage_sampler.start()
     ms = timed_stream(c, run, steps, warmup)
-    f = sm_clock_now(c) or 1965.0
+    stage_clocks = stage_sampler.stop()
+    f = stage_clocks.get("sm_mhz") or sm_clock_now(c) or 1965.0
     cnt, hid = sharding.unpack_best(int(best.item()))
     if hid != H // 3:
         raise SystemExit(f"bench.py: scoring sweep found hypothesis {hid} (count {cnt}), expected {H // 3}")
@@ -703,7 +733,8 @@ def stage_k4(c, n=50_000, H=1 << 20, steps=3, warmup=3):
             "best": {"count": cnt, "hypothesis": hid, "expected_hypothesis": H // 3},
             "roofline": {"bound": "fp32-pipe", "achieved": ach, "peak": peak, "frac": ach / peak,
                          "unit": "Gslot/s (16 FP32-pipe issue slots per (hypothesis, point))",
-                         "peak_source": f"{c.world} x {c.sms} SMs x 128 lanes x {f:.0f} MHz (nvidia-smi after the run)"},
+                         "peak_source": f"{c.world} x {c.sms} SMs x 128 lanes x {f:.0f} MHz (SM clock sampled during the steps)"},
+            "clocks": stage_clocks,
             "hbm_hypothesis_stream_gbs": H * 96 / c.world / (ms / 1e3) / 1e9,
             "sharding": "hypotheses sliced across ranks; one 8-byte ncclAllReduce(max) of (count<<32 | ~id) on the same "
                         "stream, inside psulvsb_score_batch_sharded"}
@@ -723,7 +754,7 @@ def run_cfgD(args, c):
             "data": "synthetic",
             "config": {"workload": "cfgD: 2^20 hypotheses x N=50000 correspondences, hypotheses sharded across GPUs",
                        "l2": "hypothesis stream (100 MB per GPU at N=1) read once per step; points from L2"},
-            "e2e": None, "gpu_launches": 2 * steps, "clocks": clocks,
+            "e2e": None, "gpu_launches": 3 * steps, "clocks": clocks,  # two re-layout launches + the scoring kernel
             "roofline": dict(s["roofline"], kernel="score_batch_kernel"), "best": s["best"], "sharding": s["sharding"]}
 
 

@@ -302,15 +302,13 @@ int main() {
     run_k4<6, 4, 0, 12, 1>("scalar shared + 12 LEA.HI", sms, cps, d_out, d_cyc);
     run_k4<6, 4, 0, 12, 3>("scalar shared + 12 FMNMX3", sms, cps, d_out, d_cyc);
   }
-  for (int cps : {2, 3}) {
-    run_k1<4, 4, 0>("K1 word loop, FFMA2 + LDS only", sms, cps, d_out, d_cyc);
+  for (int cps : {2}) {
     run_k1<4, 4, 1>("K1 word loop, + SHF", sms, cps, d_out, d_cyc);
     run_k1<4, 4, 2>("K1 word loop, + SHF + FMNMX3 (the kernel's loop)", sms, cps, d_out, d_cyc);
     run_k1<4, 2, 2>("K1 word loop, unroll 2", sms, cps, d_out, d_cyc);
     run_k1<4, 8, 2>("K1 word loop, unroll 8", sms, cps, d_out, d_cyc);
     run_k1<2, 4, 2>("K1 word loop, 2 rows", sms, cps, d_out, d_cyc);
     run_k1<6, 4, 2>("K1 word loop, 6 rows", sms, cps, d_out, d_cyc);
-    run_k1<8, 2, 2>("K1 word loop, 8 rows, unroll 2", sms, cps, d_out, d_cyc);
   }
   return 0;
 }

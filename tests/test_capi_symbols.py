@@ -105,7 +105,8 @@ def test_argument_validation_without_device():
 
 def test_fp32_pipe_kernels_are_packed_and_tma_staged():
     """The SASS of the consistency-mask and scoring kernels carries what DESIGN.md section 6 says they are built on:
-    packed FP32 (FFMA2) in the pair / score loops and 1-D TMA bulk copies (UBLKCP) for the tile rings."""
+    packed FP32 (FFMA2) in the pair / score loops, their 64-bit operand kept in the operand-reuse cache, and 1-D TMA
+    bulk copies (UBLKCP) for the tile rings."""
     import shutil
     import subprocess
 
@@ -118,17 +119,21 @@ def test_fp32_pipe_kernels_are_packed_and_tma_staged():
         m = re.search(r"Function : (\S+)", line)
         if m:
             name = m.group(1)
-            per_fn[name] = {"FFMA2": 0, "UBLKCP": 0, "FFMA": 0}
+            per_fn[name] = {"FFMA2": 0, "UBLKCP": 0, "FFMA": 0, "REUSE64": 0}
         elif name:
             for op in ("FFMA2", "UBLKCP"):
                 if re.search(r"\b%s\b" % op, line):
                     per_fn[name][op] += 1
             if re.search(r"\bFFMA\b", line):
                 per_fn[name]["FFMA"] += 1
+            if "FFMA2" in line and "reuse.F32x2" in line:
+                per_fn[name]["REUSE64"] += 1
     k1 = {k: v for k, v in per_fn.items() if "k1_mask_kernelILi4ELi256" in k}
     k4 = {k: v for k, v in per_fn.items() if "score_batch_kernel" in k}
     assert len(k1) == 1 and len(k4) == 1, (list(k1), list(k4))
     for ops in list(k1.values()) + list(k4.values()):
         assert ops["UBLKCP"] >= 2, ops          # both tile arrays come by bulk copy
         assert ops["FFMA2"] >= 100, ops         # the unrolled loops are packed ...
-        assert ops["FFMA2"] > 4 * ops["FFMA"], ops  # ... and what is left scalar is the rare slow / fix-up path
+        assert ops["FFMA2"] > ops["FFMA"], ops  # ... what is left scalar is the rare slow / fix-up / odd-tail code
+        # r2: two columns (K1) / two points (K4) in the halves -- the 64-bit operand is the one consecutive FFMA2 share
+        assert ops["REUSE64"] >= 40, ops

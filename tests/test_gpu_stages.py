@@ -125,6 +125,30 @@ def test_k1_threshold_band_is_resolved_in_fp64(P, O):
     assert r["border"] >= n - 1   # all of row 0 sits inside the band
 
 
+def test_k1_short_line_vectors_and_diagonal_words(P, O):
+    """Pairs with a + b <= beta^2 (both line vectors shorter than beta: the sign of the square-root-free form is not
+    the answer there) next to ordinary ones, at sizes where every row's diagonal word and the arrays' last word are
+    only partly live (odd n, n % 32 != 0): every bit against the FP64 oracle."""
+    st = P["stages"]
+    rng = np.random.default_rng(17)
+    for n in (95, 1301):
+        beta = 0.1
+        src = rng.uniform(-1.5, 1.5, (3, n))
+        k = n // 3                                        # a third of the points sit in clumps narrower than beta
+        src[:, :k] = src[:, [0]] + rng.uniform(-0.03, 0.03, (3, k))
+        src[:, k:2 * k:2] = src[:, [k]] + rng.uniform(-0.04, 0.04, (3, len(range(k, 2 * k, 2))))
+        dst = src + rng.uniform(-0.02, 0.02, (3, n))
+        dst[:, 2 * k:] = rng.uniform(-2.0, 2.0, (3, n - 2 * k))
+        perm = rng.permutation(n)                         # clumps spread over the rows / mask words
+        src, dst = np.ascontiguousarray(src[:, perm]), np.ascontiguousarray(dst[:, perm])
+        r = st.consistency_mask(src, dst, beta)
+        got = st.unpack_mask(r["mask"], n)
+        want = _upper(O.consistency_mask(src, dst, beta))
+        assert np.array_equal(got, want)
+        assert np.array_equal(r["row_counts"].cpu().numpy(), want.sum(axis=1))
+        assert want[:, :].sum() > k * (k - 1) // 4        # the clumps are there: their pairs are all consistent
+
+
 def test_k1_row_sharding_and_symmetrize(P, O):
     st, synth = P["stages"], P["synth"]
     n, beta = 777, 0.1
