@@ -1,12 +1,14 @@
 """Aggregates an ncu `--metrics gpu__time_duration.sum --csv` launch list by kernel for the LAST
-engine solve in the log (launches between the last two engine_pack_kernel launches)."""
+engine solve in the log (launches between two engine_pack_kernel launches); with a second argument, the last solve
+that launched a kernel whose name contains it (e.g. 'k1_mask_kernel<4' = the last BATCH solve, not the single-pair
+latency probe bench.py ends with)."""
 import collections
 import csv
 import re
 import sys
 
 
-def main(path):
+def main(path, must_have=None):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     allr = []
@@ -19,6 +21,14 @@ def main(path):
         allr.append((name, v))
     idx = [i for i, (n, _) in enumerate(allr) if "engine_pack" in n]
     seg = allr[idx[-2]:idx[-1]] if len(idx) >= 2 else allr
+    if must_have and len(idx) >= 2:
+        bounds = idx + [len(allr)]
+        segs = [allr[bounds[k]:bounds[k + 1]] for k in range(len(bounds) - 1)]
+        segs = [g for g in segs if any(must_have in n for n, _ in g)]
+        if len(segs) >= 2:
+            seg = segs[-2] if len(segs[-1]) < len(segs[-2]) else segs[-1]  # (the capture may cut the last one short)
+        elif segs:
+            seg = segs[-1]
     tot = sum(v for _, v in seg)
     agg = collections.OrderedDict()
     for n, v in seg:
@@ -32,4 +42,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
