@@ -282,7 +282,7 @@ int psulvsb_consistency_mask_rows(void* stream, const void* d_src_f4, const void
                            sizeof(uint32_t) * (size_t)(row_end - row_begin) * row_stride_words, st));
   DeviceJob<K1Job> dj(st);
   if (int rc = dj.put(j)) return rc;
-  return launch_consistency_mask(st, dj.d, 1, n, row_end - row_begin);
+  return launch_consistency_mask(st, dj.d, 1, n, row_end - row_begin, (row_stride_words & 7) == 0);
 }
 
 int psulvsb_consistency_mask(void* stream, const void* d_src_f4, const void* d_dst_f4, const double* d_src64,

@@ -745,7 +745,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     }
     PSU_CUDA(cudaEventRecord(ev_m0, st));
     if (!sharded || row_e > row_b)
-      if (int rc = launch_consistency_mask(st, m.k1, B, maxC, sharded ? row_e - row_b : maxC)) return rc;
+      if (int rc = launch_consistency_mask(st, m.k1, B, maxC, sharded ? row_e - row_b : maxC, true)) return rc;
     PSU_CUDA(cudaEventRecord(ev_m1, st));
     ++launches;
     if (int rc = launch_compact_edges(st, m.cj, B, maxC, true, false)) return rc;

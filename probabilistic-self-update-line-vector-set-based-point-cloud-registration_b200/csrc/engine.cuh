@@ -174,7 +174,8 @@ int launch_pack_points(cudaStream_t st, const double* pts, int n, const double c
 // per-point float4 records -> K1's pair-interleaved records (out: il_records(n) float4)
 int launch_interleave_points(cudaStream_t st, const float4* in, int n, float4* out);
 // max_n / max_rows: grid extents over all jobs
-int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows);
+// row_sectors: EVERY job's mask has stride % 8 == 0 (rows on 32-byte sector boundaries): tiles leave as whole sectors
+int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows, bool row_sectors);
 int launch_symmetrize(cudaStream_t st, uint32_t* mask, int n, int stride);
 int launch_compact_edges(cudaStream_t st, const CompactJob* d_jobs, int n_jobs, int max_n, bool scan, bool emit);
 int launch_ratio_reduced_set(cudaStream_t st, const RatioJob* d_jobs, int n_jobs, int max_n, int phase);

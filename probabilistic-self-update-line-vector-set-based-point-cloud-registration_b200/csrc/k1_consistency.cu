@@ -230,7 +230,9 @@ struct K1Ring {
   static constexpr int STAGES = TJ <= 128 ? 8 : (TJ <= 256 ? 4 : 2);  // 32 KB of tiles per CTA
 };
 
-template <int R, int TJ>
+// SECT: every job's mask rows start on 32-byte sector boundaries and hold whole tiles (stride % 8 == 0: the engine's
+// masks always do) -- a row's eight words of a tile are staged and leave as one sector; otherwise word by word.
+template <int R, int TJ, bool SECT>
 __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3 : 4)))
     k1_mask_kernel(const K1Job* __restrict__ jobs, int tiles_per_cta) {
   const K1Job& job = jobs[blockIdx.z];
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
   extern __shared__ __align__(16) uint32_t k1_stage[];
   uint32_t* __restrict__ sw = k1_stage + (threadIdx.x >> 5) * (WORDS * R * 32) + (threadIdx.x & 31);
   static_assert(WORDS == 8, "a tile is one 32-byte sector per row");
-  const bool row_sectors = (stride & 7) == 0;  // rows start on sector boundaries and hold whole tiles
+  constexpr bool row_sectors = SECT;
 
   const int row0 = row_begin + blockIdx.y * TI;
   if (row0 >= row_end) return;  // grid is sized for the largest job
@@ -331,9 +333,12 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
   const float two_beta2 = -2.f * c.two_beta2, beta4 = c.beta4, t_fast = c.t_fast;  // (pair_fast takes -4 beta^2)
   const int warp_row_min = grp_row_min[0];  // smallest row this warp owns
 
-  uint32_t cnt[R];
+  uint32_t cnt[R], row_ok[R];  // row_ok: all ones for a row inside [row_begin, row_end)
 #pragma unroll
-  for (int r = 0; r < R; ++r) cnt[r] = 0;
+  for (int r = 0; r < R; ++r) {
+    cnt[r] = 0;
+    row_ok[r] = (irow[r] < row_end) ? 0xFFFFFFFFu : 0u;
+  }
   unsigned int nborder = 0;
 
   for (int k = 0; k < nt; ++k) {
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
           const int i = irow[r];
           const uint32_t upper =
               (FULL || i < cb) ? 0xFFFFFFFFu : ((i >= cb + 31) ? 0u : (0xFFFFFFFFu << (i - cb + 1)));
-          live[r] = (i < row_end) ? (valid & upper) : 0u;
+          live[r] = FULL ? row_ok[r] : (row_ok[r] & valid & upper);
           word[r] = acc[r] & live[r];
           doubt = doubt || (live[r] != 0u && !(mv[r] > t_fast));
         }
@@ -445,11 +450,12 @@ __global__ void __launch_bounds__(K1_THREADS, (R >= 4 ? K1_R4_CTAS : (R >= 2 ? 3
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (row_sectors) sw[(wj * R + r) * 32] = word[r];  // (rows past row_end hold zeros: live == 0)
-          if (irow[r] < row_end) {
-            if (!row_sectors) mask[(size_t)irow[r] * stride + (cb >> 5)] = word[r];
-            cnt[r] += __popc(word[r]);
+          if (row_sectors) {
+            sw[(wj * R + r) * 32] = word[r];  // (rows past row_end hold zeros: live == 0)
+          } else if (row_ok[r]) {
+            mask[(size_t)irow[r] * stride + (cb >> 5)] = word[r];
           }
+          cnt[r] += __popc(word[r]);  // (a row past row_end has word == 0)
         }
       };
       if (cb >= row0 + TI && cb + 32 <= n)
@@ -631,7 +637,7 @@ K1Consts make_k1_consts(double beta, double coord_bound) {
   return k;
 }
 
-template <int R, int TJ>
+template <int R, int TJ, bool SECT>
 static int launch_k1_variant(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows) {
   constexpr int TI = K1_THREADS * R;
   const int n_tiles = (max_n + TJ - 1) / TJ;
@@ -649,15 +655,15 @@ static int launch_k1_variant(cudaStream_t st, const K1Job* d_jobs, int n_jobs, i
   constexpr int stage_bytes = (K1_THREADS / 32) * (TJ / 32) * R * 32 * (int)sizeof(uint32_t);
   static bool attr_set = false;
   if (!attr_set) {
-    PSU_CUDA(cudaFuncSetAttribute(k1_mask_kernel<R, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
+    PSU_CUDA(cudaFuncSetAttribute(k1_mask_kernel<R, TJ, SECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
     attr_set = true;
   }
-  k1_mask_kernel<R, TJ><<<grid, K1_THREADS, stage_bytes, st>>>(d_jobs, tpc);
+  k1_mask_kernel<R, TJ, SECT><<<grid, K1_THREADS, stage_bytes, st>>>(d_jobs, tpc);
   PSU_CHECK_LAUNCH("k1_mask_kernel");
   return PSULVSB_OK;
 }
 
-int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows) {
+int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, int max_n, int max_rows, bool row_sectors) {
   if (n_jobs <= 0 || max_n < 1 || max_rows < 1) return PSULVSB_OK;
   // rows per thread by the amount of work: R = 4 / 2 want enough row blocks x tiles to fill the GPU
   const double pairs = 0.5 * (double)max_rows * max_n * n_jobs;
@@ -666,10 +672,16 @@ int launch_consistency_mask(cudaStream_t st, const K1Job* d_jobs, int n_jobs, in
   int variant = pairs >= 5.0e8 ? 4 : (pairs >= 1.0e8 ? 2 : 1);
   if (debug_knobs().k1_variant >= 1 && debug_knobs().k1_variant <= 4) variant = debug_knobs().k1_variant;
   // 256-column tiles (measured: half the barrier stalls of 128-column tiles; 512 is no better)
-  if (variant == 3) return launch_k1_variant<3, 256>(st, d_jobs, n_jobs, max_n, max_rows);
-  if (variant == 4) return launch_k1_variant<4, 256>(st, d_jobs, n_jobs, max_n, max_rows);
-  if (variant == 2) return launch_k1_variant<2, 256>(st, d_jobs, n_jobs, max_n, max_rows);
-  return launch_k1_variant<1, 256>(st, d_jobs, n_jobs, max_n, max_rows);
+  if (row_sectors) {
+    if (variant == 3) return launch_k1_variant<3, 256, true>(st, d_jobs, n_jobs, max_n, max_rows);
+    if (variant == 4) return launch_k1_variant<4, 256, true>(st, d_jobs, n_jobs, max_n, max_rows);
+    if (variant == 2) return launch_k1_variant<2, 256, true>(st, d_jobs, n_jobs, max_n, max_rows);
+    return launch_k1_variant<1, 256, true>(st, d_jobs, n_jobs, max_n, max_rows);
+  }
+  if (variant == 3) return launch_k1_variant<3, 256, false>(st, d_jobs, n_jobs, max_n, max_rows);
+  if (variant == 4) return launch_k1_variant<4, 256, false>(st, d_jobs, n_jobs, max_n, max_rows);
+  if (variant == 2) return launch_k1_variant<2, 256, false>(st, d_jobs, n_jobs, max_n, max_rows);
+  return launch_k1_variant<1, 256, false>(st, d_jobs, n_jobs, max_n, max_rows);
 }
 
 int launch_pack_points(cudaStream_t st, const double* pts, int n, const double center[3], float4* out) {

@@ -128,7 +128,7 @@ def test_fp32_pipe_kernels_are_packed_and_tma_staged():
                 per_fn[name]["FFMA"] += 1
             if "FFMA2" in line and "reuse.F32x2" in line:
                 per_fn[name]["REUSE64"] += 1
-    k1 = {k: v for k, v in per_fn.items() if "k1_mask_kernelILi4ELi256" in k}
+    k1 = {k: v for k, v in per_fn.items() if "k1_mask_kernelILi4ELi256ELb1" in k}
     k4 = {k: v for k, v in per_fn.items() if "score_batch_kernel" in k}
     assert len(k1) == 1 and len(k4) == 1, (list(k1), list(k4))
     for ops in list(k1.values()) + list(k4.values()):
