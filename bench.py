@@ -671,7 +671,7 @@ def stage_k1(c, n=100_000, steps=3, warmup=2):
                         "all-gathered in place (grouped ncclBroadcast), RANSAC replicated"}
 
 
-def stage_k4(c, n=50_000, H=1 << 20, steps=5, warmup=3):
+def stage_k4(c, n=50_000, H=1 << 20, steps=5, warmup=3, with_e2e=False):
     """cfg-D: hypotheses sharded over the ranks; psulvsb_score_batch_sharded ends with the 8-byte ncclAllReduce(max)."""
     torch, capi = c.torch, c.capi
     from psulvsb_b200 import sharding, stages
@@ -725,6 +725,22 @@ def stage_k4(c, n=50_000, H=1 << 20, steps=5, warmup=3):
     cnt, hid = sharding.unpack_best(int(best.item()))
     if hid != H // 3:
         raise SystemExit(f"bench.py: scoring sweep found hypothesis {hid} (count {cnt}), expected {H // 3}")
+    # end to end: this rank's hypotheses start in pinned host memory, the packed best key ends on the host
+    e2e = None
+    if with_e2e:
+        hyp_host = hyp_local.cpu().pin_memory()
+        best_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+        def run_e2e():
+            hyp_local.copy_(hyp_host, non_blocking=True)
+            run()
+            best_host.copy_(best, non_blocking=True)
+
+        ms_e2e = timed_stream(c, run_e2e, steps, 1)
+        e2e = {"value": H * n / (ms_e2e / 1e3), "unit": "scores/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(hyp_host.numel() * 8) * c.world, "d2h_bytes_per_step": 8 * c.world,
+               "how": "every step copies the rank's hypotheses (96 B each) from pinned host memory, scores, and reads the "
+                      "packed best key back; the correspondences stay resident"}
     units = H * n
     peak = c.world * c.sms * 128 * f * 1e6 / 1e9
     ach = units * 16 / (ms / 1e3) / 1e9
@@ -734,7 +750,7 @@ def stage_k4(c, n=50_000, H=1 << 20, steps=5, warmup=3):
             "roofline": {"bound": "fp32-pipe", "achieved": ach, "peak": peak, "frac": ach / peak,
                          "unit": "Gslot/s (16 FP32-pipe issue slots per (hypothesis, point))",
                          "peak_source": f"{c.world} x {c.sms} SMs x 128 lanes x {f:.0f} MHz (SM clock sampled during the steps)"},
-            "clocks": stage_clocks,
+            "clocks": stage_clocks, "e2e": e2e,
             "hbm_hypothesis_stream_gbs": H * 96 / c.world / (ms / 1e3) / 1e9,
             "sharding": "hypotheses sliced across ranks; one 8-byte ncclAllReduce(max) of (count<<32 | ~id) on the same "
                         "stream, inside psulvsb_score_batch_sharded"}
@@ -744,7 +760,7 @@ def run_cfgD(args, c):
     steps, W = max(args.steps, 3), max(args.warmup, 3)
     sampler = ClockSampler(c.local_rank)
     sampler.start()
-    s = stage_k4(c, steps=steps, warmup=W)
+    s = stage_k4(c, steps=steps, warmup=W, with_e2e=True)
     clocks = sampler.stop()
     if c.rank != 0:
         return None
@@ -754,7 +770,7 @@ def run_cfgD(args, c):
             "data": "synthetic",
             "config": {"workload": "cfgD: 2^20 hypotheses x N=50000 correspondences, hypotheses sharded across GPUs",
                        "l2": "hypothesis stream (100 MB per GPU at N=1) read once per step; points from L2"},
-            "e2e": None, "gpu_launches": 3 * steps, "clocks": clocks,  # two re-layout launches + the scoring kernel
+            "e2e": s["e2e"], "gpu_launches": 3 * steps, "clocks": clocks,  # two re-layout launches + the scoring kernel
             "roofline": dict(s["roofline"], kernel="score_batch_kernel"), "best": s["best"], "sharding": s["sharding"]}
 
 
