@@ -194,6 +194,7 @@ int psulvsb_debug_set(const char* name, double value) {
   else if (n == "gnc_cluster") k.gnc_cluster = (int)value;
   else if (n == "gnc_park_pct") k.gnc_park_pct = (int)value;
   else if (n == "gnc_cps") k.gnc_cps = (int)value;
+  else if (n == "gnc_grid_lv") k.gnc_grid_lv = (int)value;
   else if (n == "sample_list_cap_test") k.sample_list_cap_test = (int)value;
   else if (n == "k1_variant") k.k1_variant = (int)value;
   else if (n == "upload_prof") k.upload_prof = (int)value;

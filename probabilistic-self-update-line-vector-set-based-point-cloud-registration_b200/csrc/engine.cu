@@ -926,7 +926,8 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     // give each a few thousand line vectors and as the SMs allow
     if (gnc_cluster == 8 && grid_ctas_max >= 16) {
       const long long k_est = (long long)(0.03 * (double)max_nred);
-      const long long g = std::min<long long>(grid_ctas_max, k_est / 4096);
+      const int lv_per_cta = debug_knobs().gnc_grid_lv > 0 ? debug_knobs().gnc_grid_lv : 4096;
+      const long long g = std::min<long long>(grid_ctas_max, k_est / lv_per_cta);
       if (g >= 16) gnc_cluster = (int)g;
     }
     int gnc_cap = (int)((0.03 * (double)max_nred) / (double)gnc_cluster) + 64;

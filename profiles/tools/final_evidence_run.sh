@@ -2,6 +2,7 @@ set -x
 mkdir -p gpurun_out/final
 O=gpurun_out/final
 env | grep -i nccl > $O/env_nccl.txt; python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1
+[ -x profiles/tools/build/fp32_pipe_probe ] || (mkdir -p profiles/tools/build && nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o profiles/tools/build/fp32_pipe_probe profiles/tools/fp32_pipe_probe.cu)
 profiles/tools/build/fp32_pipe_probe > $O/fp32_pipe_probe.jsonl 2>&1
 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 python bench.py --impl reference > $O/bench_reference_n1.json 2> $O/bench_reference_n1.err
