@@ -22,10 +22,12 @@
 // word with any pair below it is redone with the accurate difference form above, whose own band
 // decides what goes to FP64.
 //
-// Mapping.  One thread owns R rows (its points live in registers), the CTA's column tile is staged
+// Mapping.  One thread owns R rows (its points live in registers as scalars), the CTA's column tile -- pair-
+// interleaved records, so that two neighbouring columns share a 64-bit register pair (see pair_fast2) -- is staged
 // in shared memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) and read as warp-wide
 // broadcasts; a thread accumulates the 32 result bits of a mask word with a funnel shift of v's
-// sign bit, so no ballot and no divergence on the fast path.
+// sign bit, so no ballot and no divergence on the fast path.  Words that are only partly live for some row (its
+// diagonal, the arrays' end) keep their dead columns out of the doubt test (eval_word_masked).
 #include <cuda_runtime.h>
 
 #include <type_traits>
