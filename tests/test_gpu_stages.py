@@ -149,6 +149,28 @@ def test_k1_short_line_vectors_and_diagonal_words(P, O):
         assert want[:, :].sum() > k * (k - 1) // 4        # the clumps are there: their pairs are all consistent
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+def test_k1_rows_per_thread_variants_agree_with_the_oracle(P, O, variant):
+    """The launcher picks 1, 2 or 4 rows per thread by the amount of work (3 is an option); every variant has its own
+    row-to-warp mapping along the diagonal: all of them bit for bit, on sizes with partly live diagonal / last words,
+    whole and as row ranges."""
+    st, synth, capi = P["stages"], P["synth"], P["capi"]
+    capi.debug_set("k1_variant", variant)
+    try:
+        for n, seed in ((1301, 21), (2049, 22)):
+            pair = synth.make_pair(n, 0.9, seed)
+            want = _upper(O.consistency_mask(pair["src"], pair["dst"], 0.1))
+            r = st.consistency_mask(pair["src"], pair["dst"], 0.1)
+            assert np.array_equal(st.unpack_mask(r["mask"], n), want)
+            assert np.array_equal(r["row_counts"].cpu().numpy(), want.sum(axis=1))
+            a = st.consistency_mask(pair["src"], pair["dst"], 0.1, 0, 517)
+            b = st.consistency_mask(pair["src"], pair["dst"], 0.1, 517, n)
+            merged = torch.cat([a["mask"][:517], b["mask"][517:]])
+            assert np.array_equal(st.unpack_mask(merged, n), want)
+    finally:
+        capi.debug_set("reset", 0)
+
+
 def test_k1_row_sharding_and_symmetrize(P, O):
     st, synth = P["stages"], P["synth"]
     n, beta = 777, 0.1
