@@ -39,7 +39,7 @@ constexpr int SMP_THREADS = 256;            // emit pass
 constexpr int SMP_CHUNK = SMP_THREADS * 4;  // draws per chunk (one Philox block per thread)
 constexpr int SMB_THREADS = 1024;           // bucket pass (one CTA per SM: the table fills shared memory)
 constexpr int SMP_BW = 49152;               // values per bucket (192 KB of shared memory)
-constexpr int SMP_MAX_LIST_BUCKETS = 256;   // bucket lists are used for 3 .. 256 buckets
+constexpr int SMP_MAX_LIST_BUCKETS = 512;   // bucket lists are used for 3 .. 512 buckets
 
 // layout of the bucket lists for (n, max_draws).  An entry is ONE 32-bit word, (k << w_bits) | (v - lo): the draw
 // index takes the bits it needs and the rest addresses the value inside its bucket, so the bucket width shrinks
@@ -48,29 +48,52 @@ constexpr int SMP_MAX_LIST_BUCKETS = 256;   // bucket lists are used for 3 .. 25
 // small -> every bucket CTA walks the whole window.
 struct ListPlan {
   unsigned int n_buckets, w_bits, width;
+  unsigned int wide;  // 1: an entry is TWO words, (v - lo, k): long windows over long ranges (cfg-B: 2.3 M draws out of 2 * 10^7
+                      // values), where k and a useful in-bucket offset do not fit one word; buckets of SMP_BW values
   unsigned long long cap_b;
 };
+__host__ __device__ inline unsigned long long list_cap_for(unsigned long long n, unsigned long long max_draws,
+                                                          unsigned long long width) {
+  const unsigned long long mean = (max_draws * width + n - 1) / n + 1;
+  unsigned long long s = 1;
+  while (s * s < mean) ++s;  // ceil(sqrt(mean)), integer: identical on host and device
+  return (mean + 10 * s + 64 + 3) & ~3ull;
+}
 __host__ __device__ inline bool sample_list_plan(unsigned long long n, unsigned long long max_draws,
                                                  unsigned long long blist_cap, ListPlan& p) {
   p.n_buckets = 0;
   p.cap_b = 0;
+  p.wide = 0;
   if (max_draws < 2 || n < 3ull * SMP_BW) return false;
   unsigned int k_bits = 1;
   while (((max_draws - 1) >> k_bits) != 0ull) ++k_bits;
-  if (k_bits > 24) return false;  // buckets of fewer than 256 values: not worth it
-  p.w_bits = 32u - k_bits;
-  p.width = (p.w_bits >= 16u) ? (unsigned int)SMP_BW : (1u << p.w_bits);
-  const unsigned long long nb = (n + p.width - 1) / p.width;
-  if (nb < 3 || nb > (unsigned long long)SMP_MAX_LIST_BUCKETS) return false;
-  p.n_buckets = (unsigned int)nb;
-  const unsigned long long mean = (max_draws * (unsigned long long)p.width + n - 1) / n + 1;
-  unsigned long long s = 1;
-  while (s * s < mean) ++s;  // ceil(sqrt(mean)), integer: identical on host and device
-  p.cap_b = (mean + 10 * s + 64 + 3) & ~3ull;
-  return nb * p.cap_b <= blist_cap;
+  if (k_bits <= 24) {  // (narrower buckets than 256 values are not worth it)
+    p.w_bits = 32u - k_bits;
+    p.width = (p.w_bits >= 16u) ? (unsigned int)SMP_BW : (1u << p.w_bits);
+    const unsigned long long nb = (n + p.width - 1) / p.width;
+    if (nb >= 3 && nb <= (unsigned long long)SMP_MAX_LIST_BUCKETS) {
+      p.n_buckets = (unsigned int)nb;
+      p.cap_b = list_cap_for(n, max_draws, p.width);
+      if (nb * p.cap_b <= blist_cap) return true;
+    }
+  }
+  // two-word entries: k in full, buckets of SMP_BW values
+  if (k_bits > 32) return false;
+  p.w_bits = 32u;
+  p.width = (unsigned int)SMP_BW;
+  const unsigned long long nbw = (n + SMP_BW - 1) / SMP_BW;
+  if (nbw < 3 || nbw > (unsigned long long)SMP_MAX_LIST_BUCKETS) {
+    p.n_buckets = 0;
+    p.cap_b = 0;
+    return false;
+  }
+  p.n_buckets = (unsigned int)nbw;
+  p.cap_b = list_cap_for(n, max_draws, p.width);
+  p.wide = 1;
+  return 2ull * nbw * p.cap_b <= blist_cap;
 }
 __device__ __forceinline__ uint32_t list_bucket(uint32_t v, const ListPlan& p) {
-  return (p.w_bits >= 16u) ? v / (uint32_t)SMP_BW : v >> p.w_bits;
+  return (p.w_bits >= 16u) ? v / (uint32_t)SMP_BW : v >> p.w_bits;  // (wide entries: w_bits = 32)
 }
 
 // (word >> 1) % n with the division replaced by a multiply-high: magic = ceil(2^64 / n) gives the exact
@@ -174,15 +197,15 @@ __global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __re
       }
     __syncthreads();
     // per bucket: total of the step -> one global reservation; per warp: exclusive offset inside it
-    if (tid < (int)n_buckets) {
+    for (int bk = tid; bk < (int)n_buckets; bk += 256) {
       unsigned int run = 0u;
 #pragma unroll
       for (int w = 0; w < 8; ++w) {
-        const unsigned int c = wh[w][tid];
-        wh[w][tid] = run;
+        const unsigned int c = wh[w][bk];
+        wh[w][bk] = run;
         run += c;
       }
-      if (run != 0u) base[tid] = atomicAdd(&job.bcount[tid], run);
+      if (run != 0u) base[bk] = atomicAdd(&job.bcount[bk], run);
     }
     __syncthreads();
 #pragma unroll
@@ -193,10 +216,14 @@ __global__ void __launch_bounds__(256) sample_draws_kernel(const SampleJob* __re
         if (vv[u][l] == 0xFFFFFFFFu) continue;
         const uint32_t b = list_bucket(vv[u][l], plan);
         const unsigned long long pos = (unsigned long long)base[b] + wh[wid][b] + rk[u][l];
-        if (pos < cap_fill)
-          job.blist[(unsigned long long)b * cap_b + pos] =
-              (uint32_t)((((q << 2) + l) << plan.w_bits) | (unsigned long long)(vv[u][l] - b * plan.width));
-        else
+        if (pos < cap_fill) {
+          if (plan.wide)
+            reinterpret_cast<uint2*>(job.blist)[(unsigned long long)b * cap_b + pos] =
+                make_uint2(vv[u][l] - b * plan.width, (uint32_t)((q << 2) + l));
+          else
+            job.blist[(unsigned long long)b * cap_b + pos] =
+                (uint32_t)((((q << 2) + l) << plan.w_bits) | (unsigned long long)(vv[u][l] - b * plan.width));
+        } else
           atomicExch(&job.bcount[SMP_MAX_LIST_BUCKETS], 1u);  // a list overflowed (10 sigma): the bucket pass walks instead
       }
     }
@@ -236,7 +263,37 @@ __global__ void __launch_bounds__(SMB_THREADS, 1) sample_bucket_kernel(const Sam
     const Philox4 o = philox4x32_10(job.seed, job.domain, job.event, q);
     return make_uint4(draw_value(o.w[0], fm), draw_value(o.w[1], fm), draw_value(o.w[2], fm), draw_value(o.w[3], fm));
   };
-  if (lists) {
+  if (lists && plan.wide) {
+    // two-word entries (v - lo, k): read from the list in each of the three short walks (a bucket holds a few thousand)
+    const uint2* __restrict__ lists2 = reinterpret_cast<const uint2*>(job.blist);
+    for (uint32_t i = tid; i < plan.width; i += SMB_THREADS) table[i] = 0xFFFFFFFFu;
+    for (unsigned int b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+      const uint2* __restrict__ list = lists2 + (unsigned long long)b * plan.cap_b;
+      const uint32_t cnt = __ldcg(job.bcount + b);
+      if (vbits)
+        for (uint32_t i = tid; i < (plan.width >> 5); i += SMB_THREADS) wbm[i] = 0u;
+      __syncthreads();  // the table is clean (initialisation / the previous bucket's third walk)
+      for (uint32_t i = tid; i < cnt; i += SMB_THREADS) {
+        const uint2 e = __ldcg(list + i);
+        atomicMin(&table[e.x], e.y);
+      }
+      __syncthreads();
+      const uint32_t lo_b = b * plan.width;
+      for (uint32_t i = tid; i < cnt; i += SMB_THREADS) {
+        const uint2 e = __ldcg(list + i);
+        if (table[e.x] == e.y) {
+          atomicOr(&accept[e.y >> 5], 1u << (e.y & 31));
+          if (vbits) atomicOr(&wbm[e.x >> 5], 1u << (e.x & 31u));
+        }
+      }
+      __syncthreads();
+      if (vbits)
+        for (uint32_t i = tid; i < (plan.width >> 5); i += SMB_THREADS)
+          if (wbm[i] && ((unsigned long long)lo_b + 32ull * i) < job.n) vbits[(lo_b >> 5) + i] = wbm[i];
+      for (uint32_t i = tid; i < cnt; i += SMB_THREADS) table[__ldcg(list + i).x] = 0xFFFFFFFFu;
+      if (tid == 0) job.bcount[b] = 0u;  // zero on exit, like the accept bitmask
+    }
+  } else if (lists) {
     // every draw of bucket b sits in its list as (k << w_bits | v - lo).  A thread keeps its entries of the bucket in
     // registers for the three short walks (first occurrence, accept, clean the table) and already has the next
     // bucket's entries in flight while it works: one exposed HBM latency per CTA instead of three per bucket.
@@ -572,7 +629,7 @@ unsigned long long sample_default_max_draws(unsigned long long n, unsigned long 
 unsigned long long sample_list_entries(unsigned long long n, unsigned long long max_draws) {
   ListPlan p;
   if (!sample_list_plan(n, max_draws, ~0ull, p)) return 0;
-  return (unsigned long long)p.n_buckets * p.cap_b;
+  return (unsigned long long)p.n_buckets * p.cap_b * (p.wide ? 2ull : 1ull);  // in 32-bit words
 }
 unsigned long long sample_list_counters() { return SMP_MAX_LIST_BUCKETS + 4; }
 

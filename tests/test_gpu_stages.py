@@ -37,7 +37,10 @@ def test_philox_stream_matches_oracle(P, O):
 
 
 @pytest.mark.parametrize("n,count", [(10, 10), (1000, 100), (1000, 1000), (65536, 20000), (627562, 62756), (7, 1),
-                                     (147457, 14000), (150000, 75000), (2000000, 200000), (98304, 30000)])
+                                     (147457, 14000), (150000, 75000), (2000000, 200000), (98304, 30000),
+                                     # two-word bucket lists (cfg-B's L sample and basic subset): long windows over
+                                     # long ranges; and a range that needs more than 256 one-word buckets
+                                     (20_700_000, 2_070_000), (2_070_000, 621_000), (24_000_000, 300_000)])
 def test_sampler_replays_rejection_sampling(P, O, n, count):
     st = P["stages"]
     for seed, dom, ev in [(1, 1, 0), (99, 2, 13)]:
