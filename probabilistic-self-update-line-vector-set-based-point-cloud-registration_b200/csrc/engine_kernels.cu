@@ -487,16 +487,23 @@ __global__ void __launch_bounds__(BLK)
 
   // ---- points handed to the translation solver: unique endpoints of the rotation inliers
   // (registration.cc:1114-1155), or every point in the max-clique round with selection NONE (:1066-1084)
-  for (int j0 = 0; j0 < C; j0 += BLK) {
-    const int j = j0 + tid;
-    // clique round: the clique's points (registration.cc:1238-1244); selection NONE: every point (:1066-1084)
-    const int f = (j < C && (clique_round ? (use_clique ? J.clique_flags[j] != 0 : true) : J.rot_flags[j] != 0)) ? 1 : 0;
+  // (each thread takes a contiguous slice: one block scan for the whole set instead of one per 1024 points -- at
+  // C = 100 000 the 98 scans were a quarter of this kernel; ascending j either way)
+  {
+    auto flagged = [&](int j) -> bool {
+      // clique round: the clique's points (registration.cc:1238-1244); selection NONE: every point (:1066-1084)
+      return clique_round ? (use_clique ? J.clique_flags[j] != 0 : true) : J.rot_flags[j] != 0;
+    };
+    const int per = (C + BLK - 1) / BLK;
+    const int lo = min(C, tid * per), hi = min(C, lo + per);
+    int c = 0;
+    for (int j = lo; j < hi; ++j) c += flagged(j) ? 1 : 0;
     int ea, eb, ta, tb;
-    block_scan2(&scratch, f, 0, ea, eb, ta, tb);
-    const int base = base_s[0];
-    if (f) J.idx[base + ea] = j;
-    __syncthreads();
-    if (tid == 0) base_s[0] = base + ta;
+    block_scan2(&scratch, c, 0, ea, eb, ta, tb);
+    int pos = ea;
+    for (int j = lo; j < hi; ++j)
+      if (flagged(j)) J.idx[pos++] = j;
+    if (tid == 0) base_s[0] = ta;
     __syncthreads();
   }
   const int n_rot_pts = base_s[0];
