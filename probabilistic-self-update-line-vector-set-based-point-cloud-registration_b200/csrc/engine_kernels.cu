@@ -617,50 +617,79 @@ __global__ void __launch_bounds__(BLK)
     const uint32_t ev = (uint32_t)J.host_scorings;
     const int M = J.M;
     int curr = 0;
-    for (int j0 = 0; j0 < M; j0 += BLK) {
-      const int j = j0 + tid;
-      int add = 0, imap = 0;
-      if (j < M) {
-        const double res = residual_ref(J.ori_src + 3 * (size_t)j, J.ori_dst + 3 * (size_t)j, X.s, X.R, X.t);
-        if (res <= J.tau) {
-          ++curr;
-          J.inlier_counter[j] += 1;
-          const int km = J.keep_mask[j];
-          if (km == 0) {
-            const int hst = J.inlier_history[j];
-            if (hst == -1 || hst == 1)
-              add = 1;
-            else if (hst == 0)
-              add = (philox_uniform01(J.seed, PSULVSB_DOMAIN_UNIFORM, ev, (uint64_t)j) <=
-                     inlier_probability(res, P.score_sigma))
-                        ? 1
-                        : 0;
+    // The two output lists (new correspondences, inlier map) are in ascending j.  The points go through in super-chunks
+    // of 65 536: every warp leaves its decisions as two ballot words per 32 points in shared memory, then ONE block scan
+    // per super-chunk places them (a scan per 1024 points was 98 scans and 200 barriers per host scoring at M = 100 000)
+    constexpr int SUPER = 65536;
+    __shared__ uint32_t addw_s[SUPER / 32], imapw_s[SUPER / 32];
+    const int lane = tid & 31;
+    for (int s0 = 0; s0 < M; s0 += SUPER) {
+      const int s1 = min(M, s0 + SUPER);
+      for (int j0 = s0; j0 < s1; j0 += BLK) {
+        const int j = j0 + tid;
+        int add = 0, imap = 0;
+        if (j < s1) {
+          const double res = residual_ref(J.ori_src + 3 * (size_t)j, J.ori_dst + 3 * (size_t)j, X.s, X.R, X.t);
+          if (res <= J.tau) {
+            ++curr;
+            J.inlier_counter[j] += 1;
+            const int km = J.keep_mask[j];
+            if (km == 0) {
+              const int hst = J.inlier_history[j];
+              if (hst == -1 || hst == 1)
+                add = 1;
+              else if (hst == 0)
+                add = (philox_uniform01(J.seed, PSULVSB_DOMAIN_UNIFORM, ev, (uint64_t)j) <=
+                       inlier_probability(res, P.score_sigma))
+                          ? 1
+                          : 0;
+            }
+            if (add) {
+              J.final_inliers[j] = 1;
+            } else if (km == 1) {
+              imap = 1;
+              J.final_inliers[j] = 1;
+            }
+            J.inlier_history[j] = 1;
+          } else {
+            // registration.cc:1438 (assignment-in-condition, SURVEY defect 2): the draw decides whether the
+            // point's final_inliers flag is cleared; history := 0
+            const double u = philox_uniform01(J.seed, PSULVSB_DOMAIN_UNIFORM, ev, (uint64_t)j);
+            if (u > inlier_probability(J.residual_history[j], P.score_sigma)) J.final_inliers[j] = 0;
+            J.inlier_history[j] = 0;
           }
-          if (add) {
-            J.final_inliers[j] = 1;
-          } else if (km == 1) {
-            imap = 1;
-            J.final_inliers[j] = 1;
-          }
-          J.inlier_history[j] = 1;
-        } else {
-          // registration.cc:1438 (assignment-in-condition, SURVEY defect 2): the draw decides whether the
-          // point's final_inliers flag is cleared; history := 0
-          const double u = philox_uniform01(J.seed, PSULVSB_DOMAIN_UNIFORM, ev, (uint64_t)j);
-          if (u > inlier_probability(J.residual_history[j], P.score_sigma)) J.final_inliers[j] = 0;
-          J.inlier_history[j] = 0;
+          J.residual_history[j] = res;
         }
-        J.residual_history[j] = res;
+        const unsigned int ab = __ballot_sync(0xffffffffu, add != 0), ib = __ballot_sync(0xffffffffu, imap != 0);
+        if (lane == 0) {
+          addw_s[(j0 - s0 + tid) >> 5] = ab;
+          imapw_s[(j0 - s0 + tid) >> 5] = ib;
+        }
+      }
+      __syncthreads();
+      // thread t owns words 2t, 2t + 1 of the super-chunk (points s0 + 64 t .. + 63)
+      const int nwords = (s1 - s0 + 31) >> 5;
+      uint32_t wa[2], wi[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int w = 2 * tid + k;
+        // (the last word's bits past s1 are clear: add / imap are 0 for j >= s1; words past the chunk were not written)
+        wa[k] = (w < nwords) ? addw_s[w] : 0u;
+        wi[k] = (w < nwords) ? imapw_s[w] : 0u;
       }
       int ea, eb, ta, tb;
-      block_scan2(&scratch, add, imap, ea, eb, ta, tb);
-      const int b0 = base_s[0], b1 = base_s[1];
-      if (add) J.new_corr[b0 + ea] = j;
-      if (imap) J.inlier_map[b1 + eb] = J.reduce_map[j];
+      block_scan2(&scratch, __popc(wa[0]) + __popc(wa[1]), __popc(wi[0]) + __popc(wi[1]), ea, eb, ta, tb);
+      int pa = base_s[0] + ea, pi = base_s[1] + eb;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int jb = s0 + (2 * tid + k) * 32;
+        for (uint32_t w = wa[k]; w; w &= w - 1) J.new_corr[pa++] = jb + __ffs(w) - 1;
+        for (uint32_t w = wi[k]; w; w &= w - 1) J.inlier_map[pi++] = J.reduce_map[jb + __ffs(w) - 1];
+      }
       __syncthreads();
       if (tid == 0) {
-        base_s[0] = b0 + ta;
-        base_s[1] = b1 + tb;
+        base_s[0] += ta;
+        base_s[1] += tb;
       }
       __syncthreads();
     }
