@@ -877,7 +877,15 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     sampler_scratch_sig = sig;
     sampler_scratch_clean = false;  // until this solve completes
   }
-  engine_init_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, m.n_edges, P, m.n_done);
+  {
+    // CTAs per job: enough that a lone large registration's copies use the whole GPU, one when the batch fills it
+    int init_y = (int)(((long long)sm_count() * 2 + B - 1) / B);
+    const int by_size = (std::max(maxM, maxC) + 4 * kCtlThreads - 1) / (4 * kCtlThreads);
+    if (init_y > by_size) init_y = by_size;
+    if (init_y < 1) init_y = 1;
+    engine_init_kernel<<<dim3((unsigned)B, (unsigned)init_y), kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, m.n_edges, P,
+                                                                                    m.n_done);
+  }
   PSU_CHECK_LAUNCH("engine_init_kernel");
   ++launches;
   PSU_CUDA(cudaEventRecord(ev_k1, st));

@@ -142,14 +142,17 @@ __global__ void __launch_bounds__(BLK)
                        const unsigned long long* __restrict__ n_edges, EngineParams P,
                        int* __restrict__ n_done) {
   JobCtl& J = jobs[blockIdx.x];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 3 * J.C0; i += BLK) {
+  // grid.y CTAs share a job's copies (one registration of 10^5 points alone: 12 MB through one SM took 0.8 ms); the
+  // scalar state is thread 0's of the job's first CTA.  Nothing here reads what that thread writes.
+  const int tid = blockIdx.y * BLK + threadIdx.x;
+  const int stride = gridDim.y * BLK;
+  for (int i = tid; i < 3 * J.C0; i += stride) {
     J.src[i] = J.src0[i];
     J.dst[i] = J.dst0[i];
   }
   // 64-byte point records (sx sy sz tx ty tz 0 0): the GNC prologue forms each line vector from two of them with
   // six 16-byte loads instead of twelve scattered 8-byte ones
-  for (int i = tid; i < J.C0; i += BLK) {
+  for (int i = tid; i < J.C0; i += stride) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       J.pts8[8 * (size_t)i + r] = J.src0[3 * (size_t)i + r];
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(BLK)
     J.pts8[8 * (size_t)i + 6] = 0.0;
     J.pts8[8 * (size_t)i + 7] = 0.0;
   }
-  for (int j = tid; j < J.M; j += BLK) {
+  for (int j = tid; j < J.M; j += stride) {
     J.keep_mask[j] = J.keep_mask0[j];
     J.reduce_map[j] = J.reduce_map0[j];
     J.inlier_counter[j] = 0;
@@ -170,10 +173,10 @@ __global__ void __launch_bounds__(BLK)
   // sampler scratch that every use leaves zeroed: only cleared when the host cannot vouch for it (first solve on this
   // arena layout, or the previous solve did not complete)
   if (P.zero_sampler_scratch)
-    for (unsigned long long i = tid; i < J.first_words; i += BLK) J.first[i] = 0u;  // sampler accept bitmask
-  for (int i = tid; i < P.sampler_counters; i += BLK) J.bcount[i] = 0u;  // sampler list counters
+    for (unsigned long long i = tid; i < J.first_words; i += stride) J.first[i] = 0u;  // sampler accept bitmask
+  for (int i = tid; i < P.sampler_counters; i += stride) J.bcount[i] = 0u;  // sampler list counters
   if (P.zero_sampler_scratch)
-    for (unsigned long long i = tid; i < (J.edge_cap + 31) / 32 + 32; i += BLK) J.vbits[i] = 0u;
+    for (unsigned long long i = tid; i < (J.edge_cap + 31) / 32 + 32; i += stride) J.vbits[i] = 0u;
   if (tid == 0) {
     *J.ticket = 0u;
     J.C = J.C0;
