@@ -320,7 +320,7 @@ int launch_score_batch(cudaStream_t st, const float4* src, const float4* dst, co
   a.coord_bound = (float)(coord_bound * 1.0000002);
   const unsigned long long per_cta = (unsigned long long)SB_THREADS * SB_HPT;
   const unsigned long long gx = (n_hyp + per_cta - 1) / per_cta;
-  // slice the correspondences too (grid.y) until the grid is >= 10 waves deep (2 CTAs per SM), >= 2 tiles per slice; among
+  // slice the correspondences too (grid.y): slices of >= 4 tiles, preferably >= 10 waves of 2 CTAs per SM; among
   // the admissible slice lengths take the one that fills its last wave best (2^20 hypotheses x 50 000 points in three
   // slices of 8 tiles are 10.4 waves: the eleventh runs a third full, 6 % of the sweep)
   const unsigned long long slots = (unsigned long long)sm_count() * 2ull;
