@@ -712,11 +712,11 @@ def stage_k4(c, n=50_000, H=1 << 20, steps=5, warmup=3, with_e2e=False):
     # inside the default line this stage follows seconds of host-only work (CPU baseline, parity check): the SM clock
     # has dropped to idle by then and three 26 ms warm-up launches do not bring it back (measured: 29.9 ms against
     # 26.5 ms with the clocks up) -- warm up for half a second, then time with the clock sampled DURING the steps
-    import time as _time
-    t_w = _time.perf_counter()
-    while _time.perf_counter() - t_w < 0.5:
+    # (a FIXED number of launches -- every rank must make the same number of calls: run() ends with a collective --
+    # of about half a second in total: 20 launches of 26 ms on one GPU, 160 of 3.4 ms on eight)
+    for _ in range(min(20 * c.world, 200)):
         run()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
     stage_sampler = ClockSampler(c.local_rank)
     stage_sampler.start()
     ms = timed_stream(c, run, steps, warmup)
