@@ -41,11 +41,12 @@ constexpr int SMB_THREADS = 1024;           // bucket pass (one CTA per SM: the 
 constexpr int SMP_BW = 49152;               // values per bucket (192 KB of shared memory)
 constexpr int SMP_MAX_LIST_BUCKETS = 512;   // bucket lists are used for 3 .. 512 buckets
 
-// layout of the bucket lists for (n, max_draws).  An entry is ONE 32-bit word, (k << w_bits) | (v - lo): the draw
+// layout of the bucket lists for (n, max_draws).  An entry is ONE 32-bit word where that works, (k << w_bits) | (v - lo): the draw
 // index takes the bits it needs and the rest addresses the value inside its bucket, so the bucket width shrinks
 // from SMP_BW to a power of two when the draw window is long (2^17 draws -> 32 768 values per bucket).  n_buckets
-// regions of cap_b entries (mean + 10 sigma + 64 of the uniform draws).  false: lists not applicable / scratch too
-// small -> every bucket CTA walks the whole window.
+// regions of cap_b entries (mean + 10 sigma + 64 of the uniform draws).  When that would take more than
+// SMP_MAX_LIST_BUCKETS buckets, two-word entries (`wide`).  false: lists not applicable / scratch too small -> every
+// bucket CTA walks the whole window.
 struct ListPlan {
   unsigned int n_buckets, w_bits, width;
   unsigned int wide;  // 1: an entry is TWO words, (v - lo, k): long windows over long ranges (cfg-B: 2.3 M draws out of 2 * 10^7
