@@ -595,6 +595,7 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
         J.new_corr = bw.take<int>((size_t)L.M);
         J.inlier_history = bw.take<int>((size_t)L.M);
         J.final_inliers = bw.take<int>((size_t)L.M);
+        J.hs_bits = bw.take<uint32_t>(2 * (((size_t)L.M + 31) / 32) + 2);
         J.inlier_map = bw.take<int>((size_t)L.Ccap);
         J.idx = bw.take<int>((size_t)L.Ccap);
         J.adj_stride = (L.Ccap + 31) / 32;
@@ -859,6 +860,9 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
   P.self_update = params->self_update;
   P.inlier_selection_mode = params->inlier_selection_mode;
   P.max_local_iters = 4096;
+  // one registration's M points scored by ONE CTA is fine at M = 5000 (and two launches per tick would cost a batch of
+  // small problems more than it gains); from 32 768 points on the scoring gets a grid-wide kernel of its own
+  P.split_host_scoring = (maxM >= 32768) ? 1 : 0;
   P.sampler_counters = (int)sample_list_counters();
   {
     // The sampler leaves its accept bitmask and value bitmap zeroed after every use.  They are cleared here only when
@@ -946,6 +950,14 @@ int Engine::solve_once(const psulvsb_params_t* params, const uint64_t* seeds, ps
     engine_local_control_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sl, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
     PSU_CHECK_LAUNCH("engine_local_control_kernel");
     launches += 5;
+    if (P.split_host_scoring) {  // large M: the host scoring of a tick on the whole GPU (both exit at once when no job asks)
+      engine_host_score_kernel<<<dim3((unsigned)((maxM + kCtlThreads - 1) / kCtlThreads), (unsigned)B), kCtlThreads, 0, st>>>(
+          m.jobs, P);
+      PSU_CHECK_LAUNCH("engine_host_score_kernel");
+      engine_host_finish_kernel<<<B, kCtlThreads, 0, st>>>(m.jobs, m.sb, m.gj, m.cq, P, elapsed, m.n_done);
+      PSU_CHECK_LAUNCH("engine_host_finish_kernel");
+      launches += 2;
+    }
     ++ticks;
     PSU_CUDA(cudaMemcpyAsync((void*)h_done, m.n_done, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     PSU_CUDA(cudaStreamSynchronize(st));

@@ -436,6 +436,87 @@ __global__ void __launch_bounds__(BLK)
 // local control: everything of one local iteration after the rotation solve
 // (registration.cc:1114-1488)
 // ------------------------------------------------------------------------------------------
+// host scoring of ONE of the M correspondences (registration.cc:1417-1444): residual, inlier counter, self-update
+// decision (add), inlier map entry (imap), histories.  Independent per point.
+__device__ __forceinline__ void host_score_point(JobCtl& J, const EngineParams& P, const Xform& X, const uint32_t ev,
+                                                 const int j, int& add, int& imap, int& inl) {
+    const double res = residual_ref(J.ori_src + 3 * (size_t)j, J.ori_dst + 3 * (size_t)j, X.s, X.R, X.t);
+    if (res <= J.tau) {
+      inl = 1;
+      J.inlier_counter[j] += 1;
+      const int km = J.keep_mask[j];
+      if (km == 0) {
+        const int hst = J.inlier_history[j];
+        if (hst == -1 || hst == 1)
+          add = 1;
+        else if (hst == 0)
+          add = (philox_uniform01(J.seed, PSULVSB_DOMAIN_UNIFORM, ev, (uint64_t)j) <=
+                 inlier_probability(res, P.score_sigma))
+                    ? 1
+                    : 0;
+      }
+      if (add) {
+        J.final_inliers[j] = 1;
+      } else if (km == 1) {
+        imap = 1;
+        J.final_inliers[j] = 1;
+      }
+      J.inlier_history[j] = 1;
+    } else {
+      // registration.cc:1438 (assignment-in-condition, SURVEY defect 2): the draw decides whether the
+      // point's final_inliers flag is cleared; history := 0
+      const double u = philox_uniform01(J.seed, PSULVSB_DOMAIN_UNIFORM, ev, (uint64_t)j);
+      if (u > inlier_probability(J.residual_history[j], P.score_sigma)) J.final_inliers[j] = 0;
+      J.inlier_history[j] = 0;
+    }
+    J.residual_history[j] = res;
+}
+
+// the end of a host round (registration.cc:1454-1488): best-host update, p_host, stop rules, next phase.  One thread.
+__device__ void finish_host_round(JobCtl& J, const EngineParams& P, const Xform& X, const int curr, const double elapsed_s,
+                                  SampleJob& sbj, GncJob& gjj, CliqueJob& cqj, int* __restrict__ n_done,
+                                  const int new_corr_count, const int inlier_map_size) {
+  const int M = J.M;
+  J.host_r += J.local_r;
+  J.host_scorings += 1;
+  J.new_corr_count = new_corr_count;
+  J.inlier_map_size = inlier_map_size;
+  // the reference tests the already-escalated rate here (registration.cc:1454), not the one in
+  // force when the iteration started
+  const double b_now = kBRate[J.rate_idx];
+  if (curr > J.best_host_cnt || J.pro_host == 0.0 || (b_now == 1.0 && curr >= J.best_host_cnt)) {
+    J.best_host = X;
+    J.best_host_cnt = curr;
+  }
+  J.last_best = J.best_host;
+  J.pro_host = 1.0 - pow(1.0 - (double)((double)J.best_host_cnt / (double)M), J.host_r);
+  const bool timeup = P.wallclock_cap_s > 0.0 && elapsed_s > P.wallclock_cap_s;
+  if (J.pro_host > P.tpro_host || J.longholi || timeup) J.pro_host_not_over = 0;
+  if (kLRate[J.rate_idx] == 1.0 && b_now == 1.0) J.longholi = 1;
+  if (J.host_trace && J.n_host_trace < J.host_trace_cap) {
+    psulvsb_host_trace_t& T = J.host_trace[J.n_host_trace++];
+    T.host_round = J.host_round;
+    T.curr_count = curr;
+    T.best_host = J.best_host_cnt;
+    T.new_corr_count = P.self_update ? J.new_corr_count : 0;
+    T.inlier_map_size = J.inlier_map_size;
+    T.host_r = J.host_r;
+    T.p_host = J.pro_host;
+  }
+  J.host_round += 1;
+  sbj.active = 0;
+  gjj.active = 0;
+  cqj.active = 0;
+  if (J.pro_host_not_over && J.rounds_left > 0) {
+    J.phase = PHASE_ROUND_START;
+    atomicAdd(n_done + 1, 1);
+  } else {
+    J.valid = 1;
+    J.phase = PHASE_DONE;
+    atomicAdd(n_done, 1);
+  }
+}
+
 __global__ void __launch_bounds__(BLK)
     engine_local_control_kernel(JobCtl* __restrict__ jobs, SampleJob* __restrict__ sl, SampleJob* __restrict__ sb,
                                 GncJob* __restrict__ gj, CliqueJob* __restrict__ cq, EngineParams P, double elapsed_s,
@@ -614,6 +695,14 @@ __global__ void __launch_bounds__(BLK)
   }
   __syncthreads();
 
+  if (J.pro_local > P.tpro_local && P.split_host_scoring) {
+    // large M: engine_host_score_kernel (grid-wide) and engine_host_finish_kernel take over, in this tick
+    if (tid == 0) {
+      J.hs_curr = 0;
+      J.phase = PHASE_HOST_SCORE;
+    }
+    return;
+  }
   if (J.pro_local > P.tpro_local) {
     // ---- host scoring over all M correspondences + self-update decision (registration.cc:1399-1452)
     const Xform X = J.best_sampled;
@@ -632,36 +721,9 @@ __global__ void __launch_bounds__(BLK)
         const int j = j0 + tid;
         int add = 0, imap = 0;
         if (j < s1) {
-          const double res = residual_ref(J.ori_src + 3 * (size_t)j, J.ori_dst + 3 * (size_t)j, X.s, X.R, X.t);
-          if (res <= J.tau) {
-            ++curr;
-            J.inlier_counter[j] += 1;
-            const int km = J.keep_mask[j];
-            if (km == 0) {
-              const int hst = J.inlier_history[j];
-              if (hst == -1 || hst == 1)
-                add = 1;
-              else if (hst == 0)
-                add = (philox_uniform01(J.seed, PSULVSB_DOMAIN_UNIFORM, ev, (uint64_t)j) <=
-                       inlier_probability(res, P.score_sigma))
-                          ? 1
-                          : 0;
-            }
-            if (add) {
-              J.final_inliers[j] = 1;
-            } else if (km == 1) {
-              imap = 1;
-              J.final_inliers[j] = 1;
-            }
-            J.inlier_history[j] = 1;
-          } else {
-            // registration.cc:1438 (assignment-in-condition, SURVEY defect 2): the draw decides whether the
-            // point's final_inliers flag is cleared; history := 0
-            const double u = philox_uniform01(J.seed, PSULVSB_DOMAIN_UNIFORM, ev, (uint64_t)j);
-            if (u > inlier_probability(J.residual_history[j], P.score_sigma)) J.final_inliers[j] = 0;
-            J.inlier_history[j] = 0;
-          }
-          J.residual_history[j] = res;
+          int inl = 0;
+          host_score_point(J, P, X, ev, j, add, imap, inl);
+          curr += inl;
         }
         const unsigned int ab = __ballot_sync(0xffffffffu, add != 0), ib = __ballot_sync(0xffffffffu, imap != 0);
         if (lane == 0) {
@@ -699,44 +761,7 @@ __global__ void __launch_bounds__(BLK)
     int dummy = 0;
     block_sum_int2(&scratch, curr, dummy);
     if (tid == 0) {
-      J.host_r += J.local_r;
-      J.host_scorings += 1;
-      J.new_corr_count = base_s[0];
-      J.inlier_map_size = base_s[1];
-      // the reference tests the already-escalated rate here (registration.cc:1454), not the one in
-      // force when the iteration started
-      const double b_now = kBRate[J.rate_idx];
-      if (curr > J.best_host_cnt || J.pro_host == 0.0 || (b_now == 1.0 && curr >= J.best_host_cnt)) {
-        J.best_host = X;
-        J.best_host_cnt = curr;
-      }
-      J.last_best = J.best_host;
-      J.pro_host = 1.0 - pow(1.0 - (double)((double)J.best_host_cnt / (double)M), J.host_r);
-      const bool timeup = P.wallclock_cap_s > 0.0 && elapsed_s > P.wallclock_cap_s;
-      if (J.pro_host > P.tpro_host || J.longholi || timeup) J.pro_host_not_over = 0;
-      if (kLRate[J.rate_idx] == 1.0 && b_now == 1.0) J.longholi = 1;
-      if (J.host_trace && J.n_host_trace < J.host_trace_cap) {
-        psulvsb_host_trace_t& T = J.host_trace[J.n_host_trace++];
-        T.host_round = J.host_round;
-        T.curr_count = curr;
-        T.best_host = J.best_host_cnt;
-        T.new_corr_count = P.self_update ? J.new_corr_count : 0;
-        T.inlier_map_size = J.inlier_map_size;
-        T.host_r = J.host_r;
-        T.p_host = J.pro_host;
-      }
-      J.host_round += 1;
-      sb[blockIdx.x].active = 0;
-      gj[blockIdx.x].active = 0;
-      cq[blockIdx.x].active = 0;
-      if (J.pro_host_not_over && J.rounds_left > 0) {
-        J.phase = PHASE_ROUND_START;
-        atomicAdd(n_done + 1, 1);
-      } else {
-        J.valid = 1;
-        J.phase = PHASE_DONE;
-        atomicAdd(n_done, 1);
-      }
+      finish_host_round(J, P, X, curr, elapsed_s, sb[blockIdx.x], gj[blockIdx.x], cq[blockIdx.x], n_done, base_s[0], base_s[1]);
     }
   } else if (tid == 0) {
     J.sampled_first_time = 0;
@@ -751,6 +776,74 @@ __global__ void __launch_bounds__(BLK)
       prepare_local(J, sb[blockIdx.x], gj[blockIdx.x], cq[blockIdx.x], P);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// split host scoring (large M): what the control kernel does in its last third, on the whole GPU.  One registration of
+// 10^5 correspondences scored by ONE CTA -- a Philox draw and an erfc per outlier -- was ~ 0.3 ms of every tick.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLK)
+    engine_host_score_kernel(JobCtl* __restrict__ jobs, EngineParams P) {
+  JobCtl& J = jobs[blockIdx.y];
+  if (J.phase != PHASE_HOST_SCORE) return;
+  const int M = J.M;
+  const int j0 = blockIdx.x * BLK;
+  if (j0 >= M) return;
+  const int j = j0 + threadIdx.x;
+  const Xform X = J.best_sampled;
+  const uint32_t ev = (uint32_t)J.host_scorings;
+  int add = 0, imap = 0, inl = 0;
+  if (j < M) host_score_point(J, P, X, ev, j, add, imap, inl);
+  const unsigned int ab = __ballot_sync(0xffffffffu, add != 0), ib = __ballot_sync(0xffffffffu, imap != 0);
+  const unsigned int nb = __ballot_sync(0xffffffffu, inl != 0);
+  if ((threadIdx.x & 31) == 0 && j < M) {  // (a warp whose first point is past M has no word)
+    const int nw = (M + 31) >> 5;
+    J.hs_bits[j >> 5] = ab;
+    J.hs_bits[nw + (j >> 5)] = ib;
+    if (nb) atomicAdd(&J.hs_curr, __popc(nb));
+  }
+}
+
+__global__ void __launch_bounds__(BLK)
+    engine_host_finish_kernel(JobCtl* __restrict__ jobs, SampleJob* __restrict__ sb, GncJob* __restrict__ gj,
+                              CliqueJob* __restrict__ cq, EngineParams P, double elapsed_s, int* __restrict__ n_done) {
+  JobCtl& J = jobs[blockIdx.x];
+  if (J.phase != PHASE_HOST_SCORE) return;
+  __shared__ BlockScratch scratch;
+  __shared__ int base_s[2];
+  const int tid = threadIdx.x;
+  const int M = J.M, nw = (M + 31) >> 5;
+  if (tid == 0) base_s[0] = base_s[1] = 0;
+  __syncthreads();
+  // the two ordered lists from the decision bits: thread t owns words 2t, 2t + 1 of a super-chunk of 65 536 points
+  constexpr int SUPER = 65536;
+  for (int s0 = 0; s0 < M; s0 += SUPER) {
+    uint32_t wa[2], wi[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int w = (s0 >> 5) + 2 * tid + k;
+      wa[k] = (w < nw) ? J.hs_bits[w] : 0u;
+      wi[k] = (w < nw) ? J.hs_bits[nw + w] : 0u;
+    }
+    int ea, eb, ta, tb;
+    block_scan2(&scratch, __popc(wa[0]) + __popc(wa[1]), __popc(wi[0]) + __popc(wi[1]), ea, eb, ta, tb);
+    int pa = base_s[0] + ea, pi = base_s[1] + eb;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int jb = s0 + (2 * tid + k) * 32;
+      for (uint32_t w = wa[k]; w; w &= w - 1) J.new_corr[pa++] = jb + __ffs(w) - 1;
+      for (uint32_t w = wi[k]; w; w &= w - 1) J.inlier_map[pi++] = J.reduce_map[jb + __ffs(w) - 1];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      base_s[0] += ta;
+      base_s[1] += tb;
+    }
+    __syncthreads();
+  }
+  if (tid == 0)
+    finish_host_round(J, P, J.best_sampled, J.hs_curr, elapsed_s, sb[blockIdx.x], gj[blockIdx.x], cq[blockIdx.x], n_done,
+                      base_s[0], base_s[1]);
 }
 
 // ------------------------------------------------------------------------------------------

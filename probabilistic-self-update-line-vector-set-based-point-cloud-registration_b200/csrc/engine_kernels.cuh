@@ -15,6 +15,9 @@ __global__ void engine_round_start_kernel(JobCtl* jobs, SampleJob* sl, SampleJob
 __global__ void engine_scale_kernel(JobCtl* jobs, GncJob* gj, CliqueJob* cq, EngineParams P);
 __global__ void engine_local_control_kernel(JobCtl* jobs, SampleJob* sl, SampleJob* sb, GncJob* gj, CliqueJob* cq,
                                             EngineParams P, double elapsed_s, int* n_done);
+__global__ void engine_host_score_kernel(JobCtl* jobs, EngineParams P);
+__global__ void engine_host_finish_kernel(JobCtl* jobs, SampleJob* sb, GncJob* gj, CliqueJob* cq, EngineParams P,
+                                          double elapsed_s, int* n_done);
 __global__ void engine_refine_kernel(JobCtl* jobs, psulvsb_solution_t* out, const unsigned long long* border);
 __global__ void engine_export_points_kernel(const JobCtl* jobs, int job, int* final_inliers, int* inlier_counter);
 

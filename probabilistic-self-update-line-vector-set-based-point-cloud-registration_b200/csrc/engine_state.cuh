@@ -13,7 +13,8 @@
 
 namespace psulvsb {
 
-enum : int { PHASE_ROUND_START = 0, PHASE_LOCAL = 1, PHASE_DONE = 2 };
+enum : int { PHASE_ROUND_START = 0, PHASE_LOCAL = 1, PHASE_DONE = 2,
+             PHASE_HOST_SCORE = 3 };  // (split host scoring only: between the control kernel and the two kernels after it)
 
 struct Xform {
   double s;
@@ -42,6 +43,7 @@ struct EngineParams {
   int self_update;
   int inlier_selection_mode;
   int max_local_iters;  // engine guard against the reference's non-terminating inputs
+  int split_host_scoring;  // 1: the host scoring of all M points runs as a grid-wide kernel of its own (large M)
 };
 
 struct JobCtl {
@@ -61,6 +63,8 @@ struct JobCtl {
   int* new_corr;        // [M]
   int* inlier_history;  // [M]
   int* final_inliers;   // [M]
+  uint32_t* hs_bits;    // [2 * ceil(M / 32)] split host scoring: per-point decisions (new correspondence, inlier map)
+  int hs_curr;          // split host scoring: inliers counted so far
   double* residual_history;  // [M]
   int* inlier_map;           // [Ccap]
   int* idx;                  // [Ccap] translation scratch
